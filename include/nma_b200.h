@@ -1,0 +1,126 @@
+/*
+ * nma_b200.h — C-ABI of the B200-native NMA (Neural Moving Average) ELBO step.
+ *
+ * The reference (mehrnazmo/VIforSSMs) has no FFI: its only process/device seam
+ * is the TensorFlow session call
+ *     sess.run([self.train_step, self.merged], feed_dict={time_feats, mask, shift})
+ * (AR.py:300-301; fitz_nag_NVP.py:389-390; SV_dense.py:341-342).  Everything that
+ * one call executes — window gather, NMA flow, ELBO terms, gradients, clip +
+ * Adamax — is what this library replaces.  Each entry point cites the reference
+ * lines it stands in for.
+ *
+ * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller;
+ * every call is asynchronous on the given cudaStream_t (passed as void*), is
+ * CUDA-graph capturable, allocates nothing after nma_create, returns 0 on
+ * success and a negative code on failure (message via nma_last_error()).
+ * No exception ever crosses this boundary.
+ */
+#ifndef NMA_B200_H
+#define NMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMA_MAX_CHAN   32
+#define NMA_MAX_ARRAYS 8
+#define NMA_MAX_FLOWS  8
+
+/* model kinds (which _ELBO is evaluated) */
+#define NMA_MODEL_AR  0   /* AR.py:168-187 */
+#define NMA_MODEL_FHN 1   /* fitz_nag_NVP.py:232-266 */
+#define NMA_MODEL_SV  2   /* SV_dense.py:203-234 */
+
+/* objectives (which scalar is differentiated) */
+#define NMA_OBJ_ELBO    0 /* -sum_rows scale*(sde - logq + obs)   AR.py:184-185,228-229 */
+#define NMA_OBJ_NEG_OBS 1 /* -sum_rows obs_log_prob               AR.py:201-202 (pre-train) */
+#define NMA_OBJ_PATH_SQ 2 /* sum (lf_sample - target)^2           fitz_nag_NVP.py:288-289; SV_dense.py:251-252 */
+
+typedef struct nma_config {
+    int32_t model;
+    int32_t p;          /* max rows per step: MC samples == subsequences (AR.py:117,263-265) */
+    int32_t K;          /* kernel_len */
+    int32_t B;          /* batch_dims */
+    int32_t D;          /* flow_dims: 1, or 2 = two latent components interleaved on the time axis */
+    int32_t F;          /* no_flows */
+    int32_t C;          /* network_dims[0]; must be 50 */
+    int32_t H;          /* hidden 1x1 layers = len(network_dims)-2 */
+    int32_t bn;         /* inference-mode batch-norm affine after each hidden layer (fitz_nag_NVP.py:93) */
+    int32_t Cf;         /* channels of time_feats */
+    int32_t feat_aug;   /* SV_dense.py:53: features at slot+1 plus first differences of the first Cf-2 */
+    int32_t dtheta;
+    int32_t n_arrays;   /* number of base arrays given to nma_set_series */
+    int32_t obs_array;  /* base array evaluated by the observation term */
+    int32_t bin_array;  /* base array holding the observation indicator */
+    int32_t head_offset;
+    int32_t chan_array[NMA_MAX_CHAN];  /* time_feats[r, j, c] = base[chan_array[c]][D*idx[r] + j + chan_offset[c]] */
+    int32_t chan_offset[NMA_MAX_CHAN];
+    double  scale;      /* T / batch_dims (AR.py:184) */
+    float   dt;
+    float   obs_std;
+    float   x0[2];
+} nma_config;
+
+typedef struct nma_handle_s* nma_handle;
+
+const char* nma_last_error(void);
+int nma_version(void);
+
+/* Model assembly — VI_SSM.__init__ + build_flow (AR.py:115-159,189-238): sizes every workspace. */
+int nma_create(const nma_config* cfg, nma_handle* out);
+int nma_destroy(nma_handle h);
+
+/* number of fp32 values in the flat parameter blob / per-flow section table
+ * (TF variable creation order, AR.py:53-78).  offsets: int64[F * 32] (see nma_api.cu). */
+int64_t nma_param_count(nma_handle h);
+int nma_param_layout(nma_handle h, int64_t* offsets_out, int32_t n);
+/* bytes of device workspace held by the handle */
+int64_t nma_workspace_bytes(nma_handle h);
+
+/* Padded base arrays exactly as VI_SSM.__init__ builds them (AR.py:135-150), already cast to fp32
+ * (the feed_dict cast, AR.py:300-301).  Pointers are borrowed until nma_destroy / the next call. */
+int nma_set_series(nma_handle h, const float* const* d_arrays, const int64_t* lengths, int32_t n_arrays);
+
+/* A1 — window gather (AR.py:267-288): d_time_feats [p,L0,Cf], d_mask/d_shift [p,D,B+1] (may be NULL). */
+int nma_gather(nma_handle h, const int64_t* d_idx, int32_t p, float* d_time_feats, float* d_mask,
+               float* d_shift, void* stream);
+
+/* A2-A8 — one fused ELBO + gradient evaluation (the body of sess.run(train_step), AR.py:300 →
+ * AR.py:44-110,168-187,226-229).  d_eps [p,L0] and d_idx [p] are injected by the host
+ * (indices stay bit-exact numpy draws, AR.py:263-265).
+ *   d_terms       [p,4]  sde_log_prob, obs_log_prob, lf_log_prob (logq), base_log_prob
+ *   d_lf          [p,L_F] final flow sample (lf_sample before any reshape)
+ *   d_grad_params [n_params]  d objective / d params   (overwritten)
+ *   d_grad_theta  [p,dtheta]  d objective / d theta    (overwritten)
+ *   d_flags       [p]    bit0 = non-finite ELBO term in that row (fitz_nag_NVP.py:378-381 needs it)
+ */
+int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
+                     const int64_t* d_idx, int32_t p, int32_t objective, float path_target,
+                     float* d_terms, float* d_lf, float* d_grad_params, float* d_grad_theta,
+                     uint32_t* d_flags, void* stream);
+
+/* forward only — save_paths (AR.py:323-362; fitz_nag_NVP.py:409-448) */
+int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
+                      const int64_t* d_idx, int32_t p, float* d_terms, float* d_lf, void* stream);
+
+/* A9 — tf.global_norm + clip_by_global_norm + AdamaxOptimizer._apply_dense
+ * (AR.py:230-234; optimisers/adamax.py:42-58).  d_norm_out[0] = global norm (pre-clip).
+ * d_scratch: >= 1024 floats. */
+int nma_adamax_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float clip,
+                    float* d_norm_out, float* d_scratch, void* stream);
+
+/* A12 — AR(1) series simulation (AR_dat_gen.py:11-15) as an affine-map prefix scan.
+ * x[0] = x0; x[i] = a*x[i-1] + b + c*z[i-1]  (i = 1..n);  d_z: n standard normals. d_x: n+1. */
+int nma_scan_ar1(const double* d_z, double* d_x, int64_t n, double x0, double a, double b, double c,
+                 void* d_scratch, int64_t scratch_bytes, void* stream);
+/* A13 — hold-fill + time-till-next-observation (AR_dat_gen.py:17-31) for every-`impute`-th sampling. */
+int nma_time_till(const double* d_obs, int64_t n, int32_t impute, double* d_obs_fill, double* d_obs_binary,
+                  double* d_time_till, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMA_B200_H */

@@ -1,0 +1,262 @@
+"""CPU oracle for the NMA ELBO step  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
+`--impl reference` legs may import this module.  The product path
+(`viforssms_b200/`) never does; it fails loudly when the CUDA library is missing.
+
+What it restates.  The reference (mehrnazmo/VIforSSMs) is TensorFlow-1.8 Python;
+TensorFlow cannot be installed here (no wheel for CPython 3.12, no network), so
+the arithmetic that TF's own kernels would run is restated with plain
+numpy / torch-CPU ops, following the reference scripts line by line:
+
+  pad_series_ar        AR.py:135-150           series padding (numpy, float64)
+  sample_indices       AR.py:257-265           np.random.choice index draw
+  gather_feed_ar       AR.py:267-288           window gather -> time_feats/mask/shift
+  flow_forward         AR.py:24-35,44-110      base dist, IAF layer, Flow_Stack
+                       fitz_nag_NVP.py:56-156  stride-2 head, interleave, Permute
+                       SV_dense.py:37-89       delta-augmented features
+  elbo_terms           AR.py:168-187           (+ fitz_nag_NVP.py:232-266, SV_dense.py:203-234)
+  adamax_step          optimisers/adamax.py:42-58 + AR.py:226-234 (global-norm clip)
+
+PARITY STATUS.  The numpy half (padding, index draw, gather, data generation) is
+PINNED: tests/golden/ar_golden.npz holds what the reference's own unmodified
+code fed to its session (tests/golden/make_golden.py runs AR.py's VI_SSM.train
+under a stub `tensorflow`).  The torch half (flow, ELBO, gradients, Adamax) is
+"parity unpinned": the reference records no ELBO / gradient / parameter value
+anywhere and its TF graph cannot be executed here; it is pinned only by fp64
+autograd + gradcheck of this restatement (tests/test_oracle.py).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as Fnn
+
+LOG2PI = math.log(2.0 * math.pi)
+
+
+# ----------------------------------------------------------------------------
+# numpy half: padding, sampling, gather (pinned by tests/golden/ar_golden.npz)
+# ----------------------------------------------------------------------------
+
+def pad_series_ar(obs, obs_bin, time_till, x0, T, F, K, fw) -> Dict[str, object]:
+    """AR.py:135-150.  Returns the same seven padded objects the reference keeps on `self`."""
+    P = F * K + 1
+    T = int(np.int32(T))
+    store = []
+    for i in range(fw):
+        store.append(np.concatenate((np.zeros(P - i), obs, np.zeros(i)), axis=0))
+    return {
+        "obs_pad_store": store,
+        "time_pad": np.concatenate((np.zeros(P), np.arange(T + 1)), axis=0),
+        "bin_feats": np.float32(np.concatenate((np.ones(P), np.zeros(T)), axis=0)),
+        "obs_bin": np.concatenate((np.zeros(P), obs_bin), axis=0),
+        "mask_vals": np.concatenate((np.zeros((1, 1)), np.ones((1, T))), axis=1),
+        "shift_vals": np.concatenate((np.array([[x0]]), np.zeros((1, T))), axis=1),
+        "time_till": np.concatenate((np.arange(P + time_till[0], time_till[0], -1), time_till), axis=0),
+    }
+
+
+def sample_indices(T, B, p, rng=np.random) -> np.ndarray:
+    """AR.py:257-265: p subsequence starts drawn from arange(0,T,B), with replacement iff B*p >= T."""
+    cand = np.arange(0, T, B)
+    return rng.choice(cand, size=p, replace=bool(B * p >= T))
+
+
+def gather_feed_ar(pads, batch_select, L0, B) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """AR.py:267-288: (time_feats [p,L0,fw+4], mask [p,B+1], shift [p,B+1]), float64 like the feed."""
+    def win(arr):
+        return np.stack([arr[i:i + L0] for i in batch_select], axis=0)[:, :, None]
+    chans = [win(a) for a in pads["obs_pad_store"]]
+    chans += [win(pads["bin_feats"]), win(pads["time_pad"]), win(pads["time_till"]), win(pads["obs_bin"])]
+    time_feats = np.concatenate(chans, axis=2)
+    mask = np.stack([pads["mask_vals"][0, i:i + B + 1] for i in batch_select], axis=0)
+    shift = np.stack([pads["shift_vals"][0, i:i + B + 1] for i in batch_select], axis=0)
+    return time_feats, mask, shift
+
+
+# ----------------------------------------------------------------------------
+# torch half: flow, ELBO, gradients, Adamax ("parity unpinned", see header)
+# ----------------------------------------------------------------------------
+
+def unpack_params(flat: torch.Tensor, layout) -> Dict[str, torch.Tensor]:
+    return {k: flat[o:o + int(np.prod(s))].reshape(s) for k, (o, s) in layout.items()}
+
+
+def _bn_affine(x, gamma, beta):
+    """tf.layers.batch_normalization with training=False and never-updated moving stats
+    (fitz_nag_NVP.py:93): gamma * (x - 0) / sqrt(1 + 1e-3) + beta."""
+    return x * (gamma / math.sqrt(1.0 + 1e-3)) + beta
+
+
+def flow_forward(cfg, P: Dict[str, torch.Tensor], eps: torch.Tensor, theta: torch.Tensor,
+                 time_feats: torch.Tensor):
+    """Flow_Stack.slp(): returns (x_final [p, L_F], logq [p]).
+
+    eps [p, L0] is the base sample (AR.py:31-32, injected instead of sampled),
+    theta [p, dtheta], time_feats [p, L0, Cf].
+    """
+    K, S, D = cfg.K, cfg.S, cfg.D
+    x = eps
+    # init_dist.slp: sum over the last S slots of log N(eps; 0, 1)            (AR.py:33-34)
+    logq = (-0.5 * eps[:, -S:] ** 2 - 0.5 * LOG2PI).sum(dim=1)
+    for i in range(cfg.F):
+        ts = time_feats[:, i * K:, :]                                         # AR.py:192-193
+        if cfg.feat_aug:                                                      # SV_dense.py:53
+            f = torch.cat([ts[:, 1:, :], ts[:, 1:, :-2] - ts[:, :-1, :-2]], dim=2)
+        else:
+            f = ts[:, :-1, :]                                                 # AR.py:53
+        for l in range(4):                                                    # AR.py:54-56
+            f = Fnn.elu(f @ P[f"f{i}.feat{l}.w"] + P[f"f{i}.feat{l}.b"])
+        inp = torch.cat([x[:, :-1, None], f], dim=2)                          # AR.py:58-59
+        W = P[f"f{i}.conv.w"]                                                 # [K, Cin, Cout]
+        A = Fnn.conv1d(inp.transpose(1, 2), W.permute(2, 1, 0), P[f"f{i}.conv.b"]).transpose(1, 2)  # AR.py:61-62
+        b = theta
+        for l in range(3):                                                    # AR.py:63-68
+            b = b @ P[f"f{i}.th{l}.w"] + P[f"f{i}.th{l}.b"]
+        h = Fnn.elu(A + b[:, None, :])                                        # AR.py:70-72
+        for l in range(cfg.H):                                                # AR.py:74-76
+            h = Fnn.elu(h @ P[f"f{i}.hid{l}.w"] + P[f"f{i}.hid{l}.b"])
+            if cfg.bn:
+                h = _bn_affine(h, P[f"f{i}.hid{l}.gamma"], P[f"f{i}.hid{l}.beta"])
+        if D == 1:
+            out = h @ P[f"f{i}.head.w"] + P[f"f{i}.head.b"]                   # AR.py:77-78
+            mu, s = out[..., 0], out[..., 1]
+            sigma = Fnn.softplus(s) + 1e-10                                   # AR.py:83
+        else:
+            # 1x1 conv with strides=2 -> heads at even conv positions          (fitz_nag_NVP.py:95-96)
+            out = h[:, ::2, :] @ P[f"f{i}.head.w"] + P[f"f{i}.head.b"]
+            mu_t, s_t = out[..., 0], out[..., 1]
+            mu = torch.stack([torch.zeros_like(mu_t), mu_t], dim=2).reshape(x.shape[0], -1)       # :99-100
+            sigma = torch.stack([torch.ones_like(s_t), Fnn.softplus(s_t) + 1e-10], dim=2).reshape(x.shape[0], -1)
+        logq = logq - torch.log(sigma[:, -S:]).sum(dim=1)                     # AR.py:84,88
+        x = x[:, K:] * sigma + mu                                             # AR.py:85
+        if D == 2 and i < cfg.F - 1:
+            # Permute: scatter_nd swaps each adjacent slot pair               (fitz_nag_NVP.py:145-153,205-211)
+            x = x.reshape(x.shape[0], -1, 2).flip(2).reshape(x.shape[0], -1)
+    return x, logq
+
+
+def normal_logpdf(x, loc, scale):
+    """tfd.Normal.log_prob."""
+    scale = torch.as_tensor(scale, dtype=x.dtype)
+    return -0.5 * ((x - loc) / scale) ** 2 - 0.5 * LOG2PI - torch.log(scale)
+
+
+def elbo_terms(cfg, x_final: torch.Tensor, theta: torch.Tensor, time_feats: torch.Tensor,
+               extra: Optional[Dict[str, torch.Tensor]] = None):
+    """Per-row (sde_log_prob, obs_log_prob) and the latent path `lf_sample`."""
+    B = cfg.B
+    p = x_final.shape[0]
+    if cfg.model == 0:      # AR.py:168-176
+        lf = x_final                                                          # [p, B+1]
+        obs_eval = time_feats[:, -B:, 0]                                      # AR.py:155
+        w = time_feats[:, -B:, -1]
+        obs_lp = (normal_logpdf(lf[:, 1:], obs_eval, cfg.obs_std) * w).sum(dim=1)
+        head, tail = lf[:, :-1], lf[:, 1:]
+        th = [theta[:, k:k + 1] for k in range(3)]
+        sde_lp = normal_logpdf(tail, th[1] * head + th[0], torch.exp(th[2])).sum(dim=1)
+        return sde_lp, obs_lp, lf
+    if cfg.model == 1:      # fitz_nag_NVP.py:232-255
+        lf = x_final.reshape(p, -1, 2).transpose(1, 2)                        # :282-283  [p,2,B+1]
+        obs_eval = time_feats[:, -2 * B:, 0].reshape(p, -1, 2).transpose(1, 2)  # :216-217
+        obs_lp = (normal_logpdf(lf[:, :, 1:], obs_eval, 0.1) * extra["bin_feed"]).reshape(p, -1).sum(dim=1)
+        head, tail = lf[:, :, :-1], lf[:, :, 1:]
+        diff = tail - head
+        x1, x2 = head[:, 0, :], head[:, 1, :]
+        th = [theta[:, k:k + 1] for k in range(5)]
+        dt = cfg.dt
+        d1 = torch.exp(th[0]) * (x1 - x1 ** 3 - x2 + th[1])
+        d2 = th[2] * x1 - x2 + 1.4
+        s1 = math.sqrt(dt) * torch.sqrt(torch.exp(th[3])).expand_as(x1)
+        s2 = math.sqrt(dt) * torch.sqrt(torch.exp(th[4])).expand_as(x1)
+        sde_lp = (normal_logpdf(diff[:, 0, :], dt * d1, s1) + normal_logpdf(diff[:, 1, :], dt * d2, s2)).sum(dim=1)
+        return sde_lp, obs_lp, lf
+    if cfg.model == 2:      # SV_dense.py:203-246
+        lat = x_final * extra["mask"] + extra["shift"]
+        lf = torch.stack([extra["dim_one"], lat], dim=1)                      # :245-246  [p,2,B+1]
+        head, tail = lf[:, :, :-1], lf[:, :, 1:]
+        diff = tail - head
+        x1, x2 = head[:, 0, :], head[:, 1, :]
+        th = [theta[:, k:k + 1] for k in range(4)]
+        dt = cfg.dt
+        d1 = th[0] * x1
+        d2 = th[1] - torch.exp(th[2]) * x2
+        s1 = math.sqrt(dt) * x1 * torch.exp(0.5 * x2)
+        s2 = math.sqrt(dt) * torch.exp(th[3]).expand_as(x1)
+        sde_lp = (normal_logpdf(diff[:, 0, :], dt * d1, s1) + normal_logpdf(diff[:, 1, :], dt * d2, s2)).sum(dim=1)
+        return sde_lp, torch.zeros_like(sde_lp), lf
+    raise ValueError("unknown model")
+
+
+def objective(cfg, obj: int, P, eps, theta, time_feats, extra=None, path_target: float = 0.0):
+    """Scalar the library differentiates, plus the per-row terms [p,4] = (sde, obs, logq, base_lp).
+
+    obj 0: -sum_rows scale*(sde - logq + obs)   [ELBO minus the host-side prior - log q(theta); AR.py:184-185,228-229]
+    obj 1: -sum_rows obs                         [AR.py:201-202]
+    obj 2: sum (lf_sample - path_target)^2       [fitz_nag_NVP.py:288-289; SV_dense.py:251-252]
+    """
+    x_final, logq = flow_forward(cfg, P, eps, theta, time_feats)
+    sde, obs, lf = elbo_terms(cfg, x_final, theta, time_feats, extra)
+    base = (-0.5 * eps[:, -cfg.S:] ** 2 - 0.5 * LOG2PI).sum(dim=1)
+    terms = torch.stack([sde, obs, logq, base], dim=1)
+    if obj == 0:
+        loss = -(cfg.scale * (sde - logq + obs)).sum()
+    elif obj == 1:
+        loss = -obs.sum()
+    elif obj == 2:
+        loss = ((lf - path_target) ** 2).sum()
+    else:
+        raise ValueError("objective")
+    return loss, terms, lf, x_final
+
+
+def step_reference(cfg, layout, flat_params: torch.Tensor, eps, theta, time_feats, obj=0, extra=None,
+                   path_target: float = 0.0):
+    """Forward + autograd gradients of `objective` w.r.t. the flat blob and theta."""
+    fp = flat_params.detach().clone().requires_grad_(True)
+    th = theta.detach().clone().requires_grad_(True)
+    loss, terms, lf, x_final = objective(cfg, obj, unpack_params(fp, layout), eps, th, time_feats, extra, path_target)
+    gp, gth = torch.autograd.grad(loss, [fp, th], allow_unused=True)
+    if gp is None:
+        gp = torch.zeros_like(fp)
+    if gth is None:
+        gth = torch.zeros_like(th)
+    return {"loss": loss.detach(), "terms": terms.detach(), "lf": lf.detach(), "x_final": x_final.detach(),
+            "grad_params": gp, "grad_theta": gth}
+
+
+def adamax_step(w, g, m, v, lr, beta1, beta2=0.999, eps=1e-8, clip=None):
+    """AR.py:230-234 (clip_by_global_norm over ALL gradients) + optimisers/adamax.py:51-57.
+
+    `g` here is the gradient slice for these variables; pass `clip=(clip_norm, global_norm)` to
+    apply TF's `g * clip_norm / max(global_norm, clip_norm)`.
+    No bias correction; eps sits inside the max.  Returns (w, m, v) updated copies.
+    """
+    if clip is not None:
+        clip_norm, gnorm = clip
+        g = g * (clip_norm / max(gnorm, clip_norm))
+    v = beta1 * v + (1.0 - beta1) * g
+    m = torch.maximum(beta2 * m + eps, g.abs())
+    w = w - lr * (v / m)
+    return w, m, v
+
+
+def glorot_init(layout, total, gen: torch.Generator, dtype=torch.float32) -> torch.Tensor:
+    """TF defaults: Glorot-uniform kernels, zero biases, BN gamma=1 beta=0."""
+    flat = torch.zeros(total, dtype=dtype)
+    for name, (off, shape) in layout.items():
+        n = int(np.prod(shape))
+        if name.endswith(".w"):
+            if len(shape) == 3:       # conv kernel [K, Cin, Cout]: fan_in = K*Cin, fan_out = K*Cout
+                fan_in, fan_out = shape[0] * shape[1], shape[0] * shape[2]
+            else:
+                fan_in, fan_out = shape
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            flat[off:off + n] = (torch.rand(n, generator=gen, dtype=torch.float64) * 2 - 1).to(dtype) * lim
+        elif name.endswith(".gamma"):
+            flat[off:off + n] = 1.0
+    return flat

@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+injected inputs (weights, base noise, theta, subsequence indices).
+
+Bars (BASELINE.json north_star): indices and gathered windows bit-exact; ELBO terms and gradients
+within 1e-4 relative in fp32 (the oracle runs in fp64 from the same fp32 inputs; gradient tensors are
+compared in relative L2 norm per variable)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nma_oracle as O
+from viforssms_b200 import feed
+from viforssms_b200.config import ar_config, param_layout, NMAConfig
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-4
+
+
+def _engine(cfg):
+    from viforssms_b200.engine import NMAEngine
+    return NMAEngine(cfg)
+
+
+def _load_dat():
+    d = os.path.join(ROOT, "dat")
+    return (np.loadtxt(os.path.join(d, "AR_obs_partial.txt"), np.float32),
+            np.loadtxt(os.path.join(d, "AR_obs_binary.txt"), np.float32),
+            np.loadtxt(os.path.join(d, "AR_time_till.txt"), np.float32))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_library_loaded_and_versioned():
+    from viforssms_b200 import lib
+    L = lib.load()
+    assert L.nma_version() >= 100
+    assert os.path.basename(lib.LIB_PATH) == "libnma_b200.so"
+
+
+def test_gather_bit_exact_against_reference_feed(golden):
+    """nma_gather reproduces what AR.py:267-288 fed (after the float64->float32 feed cast), bit for bit."""
+    obs, obs_bin, tt = _load_dat()
+    cfg = ar_config()
+    eng = _engine(cfg)
+    eng.set_series(feed.ar_base_arrays(obs, obs_bin, tt, 5000, 3, 50, 10))
+    for it in range(3):
+        sel = golden["it%d_batch_select" % it]
+        tf, mask, shift = eng.gather(sel)
+        tf = tf.cpu().numpy()
+        assert _sha(tf) == str(golden["it%d_time_feats_f32_sha256" % it])
+        assert np.array_equal(tf[:5], golden["it%d_time_feats_rows" % it].astype(np.float32))
+        assert np.array_equal(mask.cpu().numpy()[:, 0, :], golden["it%d_mask" % it].astype(np.float32))
+        assert np.array_equal(shift.cpu().numpy()[:, 0, :], golden["it%d_shift" % it].astype(np.float32))
+
+
+def test_gather_edges_first_and_last_window(golden):
+    """idx = 0 (x0 pinned by mask/shift, left pad) and idx = T-B (window ends exactly at the array end)."""
+    obs, obs_bin, tt = _load_dat()
+    cfg = ar_config(p=2)
+    eng = _engine(cfg)
+    eng.set_series(feed.ar_base_arrays(obs, obs_bin, tt, 5000, 3, 50, 10))
+    sel = np.array([0, 4950])
+    pads = O.pad_series_ar(obs, obs_bin, tt, 10.0, 5000, 3, 50, 10)
+    want_tf, want_mask, want_shift = O.gather_feed_ar(pads, sel, 201, 50)
+    tf, mask, shift = eng.gather(sel)
+    assert np.array_equal(tf.cpu().numpy(), want_tf.astype(np.float32))
+    assert np.array_equal(mask.cpu().numpy()[:, 0], want_mask.astype(np.float32))
+    assert np.array_equal(shift.cpu().numpy()[:, 0], want_shift.astype(np.float32))
+    assert shift.cpu().numpy()[0, 0, 0] == 10.0 and mask.cpu().numpy()[0, 0, 0] == 0.0
+
+
+def test_gather_imputed_series(golden):
+    cfg = ar_config(p=7, K=20, B=25, F=2, feat_window=4, T=600, obs_std=0.3, x0=2.0)
+    eng = _engine(cfg)
+    eng.set_series(feed.ar_base_arrays(golden["imp_obs"], golden["imp_obs_bin"], golden["imp_time_till"], 600, 2, 20, 4))
+    tf, mask, shift = eng.gather(golden["imp_batch_select"])
+    assert np.array_equal(tf.cpu().numpy(), golden["imp_time_feats"].astype(np.float32))
+    assert np.array_equal(mask.cpu().numpy()[:, 0], golden["imp_mask"].astype(np.float32))
+    assert np.array_equal(shift.cpu().numpy()[:, 0], golden["imp_shift"].astype(np.float32))
+
+
+def test_device_param_layout_matches_host():
+    cfg = ar_config(H=3)
+    eng = _engine(cfg)
+    layout, n = param_layout(cfg)
+    dev = eng.device_layout()
+    for i in range(cfg.F):
+        assert dev[i, 0] == layout[f"f{i}.feat0.w"][0]
+        assert dev[i, 8] == layout[f"f{i}.conv.w"][0]
+        assert dev[i, 9] == layout[f"f{i}.conv.b"][0]
+        assert dev[i, 10] == layout[f"f{i}.th0.w"][0]
+        assert dev[i, 16 + 2] == layout[f"f{i}.hid2.w"][0]
+        assert dev[i, 28] == layout[f"f{i}.head.w"][0]
+        assert dev[i, 29] == layout[f"f{i}.head.b"][0]
+
+
+# ---------------------------------------------------------------------------------------------------
+
+
+def _ar_case(cfg, T, seed, real_series=True):
+    """Injected inputs for one step on a synthetic AR series of length T."""
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    fw = cfg.Cf - 4
+    if real_series and T == 5000:
+        obs, obs_bin, tt = _load_dat()
+    else:
+        obs = rs.normal(8.0, 3.0, size=T).astype(np.float32)
+        obs_bin = (rs.uniform(size=T) < 0.7).astype(np.float32)
+        tt = rs.randint(1, 4, size=T).astype(np.float32)
+    arrays = feed.ar_base_arrays(obs, obs_bin, tt, T, cfg.F, cfg.K, fw)
+    pads = O.pad_series_ar(obs, obs_bin, tt, 10.0, T, cfg.F, cfg.K, fw)
+    idx = feed.sample_indices(T, cfg.B, cfg.p, rs)
+    tf64, _, _ = O.gather_feed_ar(pads, idx, cfg.L0, cfg.B)
+    layout, n = param_layout(cfg)
+    params = O.glorot_init(layout, n, g, torch.float32)
+    for name, (off, shape) in layout.items():
+        if name.endswith(".b"):
+            k = int(np.prod(shape))
+            params[off:off + k] = 0.05 * torch.randn(k, generator=g)
+    # the raw time index channel reaches T: scale the first feature layer so activations stay O(1)-O(10)
+    for i in range(cfg.F):
+        off, shape = layout[f"f{i}.feat0.w"]
+        k = int(np.prod(shape))
+        w = params[off:off + k].reshape(shape)
+        w[fw + 1, :] *= 10.0 / max(T, 1)
+    eps = torch.randn(cfg.p, cfg.L0, generator=g)
+    theta = torch.stack([torch.randn(cfg.p, generator=g) * 0.5 + 4.0,
+                         torch.randn(cfg.p, generator=g) * 0.1 + 0.5,
+                         torch.randn(cfg.p, generator=g) * 0.2 + 1.0], dim=1).float()
+    tf32 = torch.from_numpy(tf64.astype(np.float32))
+    return arrays, idx, layout, params, eps, theta, tf32
+
+
+def _rel(a, b):
+    a = a.double(); b = b.double()
+    d = (a - b).norm().item()
+    n = b.norm().item()
+    return d / n if n > 0 else d
+
+
+def _check_step(cfg, T, seed, objective=0, path_target=0.0):
+    arrays, idx, layout, params, eps, theta, tf32 = _ar_case(cfg, T, seed)
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf32.double(), obj=objective,
+                           path_target=path_target)
+    eng = _engine(cfg)
+    eng.set_series(arrays)
+    dev = torch.device("cuda")
+    out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev),
+                           objective=objective, path_target=path_target)
+    torch.cuda.synchronize()
+    terms = out["terms"].cpu().double()
+    # ELBO terms: sde, obs, logq, base
+    for k, name in enumerate(("sde", "obs", "logq", "base")):
+        want = ref["terms"][:, k]
+        got = terms[:, k]
+        tol = RTOL * max(1.0, want.abs().max().item())
+        assert (got - want).abs().max().item() <= tol, (name, (got - want).abs().max().item(), tol)
+    assert _rel(out["lf"].cpu(), ref["x_final"]) < RTOL
+    assert int(out["flags"].sum().item()) == 0
+    # gradients, per variable
+    gp = out["grad_params"].cpu()
+    gn_all = ref["grad_params"].norm().item()
+    worst = 0.0
+    for name, (off, shape) in layout.items():
+        k = int(np.prod(shape))
+        want = ref["grad_params"][off:off + k]
+        got = gp[off:off + k].double()
+        err = (got - want).norm().item()
+        scale = max(want.norm().item(), 1e-6 * gn_all)
+        worst = max(worst, err / scale)
+        assert err <= RTOL * scale, (name, err, want.norm().item())
+    assert _rel(gp, ref["grad_params"]) < RTOL
+    gth = out["grad_theta"].cpu().double()
+    assert (gth - ref["grad_theta"]).norm().item() <= RTOL * max(ref["grad_theta"].norm().item(), 1e-6 * gn_all)
+    return worst
+
+
+@pytest.mark.parametrize("shape", [
+    dict(p=3, K=10, B=7, F=2, H=1, feat_window=3),      # tiny
+    dict(p=5, K=20, B=13, F=3, H=3, feat_window=5),     # hidden stack, ragged block tails
+    dict(p=4, K=7, B=5, F=2, H=0, feat_window=2),       # K not a multiple of the 10-tap unroll, no hidden layer
+    dict(p=33, K=10, B=3, F=1, H=1, feat_window=1),     # rows straddling CTAs (4 position blocks per row)
+])
+def test_step_parity_small(shape):
+    T = 400
+    cfg = ar_config(T=T, **shape)
+    _check_step(cfg, T, seed=3)
+
+
+def test_step_parity_ar_default():
+    """configs[0]: hyperparameters.txt on dat/AR_obs_partial.txt (p=50, K=50, B=50, 3 flows)."""
+    cfg = ar_config()
+    _check_step(cfg, 5000, seed=1)
+
+
+@pytest.mark.parametrize("objective,target", [(1, 0.0), (2, 0.0), (2, -7.0)])
+def test_pretrain_objectives(objective, target):
+    """A10: -obs_loss (AR.py:201-202) and the path-square heads (SV_dense.py:251-252)."""
+    cfg = ar_config(p=6, K=10, B=9, F=2, H=1, feat_window=3, T=300)
+    _check_step(cfg, 300, seed=5, objective=objective, path_target=target)
+
+
+def test_rows_are_independent_and_gradient_is_a_sum():
+    """Size-independent properties at a larger p: duplicated rows give identical terms, and the
+    gradient of the row-sum is the sum of per-subset gradients (AR.py:228-229 differentiates sum(loss))."""
+    cfg = ar_config(p=512, K=50, B=50, F=3, H=1)
+    arrays, idx, layout, params, eps, theta, _ = _ar_case(ar_config(p=64), 5000, seed=9)
+    dev = torch.device("cuda")
+    eng = _engine(cfg)
+    eng.set_series(arrays)
+    rep = 8
+    idx_t = torch.from_numpy(idx).to(dev)
+    big = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev).repeat(rep, 1), theta.to(dev).repeat(rep, 1), idx_t.repeat(rep))
+    small = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), idx_t)
+    torch.cuda.synchronize()
+    tb = big["terms"].reshape(rep, 64, 4)
+    assert torch.equal(tb[0], tb[rep - 1])                       # same row -> same bits, wherever it sits
+    assert torch.equal(tb[0], small["terms"])
+    assert _rel(big["grad_params"], rep * small["grad_params"]) < 2e-5
+    assert _rel(big["grad_theta"].reshape(rep, 64, 3)[3], small["grad_theta"]) < 1e-6
+
+
+def test_forward_paths_matches_training_forward():
+    cfg = ar_config(p=16)
+    arrays, idx, layout, params, eps, theta, _ = _ar_case(cfg, 5000, seed=2)
+    dev = torch.device("cuda")
+    eng = _engine(cfg)
+    eng.set_series(arrays)
+    a = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev))
+    terms, lf = eng.forward_paths(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev))
+    torch.cuda.synchronize()
+    assert torch.equal(terms, a["terms"]) and torch.equal(lf, a["lf"])
+
+
+def test_adamax_matches_reference_update():
+    from viforssms_b200.engine import NMAEngine
+    eng = _engine(ar_config(p=1, K=10, B=5, F=1))
+    g = torch.Generator().manual_seed(0)
+    n = 100003
+    w = torch.randn(n, generator=g); gr = torch.randn(n, generator=g) * 3
+    m = torch.rand(n, generator=g); v = torch.randn(n, generator=g) * 0.1
+    for clip in (0.0, 1e9, 5.0):
+        gn = float(gr.double().norm())
+        w_ref, m_ref, v_ref = O.adamax_step(w.double(), gr.double(), m.double(), v.double(), 1e-3, 0.95,
+                                            clip=(clip, gn) if clip > 0 else None)
+        wd, gd, md, vd = (t.clone().cuda() for t in (w, gr, m, v))
+        norm = eng.adamax_step(wd, gd, md, vd, 1e-3, 0.95, clip=clip)
+        torch.cuda.synchronize()
+        assert abs(norm.item() - gn) / gn < 1e-5
+        assert torch.allclose(wd.cpu().double(), w_ref, rtol=1e-5, atol=1e-7)
+        assert torch.allclose(md.cpu().double(), m_ref, rtol=1e-6, atol=1e-9)
+        assert torch.allclose(vd.cpu().double(), v_ref, rtol=1e-5, atol=1e-8)
+
+
+def test_scan_ar1_and_time_till_match_sequential_generator():
+    """A12/A13 vs the reference's sequential loops (AR_dat_gen.py:11-31)."""
+    from viforssms_b200.engine import scan_ar1, time_till
+    rs = np.random.RandomState(4)
+    n = 20000
+    z = rs.standard_normal(n)
+    X = np.zeros(n + 1); X[0] = 10.0
+    for i in range(1, n + 1):
+        X[i] = (X[i - 1] * 0.5 + 5.0) + 3.0 * z[i - 1]
+    got = scan_ar1(torch.from_numpy(z).cuda(), 10.0, 0.5, 5.0, 3.0).cpu().numpy()
+    assert np.max(np.abs(got - X) / np.maximum(1.0, np.abs(X))) < 1e-12
+    for impute in (1, 3, 7):
+        obs = X + rs.standard_normal(n + 1)
+        obs[impute * 5] = 0.0                      # an exact zero is treated as "not observed" (AR_dat_gen.py:21)
+        kept = obs[impute:][0::impute]
+        partial = np.concatenate([np.concatenate((np.zeros(impute - 1), [it])) for it in kept])
+        fill = np.concatenate([np.tile(it, impute) for it in kept])
+        binary = np.array([0.0 if it == 0 else 1.0 for it in partial])
+        count = 1; tt = np.zeros(len(binary))
+        for i in range(len(binary)):
+            if binary[i] == 1.0:
+                count = 1
+            else:
+                tt[i] = count; count += 1
+        want_tt = -(tt - impute)
+        f, b, t = time_till(torch.from_numpy(obs).cuda(), impute)
+        assert np.array_equal(f.cpu().numpy(), fill)
+        assert np.array_equal(b.cpu().numpy(), binary)
+        assert np.array_equal(t.cpu().numpy(), want_tt)

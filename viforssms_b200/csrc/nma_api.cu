@@ -1,0 +1,258 @@
+// C-ABI of the NMA ELBO step (include/nma_b200.h): handle, workspace arena, step orchestration.
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+#include "nma_common.cuh"
+
+int launch_feat_fwd_eps(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
+                        cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void nma_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* nma_last_error(void) { return g_err; }
+extern "C" int nma_version(void) { return 100; }
+
+SeriesView nma_series_view(const nma_handle_s* h) {
+    SeriesView sv;
+    memset(&sv, 0, sizeof(sv));
+    for (int i = 0; i < NMA_MAX_ARRAYS; ++i) {
+        sv.base[i] = h->base[i];
+        sv.len[i] = h->base_len[i];
+    }
+    for (int c = 0; c < NMA_MAX_CHAN; ++c) {
+        sv.chan_array[c] = h->cfg.chan_array[c];
+        sv.chan_offset[c] = h->cfg.chan_offset[c];
+    }
+    sv.Cf = h->cfg.Cf;
+    sv.D = h->cfg.D;
+    sv.feat_aug = h->cfg.feat_aug;
+    return sv;
+}
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static void compute_layout(nma_handle_s* h) {
+    const nma_config& c = h->cfg;
+    int64_t off = 0;
+    for (int i = 0; i < c.F; ++i) {
+        FlowParamOff& po = h->po[i];
+        for (int l = 0; l < 4; ++l) {
+            po.featw[l] = off; off += (int64_t)(l == 0 ? h->Cf_in : NMA_C) * NMA_C;
+            po.featb[l] = off; off += NMA_C;
+        }
+        po.convw = off; off += (int64_t)c.K * NMA_C1 * NMA_C;
+        po.convb = off; off += NMA_C;
+        for (int l = 0; l < 3; ++l) {
+            po.thw[l] = off; off += (int64_t)(l == 0 ? c.dtheta : NMA_C) * NMA_C;
+            po.thb[l] = off; off += NMA_C;
+        }
+        for (int l = 0; l < NMA_MAXH; ++l) { po.hidw[l] = po.hidb[l] = po.gam[l] = po.bet[l] = -1; }
+        for (int l = 0; l < c.H; ++l) {
+            po.hidw[l] = off; off += NMA_C * NMA_C;
+            po.hidb[l] = off; off += NMA_C;
+            if (c.bn) {
+                po.gam[l] = off; off += NMA_C;
+                po.bet[l] = off; off += NMA_C;
+            }
+        }
+        po.headw = off; off += NMA_C * 2;
+        po.headb = off; off += 2;
+    }
+    h->n_params = off;
+}
+
+extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
+    if (!cfg || !out) { nma_set_error("nma_create: null argument"); return -1; }
+    if (cfg->C != NMA_C) { nma_set_error("nma_create: network_dims[0] must be %d (got %d)", NMA_C, cfg->C); return -1; }
+    if (cfg->D != 1 && cfg->D != 2) { nma_set_error("nma_create: flow_dims must be 1 or 2"); return -1; }
+    if (cfg->F < 1 || cfg->F > NMA_MAX_FLOWS) { nma_set_error("nma_create: no_flows out of range"); return -1; }
+    if (cfg->H < 0 || cfg->H > NMA_MAXH) { nma_set_error("nma_create: at most %d hidden layers", NMA_MAXH); return -1; }
+    if (cfg->p < 1 || cfg->K < 1 || cfg->B < 1) { nma_set_error("nma_create: p, K, B must be positive"); return -1; }
+    if (cfg->dtheta < 1 || cfg->dtheta > 6) { nma_set_error("nma_create: dtheta must be in 1..6"); return -1; }
+    const int cf_in = cfg->Cf + (cfg->feat_aug ? cfg->Cf - 2 : 0);
+    if (cfg->Cf < 1 || cf_in > NMA_MAX_CHAN) { nma_set_error("nma_create: bad feature channel count"); return -1; }
+    if (cfg->n_arrays < 1 || cfg->n_arrays > NMA_MAX_ARRAYS) { nma_set_error("nma_create: bad n_arrays"); return -1; }
+    if (cfg->D == 2 && ((cfg->K & 1) != 0)) { nma_set_error("nma_create: flow_dims=2 needs an even kernel_len"); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        nma_set_error("nma_create: no CUDA device (this library has no CPU path)");
+        return -2;
+    }
+    nma_handle_s* h = new (std::nothrow) nma_handle_s;
+    if (!h) { nma_set_error("nma_create: out of host memory"); return -1; }
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->L0 = cfg->F * cfg->K + cfg->D * cfg->B + cfg->D;      // AR.py:132; fitz_nag_NVP.py:182-183
+    h->S = cfg->D * cfg->B;
+    h->Cf_in = cf_in;
+    h->feat_off = cfg->feat_aug ? 1 : 0;
+    h->KP = (cfg->K + 9) / 10 * 10;
+    for (int i = 0; i <= cfg->F; ++i) {
+        FlowDims& d = h->fd[i];
+        d.L = h->L0 - i * cfg->K;
+        d.Lin = d.L - 1;
+        d.N = d.L - cfg->K;
+        d.LP = (d.Lin + 3) & ~3;
+        d.NP = (d.N + 3) & ~3;
+        if (i < cfg->F && d.N < 1) { delete h; nma_set_error("nma_create: window too short"); return -1; }
+    }
+    compute_layout(h);
+    NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
+    NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
+
+    // ---- carve the workspace arena ----
+    const int64_t p = cfg->p;
+    int64_t total = 0;
+    auto reserve = [&](int64_t floats) { int64_t o = total; total += align_up(floats * 4, 256); return o; };
+    struct Off { int64_t x, dx, a[5], h[NMA_MAXH + 1], s, dA, df, tb, dtb, wpk, wdpk; } off[NMA_MAX_FLOWS + 1];
+    for (int i = 0; i <= cfg->F; ++i) {
+        const FlowDims& d = h->fd[i];
+        const int64_t XP = (d.L + 3) & ~3;
+        off[i].x = reserve(p * XP);
+        off[i].dx = reserve(p * XP);
+        if (i == cfg->F) break;
+        off[i].a[0] = reserve(p * cf_in * d.LP);
+        for (int l = 1; l < 5; ++l) off[i].a[l] = reserve(p * NMA_C * d.LP);
+        for (int l = 0; l <= cfg->H; ++l) off[i].h[l] = reserve(p * NMA_C * d.NP);
+        off[i].s = reserve(p * d.NP);
+        off[i].dA = reserve(p * NMA_C * d.NP);
+        off[i].df = reserve(p * NMA_C * d.LP);
+        off[i].tb = reserve(p * 3 * NMA_C);
+        off[i].dtb = reserve(p * NMA_C);
+        off[i].wpk = reserve((int64_t)NMA_C1 * 5 * h->KP * 12);
+        off[i].wdpk = reserve((int64_t)NMA_C * 6 * h->KP * 12);
+    }
+    h->arena_bytes = total;
+    cudaError_t e = cudaMalloc(&h->arena, (size_t)total);
+    if (e != cudaSuccess) {
+        nma_set_error("nma_create: cudaMalloc(%lld bytes) failed: %s", (long long)total, cudaGetErrorString(e));
+        delete h;
+        return -2;
+    }
+    e = cudaMemset(h->arena, 0, (size_t)total);   // pad columns must stay finite (zero) forever
+    if (e != cudaSuccess) { nma_set_error("nma_create: memset failed: %s", cudaGetErrorString(e)); cudaFree(h->arena); delete h; return -2; }
+    char* base = (char*)h->arena;
+    for (int i = 0; i <= cfg->F; ++i) {
+        FlowWs& w = h->ws[i];
+        w.x = (float*)(base + off[i].x);
+        w.dx = (float*)(base + off[i].dx);
+        if (i == cfg->F) break;
+        for (int l = 0; l < 5; ++l) w.a[l] = (float*)(base + off[i].a[l]);
+        for (int l = 0; l <= cfg->H; ++l) w.h[l] = (float*)(base + off[i].h[l]);
+        w.s = (float*)(base + off[i].s);
+        w.dA = (float*)(base + off[i].dA);
+        w.df = (float*)(base + off[i].df);
+        w.tb = (float*)(base + off[i].tb);
+        w.dtb = (float*)(base + off[i].dtb);
+        w.wpk = (float*)(base + off[i].wpk);
+        w.wdpk = (float*)(base + off[i].wdpk);
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int nma_destroy(nma_handle h) {
+    if (!h) return 0;
+    if (h->arena) cudaFree(h->arena);
+    delete h;
+    return 0;
+}
+
+extern "C" int64_t nma_param_count(nma_handle h) { return h ? h->n_params : -1; }
+extern "C" int64_t nma_workspace_bytes(nma_handle h) { return h ? h->arena_bytes : -1; }
+
+// offsets_out[i*32 + s]: s = 0..3 featw, 4..7 featb, 8 convw, 9 convb, 10..12 thw, 13..15 thb,
+// 16..19 hidw, 20..23 hidb, 24..27 gamma (or -1), 28 headw, 29 headb, 30 = -1, 31 = -1 (beta = gamma + 50)
+extern "C" int nma_param_layout(nma_handle h, int64_t* o, int32_t n) {
+    if (!h || !o || n < h->cfg.F * 32) { nma_set_error("nma_param_layout: buffer too small"); return -1; }
+    for (int i = 0; i < h->cfg.F; ++i) {
+        const FlowParamOff& po = h->po[i];
+        int64_t* q = o + i * 32;
+        for (int l = 0; l < 4; ++l) { q[l] = po.featw[l]; q[4 + l] = po.featb[l]; }
+        q[8] = po.convw; q[9] = po.convb;
+        for (int l = 0; l < 3; ++l) { q[10 + l] = po.thw[l]; q[13 + l] = po.thb[l]; }
+        for (int l = 0; l < NMA_MAXH; ++l) { q[16 + l] = po.hidw[l]; q[20 + l] = po.hidb[l]; q[24 + l] = po.gam[l]; }
+        q[28] = po.headw; q[29] = po.headb; q[30] = -1; q[31] = -1;
+    }
+    return 0;
+}
+
+extern "C" int nma_set_series(nma_handle h, const float* const* d_arrays, const int64_t* lengths, int32_t n) {
+    if (!h || !d_arrays || !lengths) { nma_set_error("nma_set_series: null argument"); return -1; }
+    if (n != h->cfg.n_arrays) { nma_set_error("nma_set_series: expected %d arrays, got %d", h->cfg.n_arrays, n); return -1; }
+    for (int c = 0; c < h->cfg.Cf; ++c)
+        if (h->cfg.chan_array[c] < 0 || h->cfg.chan_array[c] >= n) { nma_set_error("nma_set_series: channel table refers to a missing array"); return -1; }
+    for (int i = 0; i < NMA_MAX_ARRAYS; ++i) { h->base[i] = nullptr; h->base_len[i] = 0; }
+    for (int i = 0; i < n; ++i) {
+        if (!d_arrays[i] || lengths[i] <= 0) { nma_set_error("nma_set_series: array %d is empty", i); return -1; }
+        h->base[i] = d_arrays[i];
+        h->base_len[i] = lengths[i];
+    }
+    return 0;
+}
+
+static int check_step_args(nma_handle h, int p, const void* a, const void* b, const void* c, const void* d) {
+    if (!h) { nma_set_error("null handle"); return -1; }
+    if (p < 1 || p > h->cfg.p) { nma_set_error("p=%d outside 1..%d (nma_create sized the workspace)", p, h->cfg.p); return -1; }
+    if (!a || !b || !c || !d) { nma_set_error("null device pointer"); return -1; }
+    if (!h->base[0]) { nma_set_error("nma_set_series has not been called"); return -1; }
+    return 0;
+}
+
+extern "C" int nma_gather(nma_handle h, const int64_t* d_idx, int32_t p, float* d_tf, float* d_mask, float* d_shift,
+                          void* stream) {
+    if (check_step_args(h, p, d_idx, d_tf, d_tf, d_tf)) return -1;
+    return launch_gather(h, d_idx, p, d_tf, d_mask, d_shift, (cudaStream_t)stream);
+}
+
+static int forward_all(nma_handle_s* h, const float* params, const float* eps, const float* theta, const int64_t* idx,
+                       int p, bool save, cudaStream_t st) {
+    int rc;
+    if ((rc = launch_pack_weights(h, params, save, st))) return rc;
+    if ((rc = launch_theta_fwd(h, params, theta, p, st))) return rc;
+    if ((rc = launch_feat_fwd_eps(h, params, idx, eps, p, save, st))) return rc;
+    for (int i = 0; i < h->cfg.F; ++i)
+        if ((rc = launch_conv_fwd(h, i, params, p, save, st))) return rc;
+    return 0;
+}
+
+extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
+                                const int64_t* d_idx, int32_t p, int32_t objective, float path_target, float* d_terms,
+                                float* d_lf, float* d_grad_params, float* d_grad_theta, uint32_t* d_flags,
+                                void* stream) {
+    if (check_step_args(h, p, d_params, d_eps, d_theta, d_idx)) return -1;
+    if (!d_terms || !d_grad_params || !d_grad_theta) { nma_set_error("null output pointer"); return -1; }
+    if (objective < 0 || objective > 2) { nma_set_error("unknown objective %d", objective); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    NMA_CHECK_CUDA(cudaMemsetAsync(d_grad_params, 0, (size_t)h->n_params * 4, st));
+    if ((rc = forward_all(h, d_params, d_eps, d_theta, d_idx, p, true, st))) return rc;
+    if ((rc = launch_elbo(h, d_theta, d_eps, d_idx, p, objective, path_target, d_terms, d_lf, d_grad_theta, d_flags,
+                          true, st)))
+        return rc;
+    for (int i = h->cfg.F - 1; i >= 0; --i) {
+        if ((rc = launch_epi_bwd(h, i, d_params, p, objective, d_grad_params, st))) return rc;
+        if ((rc = launch_conv_dgrad(h, i, p, st))) return rc;
+        if ((rc = launch_conv_wgrad(h, i, p, d_grad_params, st))) return rc;
+        if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
+    }
+    if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, st))) return rc;
+    return 0;
+}
+
+extern "C" int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
+                                 const int64_t* d_idx, int32_t p, float* d_terms, float* d_lf, void* stream) {
+    if (check_step_args(h, p, d_params, d_eps, d_theta, d_idx)) return -1;
+    if (!d_terms) { nma_set_error("null output pointer"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = forward_all(h, d_params, d_eps, d_theta, d_idx, p, false, st))) return rc;
+    return launch_elbo(h, d_theta, d_eps, d_idx, p, NMA_OBJ_ELBO, 0.f, d_terms, d_lf, nullptr, nullptr, false, st);
+}

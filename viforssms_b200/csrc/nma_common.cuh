@@ -1,0 +1,115 @@
+// Internal declarations shared by the NMA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/nma_b200.h"
+
+#define NMA_C   50          // network_dims[0] in every reference script
+#define NMA_C1  51          // conv input channels: previous sample + C features (AR.py:58-59)
+#define NMA_MAXH 4
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "this library is written for sm_100a (B200) only"
+#endif
+
+struct FlowDims {
+    int L;      // length of the flow's input sample x^(i)         (AR.py:132: L0 - i*K)
+    int Lin;    // conv input positions = L-1                      (AR.py:53,58: [:, :-1])
+    int N;      // conv output positions = L-K = length of x^(i+1) (AR.py:61-62 'valid')
+    int LP;     // pitch (floats) of [c][Lin] tensors
+    int NP;     // pitch of [c][N] tensors
+};
+
+// offsets (floats) into the flat parameter blob, TF creation order (AR.py:53-78)
+struct FlowParamOff {
+    int64_t featw[4], featb[4];
+    int64_t convw, convb;
+    int64_t thw[3], thb[3];
+    int64_t hidw[NMA_MAXH], hidb[NMA_MAXH], gam[NMA_MAXH], bet[NMA_MAXH];
+    int64_t headw, headb;
+};
+
+struct FlowWs {
+    float* x;        // [p][L]      input sample of this flow (x^(0) = eps); index F = final sample
+    float* dx;       // [p][L]      d objective / d x^(i)
+    float* a[5];     // a[0]: [p][Cf_in][LP] gathered features; a[1..4]: [p][C][LP] feature-MLP activations
+    float* h[NMA_MAXH + 1];  // [p][C][NP] post-ELU activations e_0..e_H of the conv head
+    float* s;        // [p][NP]     pre-softplus scale logits
+    float* dA;       // [p][C][NP]  gradient w.r.t. the conv pre-activation
+    float* df;       // [p][C][LP]  gradient w.r.t. the feature channels of the conv input
+    float* tb;       // [p][3][C]   theta-MLP activations t1, t2, b(+conv bias)
+    float* dtb;      // [p][C]      sum_m dA
+    float* logsig;   // [p]         sum over the last S slots of log sigma
+    float* wpk;      // packed conv weights for the forward conv  [Cin=51][5][KP][12]
+    float* wdpk;     // packed conv weights for the data-gradient conv [Cin=50][6][KP][12]
+};
+
+struct nma_handle_s {
+    nma_config cfg;
+    int L0, S, Cf_in, feat_off, KP;
+    FlowDims fd[NMA_MAX_FLOWS + 1];
+    FlowParamOff po[NMA_MAX_FLOWS];
+    int64_t n_params;
+    FlowWs ws[NMA_MAX_FLOWS + 1];
+    const float* base[NMA_MAX_ARRAYS];
+    int64_t base_len[NMA_MAX_ARRAYS];
+    void* arena;
+    int64_t arena_bytes;
+    int sm_count;
+    int dev;
+};
+
+// device-side copy of what kernels need about the series and the channel table
+struct SeriesView {
+    const float* base[NMA_MAX_ARRAYS];
+    long long len[NMA_MAX_ARRAYS];
+    int chan_array[NMA_MAX_CHAN];
+    int chan_offset[NMA_MAX_CHAN];
+    int Cf, D, feat_aug;
+};
+
+void nma_set_error(const char* fmt, ...);
+#define NMA_CHECK_CUDA(call)                                                           \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            nma_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return -2;                                                                 \
+        }                                                                              \
+    } while (0)
+
+SeriesView nma_series_view(const nma_handle_s* h);
+
+// launchers (one per kernel family); all asynchronous on `st`
+int launch_gather(nma_handle_s* h, const int64_t* idx, int p, float* tf, float* mask, float* shift, cudaStream_t st);
+int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
+int launch_theta_fwd(nma_handle_s* h, const float* params, const float* theta, int p, cudaStream_t st);
+int launch_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, int p, bool save, cudaStream_t st);
+int launch_conv_fwd(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
+int launch_elbo(nma_handle_s* h, const float* theta, const float* eps, const int64_t* idx, int p, int objective,
+                float path_target, float* terms, float* lf, float* grad_theta, uint32_t* flags, bool want_grad,
+                cudaStream_t st);
+int launch_epi_bwd(nma_handle_s* h, int flow, const float* params, int p, int objective, float* grad_params,
+                   cudaStream_t st);
+int launch_conv_dgrad(nma_handle_s* h, int flow, int p, cudaStream_t st);
+int launch_conv_wgrad(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
+int launch_feat_bwd(nma_handle_s* h, int flow, const float* params, int p, float* grad_params, cudaStream_t st);
+int launch_theta_bwd(nma_handle_s* h, const float* params, const float* theta, int p, float* grad_params,
+                     float* grad_theta, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z); }
+// derivative of ELU expressed through its output e = elu(z): z>0 -> 1, else e+1
+__device__ __forceinline__ float elu_grad_from_out(float e) { return e > 0.f ? 1.f : e + 1.f; }
+// tf.nn.softplus, numerically stable: max(x,0) + log1p(exp(-|x|))
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

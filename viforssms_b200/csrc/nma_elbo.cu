@@ -1,0 +1,228 @@
+// A7: per-row ELBO terms (Euler-Maruyama transition log-density, masked observation log-likelihood,
+// entropy term) as one warp-per-row segmented reduction, fused with the gradient of the chosen
+// objective w.r.t. the final flow sample and theta.
+//   AR  : AR.py:168-187            FHN : fitz_nag_NVP.py:232-266            SV : SV_dense.py:203-246
+#include "nma_common.cuh"
+
+#define LOG2PI_F 1.8378770664093453f
+
+struct ElboArgs {
+    SeriesView sv;
+    const float* xF;        // [p][XPF] final flow sample
+    const float* eps;       // [p][L0]
+    const float* theta;     // [p][dth]
+    const int64_t* idx;
+    const float* s[NMA_MAX_FLOWS];   // [p][NP_i] pre-softplus scale logits saved by the flow layers
+    int N[NMA_MAX_FLOWS], NP[NMA_MAX_FLOWS];
+    float* dxF;             // [p][XPF]
+    float* terms;           // [p][4]
+    float* lf;              // [p][LF]   (may be null)
+    float* grad_theta;      // [p][dth]  (may be null)
+    uint32_t* flags;        // [p]       (may be null)
+    int p, model, F, B, D, S, L0, LF, XPF, dth, Cf, obs_array, bin_array, head_offset;
+    int objective, want_grad;
+    float scale, dt, obs_std, path_target, x0a, x0b;
+};
+
+__device__ __forceinline__ float series_raw(const SeriesView& sv, int a, long long q) {
+    return (q >= 0 && q < sv.len[a]) ? __ldg(sv.base[a] + q) : 0.f;
+}
+__device__ __forceinline__ float series_chan(const SeriesView& sv, int c, long long pos) {
+    return series_raw(sv, sv.chan_array[c], pos + sv.chan_offset[c]);
+}
+
+// log N(x; m, s) pieces
+struct G1 { float lp, dz; };   // lp = log density, dz = z/s = -d lp / d x = d lp / d m
+__device__ __forceinline__ G1 gauss(float x, float m, float s) {
+    const float z = (x - m) / s;
+    G1 g;
+    g.lp = -0.5f * z * z - 0.5f * LOG2PI_F - logf(s);
+    g.dz = z / s;
+    return g;
+}
+
+__global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.p) return;
+    const int r = warp;
+    const int B = a.B;
+    const float* x = a.xF + (size_t)r * a.XPF;
+    const float* th = a.theta + (size_t)r * a.dth;
+    const long long i0 = a.idx[r];
+    const long long win0 = (long long)a.sv.D * i0;
+    float* dx = a.dxF + (size_t)r * a.XPF;
+
+    float sde = 0.f, obs = 0.f, base = 0.f;
+    float gth[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d sde / d theta
+    // coefficients of d objective / d (sde, obs) and the path-square objective
+    float c_sde = 0.f, c_obs = 0.f, c_sq = 0.f;
+    if (a.objective == NMA_OBJ_ELBO) { c_sde = -a.scale; c_obs = -a.scale; }
+    else if (a.objective == NMA_OBJ_NEG_OBS) { c_obs = -1.f; }
+    else { c_sq = 1.f; }
+
+    // base log-prob: last S slots of the base sample (AR.py:33-34)
+    for (int j = lane; j < a.S; j += 32) {
+        const float e = a.eps[(size_t)r * a.L0 + (a.L0 - a.S) + j];
+        base += -0.5f * e * e - 0.5f * LOG2PI_F;
+    }
+
+    if (a.model == NMA_MODEL_AR) {
+        const float t0 = th[0], t1 = th[1], sd = expf(th[2]);
+        for (int j = lane; j <= B; j += 32) {
+            const float xj = x[j];
+            float g = 0.f;
+            if (j >= 1) {   // tail of step j-1 and observation of x_j
+                const G1 q = gauss(xj, fmaf(t1, x[j - 1], t0), sd);
+                g += c_sde * (-q.dz);
+                const long long slot = win0 + (a.L0 - B) + (j - 1);
+                const float y = series_chan(a.sv, 0, slot);
+                const float w = series_chan(a.sv, a.Cf - 1, slot);
+                const G1 o = gauss(xj, y, a.obs_std);       // Normal(loc=obs, scale).log_prob(x): symmetric in (x, loc)
+                obs += o.lp * w;
+                g += c_obs * (-o.dz) * w;
+            }
+            if (j < B) {    // head of step j: counted once here
+                const G1 q = gauss(x[j + 1], fmaf(t1, xj, t0), sd);
+                sde += q.lp;
+                g += c_sde * (q.dz * t1);
+                gth[0] += q.dz;
+                gth[1] += q.dz * xj;
+                const float z = q.dz * sd;
+                gth[2] += z * z - 1.f;
+            }
+            g += c_sq * 2.f * (xj - a.path_target);
+            if (a.want_grad) dx[j] = g;
+            if (a.lf) a.lf[(size_t)r * a.LF + j] = xj;
+        }
+    } else if (a.model == NMA_MODEL_FHN) {
+        // lf[d][t] = x[2t+d]  (fitz_nag_NVP.py:282-283)
+        const float e0 = expf(th[0]), t1 = th[1], t2 = th[2];
+        const float dt = a.dt, sq = sqrtf(dt);
+        const float s1 = sq * sqrtf(expf(th[3])), s2 = sq * sqrtf(expf(th[4]));
+        const long long tlen = a.sv.len[a.bin_array] / 2;
+        for (int j = lane; j <= B; j += 32) {
+            const float x1 = x[2 * j], x2 = x[2 * j + 1];
+            float g1 = 0.f, g2 = 0.f;
+            if (j >= 1) {
+                const float p1 = x[2 * j - 2], p2 = x[2 * j - 1];
+                const float m1 = dt * e0 * (p1 - p1 * p1 * p1 - p2 + t1), m2 = dt * (t2 * p1 - p2 + 1.4f);
+                const G1 q1 = gauss(x1 - p1, m1, s1), q2 = gauss(x2 - p2, m2, s2);
+                g1 += c_sde * (-q1.dz);
+                g2 += c_sde * (-q2.dz);
+                // observations: obs_eval[d][t'] = time_feats[:, -2B + 2t' + d, 0]; weight bin_feed[d][t'] (:216-217,233-234)
+                const long long slot = win0 + (a.L0 - 2 * B) + 2 * (j - 1);
+                const float y1 = series_chan(a.sv, 0, slot), y2 = series_chan(a.sv, 0, slot + 1);
+                const float w1 = series_raw(a.sv, a.bin_array, i0 + (j - 1));
+                const float w2 = series_raw(a.sv, a.bin_array, tlen + i0 + (j - 1));
+                const G1 o1 = gauss(x1, y1, 0.1f), o2 = gauss(x2, y2, 0.1f);
+                obs += o1.lp * w1 + o2.lp * w2;
+                g1 += c_obs * (-o1.dz) * w1;
+                g2 += c_obs * (-o2.dz) * w2;
+            }
+            if (j < B) {
+                const float n1 = x[2 * j + 2], n2 = x[2 * j + 3];
+                const float drift1 = e0 * (x1 - x1 * x1 * x1 - x2 + t1);
+                const float m1 = dt * drift1, m2 = dt * (t2 * x1 - x2 + 1.4f);
+                const G1 q1 = gauss(n1 - x1, m1, s1), q2 = gauss(n2 - x2, m2, s2);
+                sde += q1.lp + q2.lp;
+                // d/d x1: through the difference (+dz) and the means
+                g1 += c_sde * (q1.dz * (1.f + dt * e0 * (1.f - 3.f * x1 * x1)) + q2.dz * (dt * t2));
+                g2 += c_sde * (q1.dz * (-dt * e0) + q2.dz * (1.f - dt));
+                gth[0] += q1.dz * m1;
+                gth[1] += q1.dz * dt * e0;
+                gth[2] += q2.dz * dt * x1;
+                const float z1 = q1.dz * s1, z2 = q2.dz * s2;
+                gth[3] += 0.5f * (z1 * z1 - 1.f);
+                gth[4] += 0.5f * (z2 * z2 - 1.f);
+            }
+            g1 += c_sq * 2.f * (x1 - a.path_target);
+            g2 += c_sq * 2.f * (x2 - a.path_target);
+            if (a.want_grad) { dx[2 * j] = g1; dx[2 * j + 1] = g2; }
+            if (a.lf) { a.lf[(size_t)r * a.LF + 2 * j] = x1; a.lf[(size_t)r * a.LF + 2 * j + 1] = x2; }
+        }
+    } else {   // NMA_MODEL_SV
+        // lf[0][t] = dim_one = obs[idx+t]; lf[1][t] = x*mask + shift  (SV_dense.py:245-246,327-328)
+        const float t0 = th[0], t1 = th[1], e2 = expf(th[2]), s2 = sqrtf(a.dt) * expf(th[3]);
+        const float dt = a.dt, sq = sqrtf(dt);
+        for (int j = lane; j <= B; j += 32) {
+            const bool first = (i0 + j) == 0;
+            const float mk = first ? 0.f : 1.f, sh = first ? a.x0a : 0.f;
+            const float o1 = series_raw(a.sv, a.obs_array, i0 + j + a.head_offset);
+            const float l2 = fmaf(x[j], mk, sh);
+            float g = 0.f;
+            if (j >= 1) {
+                const bool pf = (i0 + j - 1) == 0;
+                const float p1 = series_raw(a.sv, a.obs_array, i0 + j - 1 + a.head_offset);
+                const float p2 = fmaf(x[j - 1], pf ? 0.f : 1.f, pf ? a.x0a : 0.f);
+                const G1 q2 = gauss(l2 - p2, dt * (t1 - e2 * p2), s2);
+                g += c_sde * (-q2.dz);
+                (void)p1;
+            }
+            if (j < B) {
+                const bool nf = (i0 + j + 1) == 0;
+                const float n1 = series_raw(a.sv, a.obs_array, i0 + j + 1 + a.head_offset);
+                const float n2 = fmaf(x[j + 1], nf ? 0.f : 1.f, nf ? a.x0a : 0.f);
+                const float sd1 = sq * o1 * expf(0.5f * l2);
+                const G1 q1 = gauss(n1 - o1, dt * t0 * o1, sd1);
+                const G1 q2 = gauss(n2 - l2, dt * (t1 - e2 * l2), s2);
+                sde += q1.lp + q2.lp;
+                const float z1 = q1.dz * sd1, z2 = q2.dz * s2;
+                g += c_sde * (0.5f * (z1 * z1 - 1.f) + q2.dz * (1.f - dt * e2));
+                gth[0] += q1.dz * dt * o1;
+                gth[1] += q2.dz * dt;
+                gth[2] += q2.dz * (-dt * e2 * l2);
+                gth[3] += z2 * z2 - 1.f;
+            }
+            // (lf_sample + 7)^2 pre-train covers both components; only the latent one has a gradient
+            g += c_sq * 2.f * (l2 - a.path_target);
+            if (a.want_grad) dx[j] = g * mk;
+            if (a.lf) a.lf[(size_t)r * a.LF + j] = x[j];
+        }
+    }
+
+    // - sum_i sum_{last S slots} log sigma^(i)   (AR.py:84,88; identity slots of the coupling layer have sigma = 1)
+    float lsig = 0.f;
+    for (int i = 0; i < a.F; ++i) {
+        const float* sp = a.s[i] + (size_t)r * a.NP[i];
+        for (int m = a.N[i] - a.S + lane; m < a.N[i]; m += 32) {
+            if (a.D == 1 || (m & 1)) lsig += logf(softplus_f(sp[m]) + 1e-10f);
+        }
+    }
+    sde = warp_sum(sde);
+    obs = warp_sum(obs);
+    base = warp_sum(base);
+    lsig = warp_sum(lsig);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) gth[k] = warp_sum(gth[k]);
+    if (lane == 0) {
+        const float logq = base - lsig;
+        a.terms[(size_t)r * 4 + 0] = sde;
+        a.terms[(size_t)r * 4 + 1] = obs;
+        a.terms[(size_t)r * 4 + 2] = logq;
+        a.terms[(size_t)r * 4 + 3] = base;
+        if (a.flags) a.flags[r] = (isfinite(sde) && isfinite(obs) && isfinite(logq)) ? 0u : 1u;
+        if (a.grad_theta && a.want_grad)
+            for (int k = 0; k < a.dth; ++k) a.grad_theta[(size_t)r * a.dth + k] = c_sde * gth[k];
+    }
+}
+
+int launch_elbo(nma_handle_s* h, const float* theta, const float* eps, const int64_t* idx, int p, int objective,
+                float path_target, float* terms, float* lf, float* grad_theta, uint32_t* flags, bool want_grad,
+                cudaStream_t st) {
+    ElboArgs a;
+    a.sv = nma_series_view(h);
+    const int F = h->cfg.F;
+    a.xF = h->ws[F].x; a.dxF = h->ws[F].dx; a.eps = eps; a.theta = theta; a.idx = idx;
+    for (int i = 0; i < F; ++i) { a.s[i] = h->ws[i].s; a.N[i] = h->fd[i].N; a.NP[i] = h->fd[i].NP; }
+    a.terms = terms; a.lf = lf; a.grad_theta = grad_theta; a.flags = flags;
+    a.p = p; a.model = h->cfg.model; a.F = F; a.B = h->cfg.B; a.D = h->cfg.D; a.S = h->S; a.L0 = h->L0;
+    a.LF = h->fd[F].L; a.XPF = (h->fd[F].L + 3) & ~3; a.dth = h->cfg.dtheta; a.Cf = h->cfg.Cf;
+    a.obs_array = h->cfg.obs_array; a.bin_array = h->cfg.bin_array; a.head_offset = h->cfg.head_offset;
+    a.objective = objective; a.want_grad = want_grad ? 1 : 0;
+    a.scale = (float)h->cfg.scale; a.dt = h->cfg.dt; a.obs_std = h->cfg.obs_std; a.path_target = path_target;
+    a.x0a = h->cfg.x0[0]; a.x0b = h->cfg.x0[1];
+    const int warps_per_block = 4;
+    k_elbo<<<(p + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, st>>>(a);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

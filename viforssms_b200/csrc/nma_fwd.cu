@@ -1,0 +1,532 @@
+// Forward kernels of the NMA ELBO step: weight packing, theta-bias MLP (AR.py:63-68), window gather +
+// feature MLP (AR.py:53-56, 267-283), fused conv + head + affine flow layer (AR.py:58-89), ELBO terms
+// (AR.py:168-187).  sm_100a only.
+#include "nma_conv_core.cuh"
+
+// ---------------------------------------------------------------------------
+// series access (A1): time_feats[r, slot, c] = base[chan_array[c]][win0 + slot + chan_offset[c]]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float series_val(const SeriesView& sv, int c, long long pos) {
+    const int a = sv.chan_array[c];
+    const long long q = pos + sv.chan_offset[c];
+    return (q >= 0 && q < sv.len[a]) ? __ldg(sv.base[a] + q) : 0.f;
+}
+
+// ---------------------------------------------------------------------------
+// nma_gather: materialise the feed the reference builds on the host every iteration
+// ---------------------------------------------------------------------------
+__global__ void k_gather(SeriesView sv, const int64_t* __restrict__ idx, int p, int L0, int B, float x0a, float x0b,
+                         float* __restrict__ tf, float* __restrict__ mask, float* __restrict__ shift) {
+    const int r = blockIdx.x;
+    const long long win0 = (long long)sv.D * idx[r];
+    const int n = L0 * sv.Cf;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int slot = t / sv.Cf, c = t - slot * sv.Cf;
+        tf[(size_t)r * n + t] = series_val(sv, c, win0 + slot);
+    }
+    // mask_vals = [0,1,1,...], shift_vals = [x0,0,0,...] sliced at idx (AR.py:145-148,285-288)
+    const int nm = sv.D * (B + 1);
+    for (int t = threadIdx.x; t < nm; t += blockDim.x) {
+        const int d = t / (B + 1), j = t - d * (B + 1);
+        const bool first = (idx[r] + j) == 0;
+        if (mask) mask[(size_t)r * nm + t] = first ? 0.f : 1.f;
+        if (shift) shift[(size_t)r * nm + t] = first ? (d == 0 ? x0a : x0b) : 0.f;
+    }
+}
+
+int launch_gather(nma_handle_s* h, const int64_t* idx, int p, float* tf, float* mask, float* shift, cudaStream_t st) {
+    SeriesView sv = nma_series_view(h);
+    k_gather<<<p, 256, 0, st>>>(sv, idx, p, h->L0, h->cfg.B, h->cfg.x0[0], h->cfg.x0[1], tf, mask, shift);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// weight packing: conv kernel [K][51][50] -> per input channel slabs [groups][KP][12]
+// ---------------------------------------------------------------------------
+__global__ void k_pack_fwd(const float* __restrict__ W, int K, int KP, float* __restrict__ out) {
+    // out[c][g][k][12], c<51, g<5
+    const int n = NMA_C1 * 5 * KP * CONV_WPAD;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        int q = t % CONV_WPAD;
+        int k = (t / CONV_WPAD) % KP;
+        int g = (t / (CONV_WPAD * KP)) % 5;
+        int c = t / (CONV_WPAD * KP * 5);
+        float v = 0.f;
+        if (q < 10 && k < K) v = W[((size_t)k * NMA_C1 + c) * NMA_C + g * 10 + q];
+        out[t] = v;
+    }
+}
+__global__ void k_pack_dgrad(const float* __restrict__ W, int K, int KP, float* __restrict__ out) {
+    // out[f][g][k'][12], f<50 (input = conv output channel), g<6; output o=(g,q): g<5 -> c = 1+10g+q, g==5,q==0 -> c=0
+    // tap k' uses W[K-1-k'][c][f]  (full correlation of dA with the flipped kernel)
+    const int n = NMA_C * 6 * KP * CONV_WPAD;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        int q = t % CONV_WPAD;
+        int k = (t / CONV_WPAD) % KP;
+        int g = (t / (CONV_WPAD * KP)) % 6;
+        int f = t / (CONV_WPAD * KP * 6);
+        float v = 0.f;
+        int c = -1;
+        if (g < 5 && q < 10) c = 1 + 10 * g + q;
+        if (g == 5 && q == 0) c = 0;
+        if (c >= 0 && k < K) v = W[((size_t)(K - 1 - k) * NMA_C1 + c) * NMA_C + f];
+        out[t] = v;
+    }
+}
+
+int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
+    for (int i = 0; i < h->cfg.F; ++i) {
+        k_pack_fwd<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->ws[i].wpk);
+        if (need_bwd) k_pack_dgrad<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->ws[i].wdpk);
+    }
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// theta-bias MLP (AR.py:63-68): three linear layers, no activation. tb[r] = {t1, t2, b + conv_bias}
+// ---------------------------------------------------------------------------
+struct ThetaFwdArgs {
+    const float* w[NMA_MAX_FLOWS][3];
+    const float* b[NMA_MAX_FLOWS][3];
+    const float* convb[NMA_MAX_FLOWS];
+    float* tb[NMA_MAX_FLOWS];
+};
+__global__ void k_theta_fwd(ThetaFwdArgs a, const float* __restrict__ theta, int dth) {
+    const int r = blockIdx.x, i = blockIdx.y, f = threadIdx.x;
+    __shared__ float s_in[64];
+    __shared__ float s_t[64];
+    if (f < dth) s_in[f] = theta[(size_t)r * dth + f];
+    __syncthreads();
+    float* out = a.tb[i] + (size_t)r * 3 * NMA_C;
+    float v = 0.f;
+    if (f < NMA_C) {
+        v = a.b[i][0][f];
+        for (int k = 0; k < dth; ++k) v = fmaf(s_in[k], a.w[i][0][k * NMA_C + f], v);
+        out[f] = v;
+        s_t[f] = v;
+    }
+    __syncthreads();
+    if (f < NMA_C) {
+        v = a.b[i][1][f];
+        for (int k = 0; k < NMA_C; ++k) v = fmaf(s_t[k], a.w[i][1][k * NMA_C + f], v);
+        out[NMA_C + f] = v;
+    }
+    __syncthreads();
+    if (f < NMA_C) s_t[f] = v;
+    __syncthreads();
+    if (f < NMA_C) {
+        v = a.b[i][2][f] + a.convb[i][f];
+        for (int k = 0; k < NMA_C; ++k) v = fmaf(s_t[k], a.w[i][2][k * NMA_C + f], v);
+        out[2 * NMA_C + f] = v;
+    }
+}
+
+int launch_theta_fwd(nma_handle_s* h, const float* params, const float* theta, int p, cudaStream_t st) {
+    ThetaFwdArgs a;
+    for (int i = 0; i < h->cfg.F; ++i) {
+        for (int l = 0; l < 3; ++l) {
+            a.w[i][l] = params + h->po[i].thw[l];
+            a.b[i][l] = params + h->po[i].thb[l];
+        }
+        a.convb[i] = params + h->po[i].convb;
+        a.tb[i] = h->ws[i].tb;
+    }
+    k_theta_fwd<<<dim3(p, h->cfg.F), 64, 0, st>>>(a, theta, h->cfg.dtheta);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// feature MLP (A1 + A2): gather the window of one row for one flow, run 4x dense(C, elu)
+// ---------------------------------------------------------------------------
+#define FEAT_THREADS 256
+#define FEAT_WPITCH 60   // 5 groups x 12 floats
+
+// Y[g][j] = elu(b[g] + sum_f W[f][g] X[f][j]);  thread item = (4 positions) x (10 outputs)
+__device__ __forceinline__ void dense_tile_elu(const float* Xs, int ldx, int nin, const float* Wsm, const float* bsm,
+                                               float* Ys, int ldy, int npos4, float* gout, int gld, int nvalid) {
+    for (int it = threadIdx.x; it < npos4 * 5; it += blockDim.x) {
+        const int jg = it % npos4, gg = it / npos4;
+        float4 acc[10];
+#pragma unroll
+        for (int g = 0; g < 10; ++g) {
+            const float b = bsm[gg * 10 + g];
+            acc[g] = make_float4(b, b, b, b);
+        }
+        for (int f = 0; f < nin; ++f) {
+            const float4 xv = *reinterpret_cast<const float4*>(Xs + f * ldx + 4 * jg);
+            const float4* w4 = reinterpret_cast<const float4*>(Wsm + f * FEAT_WPITCH + gg * 12);
+            const float4 wa = w4[0], wb = w4[1], wc = w4[2];
+            const float w[10] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y};
+#pragma unroll
+            for (int g = 0; g < 10; ++g) {
+                acc[g].x = fmaf(w[g], xv.x, acc[g].x);
+                acc[g].y = fmaf(w[g], xv.y, acc[g].y);
+                acc[g].z = fmaf(w[g], xv.z, acc[g].z);
+                acc[g].w = fmaf(w[g], xv.w, acc[g].w);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 10; ++g) {
+            float4 o = make_float4(elu_f(acc[g].x), elu_f(acc[g].y), elu_f(acc[g].z), elu_f(acc[g].w));
+            // keep the pad columns (>= nvalid) at zero so downstream padded reads stay finite
+            const int j0 = 4 * jg;
+            if (j0 + 0 >= nvalid) o.x = 0.f;
+            if (j0 + 1 >= nvalid) o.y = 0.f;
+            if (j0 + 2 >= nvalid) o.z = 0.f;
+            if (j0 + 3 >= nvalid) o.w = 0.f;
+            *reinterpret_cast<float4*>(Ys + (gg * 10 + g) * ldy + j0) = o;
+            if (gout) *reinterpret_cast<float4*>(gout + (size_t)(gg * 10 + g) * gld + j0) = o;
+        }
+    }
+}
+
+// stage a dense kernel [nin][50] (+bias[50]) from global into the padded smem layout [nin][60]
+__device__ __forceinline__ void stage_dense_w(const float* __restrict__ W, const float* __restrict__ b, int nin,
+                                              float* Wsm, float* bsm) {
+    for (int t = threadIdx.x; t < nin * FEAT_WPITCH; t += blockDim.x) {
+        const int f = t / FEAT_WPITCH, q = t - f * FEAT_WPITCH;
+        const int gg = q / 12, g = q - gg * 12;
+        Wsm[t] = (g < 10) ? W[f * NMA_C + gg * 10 + g] : 0.f;
+    }
+    for (int t = threadIdx.x; t < NMA_C; t += blockDim.x) bsm[t] = b[t];
+}
+
+struct FeatArgs {
+    const float* w[NMA_MAX_FLOWS][4];
+    const float* b[NMA_MAX_FLOWS][4];
+    float* a[NMA_MAX_FLOWS][5];
+    float* x0;        // ws[0].x : aligned copy of eps
+    int Lin[NMA_MAX_FLOWS], LP[NMA_MAX_FLOWS];
+    int XP0;
+};
+
+__global__ void __launch_bounds__(FEAT_THREADS) k_feat_fwd(FeatArgs fa, SeriesView sv, const int64_t* __restrict__ idx,
+                                                           const float* __restrict__ eps, int L0, int K, int Cf_in,
+                                                           int feat_off, int save) {
+    extern __shared__ __align__(128) float smem[];
+    const int r = blockIdx.x, i = blockIdx.y;
+    const int Lin = fa.Lin[i], LP = fa.LP[i];
+    const int lds = LP;                               // smem pitch
+    float* T0 = smem;                                 // [50][lds]
+    float* T1 = T0 + NMA_C * lds;                     // [50][lds]
+    float* Wsm = T1 + NMA_C * lds;                    // [50][60]
+    float* bsm = Wsm + NMA_C * FEAT_WPITCH;           // [64]
+    const long long win0 = (long long)sv.D * idx[r];
+
+    if (i == 0) {   // aligned copy of the base sample (x^(0) = eps, AR.py:31-32)
+        for (int t = threadIdx.x; t < fa.XP0; t += blockDim.x)
+            fa.x0[(size_t)r * fa.XP0 + t] = (t < L0) ? eps[(size_t)r * L0 + t] : 0.f;
+    }
+    // gather: slot = i*K + j + feat_off  (AR.py:192-193 then :53; SV_dense.py:53 uses [1:])
+    float* ga0 = save ? fa.a[i][0] + (size_t)r * Cf_in * LP : nullptr;
+    for (int t = threadIdx.x; t < Cf_in * LP; t += blockDim.x) {
+        const int c = t / LP, j = t - c * LP;
+        float v = 0.f;
+        if (j < Lin) {
+            const long long pos = win0 + (long long)i * K + j + feat_off;
+            if (c < sv.Cf)
+                v = series_val(sv, c, pos);
+            else
+                v = series_val(sv, c - sv.Cf, pos) - series_val(sv, c - sv.Cf, pos - 1);
+        }
+        T0[c * lds + j] = v;
+        if (ga0) ga0[t] = v;
+    }
+    const int npos4 = LP / 4;
+    float* cur = T0;
+    float* nxt = T1;
+    for (int l = 0; l < 4; ++l) {
+        __syncthreads();
+        const int nin = (l == 0) ? Cf_in : NMA_C;
+        stage_dense_w(fa.w[i][l], fa.b[i][l], nin, Wsm, bsm);
+        __syncthreads();
+        float* gout = (save || l == 3) ? fa.a[i][l + 1] + (size_t)r * NMA_C * LP : nullptr;
+        dense_tile_elu(cur, lds, nin, Wsm, bsm, nxt, lds, npos4, gout, LP, Lin);
+        float* t = cur; cur = nxt; nxt = t;
+    }
+}
+
+int launch_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, int p, bool save, cudaStream_t st);
+
+static int feat_smem_bytes(const nma_handle_s* h) {
+    int lp = 0;
+    for (int i = 0; i < h->cfg.F; ++i) lp = lp > h->fd[i].LP ? lp : h->fd[i].LP;
+    return (2 * NMA_C * lp + NMA_C * FEAT_WPITCH + 64) * 4;
+}
+
+// eps is passed through the handle-level wrapper (see nma_api.cu) via this file-scope pointer-free path
+int launch_feat_fwd_eps(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
+                        cudaStream_t st) {
+    FeatArgs fa;
+    for (int i = 0; i < h->cfg.F; ++i) {
+        for (int l = 0; l < 4; ++l) {
+            fa.w[i][l] = params + h->po[i].featw[l];
+            fa.b[i][l] = params + h->po[i].featb[l];
+        }
+        for (int l = 0; l < 5; ++l) fa.a[i][l] = h->ws[i].a[l];
+        fa.Lin[i] = h->fd[i].Lin;
+        fa.LP[i] = h->fd[i].LP;
+    }
+    fa.x0 = h->ws[0].x;
+    fa.XP0 = (h->fd[0].L + 3) & ~3;
+    const int smem = feat_smem_bytes(h);
+    static int configured = 0;
+    if (configured < smem) {
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_feat_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    SeriesView sv = nma_series_view(h);
+    k_feat_fwd<<<dim3(p, h->cfg.F), FEAT_THREADS, smem, st>>>(fa, sv, idx, eps, h->L0, h->cfg.K, h->Cf_in,
+                                                               h->feat_off, save ? 1 : 0);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// fused conv + theta-bias + ELU + hidden 1x1 layers + head + softplus + affine flow layer (A3-A5)
+//
+// Work decomposition: an "item" is one block of 10 consecutive output positions of one row; items of
+// all rows are numbered consecutively and every CTA takes 32 of them (one per lane), so lanes stay
+// full whatever N_i is.  A CTA therefore spans a few consecutive rows; each ring stage holds the
+// current input channel of all of them.
+// ---------------------------------------------------------------------------
+#define CONVF_WARPS 5
+#define CONVF_THREADS (CONVF_WARPS * 32)
+#define PW_WPITCH 52            // pointwise-layer weights [50][52] in smem
+#define ITEM_COLS (32 * CONV_TM)
+#define ITEM_PITCH (ITEM_COLS + 4)   // 324: multiple of 4 and (pitch/4) odd
+
+// in-place per-position dense layer on the [50][ITEM_PITCH] tile: a thread owns whole columns.
+// out[g] = act(b[g] + sum_f W[f][g] * in[f]) with optional BN-affine applied to the INPUT.
+__device__ __forceinline__ void col_dense_inplace(float* tile, const unsigned char* col_ok, const float* Wsm,
+                                                  const float* bsm, const float* in_scale, const float* in_shift) {
+    for (int col = threadIdx.x; col < ITEM_COLS; col += blockDim.x) {
+        if (!col_ok[col]) continue;
+        float* cp = tile + col;
+        float acc[52];
+#pragma unroll
+        for (int g = 0; g < 52; ++g) acc[g] = (g < NMA_C) ? bsm[g] : 0.f;
+        for (int f = 0; f < NMA_C; ++f) {
+            float xv = cp[f * ITEM_PITCH];
+            if (in_scale) xv = fmaf(xv, in_scale[f], in_shift[f]);
+            const float4* w4 = reinterpret_cast<const float4*>(Wsm + f * PW_WPITCH);
+#pragma unroll
+            for (int q = 0; q < 13; ++q) {
+                const float4 w = w4[q];
+                acc[4 * q + 0] = fmaf(xv, w.x, acc[4 * q + 0]);
+                acc[4 * q + 1] = fmaf(xv, w.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(xv, w.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(xv, w.w, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < NMA_C; ++g) cp[g * ITEM_PITCH] = elu_f(acc[g]);
+    }
+}
+
+struct ConvFwdArgs {
+    ConvSrc src;
+    const float* wpk;
+    const float* tb;         // [p][3][50]; slot 2 = theta bias + conv bias
+    const float* hidw[NMA_MAXH];
+    const float* hidb[NMA_MAXH];
+    const float* gam[NMA_MAXH];
+    const float* bet[NMA_MAXH];
+    const float* headw;      // [50][2]
+    const float* headb;      // [2]
+    const float* x_in;       // [p][XP]   input sample of this flow
+    float* x_out;            // [p][XPn]  next flow's input sample (after the pair swap when D==2)
+    float* h[NMA_MAXH + 1];  // [p][50][NP]
+    float* s;                // [p][NP]
+    int XP, XPn, N, NP, K, KP, H, bn, D, rcmax, npb, row_pitch, p, save, permute_out;
+    long long items_total;
+};
+
+__global__ void __launch_bounds__(CONVF_THREADS, 2) k_conv_fwd(ConvFwdArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t full_bar[CONV_STAGES];
+    __shared__ unsigned char col_ok[ITEM_COLS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long item0 = (long long)blockIdx.x * 32;
+    const int row_first = (int)(item0 / a.npb);
+    long long last_item = item0 + 31;
+    if (last_item >= a.items_total) last_item = a.items_total - 1;
+    const int rc = (int)(last_item / a.npb) - row_first + 1;
+
+    ConvRing rg;
+    rg.cin = NMA_C1; rg.ngroups = 5; rg.KP = a.KP; rg.rc = rc; rg.row_pitch = a.row_pitch;
+    rg.stage_floats = 5 * a.KP * CONV_WPAD + a.rcmax * a.row_pitch;
+
+    // zero the ring once: the tail of every input row must read as 0 (finite) under the padded taps
+    for (int t = tid; t < CONV_STAGES * rg.stage_floats; t += blockDim.x) smem[t] = 0.f;
+    if (tid == 0) {
+        for (int s = 0; s < CONV_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    const long long item = item0 + lane;
+    const bool active = item < a.items_total;
+    const int my_r = active ? (int)(item / a.npb) : row_first;
+    const int pb = active ? (int)(item - (long long)my_r * a.npb) : 0;
+    const int m0 = pb * CONV_TM;
+
+    float2 acc[CONV_TM][5];
+    conv_main_loop(acc, smem, full_bar, rg, a.src, a.wpk, row_first, my_r - row_first, m0, warp, active, true);
+    // (conv_main_loop ends with __syncthreads: the ring is free and is reused as the activation tile)
+
+    float* tile = smem;                               // [50][ITEM_PITCH], column = lane*10 + j
+    float* Wsm = tile + NMA_C * ITEM_PITCH;           // [50][52]
+    float* bsm = Wsm + NMA_C * PW_WPITCH;             // [64]
+    float* bns = bsm + 64;                            // [64] BN scale
+    float* bno = bns + 64;                            // [64] BN shift
+
+    for (int col = tid; col < ITEM_COLS; col += blockDim.x) {
+        const long long it = item0 + col / CONV_TM;
+        bool ok = false;
+        if (it < a.items_total) {
+            const int m = (int)(it % a.npb) * CONV_TM + col % CONV_TM;
+            ok = m < a.N;
+        }
+        col_ok[col] = ok ? 1 : 0;
+    }
+    // e_0 = elu(A + theta-bias + conv bias)  (AR.py:70-72)
+    if (active) {
+        const float* tbr = a.tb + ((size_t)my_r * 3 + 2) * NMA_C + warp * 10;
+        float bias[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) bias[q] = tbr[q];
+#pragma unroll
+        for (int j = 0; j < CONV_TM; ++j) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                float* t0 = tile + (size_t)(warp * 10 + 2 * q) * ITEM_PITCH + lane * CONV_TM + j;
+                t0[0] = elu_f(acc[j][q].x + bias[2 * q]);
+                t0[ITEM_PITCH] = elu_f(acc[j][q].y + bias[2 * q + 1]);
+            }
+        }
+    }
+    __syncthreads();
+
+    auto store_tile = [&](float* gdst) {   // tile -> global [p][50][NP]; consecutive columns are consecutive m
+        for (int t = tid; t < NMA_C * ITEM_COLS; t += blockDim.x) {
+            const int f = t / ITEM_COLS, col = t - f * ITEM_COLS;
+            if (!col_ok[col]) continue;
+            const long long it = item0 + col / CONV_TM;
+            const int r = (int)(it / a.npb);
+            const int m = (int)(it - (long long)r * a.npb) * CONV_TM + col % CONV_TM;
+            gdst[((size_t)r * NMA_C + f) * a.NP + m] = tile[(size_t)f * ITEM_PITCH + col];
+        }
+    };
+    if (a.save) store_tile(a.h[0]);
+
+    // hidden 1x1 layers (AR.py:74-76) [+ BN-affine, fitz_nag_NVP.py:93]
+    for (int l = 0; l < a.H; ++l) {
+        __syncthreads();
+        for (int t = tid; t < NMA_C * PW_WPITCH; t += blockDim.x) {
+            const int f = t / PW_WPITCH, g = t - f * PW_WPITCH;
+            Wsm[t] = (g < NMA_C) ? a.hidw[l][f * NMA_C + g] : 0.f;
+        }
+        if (tid < NMA_C) {
+            bsm[tid] = a.hidb[l][tid];
+            if (a.bn && l > 0) {   // input of layer l is BN_{l-1}(e_l)
+                bns[tid] = a.gam[l - 1][tid] * rsqrtf(1.f + 1e-3f);
+                bno[tid] = a.bet[l - 1][tid];
+            }
+        }
+        __syncthreads();
+        col_dense_inplace(tile, col_ok, Wsm, bsm, (a.bn && l > 0) ? bns : nullptr, bno);
+        __syncthreads();
+        if (a.save) store_tile(a.h[l + 1]);
+    }
+    __syncthreads();
+    // head: (mu, s) = conv1x1 -> 2 (AR.py:77-78); stride 2 when D == 2 (fitz_nag_NVP.py:95-96)
+    if (tid < NMA_C) {
+        if (a.bn && a.H > 0) {
+            bns[tid] = a.gam[a.H - 1][tid] * rsqrtf(1.f + 1e-3f);
+            bno[tid] = a.bet[a.H - 1][tid];
+        } else {
+            bns[tid] = 1.f;
+            bno[tid] = 0.f;
+        }
+        Wsm[2 * tid] = a.headw[2 * tid];
+        Wsm[2 * tid + 1] = a.headw[2 * tid + 1];
+    }
+    __syncthreads();
+    const float hb0 = a.headb[0], hb1 = a.headb[1];
+    for (int col = tid; col < ITEM_COLS; col += blockDim.x) {
+        if (!col_ok[col]) continue;
+        const long long it = item0 + col / CONV_TM;
+        const int r = (int)(it / a.npb);
+        const int m = (int)(it - (long long)r * a.npb) * CONV_TM + col % CONV_TM;
+        const float xin = a.x_in[(size_t)r * a.XP + m + a.K];
+        float xo;
+        if (a.D == 1 || (m & 1)) {
+            // D==2: odd output slot m uses the head evaluated at the even conv position m-1 (same item: 10 is even)
+            const float* cp = tile + ((a.D == 1) ? col : col - 1);
+            float mu = hb0, sr = hb1;
+            for (int g = 0; g < NMA_C; ++g) {
+                const float v = fmaf(cp[g * ITEM_PITCH], bns[g], bno[g]);
+                mu = fmaf(v, Wsm[2 * g], mu);
+                sr = fmaf(v, Wsm[2 * g + 1], sr);
+            }
+            const float sigma = softplus_f(sr) + 1e-10f;   // AR.py:83
+            xo = fmaf(xin, sigma, mu);                      // AR.py:85
+            a.s[(size_t)r * a.NP + m] = sr;
+        } else {
+            xo = xin;   // identity slot of the coupling layer (fitz_nag_NVP.py:99-102)
+        }
+        const int mo = a.permute_out ? (m ^ 1) : m;        // Permute = swap adjacent pairs (fitz_nag_NVP.py:205-211)
+        a.x_out[(size_t)r * a.XPn + mo] = xo;
+    }
+}
+
+static int conv_rows_spanned(int npb) { return (npb - 1 + 31) / npb + 1; }
+
+int launch_conv_fwd(nma_handle_s* h, int i, const float* params, int p, bool save, cudaStream_t st) {
+    const FlowDims& d = h->fd[i];
+    ConvFwdArgs a;
+    const int npb = (d.N + CONV_TM - 1) / CONV_TM;
+    a.rcmax = conv_rows_spanned(npb);
+    a.npb = npb;
+    a.items_total = (long long)p * npb;
+    a.XP = (d.L + 3) & ~3;
+    a.XPn = (h->fd[i + 1].L + 3) & ~3;
+    a.N = d.N; a.NP = d.NP; a.K = h->cfg.K; a.KP = h->KP; a.H = h->cfg.H; a.bn = h->cfg.bn; a.D = h->cfg.D;
+    a.p = p; a.save = save ? 1 : 0;
+    a.permute_out = (h->cfg.D == 2 && i < h->cfg.F - 1) ? 1 : 0;
+    int rp = npb * CONV_TM + h->KP + 4;
+    if (rp < d.LP) rp = d.LP;
+    a.row_pitch = (rp + 3) & ~3;
+    a.src.chan0 = h->ws[i].x; a.src.row_stride0 = a.XP;
+    a.src.rest = h->ws[i].a[4]; a.src.row_stride = (long long)NMA_C * d.LP; a.src.chan_stride = d.LP;
+    a.src.copy_floats = d.LP; a.src.dst_off = 0;
+    a.wpk = h->ws[i].wpk;
+    a.tb = h->ws[i].tb;
+    for (int l = 0; l < NMA_MAXH; ++l) {
+        a.hidw[l] = l < h->cfg.H ? params + h->po[i].hidw[l] : nullptr;
+        a.hidb[l] = l < h->cfg.H ? params + h->po[i].hidb[l] : nullptr;
+        a.gam[l] = (l < h->cfg.H && h->cfg.bn) ? params + h->po[i].gam[l] : nullptr;
+        a.bet[l] = (l < h->cfg.H && h->cfg.bn) ? params + h->po[i].bet[l] : nullptr;
+    }
+    for (int l = 0; l <= NMA_MAXH; ++l) a.h[l] = h->ws[i].h[l];
+    a.headw = params + h->po[i].headw; a.headb = params + h->po[i].headb;
+    a.x_in = h->ws[i].x; a.x_out = h->ws[i + 1].x; a.s = h->ws[i].s;
+
+    const size_t ring = (size_t)CONV_STAGES * (5 * h->KP * CONV_WPAD + a.rcmax * a.row_pitch);
+    const size_t epi = (size_t)NMA_C * ITEM_PITCH + NMA_C * PW_WPITCH + 3 * 64;
+    const size_t smem = (ring > epi ? ring : epi) * 4;
+    static size_t configured = 0;
+    if (configured < smem) {
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const long long grid = (a.items_total + 31) / 32;
+    k_conv_fwd<<<(unsigned)grid, CONVF_THREADS, smem, st>>>(a);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,170 @@
+"""Thin host wrapper over the C-ABI: torch owns device memory and streams, the library does the work.
+
+`NMAEngine` is what the `VI_SSM` facade (viforssms_b200/vi_ssm.py) drives in place of the reference's
+`sess.run([train_step, merged], feed_dict)` (AR.py:300-301).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int64, c_void_p
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .config import NMAConfig, param_layout
+
+
+def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class NMAEngine:
+    def __init__(self, cfg: NMAConfig, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise _lib.NMAError("NMAEngine needs a CUDA device: the NMA ELBO step has no CPU path")
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else "cuda", torch.cuda.current_device()) \
+            if not isinstance(device, torch.device) else device
+        self._lib = _lib.load()
+        self._h = c_void_p()
+        ccfg = cfg.to_c()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.nma_create(ctypes.byref(ccfg), ctypes.byref(self._h)), "nma_create")
+        self.n_params = int(self._lib.nma_param_count(self._h))
+        self.layout, n = param_layout(cfg)
+        if n != self.n_params:
+            raise _lib.NMAError(f"host/device parameter layouts disagree: {n} vs {self.n_params}")
+        self._series: List[torch.Tensor] = []
+        self._scratch = torch.zeros(1024, dtype=torch.float32, device=self.device)
+        self._norm = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.nma_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._lib.nma_workspace_bytes(self._h))
+
+    def device_layout(self) -> np.ndarray:
+        out = (c_int64 * (self.cfg.F * 32))()
+        _lib.check(self._lib.nma_param_layout(self._h, out, self.cfg.F * 32), "nma_param_layout")
+        return np.ctypeslib.as_array(out).reshape(self.cfg.F, 32).copy()
+
+    # ------------------------------------------------------------------
+    def set_series(self, arrays: Sequence) -> None:
+        """Padded base arrays (float64 numpy as the reference builds them, or fp32 tensors) -> device fp32.
+
+        The float64 -> float32 conversion is the feed_dict cast of the reference (AR.py:300-301)."""
+        dev = []
+        for a in arrays:
+            if isinstance(a, torch.Tensor):
+                t = a.to(device=self.device, dtype=torch.float32).contiguous()
+            else:
+                t = torch.from_numpy(np.ascontiguousarray(np.asarray(a).astype(np.float32))).to(self.device)
+            dev.append(t.reshape(-1))
+        self._series = dev
+        n = len(dev)
+        ptrs = (c_void_p * n)(*[t.data_ptr() for t in dev])
+        lens = (c_int64 * n)(*[t.numel() for t in dev])
+        _lib.check(self._lib.nma_set_series(self._h, ptrs, lens, n), "nma_set_series")
+
+    def _idx(self, idx) -> torch.Tensor:
+        if isinstance(idx, torch.Tensor):
+            return idx.to(device=self.device, dtype=torch.int64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(idx, dtype=np.int64))).to(self.device)
+
+    def gather(self, idx):
+        cfg = self.cfg
+        idx = self._idx(idx)
+        p = idx.numel()
+        tf = torch.empty(p, cfg.L0, cfg.Cf, dtype=torch.float32, device=self.device)
+        mask = torch.empty(p, cfg.D, cfg.B + 1, dtype=torch.float32, device=self.device)
+        shift = torch.empty_like(mask)
+        _lib.check(self._lib.nma_gather(self._h, _ptr(idx), p, _ptr(tf), _ptr(mask), _ptr(shift), _stream()),
+                   "nma_gather")
+        return tf, mask, shift
+
+    def alloc_outputs(self, p: int) -> Dict[str, torch.Tensor]:
+        cfg = self.cfg
+        d = self.device
+        return {
+            "terms": torch.empty(p, 4, dtype=torch.float32, device=d),
+            "lf": torch.empty(p, cfg.L(cfg.F), dtype=torch.float32, device=d),
+            "grad_params": torch.empty(self.n_params, dtype=torch.float32, device=d),
+            "grad_theta": torch.empty(p, cfg.dtheta, dtype=torch.float32, device=d),
+            "flags": torch.empty(p, dtype=torch.int32, device=d),
+        }
+
+    def elbo_fwd_bwd(self, params: torch.Tensor, eps: torch.Tensor, theta: torch.Tensor, idx: torch.Tensor,
+                     objective: int = 0, path_target: float = 0.0, out: Optional[Dict[str, torch.Tensor]] = None):
+        p = idx.numel()
+        assert params.is_cuda and eps.is_cuda and theta.is_cuda and idx.is_cuda
+        assert params.dtype == torch.float32 and params.numel() == self.n_params and params.is_contiguous()
+        assert eps.shape == (p, self.cfg.L0) and eps.is_contiguous() and eps.dtype == torch.float32
+        assert theta.shape == (p, self.cfg.dtheta) and theta.is_contiguous() and theta.dtype == torch.float32
+        assert idx.dtype == torch.int64
+        if out is None:
+            out = self.alloc_outputs(p)
+        _lib.check(self._lib.nma_elbo_fwd_bwd(
+            self._h, _ptr(params), _ptr(eps), _ptr(theta), _ptr(idx), p, int(objective), float(path_target),
+            _ptr(out["terms"]), _ptr(out["lf"]), _ptr(out["grad_params"]), _ptr(out["grad_theta"]),
+            _ptr(out["flags"]), _stream()), "nma_elbo_fwd_bwd")
+        return out
+
+    def forward_paths(self, params, eps, theta, idx):
+        p = idx.numel()
+        terms = torch.empty(p, 4, dtype=torch.float32, device=self.device)
+        lf = torch.empty(p, self.cfg.L(self.cfg.F), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.nma_forward_paths(self._h, _ptr(params), _ptr(eps), _ptr(theta), _ptr(idx), p,
+                                               _ptr(terms), _ptr(lf), _stream()), "nma_forward_paths")
+        return terms, lf
+
+    def adamax_step(self, params, grads, m, v, lr, beta1, beta2=0.999, eps=1e-8, clip=0.0) -> torch.Tensor:
+        """In-place clip + Adamax on flat fp32 tensors; returns the 1-element global-norm tensor (device)."""
+        n = params.numel()
+        _lib.check(self._lib.nma_adamax_step(_ptr(params), _ptr(grads), _ptr(m), _ptr(v), n, float(lr), float(beta1),
+                                             float(beta2), float(eps), float(clip), _ptr(self._norm),
+                                             _ptr(self._scratch), _stream()), "nma_adamax_step")
+        return self._norm
+
+
+def scan_ar1(z: torch.Tensor, x0: float, a: float, b: float, c: float) -> torch.Tensor:
+    """x[0]=x0, x[i] = a*x[i-1] + b + c*z[i-1] on device (float64); AR_dat_gen.py:11-14."""
+    lib = _lib.load()
+    assert z.is_cuda and z.dtype == torch.float64 and z.is_contiguous()
+    n = z.numel()
+    x = torch.empty(n + 1, dtype=torch.float64, device=z.device)
+    nblocks = (n + 4095) // 4096
+    scratch = torch.empty(nblocks * 2, dtype=torch.float64, device=z.device)
+    _lib.check(lib.nma_scan_ar1(_ptr(z), _ptr(x), n, x0, a, b, c, _ptr(scratch), scratch.numel() * 8, _stream()),
+               "nma_scan_ar1")
+    return x
+
+
+def time_till(obs: torch.Tensor, impute: int):
+    """(obs_fill, obs_binary, time_till) on device from the n+1 noisy observations; AR_dat_gen.py:17-31."""
+    lib = _lib.load()
+    assert obs.is_cuda and obs.dtype == torch.float64 and obs.is_contiguous()
+    n = obs.numel() - 1
+    m = ((n - impute) // impute + 1) * impute
+    fill = torch.empty(m, dtype=torch.float64, device=obs.device)
+    binary = torch.empty_like(fill)
+    till = torch.empty_like(fill)
+    _lib.check(lib.nma_time_till(_ptr(obs), n, impute, _ptr(fill), _ptr(binary), _ptr(till), _stream()),
+               "nma_time_till")
+    return fill, binary, till

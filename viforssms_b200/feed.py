@@ -1,0 +1,49 @@
+"""Host side of the mini-batch feed: padded base arrays and subsequence-index sampling.
+
+The reference rebuilds a [p, L0, Cf] float64 `time_feats` tensor with ~14*p numpy slices every
+iteration (AR.py:267-288).  Here the padded series are placed on the device ONCE and the kernels
+gather windows themselves from the sampled start indices, so the per-iteration host work is the index
+draw alone — which stays the reference's own legacy `np.random.choice` call so indices are bit-exact.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+
+def ar_base_arrays(obs, obs_bin, time_till, T: int, F: int, K: int, fw: int) -> List[np.ndarray]:
+    """Base arrays of the AR model in the order `config.ar_config` expects.
+
+    Equivalent to VI_SSM.__init__ (AR.py:135-150).  The reference keeps `feat_window` shifted copies of
+    the observation series (`obs_pad_store[i] = zeros(P-i) ++ obs ++ zeros(i)`); one array padded with
+    P zeros in front and fw-1 behind serves all of them: obs_pad_store[i][q] == obs_pad[q + i].
+    """
+    P = F * K + 1
+    T = int(np.int32(T))
+    obs = np.asarray(obs, dtype=np.float64)
+    obs_bin = np.asarray(obs_bin, dtype=np.float64)
+    time_till = np.asarray(time_till, dtype=np.float64)
+    if obs.shape[0] != T or obs_bin.shape[0] != T or time_till.shape[0] != T:
+        raise ValueError("series length must equal T (AR.py:135-150 assumes it)")
+    obs_pad = np.concatenate((np.zeros(P), obs, np.zeros(max(fw - 1, 0))))
+    bin_feats = np.concatenate((np.ones(P), np.zeros(T)))
+    time_pad = np.concatenate((np.zeros(P), np.arange(T + 1, dtype=np.float64)))
+    tt0 = float(time_till[0])
+    time_till_pad = np.concatenate((np.arange(P + tt0, tt0, -1), time_till))
+    obs_bin_pad = np.concatenate((np.zeros(P), obs_bin))
+    return [obs_pad, bin_feats, time_pad, time_till_pad, obs_bin_pad]
+
+
+def sample_indices(T: int, B: int, p: int, rng=None) -> np.ndarray:
+    """p subsequence starts from arange(0, T, B); with replacement iff B*p >= T (AR.py:257-265).
+
+    `rng=None` uses numpy's global legacy stream exactly like the reference."""
+    rng = np.random if rng is None else rng
+    return rng.choice(np.arange(0, T, B), size=p, replace=bool(B * p >= T)).astype(np.int64)
+
+
+def partition_indices(idx: np.ndarray, world: int, rank: int) -> np.ndarray:
+    """Row sharding for N GPUs: contiguous slices of the injected index list."""
+    per = (len(idx) + world - 1) // world
+    return idx[rank * per:(rank + 1) * per]

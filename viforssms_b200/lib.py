@@ -1,0 +1,75 @@
+"""ctypes binding of libnma_b200.so (the C-ABI in include/nma_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is present the
+import / the first call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_uint32, c_void_p
+
+from .config import CConfig
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnma_b200.so")
+
+EXPORTS = [
+    "nma_last_error", "nma_version", "nma_create", "nma_destroy", "nma_param_count", "nma_param_layout",
+    "nma_workspace_bytes", "nma_set_series", "nma_gather", "nma_elbo_fwd_bwd", "nma_forward_paths",
+    "nma_adamax_step", "nma_scan_ar1", "nma_time_till",
+]
+
+_lib = None
+
+
+class NMAError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NMAError(
+            f"{LIB_PATH} not found: build it with `python -m viforssms_b200.build` "
+            "(there is no CPU fallback for the NMA ELBO step)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.nma_last_error.restype = c_char_p
+    lib.nma_version.restype = c_int32
+    lib.nma_create.argtypes = [POINTER(CConfig), POINTER(c_void_p)]
+    lib.nma_create.restype = c_int32
+    lib.nma_destroy.argtypes = [c_void_p]
+    lib.nma_param_count.argtypes = [c_void_p]
+    lib.nma_param_count.restype = c_int64
+    lib.nma_workspace_bytes.argtypes = [c_void_p]
+    lib.nma_workspace_bytes.restype = c_int64
+    lib.nma_param_layout.argtypes = [c_void_p, POINTER(c_int64), c_int32]
+    lib.nma_param_layout.restype = c_int32
+    lib.nma_set_series.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int64), c_int32]
+    lib.nma_set_series.restype = c_int32
+    lib.nma_gather.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.nma_gather.restype = c_int32
+    lib.nma_elbo_fwd_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.nma_elbo_fwd_bwd.restype = c_int32
+    lib.nma_forward_paths.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                      c_void_p]
+    lib.nma_forward_paths.restype = c_int32
+    lib.nma_adamax_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
+                                    c_float, c_float, c_void_p, c_void_p, c_void_p]
+    lib.nma_adamax_step.restype = c_int32
+    lib.nma_scan_ar1.argtypes = [c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double, c_void_p,
+                                 c_int64, c_void_p]
+    lib.nma_scan_ar1.restype = c_int32
+    lib.nma_time_till.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.nma_time_till.restype = c_int32
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().nma_last_error()
+        raise NMAError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
