@@ -105,6 +105,13 @@ int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float* d_eps, co
 int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
                       const int64_t* d_idx, int32_t p, float* d_terms, float* d_lf, void* stream);
 
+/* Measurement hooks (no reference counterpart): re-launch one stage of the last step on the workspace it
+ * left behind (stage: 0 conv_fwd, 1 conv_dgrad, 2 conv_wgrad, 3 epi_bwd, 4 feat_fwd, 5 feat_bwd), and the
+ * number of kernels this library has launched so far in this process. */
+int nma_launch_stage(nma_handle h, int32_t stage, int32_t flow, const float* d_params, const float* d_eps,
+                     const int64_t* d_idx, int32_t p, float* d_grad_params, void* stream);
+int64_t nma_launch_count(void);
+
 /* A9 — tf.global_norm + clip_by_global_norm + AdamaxOptimizer._apply_dense
  * (AR.py:230-234; optimisers/adamax.py:42-58).  d_norm_out[0] = global norm (pre-clip).
  * d_scratch: >= 1024 floats. */

@@ -83,8 +83,10 @@ extern "C" int nma_adamax_step(float* d_params, const float* d_grads, float* d_m
     int64_t want = (n / 4 + AM_THREADS - 1) / AM_THREADS;
     int blocks = (int)(want < 1 ? 1 : (want > AM_BLOCKS ? AM_BLOCKS : want));
     k_sumsq<<<blocks, AM_THREADS, 0, st>>>(d_grads, n, d_scratch);
+    nma_count_launch(1);
     k_adamax<<<blocks, AM_THREADS, 0, st>>>(d_params, d_grads, d_m, d_v, n, lr, beta1, beta2, eps, clip, d_scratch, blocks,
                                             d_norm_out);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -247,6 +247,28 @@ extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float
     return 0;
 }
 
+// profiling hook: re-launch ONE stage of the last step on the workspace it left behind (bench.py times the
+// dominant kernel in isolation with CUDA events; results of the re-launch are discarded by the caller).
+// stage: 0 conv_fwd, 1 conv_dgrad, 2 conv_wgrad, 3 epi_bwd, 4 feat_fwd, 5 feat_bwd
+extern "C" int nma_launch_stage(nma_handle h, int32_t stage, int32_t flow, const float* d_params, const float* d_eps,
+                                const int64_t* d_idx, int32_t p, float* d_grad_params, void* stream) {
+    if (!h || flow < 0 || flow >= h->cfg.F || p < 1 || p > h->cfg.p) { nma_set_error("nma_launch_stage: bad argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (stage) {
+        case 0: return launch_conv_fwd(h, flow, d_params, p, true, st);
+        case 1: return launch_conv_dgrad(h, flow, p, st);
+        case 2: return launch_conv_wgrad(h, flow, p, d_grad_params, st);
+        case 3: return launch_epi_bwd(h, flow, d_params, p, NMA_OBJ_ELBO, d_grad_params, st);
+        case 4: return launch_feat_fwd_eps(h, d_params, d_idx, d_eps, p, true, st);
+        case 5: return launch_feat_bwd(h, flow, d_params, p, d_grad_params, st);
+        default: nma_set_error("nma_launch_stage: unknown stage %d", stage); return -1;
+    }
+}
+
+static long long g_launches = 0;
+void nma_count_launch(int n) { g_launches += n; }
+extern "C" int64_t nma_launch_count(void) { return g_launches; }
+
 extern "C" int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
                                  const int64_t* d_idx, int32_t p, float* d_terms, float* d_lf, void* stream) {
     if (check_step_args(h, p, d_params, d_eps, d_theta, d_idx)) return -1;

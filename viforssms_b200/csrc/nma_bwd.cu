@@ -304,6 +304,7 @@ int launch_epi_bwd(nma_handle_s* h, int i, const float* params, int p, int objec
         configured = smem;
     }
     k_epi_bwd<<<persistent_grid(h, p, 2), BWD_THREADS, smem, st>>>(a);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -419,6 +420,7 @@ int launch_conv_dgrad(nma_handle_s* h, int i, int p, cudaStream_t st) {
         configured = smem;
     }
     k_conv_dgrad<<<(unsigned)((a.items_total + 31) / 32), CONVD_WARPS * 32, smem, st>>>(a);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -440,8 +442,8 @@ struct ConvWgradArgs {
 __global__ void __launch_bounds__(WG_THREADS) k_conv_wgrad(ConvWgradArgs a) {
     extern __shared__ __align__(128) float smem[];
     const int tid = threadIdx.x;
-    float* I = smem;                        // [51][ip]  conv input tile of one row
-    float* Dt = I + NMA_C1 * a.ip;          // [50][dp]  dA tile
+    float* Dt = smem;                       // [50][dp]  dA tile (float4 access: keep it 16B aligned)
+    float* I = Dt + NMA_C * a.dp;           // [51][ip]  conv input tile of one row (odd pitch, scalar access)
     // item decomposition: item = (fg*ntb + tb)*51 + c ; c fastest so a warp reads 32 distinct input rows
     const int item = blockIdx.x * WG_THREADS + tid;
     const bool active = item < a.nitems;
@@ -545,6 +547,7 @@ int launch_conv_wgrad(nma_handle_s* h, int i, int p, float* gp, cudaStream_t st)
         configured = smem;
     }
     k_conv_wgrad<<<dim3(item_ctas, row_groups), WG_THREADS, smem, st>>>(a);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -640,6 +643,7 @@ int launch_feat_bwd(nma_handle_s* h, int i, const float* params, int p, float* g
         configured = smem;
     }
     k_feat_bwd<<<persistent_grid(h, p, 2), BWD_THREADS, smem, st>>>(a);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -742,6 +746,7 @@ int launch_theta_bwd(nma_handle_s* h, const float* params, const float* theta, i
     a.rows_per_cta = (p + ctas - 1) / ctas;
     ctas = (p + a.rows_per_cta - 1) / a.rows_per_cta;
     k_theta_bwd<<<dim3(ctas, h->cfg.F), BWD_THREADS, 0, st>>>(a);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -40,7 +40,6 @@ struct FlowWs {
     float* df;       // [p][C][LP]  gradient w.r.t. the feature channels of the conv input
     float* tb;       // [p][3][C]   theta-MLP activations t1, t2, b(+conv bias)
     float* dtb;      // [p][C]      sum_m dA
-    float* logsig;   // [p]         sum over the last S slots of log sigma
     float* wpk;      // packed conv weights for the forward conv  [Cin=51][5][KP][12]
     float* wdpk;     // packed conv weights for the data-gradient conv [Cin=50][6][KP][12]
 };
@@ -70,6 +69,7 @@ struct SeriesView {
 };
 
 void nma_set_error(const char* fmt, ...);
+void nma_count_launch(int n);   // kernels launched by this library (bench.py reports it)
 #define NMA_CHECK_CUDA(call)                                                           \
     do {                                                                               \
         cudaError_t e__ = (call);                                                      \

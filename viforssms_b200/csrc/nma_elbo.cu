@@ -223,6 +223,7 @@ int launch_elbo(nma_handle_s* h, const float* theta, const float* eps, const int
     a.x0a = h->cfg.x0[0]; a.x0b = h->cfg.x0[1];
     const int warps_per_block = 4;
     k_elbo<<<(p + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, st>>>(a);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

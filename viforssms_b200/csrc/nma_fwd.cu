@@ -37,6 +37,7 @@ __global__ void k_gather(SeriesView sv, const int64_t* __restrict__ idx, int p, 
 int launch_gather(nma_handle_s* h, const int64_t* idx, int p, float* tf, float* mask, float* shift, cudaStream_t st) {
     SeriesView sv = nma_series_view(h);
     k_gather<<<p, 256, 0, st>>>(sv, idx, p, h->L0, h->cfg.B, h->cfg.x0[0], h->cfg.x0[1], tf, mask, shift);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -78,6 +79,7 @@ __global__ void k_pack_dgrad(const float* __restrict__ W, int K, int KP, float* 
 int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
     for (int i = 0; i < h->cfg.F; ++i) {
         k_pack_fwd<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->ws[i].wpk);
+        nma_count_launch(1);
         if (need_bwd) k_pack_dgrad<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->ws[i].wdpk);
     }
     NMA_CHECK_CUDA(cudaGetLastError());
@@ -134,6 +136,7 @@ int launch_theta_fwd(nma_handle_s* h, const float* params, const float* theta, i
         a.tb[i] = h->ws[i].tb;
     }
     k_theta_fwd<<<dim3(p, h->cfg.F), 64, 0, st>>>(a, theta, h->cfg.dtheta);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -281,6 +284,7 @@ int launch_feat_fwd_eps(nma_handle_s* h, const float* params, const int64_t* idx
     SeriesView sv = nma_series_view(h);
     k_feat_fwd<<<dim3(p, h->cfg.F), FEAT_THREADS, smem, st>>>(fa, sv, idx, eps, h->L0, h->cfg.K, h->Cf_in,
                                                                h->feat_off, save ? 1 : 0);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -527,6 +531,7 @@ int launch_conv_fwd(nma_handle_s* h, int i, const float* params, int p, bool sav
     }
     const long long grid = (a.items_total + 31) / 32;
     k_conv_fwd<<<(unsigned)grid, CONVF_THREADS, smem, st>>>(a);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -94,8 +94,11 @@ extern "C" int nma_scan_ar1(const double* d_z, double* d_x, int64_t n, double x0
     cudaStream_t st = (cudaStream_t)stream;
     Aff* agg = (Aff*)d_scratch;
     k_scan_reduce<<<(unsigned)nblocks, SC_THREADS, 0, st>>>(d_z, n, a, b, c, agg);
+    nma_count_launch(1);
     k_scan_carry<<<1, 32, 0, st>>>(agg, nblocks, x0);
+    nma_count_launch(1);
     k_scan_apply<<<(unsigned)nblocks, SC_THREADS, 0, st>>>(d_z, d_x, n, x0, a, b, c, agg);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -134,6 +137,7 @@ extern "C" int nma_time_till(const double* d_obs, int64_t n, int32_t impute, dou
     int64_t blocks = (m_out + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_time_till<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_obs, m_out, impute, d_fill, d_binary, d_till);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libnma_b200.so")
 EXPORTS = [
     "nma_last_error", "nma_version", "nma_create", "nma_destroy", "nma_param_count", "nma_param_layout",
     "nma_workspace_bytes", "nma_set_series", "nma_gather", "nma_elbo_fwd_bwd", "nma_forward_paths",
-    "nma_adamax_step", "nma_scan_ar1", "nma_time_till",
+    "nma_adamax_step", "nma_scan_ar1", "nma_time_till", "nma_launch_stage", "nma_launch_count",
 ]
 
 _lib = None
@@ -60,6 +60,10 @@ def load() -> ctypes.CDLL:
     lib.nma_adamax_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                     c_float, c_float, c_void_p, c_void_p, c_void_p]
     lib.nma_adamax_step.restype = c_int32
+    lib.nma_launch_stage.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                     c_void_p]
+    lib.nma_launch_stage.restype = c_int32
+    lib.nma_launch_count.restype = c_int64
     lib.nma_scan_ar1.argtypes = [c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double, c_void_p,
                                  c_int64, c_void_p]
     lib.nma_scan_ar1.restype = c_int32
