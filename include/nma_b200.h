@@ -105,6 +105,20 @@ int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float* d_eps, co
 int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
                       const int64_t* d_idx, int32_t p, float* d_terms, float* d_lf, void* stream);
 
+/* The K-tap conv (AR.py:61-62) and its data gradient run on the tcgen05 tensor cores (3xTF32 split, fp32
+ * accumulate) whenever the configuration allows it (flow_dims = 1, kernel_len <= 190); the FP32 SIMT kernels
+ * remain as the correctness anchor.  on = 0 selects the SIMT conv, on = 1 the tensor-core conv (error if the
+ * configuration does not support it).  The environment variable NMA_TC=0 sets the default to SIMT. */
+int nma_set_tensor_cores(nma_handle h, int32_t on);
+int nma_get_tensor_cores(nma_handle h);
+
+/* Test hook: the bare tensor-core contraction on caller data.  d_in [Q][56] fp32, d_w [K][51][50] (conv1d kernel
+ * layout), d_out [Q][64].  mode 0: out[q][n] = sum_k sum_c in[q+k][c] w[k][c][n]; mode 1 (data gradient):
+ * out[q][n] = sum_k sum_f in[q+k][f] w[K-1-k][n][f].  nacc = 1 or 2 accumulators of 128 positions per CTA.
+ * Synchronises the stream; allocates its own scratch. */
+int nma_tc_conv_raw(const float* d_in, const float* d_w, int32_t mode, int32_t nacc, float* d_out, int64_t Q,
+                    int32_t K, void* stream);
+
 /* Measurement hooks (no reference counterpart): re-launch one stage of the last step on the workspace it
  * left behind (stage: 0 conv_fwd, 1 conv_dgrad, 2 conv_wgrad, 3 epi_bwd, 4 feat_fwd, 5 feat_bwd), and the
  * number of kernels this library has launched so far in this process. */

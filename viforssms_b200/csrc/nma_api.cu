@@ -2,7 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 #include <new>
-#include "nma_common.cuh"
+#include <stdlib.h>
+#include "nma_tc.cuh"
 
 int launch_feat_fwd_eps(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
                         cudaStream_t st);
@@ -104,6 +105,13 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         if (i < cfg->F && d.N < 1) { delete h; nma_set_error("nma_create: window too short"); return -1; }
     }
     compute_layout(h);
+    // tensor-core conv (nma_tc_conv.cu): 1-D flows whose operand tile fits in shared memory
+    h->tc_ok = (cfg->D == 1 && cfg->K <= 190) ? 1 : 0;
+    h->tc_nacc = (tc_conv_smem_floats(2, cfg->K) * 4 + 4096 <= 227 * 1024) ? 2 : 1;
+    {
+        const char* env = getenv("NMA_TC");
+        h->use_tc = h->tc_ok && !(env && env[0] == '0');
+    }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
 
@@ -111,7 +119,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     const int64_t p = cfg->p;
     int64_t total = 0;
     auto reserve = [&](int64_t floats) { int64_t o = total; total += align_up(floats * 4, 256); return o; };
-    struct Off { int64_t x, dx, a[5], h[NMA_MAXH + 1], s, dA, df, tb, dtb, wpk, wdpk; } off[NMA_MAX_FLOWS + 1];
+    struct Off { int64_t x, dx, a[5], h[NMA_MAXH + 1], s, dA, df, tb, dtb, wpk, wdpk, tin_hi, tin_lo, dat_hi, dat_lo, wtc_f, wtc_d; } off[NMA_MAX_FLOWS + 1];
     for (int i = 0; i <= cfg->F; ++i) {
         const FlowDims& d = h->fd[i];
         const int64_t XP = (d.L + 3) & ~3;
@@ -128,6 +136,16 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         off[i].dtb = reserve(p * NMA_C);
         off[i].wpk = reserve((int64_t)NMA_C1 * 5 * h->KP * 12);
         off[i].wdpk = reserve((int64_t)NMA_C * 6 * h->KP * 12);
+        if (h->tc_ok) {
+            const int64_t Q = (p * d.Lin + 255) / 256 * 256 + 640 + cfg->K;
+            h->ws[i].tin_Q = h->ws[i].dat_Q = Q;
+            off[i].tin_hi = reserve((int64_t)TC_CCH * Q * 4);
+            off[i].tin_lo = reserve((int64_t)TC_CCH * Q * 4);
+            off[i].dat_hi = reserve((int64_t)TC_CCH * Q * 4);
+            off[i].dat_lo = reserve((int64_t)TC_CCH * Q * 4);
+            off[i].wtc_f = reserve((int64_t)cfg->K * TC_WSTAGE);
+            off[i].wtc_d = reserve((int64_t)cfg->K * TC_WSTAGE);
+        }
     }
     h->arena_bytes = total;
     cudaError_t e = cudaMalloc(&h->arena, (size_t)total);
@@ -153,6 +171,11 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         w.dtb = (float*)(base + off[i].dtb);
         w.wpk = (float*)(base + off[i].wpk);
         w.wdpk = (float*)(base + off[i].wdpk);
+        if (h->tc_ok) {
+            w.tin_hi = (float*)(base + off[i].tin_hi); w.tin_lo = (float*)(base + off[i].tin_lo);
+            w.dat_hi = (float*)(base + off[i].dat_hi); w.dat_lo = (float*)(base + off[i].dat_lo);
+            w.wtc_f = (float*)(base + off[i].wtc_f); w.wtc_d = (float*)(base + off[i].wtc_d);
+        }
     }
     *out = h;
     return 0;
@@ -164,6 +187,14 @@ extern "C" int nma_destroy(nma_handle h) {
     delete h;
     return 0;
 }
+
+extern "C" int nma_set_tensor_cores(nma_handle h, int32_t on) {
+    if (!h) { nma_set_error("null handle"); return -1; }
+    if (on && !h->tc_ok) { nma_set_error("the tensor-core conv does not support this configuration (flow_dims=%d, kernel_len=%d)", h->cfg.D, h->cfg.K); return -1; }
+    h->use_tc = on ? 1 : 0;
+    return 0;
+}
+extern "C" int nma_get_tensor_cores(nma_handle h) { return h ? h->use_tc : -1; }
 
 extern "C" int64_t nma_param_count(nma_handle h) { return h ? h->n_params : -1; }
 extern "C" int64_t nma_workspace_bytes(nma_handle h) { return h ? h->arena_bytes : -1; }
@@ -239,7 +270,7 @@ extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float
         return rc;
     for (int i = h->cfg.F - 1; i >= 0; --i) {
         if ((rc = launch_epi_bwd(h, i, d_params, p, objective, d_grad_params, st))) return rc;
-        if ((rc = launch_conv_dgrad(h, i, p, st))) return rc;
+        if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, st) : launch_conv_dgrad(h, i, p, st)))) return rc;
         if ((rc = launch_conv_wgrad(h, i, p, d_grad_params, st))) return rc;
         if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
     }
@@ -256,7 +287,7 @@ extern "C" int nma_launch_stage(nma_handle h, int32_t stage, int32_t flow, const
     cudaStream_t st = (cudaStream_t)stream;
     switch (stage) {
         case 0: return launch_conv_fwd(h, flow, d_params, p, true, st);
-        case 1: return launch_conv_dgrad(h, flow, p, st);
+        case 1: return h->use_tc ? launch_conv_dgrad_tc(h, flow, p, st) : launch_conv_dgrad(h, flow, p, st);
         case 2: return launch_conv_wgrad(h, flow, p, d_grad_params, st);
         case 3: return launch_epi_bwd(h, flow, d_params, p, NMA_OBJ_ELBO, d_grad_params, st);
         case 4: return launch_feat_fwd_eps(h, d_params, d_idx, d_eps, p, true, st);

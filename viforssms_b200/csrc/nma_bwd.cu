@@ -7,7 +7,7 @@
 //   k_theta_bwd  : theta-bias MLP backward -> d/dtheta and its weight gradients
 #include "nma_conv_core.cuh"
 
-#define PW_WPITCH 52
+#include "nma_flow_epi.cuh"
 #define BWD_THREADS 256
 
 // ---------------------------------------------------------------------------
@@ -94,6 +94,10 @@ struct EpiBwdArgs {
     float* dx;                     // [p][XP]   d objective / d x^(i): direct (affine) part written here
     float* dA;                     // [p][50][NP]
     float* dtb;                    // [p][50]
+    float* dat_hi;                 // tensor-core layout of dA: [14][dat_Q][4] at q = K-1 + r*Lin + m (null: SIMT path)
+    float* dat_lo;
+    long long dat_Q;
+    int Lin;
     // gradient blob sections
     float* g_hidw[NMA_MAXH]; float* g_hidb[NMA_MAXH]; float* g_gam[NMA_MAXH]; float* g_bet[NMA_MAXH];
     float* g_headw; float* g_headb; float* g_convb;
@@ -130,6 +134,8 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
 
     if (tid < 2 * NMA_C) hw[tid] = a.headw[tid];
     const int np4 = tp / 4;
+    // the tile columns beyond NP are never loaded but are swept by wgrad_accum: they must hold finite zeros
+    for (int t = tid; t < 2 * NMA_C * tp; t += blockDim.x) smem[t] = 0.f;
 
     for (int r = blockIdx.x; r < a.p; r += gridDim.x) {
         __syncthreads();
@@ -246,6 +252,22 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
                     *reinterpret_cast<const float4*>(G + f * tp + 4 * j4);
             }
         }
+        if (a.dat_hi) {
+            const long long qb = (long long)(a.K - 1) + (long long)r * a.Lin;
+            for (int t = tid; t < 14 * N; t += blockDim.x) {
+                const int fch = t / N, m = t - fch * N;
+                float v[4], hi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int f = 4 * fch + e;
+                    v[e] = f < NMA_C ? G[f * tp + m] : 0.f;
+                    hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+                }
+                const size_t o = ((size_t)fch * a.dat_Q + qb + m) * 4;
+                *reinterpret_cast<float4*>(a.dat_hi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(a.dat_lo + o) = make_float4(v[0] - hi[0], v[1] - hi[1], v[2] - hi[2], v[3] - hi[3]);
+            }
+        }
         __syncthreads();
         if (tid < NMA_C) {
             a.dtb[(size_t)r * NMA_C + tid] = v1[tid];
@@ -292,6 +314,8 @@ int launch_epi_bwd(nma_handle_s* h, int i, const float* params, int p, int objec
     a.g_headw = gp + h->po[i].headw; a.g_headb = gp + h->po[i].headb; a.g_convb = gp + h->po[i].convb;
     a.s = h->ws[i].s; a.x_in = h->ws[i].x; a.dx_next = h->ws[i + 1].dx; a.dx = h->ws[i].dx;
     a.dA = h->ws[i].dA; a.dtb = h->ws[i].dtb;
+    a.dat_hi = h->use_tc ? h->ws[i].dat_hi : nullptr; a.dat_lo = h->use_tc ? h->ws[i].dat_lo : nullptr;
+    a.dat_Q = h->ws[i].dat_Q; a.Lin = d.Lin;
     a.XP = (d.L + 3) & ~3; a.XPn = (h->fd[i + 1].L + 3) & ~3; a.L = d.L; a.N = d.N; a.NP = d.NP; a.K = h->cfg.K;
     a.H = h->cfg.H; a.bn = h->cfg.bn; a.D = h->cfg.D; a.S = h->S; a.p = p;
     a.permute_out = (h->cfg.D == 2 && i < h->cfg.F - 1) ? 1 : 0;

@@ -42,6 +42,14 @@ struct FlowWs {
     float* dtb;      // [p][C]      sum_m dA
     float* wpk;      // packed conv weights for the forward conv  [Cin=51][5][KP][12]
     float* wdpk;     // packed conv weights for the data-gradient conv [Cin=50][6][KP][12]
+    // ---- tensor-core path (nma_tc.cuh): flattened interleaved operands, q = row*Lin + slot ----
+    float* tin_hi;   // [14][tin_Q][4]  conv input (channel 0 = x^(i), 1..50 = feature activations), 3xTF32 hi part
+    float* tin_lo;   //                 lo part
+    float* dat_hi;   // [14][dat_Q][4]  dA (gradient w.r.t. the conv pre-activation) at q = K-1 + row*Lin + m
+    float* dat_lo;
+    float* wtc_f;    // [K][2][14][64][4] packed taps of the forward conv
+    float* wtc_d;    // [K][2][14][64][4] packed taps of the data-gradient conv (flipped, transposed)
+    long long tin_Q, dat_Q;
 };
 
 struct nma_handle_s {
@@ -57,6 +65,9 @@ struct nma_handle_s {
     int64_t arena_bytes;
     int sm_count;
     int dev;
+    int tc_ok;       // the tensor-core conv supports this configuration
+    int use_tc;      // ... and is switched on (default; NMA_TC=0 or nma_set_tensor_cores(h, 0) selects the FP32 SIMT conv)
+    int tc_nacc;     // 128-position accumulators per CTA (2 when the tile fits in shared memory, else 1)
 };
 
 // device-side copy of what kernels need about the series and the channel table
@@ -87,6 +98,11 @@ int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cud
 int launch_theta_fwd(nma_handle_s* h, const float* params, const float* theta, int p, cudaStream_t st);
 int launch_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, int p, bool save, cudaStream_t st);
 int launch_conv_fwd(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
+int launch_conv_fwd_tc(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
+int launch_conv_dgrad_tc(nma_handle_s* h, int flow, int p, cudaStream_t st);
+int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
+struct FlowEpiArgs;
+void fill_flow_epi_args(nma_handle_s* h, int flow, const float* params, bool save, FlowEpiArgs& e);
 int launch_elbo(nma_handle_s* h, const float* theta, const float* eps, const int64_t* idx, int p, int objective,
                 float path_target, float* terms, float* lf, float* grad_theta, uint32_t* flags, bool want_grad,
                 cudaStream_t st);

@@ -2,6 +2,7 @@
 // feature MLP (AR.py:53-56, 267-283), fused conv + head + affine flow layer (AR.py:58-89), ELBO terms
 // (AR.py:168-187).  sm_100a only.
 #include "nma_conv_core.cuh"
+#include "nma_flow_epi.cuh"
 
 // ---------------------------------------------------------------------------
 // series access (A1): time_feats[r, slot, c] = base[chan_array[c]][win0 + slot + chan_offset[c]]
@@ -77,6 +78,7 @@ __global__ void k_pack_dgrad(const float* __restrict__ W, int K, int KP, float* 
 }
 
 int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
+    if (h->use_tc) return launch_pack_weights_tc(h, params, need_bwd, st);
     for (int i = 0; i < h->cfg.F; ++i) {
         k_pack_fwd<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->ws[i].wpk);
         nma_count_launch(1);
@@ -202,6 +204,9 @@ struct FeatArgs {
     const float* b[NMA_MAX_FLOWS][4];
     float* a[NMA_MAX_FLOWS][5];
     float* x0;        // ws[0].x : aligned copy of eps
+    float* tin_hi[NMA_MAX_FLOWS];   // tensor-core layout of the conv input (null: SIMT conv)
+    float* tin_lo[NMA_MAX_FLOWS];
+    long long tin_Q[NMA_MAX_FLOWS];
     int Lin[NMA_MAX_FLOWS], LP[NMA_MAX_FLOWS];
     int XP0;
 };
@@ -250,6 +255,28 @@ __global__ void __launch_bounds__(FEAT_THREADS) k_feat_fwd(FeatArgs fa, SeriesVi
         dense_tile_elu(cur, lds, nin, Wsm, bsm, nxt, lds, npos4, gout, LP, Lin);
         float* t = cur; cur = nxt; nxt = t;
     }
+    if (fa.tin_hi[i]) {
+        // conv input in the tensor-core layout [channel/4][q = r*Lin + slot][4], split for 3xTF32.
+        // channel 0 is the flow's input sample: eps for flow 0; flows > 0 get it from the previous flow's epilogue.
+        __syncthreads();
+        float* th = fa.tin_hi[i];
+        float* tl = fa.tin_lo[i];
+        const long long Q = fa.tin_Q[i], qrow = (long long)r * Lin;
+        for (int t = threadIdx.x; t < 14 * Lin; t += blockDim.x) {
+            const int cch = t / Lin, j = t - cch * Lin;
+            float v[4], hi[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * cch + e;
+                if (c == 0) v[e] = (i == 0) ? eps[(size_t)r * L0 + j] : 0.f;
+                else v[e] = (c <= NMA_C) ? cur[(c - 1) * lds + j] : 0.f;
+                hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+            }
+            const size_t o = ((size_t)cch * Q + qrow + j) * 4;
+            *reinterpret_cast<float4*>(th + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(tl + o) = make_float4(v[0] - hi[0], v[1] - hi[1], v[2] - hi[2], v[3] - hi[3]);
+        }
+    }
 }
 
 int launch_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, int p, bool save, cudaStream_t st);
@@ -272,6 +299,9 @@ int launch_feat_fwd_eps(nma_handle_s* h, const float* params, const int64_t* idx
         for (int l = 0; l < 5; ++l) fa.a[i][l] = h->ws[i].a[l];
         fa.Lin[i] = h->fd[i].Lin;
         fa.LP[i] = h->fd[i].LP;
+        fa.tin_hi[i] = h->use_tc ? h->ws[i].tin_hi : nullptr;
+        fa.tin_lo[i] = h->use_tc ? h->ws[i].tin_lo : nullptr;
+        fa.tin_Q[i] = h->ws[i].tin_Q;
     }
     fa.x0 = h->ws[0].x;
     fa.XP0 = (h->fd[0].L + 3) & ~3;
@@ -299,53 +329,15 @@ int launch_feat_fwd_eps(nma_handle_s* h, const float* params, const int64_t* idx
 // ---------------------------------------------------------------------------
 #define CONVF_WARPS 5
 #define CONVF_THREADS (CONVF_WARPS * 32)
-#define PW_WPITCH 52            // pointwise-layer weights [50][52] in smem
 #define ITEM_COLS (32 * CONV_TM)
 #define ITEM_PITCH (ITEM_COLS + 4)   // 324: multiple of 4 and (pitch/4) odd
-
-// in-place per-position dense layer on the [50][ITEM_PITCH] tile: a thread owns whole columns.
-// out[g] = act(b[g] + sum_f W[f][g] * in[f]) with optional BN-affine applied to the INPUT.
-__device__ __forceinline__ void col_dense_inplace(float* tile, const unsigned char* col_ok, const float* Wsm,
-                                                  const float* bsm, const float* in_scale, const float* in_shift) {
-    for (int col = threadIdx.x; col < ITEM_COLS; col += blockDim.x) {
-        if (!col_ok[col]) continue;
-        float* cp = tile + col;
-        float acc[52];
-#pragma unroll
-        for (int g = 0; g < 52; ++g) acc[g] = (g < NMA_C) ? bsm[g] : 0.f;
-        for (int f = 0; f < NMA_C; ++f) {
-            float xv = cp[f * ITEM_PITCH];
-            if (in_scale) xv = fmaf(xv, in_scale[f], in_shift[f]);
-            const float4* w4 = reinterpret_cast<const float4*>(Wsm + f * PW_WPITCH);
-#pragma unroll
-            for (int q = 0; q < 13; ++q) {
-                const float4 w = w4[q];
-                acc[4 * q + 0] = fmaf(xv, w.x, acc[4 * q + 0]);
-                acc[4 * q + 1] = fmaf(xv, w.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(xv, w.z, acc[4 * q + 2]);
-                acc[4 * q + 3] = fmaf(xv, w.w, acc[4 * q + 3]);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < NMA_C; ++g) cp[g * ITEM_PITCH] = elu_f(acc[g]);
-    }
-}
 
 struct ConvFwdArgs {
     ConvSrc src;
     const float* wpk;
     const float* tb;         // [p][3][50]; slot 2 = theta bias + conv bias
-    const float* hidw[NMA_MAXH];
-    const float* hidb[NMA_MAXH];
-    const float* gam[NMA_MAXH];
-    const float* bet[NMA_MAXH];
-    const float* headw;      // [50][2]
-    const float* headb;      // [2]
-    const float* x_in;       // [p][XP]   input sample of this flow
-    float* x_out;            // [p][XPn]  next flow's input sample (after the pair swap when D==2)
-    float* h[NMA_MAXH + 1];  // [p][50][NP]
-    float* s;                // [p][NP]
-    int XP, XPn, N, NP, K, KP, H, bn, D, rcmax, npb, row_pitch, p, save, permute_out;
+    FlowEpiArgs e;
+    int KP, rcmax, npb, row_pitch, p;
     long long items_total;
 };
 
@@ -384,19 +376,20 @@ __global__ void __launch_bounds__(CONVF_THREADS, 2) k_conv_fwd(ConvFwdArgs a) {
     // (conv_main_loop ends with __syncthreads: the ring is free and is reused as the activation tile)
 
     float* tile = smem;                               // [50][ITEM_PITCH], column = lane*10 + j
-    float* Wsm = tile + NMA_C * ITEM_PITCH;           // [50][52]
-    float* bsm = Wsm + NMA_C * PW_WPITCH;             // [64]
-    float* bns = bsm + 64;                            // [64] BN scale
-    float* bno = bns + 64;                            // [64] BN shift
-
+    __shared__ int col_r[ITEM_COLS];
+    __shared__ int col_m[ITEM_COLS];
     for (int col = tid; col < ITEM_COLS; col += blockDim.x) {
         const long long it = item0 + col / CONV_TM;
         bool ok = false;
+        int r = 0, m = 0;
         if (it < a.items_total) {
-            const int m = (int)(it % a.npb) * CONV_TM + col % CONV_TM;
-            ok = m < a.N;
+            r = (int)(it / a.npb);
+            m = (int)(it - (long long)r * a.npb) * CONV_TM + col % CONV_TM;
+            ok = m < a.e.N;
         }
         col_ok[col] = ok ? 1 : 0;
+        col_r[col] = r;
+        col_m[col] = m;
     }
     // e_0 = elu(A + theta-bias + conv bias)  (AR.py:70-72)
     if (active) {
@@ -415,114 +408,55 @@ __global__ void __launch_bounds__(CONVF_THREADS, 2) k_conv_fwd(ConvFwdArgs a) {
         }
     }
     __syncthreads();
-
-    auto store_tile = [&](float* gdst) {   // tile -> global [p][50][NP]; consecutive columns are consecutive m
-        for (int t = tid; t < NMA_C * ITEM_COLS; t += blockDim.x) {
-            const int f = t / ITEM_COLS, col = t - f * ITEM_COLS;
-            if (!col_ok[col]) continue;
-            const long long it = item0 + col / CONV_TM;
-            const int r = (int)(it / a.npb);
-            const int m = (int)(it - (long long)r * a.npb) * CONV_TM + col % CONV_TM;
-            gdst[((size_t)r * NMA_C + f) * a.NP + m] = tile[(size_t)f * ITEM_PITCH + col];
-        }
-    };
-    if (a.save) store_tile(a.h[0]);
-
-    // hidden 1x1 layers (AR.py:74-76) [+ BN-affine, fitz_nag_NVP.py:93]
-    for (int l = 0; l < a.H; ++l) {
-        __syncthreads();
-        for (int t = tid; t < NMA_C * PW_WPITCH; t += blockDim.x) {
-            const int f = t / PW_WPITCH, g = t - f * PW_WPITCH;
-            Wsm[t] = (g < NMA_C) ? a.hidw[l][f * NMA_C + g] : 0.f;
-        }
-        if (tid < NMA_C) {
-            bsm[tid] = a.hidb[l][tid];
-            if (a.bn && l > 0) {   // input of layer l is BN_{l-1}(e_l)
-                bns[tid] = a.gam[l - 1][tid] * rsqrtf(1.f + 1e-3f);
-                bno[tid] = a.bet[l - 1][tid];
-            }
-        }
-        __syncthreads();
-        col_dense_inplace(tile, col_ok, Wsm, bsm, (a.bn && l > 0) ? bns : nullptr, bno);
-        __syncthreads();
-        if (a.save) store_tile(a.h[l + 1]);
-    }
-    __syncthreads();
-    // head: (mu, s) = conv1x1 -> 2 (AR.py:77-78); stride 2 when D == 2 (fitz_nag_NVP.py:95-96)
-    if (tid < NMA_C) {
-        if (a.bn && a.H > 0) {
-            bns[tid] = a.gam[a.H - 1][tid] * rsqrtf(1.f + 1e-3f);
-            bno[tid] = a.bet[a.H - 1][tid];
-        } else {
-            bns[tid] = 1.f;
-            bno[tid] = 0.f;
-        }
-        Wsm[2 * tid] = a.headw[2 * tid];
-        Wsm[2 * tid + 1] = a.headw[2 * tid + 1];
-    }
-    __syncthreads();
-    const float hb0 = a.headb[0], hb1 = a.headb[1];
-    for (int col = tid; col < ITEM_COLS; col += blockDim.x) {
-        if (!col_ok[col]) continue;
-        const long long it = item0 + col / CONV_TM;
-        const int r = (int)(it / a.npb);
-        const int m = (int)(it - (long long)r * a.npb) * CONV_TM + col % CONV_TM;
-        const float xin = a.x_in[(size_t)r * a.XP + m + a.K];
-        float xo;
-        if (a.D == 1 || (m & 1)) {
-            // D==2: odd output slot m uses the head evaluated at the even conv position m-1 (same item: 10 is even)
-            const float* cp = tile + ((a.D == 1) ? col : col - 1);
-            float mu = hb0, sr = hb1;
-            for (int g = 0; g < NMA_C; ++g) {
-                const float v = fmaf(cp[g * ITEM_PITCH], bns[g], bno[g]);
-                mu = fmaf(v, Wsm[2 * g], mu);
-                sr = fmaf(v, Wsm[2 * g + 1], sr);
-            }
-            const float sigma = softplus_f(sr) + 1e-10f;   // AR.py:83
-            xo = fmaf(xin, sigma, mu);                      // AR.py:85
-            a.s[(size_t)r * a.NP + m] = sr;
-        } else {
-            xo = xin;   // identity slot of the coupling layer (fitz_nag_NVP.py:99-102)
-        }
-        const int mo = a.permute_out ? (m ^ 1) : m;        // Permute = swap adjacent pairs (fitz_nag_NVP.py:205-211)
-        a.x_out[(size_t)r * a.XPn + mo] = xo;
-    }
+    flow_epilogue<ITEM_COLS>(a.e, tile, col_r, col_m, col_ok);
 }
 
 static int conv_rows_spanned(int npb) { return (npb - 1 + 31) / npb + 1; }
 
+void fill_flow_epi_args(nma_handle_s* h, int i, const float* params, bool save, FlowEpiArgs& e) {
+    const FlowDims& d = h->fd[i];
+    e.XP = (d.L + 3) & ~3;
+    e.XPn = (h->fd[i + 1].L + 3) & ~3;
+    e.N = d.N; e.NP = d.NP; e.K = h->cfg.K; e.H = h->cfg.H; e.bn = h->cfg.bn; e.D = h->cfg.D;
+    e.save = save ? 1 : 0;
+    e.permute_out = (h->cfg.D == 2 && i < h->cfg.F - 1) ? 1 : 0;
+    for (int l = 0; l < NMA_MAXH; ++l) {
+        e.hidw[l] = l < h->cfg.H ? params + h->po[i].hidw[l] : nullptr;
+        e.hidb[l] = l < h->cfg.H ? params + h->po[i].hidb[l] : nullptr;
+        e.gam[l] = (l < h->cfg.H && h->cfg.bn) ? params + h->po[i].gam[l] : nullptr;
+        e.bet[l] = (l < h->cfg.H && h->cfg.bn) ? params + h->po[i].bet[l] : nullptr;
+    }
+    for (int l = 0; l <= NMA_MAXH; ++l) e.h[l] = h->ws[i].h[l];
+    e.headw = params + h->po[i].headw; e.headb = params + h->po[i].headb;
+    e.x_in = h->ws[i].x; e.x_out = h->ws[i + 1].x; e.s = h->ws[i].s;
+    const bool next_tc = h->use_tc && (i + 1 < h->cfg.F);
+    e.nx_hi = next_tc ? h->ws[i + 1].tin_hi : nullptr;
+    e.nx_lo = next_tc ? h->ws[i + 1].tin_lo : nullptr;
+    e.nx_Q = next_tc ? h->ws[i + 1].tin_Q : 0;
+    e.nx_Lin = next_tc ? h->fd[i + 1].Lin : 0;
+}
+
 int launch_conv_fwd(nma_handle_s* h, int i, const float* params, int p, bool save, cudaStream_t st) {
+    if (h->use_tc) return launch_conv_fwd_tc(h, i, params, p, save, st);
     const FlowDims& d = h->fd[i];
     ConvFwdArgs a;
     const int npb = (d.N + CONV_TM - 1) / CONV_TM;
     a.rcmax = conv_rows_spanned(npb);
     a.npb = npb;
     a.items_total = (long long)p * npb;
-    a.XP = (d.L + 3) & ~3;
-    a.XPn = (h->fd[i + 1].L + 3) & ~3;
-    a.N = d.N; a.NP = d.NP; a.K = h->cfg.K; a.KP = h->KP; a.H = h->cfg.H; a.bn = h->cfg.bn; a.D = h->cfg.D;
-    a.p = p; a.save = save ? 1 : 0;
-    a.permute_out = (h->cfg.D == 2 && i < h->cfg.F - 1) ? 1 : 0;
+    a.KP = h->KP; a.p = p;
+    fill_flow_epi_args(h, i, params, save, a.e);
     int rp = npb * CONV_TM + h->KP + 4;
     if (rp < d.LP) rp = d.LP;
     a.row_pitch = (rp + 3) & ~3;
-    a.src.chan0 = h->ws[i].x; a.src.row_stride0 = a.XP;
+    a.src.chan0 = h->ws[i].x; a.src.row_stride0 = a.e.XP;
     a.src.rest = h->ws[i].a[4]; a.src.row_stride = (long long)NMA_C * d.LP; a.src.chan_stride = d.LP;
     a.src.copy_floats = d.LP; a.src.dst_off = 0;
     a.wpk = h->ws[i].wpk;
     a.tb = h->ws[i].tb;
-    for (int l = 0; l < NMA_MAXH; ++l) {
-        a.hidw[l] = l < h->cfg.H ? params + h->po[i].hidw[l] : nullptr;
-        a.hidb[l] = l < h->cfg.H ? params + h->po[i].hidb[l] : nullptr;
-        a.gam[l] = (l < h->cfg.H && h->cfg.bn) ? params + h->po[i].gam[l] : nullptr;
-        a.bet[l] = (l < h->cfg.H && h->cfg.bn) ? params + h->po[i].bet[l] : nullptr;
-    }
-    for (int l = 0; l <= NMA_MAXH; ++l) a.h[l] = h->ws[i].h[l];
-    a.headw = params + h->po[i].headw; a.headb = params + h->po[i].headb;
-    a.x_in = h->ws[i].x; a.x_out = h->ws[i + 1].x; a.s = h->ws[i].s;
 
     const size_t ring = (size_t)CONV_STAGES * (5 * h->KP * CONV_WPAD + a.rcmax * a.row_pitch);
-    const size_t epi = (size_t)NMA_C * ITEM_PITCH + NMA_C * PW_WPITCH + 3 * 64;
+    const size_t epi = flow_epi_smem_floats<ITEM_COLS>();
     const size_t smem = (ring > epi ? ring : epi) * 4;
     static size_t configured = 0;
     if (configured < smem) {

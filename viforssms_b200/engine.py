@@ -25,7 +25,7 @@ def _stream() -> c_void_p:
 
 
 class NMAEngine:
-    def __init__(self, cfg: NMAConfig, device: Optional[torch.device] = None):
+    def __init__(self, cfg: NMAConfig, device: Optional[torch.device] = None, tensor_cores: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise _lib.NMAError("NMAEngine needs a CUDA device: the NMA ELBO step has no CPU path")
         self.cfg = cfg
@@ -36,6 +36,8 @@ class NMAEngine:
         ccfg = cfg.to_c()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.nma_create(ctypes.byref(ccfg), ctypes.byref(self._h)), "nma_create")
+        if tensor_cores is not None:
+            _lib.check(self._lib.nma_set_tensor_cores(self._h, 1 if tensor_cores else 0), "nma_set_tensor_cores")
         self.n_params = int(self._lib.nma_param_count(self._h))
         self.layout, n = param_layout(cfg)
         if n != self.n_params:
@@ -55,6 +57,11 @@ class NMAEngine:
             self.close()
         except Exception:
             pass
+
+    @property
+    def tensor_cores(self) -> bool:
+        """True when the conv and its data gradient run on the tcgen05 tensor cores (3xTF32)."""
+        return int(self._lib.nma_get_tensor_cores(self._h)) == 1
 
     @property
     def workspace_bytes(self) -> int:
@@ -141,6 +148,17 @@ class NMAEngine:
                                              float(beta2), float(eps), float(clip), _ptr(self._norm),
                                              _ptr(self._scratch), _stream()), "nma_adamax_step")
         return self._norm
+
+
+def tc_conv_raw(x: torch.Tensor, w: torch.Tensor, mode: int = 0, nacc: int = 2) -> torch.Tensor:
+    """Test hook: bare tensor-core contraction.  x [Q,56] fp32, w [K,51,50] -> [Q,64] (see nma_b200.h)."""
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 56
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[1:]) == (51, 50)
+    out = torch.empty(x.shape[0], 64, dtype=torch.float32, device=x.device)
+    _lib.check(lib.nma_tc_conv_raw(_ptr(x), _ptr(w), mode, nacc, _ptr(out), x.shape[0], w.shape[0], _stream()),
+               "nma_tc_conv_raw")
+    return out
 
 
 def scan_ar1(z: torch.Tensor, x0: float, a: float, b: float, c: float) -> torch.Tensor:
