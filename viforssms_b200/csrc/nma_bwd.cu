@@ -137,6 +137,20 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
     // the tile columns beyond NP are never loaded but are swept by wgrad_accum: they must hold finite zeros
     for (int t = tid; t < 2 * NMA_C * tp; t += blockDim.x) smem[t] = 0.f;
 
+    if (a.dat_hi && blockIdx.x == 0) {
+        // the tensor-core weight gradient sweeps whole 64-position stages: positions past the last row must read as zero
+        // (they may hold rows of an earlier, larger batch)
+        const long long q_lo = (long long)a.p * a.Lin + (a.K - 1);
+        const int ntail = 128;
+        for (int t = tid; t < 14 * ntail; t += blockDim.x) {
+            const int fch = t / ntail, q = t - fch * ntail;
+            if (q_lo + q < a.dat_Q) {
+                const size_t o = ((size_t)fch * a.dat_Q + q_lo + q) * 4;
+                *reinterpret_cast<float4*>(a.dat_hi + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(a.dat_lo + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
     for (int r = blockIdx.x; r < a.p; r += gridDim.x) {
         __syncthreads();
         // E <- e_H ; zero G, dmu, dsr

@@ -336,3 +336,4 @@ extern "C" int nma_tc_conv_raw(const float* d_in, const float* d_w, int32_t mode
     }
     return 0;
 }
+
