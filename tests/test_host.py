@@ -1,0 +1,137 @@
+"""CPU tests of the host side: the reference's CLI surface, time sharding + halo exchange over gloo
+(world_size 2), and the index feed."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nma_oracle as O
+from viforssms_b200 import feed
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _main_module():
+    spec = importlib.util.spec_from_file_location("nma_main_cli", os.path.join(ROOT, "main.py"))
+    m = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["main.py"]
+    try:
+        spec.loader.exec_module(m)
+    finally:
+        sys.argv = argv
+    return m
+
+
+def test_cli_file_and_overrides(tmp_path):
+    """main.py hyperparameters.txt with the reference's flags (main.py:14-22,112-128)."""
+    m = _main_module()
+    a = m.handle_opts([os.path.join(ROOT, "hyperparameters.txt")])
+    h = m.resolve(a)
+    assert (h["T"], h["impute"], h["x0"], h["obs_std"], h["p"]) == (5000, 1, 10.0, 1.0, 50)
+    assert (h["kernel_len"], h["batch_dims"], h["no_flows"], h["feat_window"]) == (50, 50, 3, 10)
+    assert h["network_dims"] == [50, 50, 50] and h["priors"] == [(0.0, 10.0)] * 3
+    assert h["learn_rate"] == 1e-3 and h["grad_clip"] == 2.5e8
+    assert np.array_equal(h["theta"], np.array([5.0, 0.5, 3.0]))
+    a = m.handle_opts([os.path.join(ROOT, "hyperparameters.txt"), "-time", "700", "-i", "5", "-t", "1", "-theta", "0.8",
+                       "-t", "0.5", "-xzero", "2", "-o", "0.3", "-kernel_len", "20", "-b", "25", "-feat_window", "4"])
+    h = m.resolve(a)
+    assert (h["T"], h["impute"], h["x0"], h["obs_std"], h["kernel_len"], h["batch_dims"], h["feat_window"]) == \
+        (700, 5, 2.0, 0.3, 20, 25, 4)
+    assert h["theta"].tolist() == ["1", "0.8", "0.5"]          # strings, like the reference; data_gen converts
+    # -repair output is itself a valid hyper-parameter file
+    f = tmp_path / "h.txt"
+    f.write_text(m.DEFAULT_FILE)
+    assert m.parseparams(str(f)) == m.parseparams(os.path.join(ROOT, "hyperparameters.txt"))
+    with pytest.raises(SystemExit):
+        m.resolve(m.handle_opts([str(tmp_path / "missing.txt")]))
+
+
+def test_shard_bounds_partition_the_candidates():
+    from viforssms_b200.trainer import shard_bounds
+    for T, B, world in ((5000, 50, 2), (10 ** 8, 50, 8), (1300, 25, 3), (100, 50, 4)):
+        cands = []
+        prev = 0
+        for r in range(world):
+            t0, t1 = shard_bounds(T, B, world, r)
+            assert t0 == prev and t0 % B == 0
+            cands += list(range(t0, t1, B))
+            prev = t1
+        assert prev == T and cands == list(range(0, T, B))
+
+
+def _window_from_local(arrays, cfg_chan, idx_local, L0):
+    """What the device gather computes: time_feats[slot, c] = base[a_c][idx + slot + off_c] (zero outside)."""
+    out = np.zeros((L0, len(cfg_chan)), dtype=np.float32)
+    for c, (a, off) in enumerate(cfg_chan):
+        arr = arrays[a]
+        for s in range(L0):
+            q = idx_local + s + off
+            if 0 <= q < len(arr):
+                out[s, c] = arr[q]
+    return out
+
+
+def _halo_worker(rank, world, port, T, B, F, K, fw, series, ret):
+    import torch.distributed as dist
+    from viforssms_b200.trainer import exchange_halos, local_base_arrays, shard_bounds
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        obs, obs_bin, tt = series
+        t0, t1 = shard_bounds(T, B, world, rank)
+        P = F * K + 1
+        fill = torch.from_numpy(obs[t0:t1].copy())
+        binary = torch.from_numpy(obs_bin[t0:t1].copy())
+        till = torch.from_numpy(tt[t0:t1].copy())
+        obs_ext, bin_ext, till_ext, tt0 = exchange_halos(fill, binary, till, P, fw, rank, world)
+        arrays = [a.float().numpy() for a in local_base_arrays(obs_ext, bin_ext, till_ext, tt0, t0, t1, P, fw)]
+        ret[rank] = (t0, t1, arrays)
+        # gradient all-reduce is a SUM over ranks (the reference differentiates the sum over rows, AR.py:228-229)
+        g = torch.full((5,), float(rank + 1))
+        dist.all_reduce(g)
+        assert g[0].item() == sum(range(1, world + 1))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_sharding_halo_exchange_gloo_world2():
+    """Two ranks, each owning half of the series: after the halo exchange every window a rank can draw is
+    bit-identical to the reference's window on the unsharded series (oracle gather, AR.py:267-288)."""
+    import torch.multiprocessing as mp
+    from viforssms_b200.config import ar_config
+    T, B, F, K, fw = 1200, 20, 2, 15, 4
+    rs = np.random.RandomState(5)
+    obs = rs.normal(5.0, 2.0, T)
+    obs_bin = (rs.uniform(size=T) < 0.6).astype(np.float64)
+    tt = rs.randint(1, 5, size=T).astype(np.float64)
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_halo_worker, args=(world, port, T, B, F, K, fw, (obs, obs_bin, tt), ret), nprocs=world, join=True)
+    cfg = ar_config(p=4, K=K, B=B, F=F, feat_window=fw, T=T)
+    chan = list(zip(cfg.chan_array, cfg.chan_offset))
+    pads = O.pad_series_ar(obs, obs_bin, tt, 10.0, T, F, K, fw)
+    for rank in range(world):
+        t0, t1, arrays = ret[rank]
+        for idx in (t0, t0 + B, t1 - B):
+            want, _, _ = O.gather_feed_ar(pads, np.array([idx]), cfg.L0, B)
+            got = _window_from_local(arrays, chan, idx - t0, cfg.L0)
+            assert np.array_equal(got, want[0].astype(np.float32)), (rank, idx)
+
+
+def test_index_feeder_matches_reference_draw():
+    from viforssms_b200.trainer import IndexFeeder
+    cand = np.arange(0, 5000, 50)
+    f = IndexFeeder(cand, rows=50, replace=False, seed=1, offset=0, pinned=False)
+    try:
+        got = [f.get().numpy().copy() for _ in range(3)]
+    finally:
+        f.close()
+    rs = np.random.RandomState(1)
+    for g in got:
+        assert np.array_equal(g, rs.choice(cand, size=50, replace=False))
+    np.random.seed(1)
+    assert np.array_equal(feed.sample_indices(5000, 50, 50), got[0])

@@ -70,6 +70,44 @@ def local_base_arrays(obs_ext: torch.Tensor, bin_ext: torch.Tensor, till_ext: to
     return [obs_pad, bin_feats, time_pad, time_till_pad, obs_bin_pad]
 
 
+def exchange_halos(fill: torch.Tensor, binary: torch.Tensor, till: torch.Tensor, P: int, fw: int, rank: int,
+                   world: int):
+    """Neighbour exchange for a time-sharded series (works on any torch.distributed backend).
+
+    Every rank holds its own steps of the three series (hold-filled observations, observation indicator,
+    time-till-next-observation).  A window needs P = no_flows*kernel_len + 1 samples to the left of the shard
+    (all three series) and feat_window - 1 observations to the right (look-ahead channels, AR.py:136-138):
+    rank r sends its last P samples to r+1 and its first fw-1 observations to r-1.  Outside [0, T) the halos
+    are the reference's zero padding.  Returns (obs_ext [P+n+fw-1], bin_ext [P+n], till_ext [P+n], time_till[0] of
+    the GLOBAL series, which the leading pad counts down from, AR.py:149-150)."""
+    import torch.distributed as dist
+    dev, dt = fill.device, fill.dtype
+    nr = max(fw - 1, 0)
+    left = [torch.zeros(P, dtype=dt, device=dev) for _ in range(3)]
+    right = torch.zeros(nr, dtype=dt, device=dev)
+    tt0 = torch.tensor([float(till[0].item())], dtype=torch.float64, device=dev)
+    if world > 1:
+        if fill.numel() < P:
+            raise ValueError("a time shard must be at least no_flows*kernel_len+1 steps long")
+        dist.broadcast(tt0, src=0)
+        send_l = [fill[-P:].contiguous(), binary[-P:].contiguous(), till[-P:].contiguous()]
+        send_r = fill[:nr].contiguous()
+        ops = []
+        if rank + 1 < world:
+            ops += [dist.P2POp(dist.isend, t, rank + 1) for t in send_l]
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, right, rank + 1))
+        if rank > 0:
+            ops += [dist.P2POp(dist.irecv, t, rank - 1) for t in left]
+            if nr:
+                ops.append(dist.P2POp(dist.isend, send_r, rank - 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+    return (torch.cat([left[0], fill, right]), torch.cat([left[1], binary]), torch.cat([left[2], till]),
+            float(tt0.item()))
+
+
 class IndexFeeder:
     """Background draw of subsequence starts with the reference's own call (AR.py:263-265) into pinned
     host buffers: the legacy permutation of 2*10^6 candidates costs tens of ms and must not sit on the
@@ -191,32 +229,8 @@ class ARStepper:
             raise ValueError("shard length must be a multiple of impute")
         fill, binary, till = time_till(obs.contiguous(), int(impute))
         del obs
-        tt0_local = float(till[0].item())
-        tt0 = tt0_local
-        left = [torch.zeros(P, dtype=torch.float64, device=dev) for _ in range(3)]
-        right = torch.zeros(max(fw - 1, 0), dtype=torch.float64, device=dev)
-        if self.world > 1:
-            t = torch.tensor([tt0_local], dtype=torch.float64, device=dev)
-            dist.broadcast(t, src=0)
-            tt0 = float(t.item())
-            ops = []
-            send_l = [fill[-P:].contiguous(), binary[-P:].contiguous(), till[-P:].contiguous()]
-            send_r = fill[:max(fw - 1, 0)].contiguous()
-            if self.rank + 1 < self.world:
-                ops += [dist.P2POp(dist.isend, s, self.rank + 1) for s in send_l]
-                if fw > 1:
-                    ops.append(dist.P2POp(dist.irecv, right, self.rank + 1))
-            if self.rank > 0:
-                ops += [dist.P2POp(dist.irecv, l, self.rank - 1) for l in left]
-                if fw > 1:
-                    ops.append(dist.P2POp(dist.isend, send_r, self.rank - 1))
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-        obs_ext = torch.cat([left[0], fill, right]).float()
-        bin_ext = torch.cat([left[1], binary]).float()
-        till_ext = torch.cat([left[2], till]).float()
-        return obs_ext, bin_ext, till_ext, tt0
+        obs_ext, bin_ext, till_ext, tt0 = exchange_halos(fill, binary, till, P, fw, self.rank, self.world)
+        return obs_ext.float(), bin_ext.float(), till_ext.float(), tt0
 
     def _slice_series(self, series, P, fw):
         """Host series (obs, obs_bin, time_till of length T, float64 numpy) -> this rank's extended slices."""
