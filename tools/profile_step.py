@@ -1,0 +1,21 @@
+"""A few plain training steps at a fixed size: the command ncu wraps (tools/gpu_profile.sh)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from viforssms_b200.trainer import ARStepper  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=2048)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--T", type=int, default=10 ** 6)
+a = ap.parse_args()
+st = ARStepper(T=a.T, rows=a.rows, device=torch.device("cuda", 0))
+for _ in range(a.steps):
+    st.step_resident()
+torch.cuda.synchronize()
+print("ok", float(st.last_elbo.item()))
+st.close()

@@ -47,8 +47,8 @@ struct FlowWs {
     float* tin_lo;   //                 lo part
     float* dat_hi;   // [14][dat_Q][4]  dA (gradient w.r.t. the conv pre-activation) at q = K-1 + row*Lin + m
     float* dat_lo;
-    float* wtc_f;    // [K][2][14][64][4] packed taps of the forward conv
-    float* wtc_d;    // [K][2][14][64][4] packed taps of the data-gradient conv (flipped, transposed)
+    float* wtc_f;    // [K][14][64 hi | 64 lo rows][4] packed taps of the forward conv
+    float* wtc_d;    // same, data-gradient conv (flipped, transposed)
     long long tin_Q, dat_Q;
 };
 

@@ -17,8 +17,9 @@
 #define TC_CCH 14                 // reduction chunks of 4 channels: 56 >= 51 (fwd) / 50 (dgrad)
 #define TC_N 64                   // UMMA N: 50 / 51 outputs padded to 64 (M=128 needs N % 16 == 0)
 #define TC_M 128
-#define TC_WHALF (TC_CCH * TC_N * 4)          // floats of one (hi or lo) weight slab of one tap
-#define TC_WSTAGE (2 * TC_WHALF)              // hi + lo: 7168 floats = 28672 B
+#define TC_WHALF (TC_CCH * TC_N * 4)          // floats of one (hi or lo) weight part of one tap
+#define TC_WSTAGE (2 * TC_WHALF)              // one tap = [14][128 rows: 64 hi | 64 lo][4]: 7168 floats = 28672 B
+#define TC_WROWS (2 * TC_N)                   // B-operand rows per channel chunk (hi rows then lo rows)
 #define TC_STAGES 3
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
@@ -139,9 +140,35 @@ struct TcConvSrc {
     const float* a_hi;     // [14][Qalloc][4]   hi parts of the flattened input (position q = row*Lin + slot)
     const float* a_lo;
     long long Qalloc;
-    const float* wt;       // [K][2][14][64][4] packed taps (hi slab, lo slab)
+    const float* wt;       // [K][14][128][4] packed taps (rows 0-63 hi parts, rows 64-127 lo parts)
     int K;
 };
+
+// one lane of a converged warp; the surrounding control flow stays warp-uniform so descriptors live in
+// uniform registers and the MMA issues as a plain predicated UTCHMMA
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n"
+        : "+r"(pred));
+    return pred;
+}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+// low word of a SWIZZLE_NONE descriptor: start address and leading byte offset, both >> 4
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr >> 4) & 0x3fffu) | ((lbo_bytes >> 4) << 16);
+}
+// high word: stride byte offset >> 4, descriptor version 1 (bit 46 of the descriptor)
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
 
 // Runs the whole contraction for NACC x 128 consecutive flattened positions starting at q0.
 // Must be called by ALL threads of the CTA (>= 2 warps); returns after every MMA has retired and the
@@ -151,54 +178,68 @@ struct TcConvSrc {
 template <int NACC>
 __device__ __forceinline__ void tc_conv_mainloop(const TcConvSmem& s, const TcConvSrc& src, long long q0, int npos,
                                                  uint32_t tmem_base) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
         const uint32_t slab_bytes = (uint32_t)npos * 16u;
-        mbar_expect_tx(s.a_bar, 2u * TC_CCH * slab_bytes);
-        for (int c = 0; c < TC_CCH; ++c) {
-            bulk_g2s(s.a_hi + (size_t)c * npos * 4, src.a_hi + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, s.a_bar);
-            bulk_g2s(s.a_lo + (size_t)c * npos * 4, src.a_lo + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, s.a_bar);
+        if (elect_one()) {
+            mbar_expect_tx(s.a_bar, 2u * TC_CCH * slab_bytes);
+            for (int c = 0; c < TC_CCH; ++c) {
+                bulk_g2s(s.a_hi + (size_t)c * npos * 4, src.a_hi + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, s.a_bar);
+                bulk_g2s(s.a_lo + (size_t)c * npos * 4, src.a_lo + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, s.a_bar);
+            }
         }
+        __syncwarp();
         for (int k = 0; k < src.K; ++k) {
             const int st = k % TC_STAGES;
             if (k >= TC_STAGES) mbar_wait_backoff(&s.empty[st], (uint32_t)(((k / TC_STAGES) - 1) & 1));
-            mbar_expect_tx(&s.full[st], TC_WSTAGE * 4u);
-            bulk_g2s(s.wring + (size_t)st * TC_WSTAGE, src.wt + (size_t)k * TC_WSTAGE, TC_WSTAGE * 4u, &s.full[st]);
+            if (elect_one()) {
+                mbar_expect_tx(&s.full[st], TC_WSTAGE * 4u);
+                bulk_g2s(s.wring + (size_t)st * TC_WSTAGE, src.wt + (size_t)k * TC_WSTAGE, TC_WSTAGE * 4u, &s.full[st]);
+            }
+            __syncwarp();
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = umma_idesc_tf32(TC_M, TC_N, 0, 0);
-        const uint32_t a_hi_addr = smem_u32(s.a_hi), a_lo_addr = smem_u32(s.a_lo), w_addr = smem_u32(s.wring);
         const uint32_t a_lbo = (uint32_t)npos * 16u;          // between channel chunks
+        const uint32_t ah_lo0 = desc_lo(smem_u32(s.a_hi), a_lbo), al_lo0 = desc_lo(smem_u32(s.a_lo), a_lbo);
+        const uint32_t a_hi32 = desc_hi(128u), b_hi32 = desc_hi(128u);
+        const uint32_t w_lo0 = desc_lo(smem_u32(s.wring), TC_WROWS * 16u);
+        const uint32_t ks_step_a = 2u * (uint32_t)npos;       // (2 channel chunks) >> 4
+        constexpr uint32_t ks_step_b = 2u * TC_WROWS;         // 2 chunks of 128 rows x 16 B, >> 4
+        constexpr uint32_t idesc_wide = umma_idesc_tf32(TC_M, 2 * TC_N, 0, 0);
         mbar_wait_backoff(s.a_bar, 0);
         for (int k = 0; k < src.K; ++k) {
             const int st = k % TC_STAGES;
             mbar_wait_backoff(&s.full[st], (uint32_t)((k / TC_STAGES) & 1));
             tc_fence_after();
-            const uint32_t wb = w_addr + (uint32_t)st * (TC_WSTAGE * 4u);
+            if (elect_one()) {
+                const uint32_t wb = w_lo0 + (uint32_t)st * (TC_WSTAGE * 4u / 16u);
 #pragma unroll
-            for (int a = 0; a < NACC; ++a) {
-                const uint32_t row_off = (uint32_t)(a * TC_M + k) * 16u;
-#pragma unroll
-                for (int ks = 0; ks < TC_CCH / 2; ++ks) {
-                    const uint64_t ah = umma_desc(a_hi_addr + (uint32_t)(2 * ks) * a_lbo + row_off, a_lbo, 128u);
-                    const uint64_t al = umma_desc(a_lo_addr + (uint32_t)(2 * ks) * a_lbo + row_off, a_lbo, 128u);
-                    const uint64_t bh = umma_desc(wb + (uint32_t)(2 * ks) * (TC_N * 16u), TC_N * 16u, 128u);
-                    const uint64_t bl = umma_desc(wb + TC_WHALF * 4u + (uint32_t)(2 * ks) * (TC_N * 16u), TC_N * 16u, 128u);
-                    // the tensor core accumulates with truncation: keep the (2^-11 smaller) correction terms in
-                    // their own accumulator so the main chain is 3x shorter; the epilogue adds the two in fp32.
+                for (int a = 0; a < NACC; ++a) {
+                    const uint32_t row = (uint32_t)(a * TC_M + k);     // 16-byte units
                     const uint32_t d = tmem_base + (uint32_t)(a * 2 * TC_N);
-                    umma_tf32(d, ah, bh, idesc, (k | ks) ? 1u : 0u);
-                    umma_tf32(d + TC_N, al, bh, idesc, (k | ks) ? 1u : 0u);
-                    umma_tf32(d + TC_N, ah, bl, idesc, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < TC_CCH / 2; ++ks) {
+                        const uint64_t ah = desc_pack(ah_lo0 + row + (uint32_t)ks * ks_step_a, a_hi32);
+                        const uint64_t al = desc_pack(al_lo0 + row + (uint32_t)ks * ks_step_a, a_hi32);
+                        const uint64_t bw = desc_pack(wb + (uint32_t)ks * ks_step_b, b_hi32);
+                        // 3xTF32: the B tile holds 64 hi rows then 64 lo rows, so ONE N=128 MMA with a_hi gives
+                        // a_hi*b_hi (columns 0-63, the main sum) and a_hi*b_lo (columns 64-127, the correction sum)
+                        // for a single read of A; a_lo*b_hi (N=64) then lands on the correction columns.
+                        // The tensor core accumulates with truncation: keeping the 2^-11 smaller correction terms in
+                        // their own accumulator makes the main chain 3x shorter; the epilogue adds the two in fp32.
+                        umma_tf32(d, ah, bw, idesc_wide, (k | ks) ? 1u : 0u);
+                        umma_tf32(d + TC_N, al, bw, idesc, 1u);
+                    }
                 }
+                tc_commit(&s.empty[st]);      // frees the weight stage once these MMAs have read it
+                if (k == src.K - 1) tc_commit(s.acc_bar);
             }
-            tc_commit(&s.empty[st]);      // frees the weight stage once these MMAs have read it
+            __syncwarp();
         }
-        tc_commit(s.acc_bar);
     }
-    __syncwarp();
     mbar_wait_backoff(s.acc_bar, 0);
     tc_fence_after();
 }

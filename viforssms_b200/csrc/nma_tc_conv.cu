@@ -1,6 +1,6 @@
 // tcgen05 (5th-gen tensor core) form of the K-tap moving-average conv (A3, AR.py:61-62) and of its
 // data gradient, each fused with its epilogue.  See nma_tc.cuh for the operand layouts.
-//   k_tc_pack_w      : conv kernel [K][51][50] -> per-tap UMMA B slabs [K][hi|lo][14][64][4] (fwd / flipped+transposed)
+//   k_tc_pack_w      : conv kernel [K][51][50] -> per-tap UMMA B tiles [K][14][64 hi rows | 64 lo rows][4] (fwd / flipped+transposed)
 //   k_conv_fwd_tc    : conv + theta-bias + ELU (TMEM -> smem tile) + flow_epilogue (hidden 1x1, head, affine update)
 //   k_conv_dgrad_tc  : full correlation of dA with the flipped kernel -> df (feature channels) and dx (channel 0)
 //   nma_tc_conv_raw  : test hook, the bare contraction on caller-provided data
@@ -37,9 +37,9 @@ __global__ void k_tc_pack_w(const float* __restrict__ W, int K, int mode, float*
             if (c < NMA_C && n < NMA_C1) v = W[((size_t)(K - 1 - k) * NMA_C1 + n) * NMA_C + c];
         }
         const float hi = tf32_hi(v);
-        const size_t o = (size_t)k * TC_WSTAGE + (size_t)(t - k * TC_WHALF);
+        const size_t o = (size_t)k * TC_WSTAGE + ((size_t)cch * TC_WROWS + n) * 4 + e;     // [k][cch][128 rows][4]
         out[o] = hi;
-        out[o + TC_WHALF] = v - hi;
+        out[o + TC_N * 4] = v - hi;                                                         // lo rows follow the hi rows
     }
 }
 
@@ -202,13 +202,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_dgrad_tc(ConvDgradTcArgs
     }
     tc_fence_before();
     __syncthreads();
+    // column -> (row, slot) once per column (no 64-bit division in the store loop)
+    int* col_r = reinterpret_cast<int*>(tile + (size_t)NMA_C1 * PITCH);
+    int* col_j = col_r + NCOLS;
     const long long qtot = (long long)a.p * a.Lin;
+    for (int col = tid; col < NCOLS; col += blockDim.x) {
+        const long long q = q0 + col;
+        const int r = (int)(q / a.Lin);
+        col_r[col] = q < qtot ? r : -1;
+        col_j[col] = (int)(q - (long long)r * a.Lin);
+    }
+    __syncthreads();
     for (int t = tid; t < NMA_C1 * NCOLS; t += blockDim.x) {
         const int n = t / NCOLS, col = t - n * NCOLS;
-        const long long q = q0 + col;
-        if (q >= qtot) continue;
-        const int r = (int)(q / a.Lin);
-        const int j = (int)(q - (long long)r * a.Lin);
+        const int r = col_r[col], j = col_j[col];
+        if (r < 0) continue;
         const float v = tile[(size_t)n * PITCH + col];
         if (n >= 1) a.df[((size_t)r * NMA_C + (n - 1)) * a.LP + j] = v;
         else if (a.need_dx) a.dx[(size_t)r * a.XP + j] += v;
@@ -229,7 +237,7 @@ int launch_conv_dgrad_tc(nma_handle_s* h, int i, int p, cudaStream_t st) {
     const int ncols = nacc * TC_M;
     const unsigned grid = (unsigned)((qtot + ncols - 1) / ncols);
     if (nacc == 2) {
-        const int smem = tc_smem_bytes(2, h->cfg.K, (size_t)NMA_C1 * (2 * TC_M + 4));
+        const int smem = tc_smem_bytes(2, h->cfg.K, (size_t)NMA_C1 * (2 * TC_M + 4) + 4 * TC_M);
         static int configured = 0;
         if (configured < smem) {
             NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -237,7 +245,7 @@ int launch_conv_dgrad_tc(nma_handle_s* h, int i, int p, cudaStream_t st) {
         }
         k_conv_dgrad_tc<2><<<grid, TC_THREADS, smem, st>>>(a);
     } else {
-        const int smem = tc_smem_bytes(1, h->cfg.K, (size_t)NMA_C1 * (TC_M + 4));
+        const int smem = tc_smem_bytes(1, h->cfg.K, (size_t)NMA_C1 * (TC_M + 4) + 2 * TC_M);
         static int configured = 0;
         if (configured < smem) {
             NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
