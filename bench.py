@@ -155,7 +155,8 @@ def workload_config(args, rows_note=None):
                      "feat_window=10 (BASELINE.json configs[4])" % args.T,
          "rows_per_gpu_per_step": args.rows, "units_per_row": B_DIMS,
          "l2": "per-step working set (activations %.1f GB at these rows) far exceeds the 126 MB L2; no flush needed",
-         "parallelism": "time-sharded series, rows sharded %d-way, NCCL gradient all-reduce" % args.gpus}
+         "parallelism": "time-sharded series, rows sharded %d-way, NCCL gradient all-reduce" % args.gpus,
+         "launch": "eager" if args.no_graph else "one CUDA graph per step"}
     if rows_note:
         c["note"] = rows_note
     return c
@@ -229,13 +230,18 @@ def run_native(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg ----------------
+    if not args.no_graph:
+        stepper.capture()          # the iteration as one CUDA graph (3 eager warm-up steps inside)
+    else:
+        n0 = L.nma_launch_count()
+        stepper.step_resident()
+        stepper.launches_per_step = int(L.nma_launch_count() - n0)
     for _ in range(args.warmup):
         stepper.step_resident()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    n0 = L.nma_launch_count()
     st = torch.cuda.current_stream()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(st)
@@ -243,7 +249,7 @@ def run_native(args):
         stepper.step_resident()
     e1.record(st)
     barrier()
-    launches = int(L.nma_launch_count() - n0)
+    launches = stepper.launches_per_step * args.steps     # kernels of this library per step (counted on an eager step) x steps
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -314,6 +320,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=100)
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -82,6 +82,22 @@ def test_stepper_resident_and_e2e_agree_on_shapes_and_progress():
         st.close()
 
 
+def test_stepper_cuda_graph_step():
+    """The whole iteration captured as one CUDA graph: replays keep training and stay finite."""
+    from viforssms_b200.trainer import ARStepper
+    st = ARStepper(T=100000, rows=64, device=torch.device("cuda", 0))
+    try:
+        st.capture()
+        assert st.launches_per_step and st.launches_per_step > 10
+        w0 = st.blob.clone()
+        vals = [float(st.step_resident().item()) for _ in range(20)]
+        vals.append(st.step_e2e())
+        assert all(np.isfinite(v) for v in vals)
+        assert torch.isfinite(st.blob).all() and not torch.equal(st.blob, w0)
+    finally:
+        st.close()
+
+
 def test_stepper_sharded_series_matches_unsharded_windows():
     """A rank's local arrays (rank 1 of 2, halos taken from the host series) give the same gathered windows as
     the unsharded engine."""

@@ -118,8 +118,18 @@ class ThetaFlow:
         return self.base_loc + self.base_scale * torch.randn(p, self.d, generator=gen, device=device)
 
 
-def prior_log_prob(theta: torch.Tensor, priors: Sequence[Tuple[float, float]]) -> torch.Tensor:
-    """MultivariateNormalDiag(prior_mean, prior_scale).log_prob(theta) (AR.py:178-182)."""
-    mean = torch.tensor([m for m, _ in priors], dtype=theta.dtype, device=theta.device)
-    scale = torch.tensor([s for _, s in priors], dtype=theta.dtype, device=theta.device)
+def prior_tensors(priors: Sequence[Tuple[float, float]], device, dtype=torch.float32):
+    """(mean, scale) of the diagonal Gaussian prior as device tensors (build once: no H2D copy per step)."""
+    mean = torch.tensor([m for m, _ in priors], dtype=dtype, device=device)
+    scale = torch.tensor([s for _, s in priors], dtype=dtype, device=device)
+    return mean, scale
+
+
+def prior_log_prob(theta: torch.Tensor, priors) -> torch.Tensor:
+    """MultivariateNormalDiag(prior_mean, prior_scale).log_prob(theta) (AR.py:178-182).
+    `priors`: list of (mean, scale) pairs, or the (mean, scale) tensors of `prior_tensors`."""
+    if isinstance(priors, tuple) and len(priors) == 2 and isinstance(priors[0], torch.Tensor):
+        mean, scale = priors
+    else:
+        mean, scale = prior_tensors(priors, theta.device, theta.dtype)
     return (-0.5 * ((theta - mean) / scale) ** 2 - 0.5 * math.log(2 * math.pi) - torch.log(scale)).sum(dim=1)

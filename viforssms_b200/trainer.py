@@ -20,7 +20,7 @@ import torch
 from . import lib as _lib
 from .config import NMAConfig, ar_config, param_layout
 from .engine import NMAEngine, scan_ar1, time_till
-from .theta_flow import ThetaFlow, prior_log_prob
+from .theta_flow import ThetaFlow, prior_log_prob, prior_tensors
 
 
 def shard_bounds(T: int, B: int, world: int, rank: int) -> Tuple[int, int]:
@@ -185,8 +185,12 @@ class ARStepper:
         self.flow.bind(self.theta_leaf)
         self.out = self.eng.alloc_outputs(rows)
         self.out["grad_params"] = self.grad[:n_nma]
-        self.gen = torch.Generator(device=self.device)
-        self.gen.manual_seed(seed * 1000 + rank)
+        # eps / theta base noise come from torch's default CUDA generator (graph-capture safe)
+        torch.cuda.manual_seed(seed * 1000 + rank)
+        self.prior_t = prior_tensors(priors, self.device)
+        self.graph = None
+        self._elbo_static = None
+        self.launches_per_step = None
 
         # ---- index feed ----
         cand = np.arange(self.t0, self.t1, B)
@@ -250,12 +254,12 @@ class ARStepper:
     # ------------------------------------------------------------------
     def _step(self, idx_dev: torch.Tensor) -> torch.Tensor:
         cfg, rows = self.cfg, self.rows
-        z0 = self.flow.base_sample(rows, self.gen, self.device)
+        z0 = self.flow.base_sample(rows, None, self.device)
         theta, logq_theta = self.flow.sample_and_log_prob(z0)
-        eps = torch.randn(rows, cfg.L0, device=self.device, generator=self.gen)
+        eps = torch.randn(rows, cfg.L0, device=self.device)
         out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), idx_dev, out=self.out)
         # host-side remainder of -sum(ELBO): the theta path (AR.py:178-185)
-        tail = prior_log_prob(theta, self.priors) - logq_theta
+        tail = prior_log_prob(theta, self.prior_t) - logq_theta
         host_loss = (out["grad_theta"] * theta).sum() - tail.sum()
         self.theta_leaf.grad = None
         host_loss.backward()
@@ -268,24 +272,46 @@ class ARStepper:
         elbo = (float(cfg.scale) * (t[:, 0] - t[:, 2] + t[:, 1]) + tail.detach()).mean()
         return elbo
 
+    def capture(self) -> None:
+        """Capture the whole iteration (theta flow, ELBO + gradients, all-reduce, clip + Adamax) into ONE CUDA
+        graph: a step becomes a single launch, which is what makes the p=50 reference configuration and the
+        host-fed loop stop being launch-bound.  Inputs (`idx_dev`) and outputs (`_elbo_static`) are static."""
+        L = _lib.load()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for it in range(3):
+                n0 = L.nma_launch_count()
+                self._step(self.idx_dev)
+                self.launches_per_step = int(L.nma_launch_count() - n0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._elbo_static = self._step(self.idx_dev)
+        self.graph = g
+
     def step_resident(self) -> torch.Tensor:
         """One step with the subsequence indices already on the device."""
-        self.last_elbo = self._step(self.idx_dev)
+        if self.graph is not None:
+            self.graph.replay()
+            self.last_elbo = self._elbo_static
+        else:
+            self.last_elbo = self._step(self.idx_dev)
         return self.last_elbo
 
     def step_e2e(self) -> float:
         """One step through host buffers: pinned index batch -> device, ELBO scalar -> host."""
         host_idx = self.feeder.get()
         self.idx_dev.copy_(host_idx, non_blocking=True)
-        elbo = self._step(self.idx_dev)
-        return float(elbo.item())
+        return float(self.step_resident().item())
 
     # ------------------------------------------------------------------
     def time_stage(self, stage: int, flow: int, reps: int = 5) -> float:
         """Average device time (ms) of ONE kernel of the last step, re-launched on the workspace it left."""
         L = _lib.load()
         st = torch.cuda.current_stream()
-        eps = torch.randn(self.rows, self.cfg.L0, device=self.device, generator=self.gen)
+        eps = torch.randn(self.rows, self.cfg.L0, device=self.device)
         scratch = torch.zeros_like(self.grad)
 
         def launch():

@@ -21,7 +21,7 @@ import torch
 from . import feed
 from .config import OBJ_ELBO, OBJ_NEG_OBS, ar_config, param_layout
 from .engine import NMAEngine
-from .theta_flow import ThetaFlow, prior_log_prob
+from .theta_flow import ThetaFlow, prior_log_prob, prior_tensors
 from .trainer import glorot_blob
 
 
@@ -81,6 +81,7 @@ class VI_SSM:
         self.gen.manual_seed(self.seed)
         self.idx_dev = torch.empty(self.p, dtype=torch.int64, device=self.device)
         self.scalars = {}
+        self.prior_t = prior_tensors(self.priors, self.device)
 
     # ------------------------------------------------------------------
     def _iteration(self, batch_select: np.ndarray, pre_train: bool) -> None:
@@ -93,7 +94,7 @@ class VI_SSM:
         obj = OBJ_NEG_OBS if pre_train else OBJ_ELBO
         out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), self.idx_dev,
                                     objective=obj, out=self.out)
-        prior = prior_log_prob(theta, self.priors)
+        prior = prior_log_prob(theta, self.prior_t)
         host_loss = (out["grad_theta"] * theta).sum()
         if not pre_train:
             host_loss = host_loss - (prior - logq_theta).sum()          # AR.py:184-185
