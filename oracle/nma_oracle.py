@@ -78,6 +78,38 @@ def gather_feed_ar(pads, batch_select, L0, B) -> Tuple[np.ndarray, np.ndarray, n
     return time_feats, mask, shift
 
 
+def pad_series_fhn(obs, time_till, x0, dt, T, target_dims, F, K, fw) -> Dict[str, object]:
+    """fitz_nag_NVP.py:165,187-202 (flow_dims = 2; the two components interleave on the time axis)."""
+    D = 2
+    obs_flatten = np.reshape(obs, -1, 'F')
+    store = []
+    for i in range(0, fw * 5, 5):
+        store.append(np.concatenate((np.zeros(F * K + D - i), obs_flatten, np.zeros(i)), axis=0))
+    time_pad = np.concatenate((np.zeros(F * K + D), np.repeat(np.arange(dt, T + dt, dt), D)), axis=0)
+    time_till_pad = np.reshape(np.repeat(np.arange(np.round((F * K + D) * (dt / D), 1), -dt, -dt), D), (D, -1), 'F')
+    return {
+        "obs_pad_store": store,
+        "time_pad": time_pad,
+        "time_till": np.reshape(np.concatenate((time_till_pad, time_till), 1), -1, 'F'),
+        "bin_feats": np.float32(np.concatenate((np.ones(F * K + D), np.zeros(target_dims * D)), axis=0)),
+        "mask_vals": np.concatenate((np.zeros((2, 1)), np.ones((D, target_dims))), axis=1),
+        "shift_vals": np.concatenate((np.expand_dims(x0, 1), np.zeros((D, target_dims))), axis=1),
+    }
+
+
+def gather_feed_fhn(pads, obs_bin, batch_select, L0, B):
+    """fitz_nag_NVP.py:350-370: (time_feats [p,L0,fw+3], mask, shift [p,2,B+1], bin_feed [p,2,B])."""
+    def win(arr):
+        return np.stack([arr[i:i + L0] for i in 2 * batch_select], axis=0)[:, :, None]
+    chans = [win(a) for a in pads["obs_pad_store"]]
+    chans += [win(pads["bin_feats"]), win(pads["time_pad"]), win(pads["time_till"])]
+    time_feats = np.concatenate(chans, axis=2)
+    mask = np.stack([pads["mask_vals"][:, i:i + B + 1] for i in batch_select], axis=0)
+    shift = np.stack([pads["shift_vals"][:, i:i + B + 1] for i in batch_select], axis=0)
+    bin_feed = np.stack([obs_bin[:, i:i + B] for i in batch_select], axis=0)
+    return time_feats, mask, shift, bin_feed
+
+
 # ----------------------------------------------------------------------------
 # torch half: flow, ELBO, gradients, Adamax ("parity unpinned", see header)
 # ----------------------------------------------------------------------------

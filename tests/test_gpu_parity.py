@@ -13,7 +13,7 @@ import torch
 
 from oracle import nma_oracle as O
 from viforssms_b200 import feed
-from viforssms_b200.config import ar_config, param_layout, NMAConfig
+from viforssms_b200.config import ar_config, fhn_config, param_layout, NMAConfig
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -328,3 +328,80 @@ def test_scan_ar1_and_time_till_match_sequential_generator():
         assert np.array_equal(f.cpu().numpy(), fill)
         assert np.array_equal(b.cpu().numpy(), binary)
         assert np.array_equal(t.cpu().numpy(), want_tt)
+
+
+# ---------------------------------------------------------------------------------------------------
+# FitzHugh-Nagumo (configs[2]): two interleaved components, stride-2 head, coupling interleave, Permute, BN affine
+# ---------------------------------------------------------------------------------------------------
+
+def _fhn_case(cfg, target_dims, dt, seed):
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    fw = cfg.Cf - 3
+    T = target_dims * dt
+    obs = rs.normal(0.5, 1.0, size=(2, target_dims))
+    obs_bin = (rs.uniform(size=(2, target_dims)) < 0.3).astype(np.float64)
+    obs = obs * obs_bin
+    tt = rs.uniform(0.0, 1.0, size=(2, target_dims)).round(1)
+    arrays = feed.fhn_base_arrays(obs, obs_bin, tt, dt, T, target_dims, cfg.F, cfg.K, fw)
+    pads = O.pad_series_fhn(obs, tt, np.array([2.0, 3.0]), dt, T, target_dims, cfg.F, cfg.K, fw)
+    idx = rs.choice(np.arange(0, target_dims, cfg.B), size=cfg.p, replace=bool(cfg.B * cfg.p >= target_dims))
+    idx[0] = 0
+    idx[-1] = (target_dims // cfg.B - 1) * cfg.B
+    tf64, _, _, bin_feed = O.gather_feed_fhn(pads, obs_bin, idx, cfg.L0, cfg.B)
+    layout, n = param_layout(cfg)
+    params = O.glorot_init(layout, n, g, torch.float32)
+    for name, (off, shape) in layout.items():
+        k = int(np.prod(shape))
+        if name.endswith(".b") or name.endswith(".beta"):
+            params[off:off + k] = 0.05 * torch.randn(k, generator=g)
+        if name.endswith(".gamma"):
+            params[off:off + k] = 1.0 + 0.1 * torch.randn(k, generator=g)
+    eps = torch.randn(cfg.p, cfg.L0, generator=g)
+    theta = torch.stack([torch.randn(cfg.p, generator=g) * 0.2 + 0.7, torch.randn(cfg.p, generator=g) * 0.2 + 1.0,
+                         torch.randn(cfg.p, generator=g) * 0.2 + 1.5, torch.randn(cfg.p, generator=g) * 0.2 - 0.7,
+                         torch.randn(cfg.p, generator=g) * 0.2 - 1.2], dim=1).float()
+    return arrays, idx.astype(np.int64), layout, params, eps, theta, tf64, bin_feed
+
+
+@pytest.mark.parametrize("objective,target", [(0, 0.0), (2, 0.0)])
+@pytest.mark.parametrize("shape", [
+    dict(p=6, K=8, B=6, F=3, H=3, feat_window=3),
+    dict(p=9, K=20, B=11, F=3, H=3, feat_window=10),       # the script's kernel_len / network depth
+    dict(p=4, K=4, B=3, F=2, H=1, feat_window=2),
+])
+def test_fhn_step_parity(shape, objective, target):
+    """fitz_nag_NVP.py: gather (window start 2*idx, look-ahead shifts of 5 slots, the longer time_till pad) bit-exact;
+    flow with stride-2 head / identity-affine interleave / pair-swap Permute / BN affine, diag-Gaussian
+    Euler-Maruyama ELBO and all gradients within 1e-4."""
+    target_dims, dt = 240, 0.1
+    cfg = fhn_config(target_dims=target_dims, dt=dt, **shape)
+    arrays, idx, layout, params, eps, theta, tf64, bin_feed = _fhn_case(cfg, target_dims, dt, seed=7)
+    eng = _engine(cfg)
+    assert not eng.tensor_cores                     # flow_dims = 2 runs on the FP32 SIMT conv
+    eng.set_series(arrays)
+    got_tf, _, _ = eng.gather(idx)
+    assert np.array_equal(got_tf.cpu().numpy(), tf64.astype(np.float32))
+    tf32 = torch.from_numpy(tf64.astype(np.float32))
+    extra = {"bin_feed": torch.from_numpy(bin_feed.astype(np.float32)).double()}
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf32.double(), obj=objective,
+                           extra=extra, path_target=target)
+    dev = torch.device("cuda")
+    out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev),
+                           objective=objective, path_target=target)
+    torch.cuda.synchronize()
+    terms = out["terms"].cpu().double()
+    for k, name in enumerate(("sde", "obs", "logq", "base")):
+        want = ref["terms"][:, k]
+        tol = RTOL * max(1.0, want.abs().max().item())
+        assert (terms[:, k] - want).abs().max().item() <= tol, name
+    assert _rel(out["lf"].cpu(), ref["x_final"]) < RTOL
+    gp = out["grad_params"].cpu()
+    gn_all = ref["grad_params"].norm().item()
+    for name, (off, shape_) in layout.items():
+        k = int(np.prod(shape_))
+        want = ref["grad_params"][off:off + k]
+        err = (gp[off:off + k].double() - want).norm().item()
+        assert err <= RTOL * max(want.norm().item(), 1e-6 * gn_all), (name, err, want.norm().item())
+    gth = out["grad_theta"].cpu().double()
+    assert (gth - ref["grad_theta"]).norm().item() <= RTOL * max(ref["grad_theta"].norm().item(), 1e-6 * gn_all)

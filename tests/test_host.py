@@ -135,3 +135,29 @@ def test_index_feeder_matches_reference_draw():
         assert np.array_equal(g, rs.choice(cand, size=50, replace=False))
     np.random.seed(1)
     assert np.array_equal(feed.sample_indices(5000, 50, 50), got[0])
+
+
+def test_fhn_feed_arrays_match_reference_restatement():
+    """Product-side FHN base arrays + channel table reproduce the windows of fitz_nag_NVP.py:187-202,350-370."""
+    from viforssms_b200.config import fhn_config
+    rs = np.random.RandomState(0)
+    N, dt = 240, 0.1
+    T = N * dt
+    for (K, B, F, fw) in ((8, 6, 3, 3), (20, 12, 3, 10)):
+        cfg = fhn_config(p=4, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=N, dt=dt)
+        obs = rs.normal(size=(2, N))
+        ob = (rs.uniform(size=(2, N)) < .3).astype(float)
+        tt = rs.uniform(size=(2, N)).round(1)
+        arrays = feed.fhn_base_arrays(obs, ob, tt, dt, T, N, F, K, fw)
+        pads = O.pad_series_fhn(obs, tt, np.array([2., 3.]), dt, T, N, F, K, fw)
+        idx = np.array([0, B, (N // B - 1) * B])
+        tf, mask, shift, bf = O.gather_feed_fhn(pads, ob, idx, cfg.L0, cfg.B)
+        assert tf.shape == (3, cfg.L0, fw + 3) and bf.shape == (3, 2, B)
+        assert len(pads["time_till"]) == len(pads["time_pad"]) + 2          # the FHN quirk (SURVEY Appendix C)
+        for r, i in enumerate(idx):
+            for c in range(cfg.Cf):
+                a = arrays[cfg.chan_array[c]]
+                off = cfg.chan_offset[c]
+                w = np.array([a[2 * i + s + off] if 0 <= 2 * i + s + off < len(a) else 0. for s in range(cfg.L0)])
+                assert np.array_equal(w, tf[r, :, c]), (r, c)
+            assert np.array_equal(arrays[4].reshape(2, N)[:, i:i + B], bf[r])

@@ -194,3 +194,19 @@ def ar_config(p=50, K=50, B=50, F=3, H=1, feat_window=10, T=5000, obs_std=1.0, x
         scale=float(T) / float(B), dt=1.0, obs_std=obs_std, x0=(x0, 0.0), n_arrays=5,
         chan_array=[0] * fw + [1, 2, 3, 4], chan_offset=list(range(fw)) + [0, 0, 0, 0],
         obs_array=0, bin_array=4)
+
+
+def fhn_config(p=50, K=20, B=50, F=3, H=3, feat_window=10, target_dims=1000000, dt=0.1) -> NMAConfig:
+    """The FitzHugh-Nagumo model of fitz_nag_NVP.py (RealNVP-style coupling on a time axis that interleaves the
+    two latent components).
+
+    Base arrays (fitz_nag_NVP.py:187-202): 0 = 'F'-flattened observations padded with no_flows*kernel_len + 2
+    zeros (look-ahead channels read it at offsets 0, 5, ..., 5*(feat_window-1)), 1 = bin_feats, 2 = time_pad,
+    3 = interleaved time_till (its pad is 2 slots longer than the others), 4 = obs_bin
+    [2, target_dims] row-major (bin_feed, fitz_nag_NVP.py:369-370).  Channel order fitz_nag_NVP.py:362-363."""
+    fw = feat_window
+    return NMAConfig(
+        model=MODEL_FHN, p=p, K=K, B=B, D=2, F=F, H=H, bn=1, Cf=fw + 3, feat_aug=0, dtheta=5,
+        scale=float(target_dims) / float(B), dt=dt, obs_std=0.1, x0=(0.0, 0.0), n_arrays=5,
+        chan_array=[0] * fw + [1, 2, 3], chan_offset=[5 * i for i in range(fw)] + [0, 0, 0],
+        obs_array=0, bin_array=4)

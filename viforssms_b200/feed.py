@@ -47,3 +47,18 @@ def partition_indices(idx: np.ndarray, world: int, rank: int) -> np.ndarray:
     """Row sharding for N GPUs: contiguous slices of the injected index list."""
     per = (len(idx) + world - 1) // world
     return idx[rank * per:(rank + 1) * per]
+
+
+def fhn_base_arrays(obs, obs_bin, time_till, dt: float, T: float, target_dims: int, F: int, K: int,
+                    fw: int) -> List[np.ndarray]:
+    """Base arrays of the FitzHugh-Nagumo model in the order `config.fhn_config` expects
+    (fitz_nag_NVP.py:165,187-202).  obs, obs_bin, time_till: [2, target_dims]."""
+    D = 2
+    P2 = F * K + D
+    obs_flat = np.reshape(np.asarray(obs, dtype=np.float64), -1, 'F')
+    obs_pad = np.concatenate((np.zeros(P2), obs_flat, np.zeros(5 * max(fw - 1, 0))))
+    bin_feats = np.concatenate((np.ones(P2), np.zeros(target_dims * D)))
+    time_pad = np.concatenate((np.zeros(P2), np.repeat(np.arange(dt, T + dt, dt), D)))
+    lead = np.reshape(np.repeat(np.arange(np.round(P2 * (dt / D), 1), -dt, -dt), D), (D, -1), 'F')
+    tt = np.reshape(np.concatenate((lead, np.asarray(time_till, dtype=np.float64)), 1), -1, 'F')
+    return [obs_pad, bin_feats, time_pad, tt, np.asarray(obs_bin, dtype=np.float64).reshape(-1)]
