@@ -110,6 +110,41 @@ def gather_feed_fhn(pads, obs_bin, batch_select, L0, B):
     return time_feats, mask, shift, bin_feed
 
 
+def pad_series_sv(obs, x0, dt, T, target_dims, F, K, fw) -> Dict[str, object]:
+    """SV_dense.py:159-184."""
+    var_store = []
+    for i in range(0, obs.shape[0] - K):
+        var_store.append(np.var(obs[i:i + K]))
+    var_pad = np.concatenate((np.zeros((F + 1) * K), var_store), axis=0)
+    var_diff_store = []
+    obs_diff = obs[1:] - obs[:-1]
+    for i in range(0, obs_diff.shape[0] - K):
+        var_diff_store.append(np.var(obs_diff[i:i + K]))
+    var_diff_pad = np.concatenate((np.zeros((F + 1) * K), np.log(var_diff_store), np.zeros(1)), axis=0)
+    store = []
+    for i in range(0, fw * 5, 5):
+        store.append(np.concatenate((np.zeros(F * K - i), obs, np.zeros(i)), axis=0))
+    return {
+        "obs": obs, "obs_pad_store": store, "var_pad": var_pad, "var_diff_pad": var_diff_pad,
+        "time_pad": np.concatenate((np.zeros(F * K + 1), np.arange(0.1, T + dt, dt)), axis=0),
+        "mask_vals": np.concatenate((np.zeros((1, 1)), np.ones((1, target_dims))), axis=1),
+        "shift_vals": np.concatenate((np.array([[x0]]), np.zeros((1, target_dims))), axis=1),
+    }
+
+
+def gather_feed_sv(pads, batch_select, L0, B):
+    """SV_dense.py:305-328: (time_feats [p,L0,fw+3], mask, shift, dim_one [p,B+1])."""
+    def win(arr):
+        return np.stack([arr[i:i + L0] for i in batch_select], axis=0)[:, :, None]
+    chans = [win(a) for a in pads["obs_pad_store"]]
+    chans += [win(pads["time_pad"]), win(pads["var_pad"]), win(pads["var_diff_pad"])]
+    time_feats = np.concatenate(chans, axis=2)
+    mask = np.stack([pads["mask_vals"][0, i:i + B + 1] for i in batch_select], axis=0)
+    shift = np.stack([pads["shift_vals"][0, i:i + B + 1] for i in batch_select], axis=0)
+    dim_one = np.stack([pads["obs"][i:i + B + 1] for i in batch_select], axis=0)
+    return time_feats, mask, shift, dim_one
+
+
 # ----------------------------------------------------------------------------
 # torch half: flow, ELBO, gradients, Adamax ("parity unpinned", see header)
 # ----------------------------------------------------------------------------

@@ -13,7 +13,7 @@ import torch
 
 from oracle import nma_oracle as O
 from viforssms_b200 import feed
-from viforssms_b200.config import ar_config, fhn_config, param_layout, NMAConfig
+from viforssms_b200.config import ar_config, fhn_config, sv_config, param_layout, NMAConfig
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -395,6 +395,77 @@ def test_fhn_step_parity(shape, objective, target):
         want = ref["terms"][:, k]
         tol = RTOL * max(1.0, want.abs().max().item())
         assert (terms[:, k] - want).abs().max().item() <= tol, name
+    assert _rel(out["lf"].cpu(), ref["x_final"]) < RTOL
+    gp = out["grad_params"].cpu()
+    gn_all = ref["grad_params"].norm().item()
+    for name, (off, shape_) in layout.items():
+        k = int(np.prod(shape_))
+        want = ref["grad_params"][off:off + k]
+        err = (gp[off:off + k].double() - want).norm().item()
+        assert err <= RTOL * max(want.norm().item(), 1e-6 * gn_all), (name, err, want.norm().item())
+    gth = out["grad_theta"].cpu().double()
+    assert (gth - ref["grad_theta"]).norm().item() <= RTOL * max(ref["grad_theta"].norm().item(), 1e-6 * gn_all)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Stochastic volatility (configs[3]): delta-augmented features, fixed first component, mask/shift pin of x0
+# ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("objective,target", [(0, 0.0), (2, -7.0)])
+@pytest.mark.parametrize("shape", [
+    dict(p=6, K=10, B=7, F=3, H=3, feat_window=2),
+    dict(p=5, K=50, B=52, F=5, H=3, feat_window=5),        # the script's shape (SV_dense.py:409-416), p reduced
+])
+def test_sv_step_parity(shape, objective, target, tc):
+    rs = np.random.RandomState(21)
+    g = torch.Generator().manual_seed(21)
+    N = 600                                      # target_dims; the series has N + 1 prices
+    obs = np.exp(rs.normal(0.0, 0.3, size=N + 1).cumsum() * 0.05 + 2.0)
+    dt, T = 1.0, float(N)
+    cfg = sv_config(target_dims=N, dt=dt, x0=-8.5, **shape)
+    fw = cfg.Cf - 3
+    arrays = feed.sv_base_arrays(obs, dt, T, cfg.F, cfg.K, fw)
+    pads = O.pad_series_sv(obs, -8.5, dt, T, N, cfg.F, cfg.K, fw)
+    idx = rs.choice(np.arange(0, N, cfg.B), size=cfg.p, replace=bool(cfg.B * cfg.p >= N)).astype(np.int64)
+    idx[0] = 0                                   # the row whose first latent is pinned to x0 by mask/shift
+    idx[-1] = ((N - cfg.B - 1) // cfg.B) * cfg.B
+    tf64, mask, shift, dim_one = O.gather_feed_sv(pads, idx, cfg.L0, cfg.B)
+    layout, n = param_layout(cfg)
+    params = O.glorot_init(layout, n, g, torch.float32)
+    for name, (off, shape_) in layout.items():
+        k = int(np.prod(shape_))
+        if name.endswith(".b") or name.endswith(".beta"):
+            params[off:off + k] = 0.05 * torch.randn(k, generator=g)
+        if name.endswith(".gamma"):
+            params[off:off + k] = 1.0 + 0.1 * torch.randn(k, generator=g)
+    for i in range(cfg.F):                       # the raw time channel (and its copy in the augmented block) reaches T
+        off, shape_ = layout[f"f{i}.feat0.w"]
+        params[off:off + shape_[0] * shape_[1]].reshape(shape_)[fw, :] *= 10.0 / N
+    eps = torch.randn(cfg.p, cfg.L0, generator=g)
+    theta = torch.stack([torch.randn(cfg.p, generator=g) * 0.001 + 0.001, torch.randn(cfg.p, generator=g) * 0.1 - 0.6,
+                         torch.randn(cfg.p, generator=g) * 0.1 - 2.5, torch.randn(cfg.p, generator=g) * 0.1 - 0.7],
+                        dim=1).float()
+    eng = _engine(cfg, tc)
+    assert eng.tensor_cores == tc
+    eng.set_series(arrays)
+    got_tf, got_mask, got_shift = eng.gather(idx)
+    assert np.array_equal(got_tf.cpu().numpy(), tf64.astype(np.float32))
+    assert np.array_equal(got_mask.cpu().numpy()[:, 0], mask.astype(np.float32))
+    assert np.array_equal(got_shift.cpu().numpy()[:, 0], shift.astype(np.float32))
+    f32 = lambda a: torch.from_numpy(a.astype(np.float32)).double()
+    extra = {"mask": f32(mask), "shift": f32(shift), "dim_one": f32(dim_one)}
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), f32(tf64), obj=objective,
+                           extra=extra, path_target=target)
+    dev = torch.device("cuda")
+    out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev),
+                           objective=objective, path_target=target)
+    torch.cuda.synchronize()
+    terms = out["terms"].cpu().double()
+    for k, name in enumerate(("sde", "obs", "logq", "base")):
+        want = ref["terms"][:, k]
+        tol = RTOL * max(1.0, want.abs().max().item())
+        assert (terms[:, k] - want).abs().max().item() <= tol, (name, (terms[:, k] - want).abs().max().item(), tol)
     assert _rel(out["lf"].cpu(), ref["x_final"]) < RTOL
     gp = out["grad_params"].cpu()
     gn_all = ref["grad_params"].norm().item()

@@ -161,3 +161,30 @@ def test_fhn_feed_arrays_match_reference_restatement():
                 w = np.array([a[2 * i + s + off] if 0 <= 2 * i + s + off < len(a) else 0. for s in range(cfg.L0)])
                 assert np.array_equal(w, tf[r, :, c]), (r, c)
             assert np.array_equal(arrays[4].reshape(2, N)[:, i:i + B], bf[r])
+
+
+def test_sv_feed_arrays_and_rolling_variance():
+    """Product-side SV base arrays reproduce the windows of SV_dense.py:159-184,305-328; the O(T) prefix-sum
+    rolling variance (A14) agrees with the reference's np.var loop."""
+    from viforssms_b200.config import sv_config
+    rs = np.random.RandomState(21)
+    N = 600
+    obs = np.exp(rs.normal(0, 0.3, size=N + 1).cumsum() * 0.05 + 2.0)
+    for (K, B, F, fw) in ((10, 7, 3, 2), (50, 52, 5, 5)):
+        cfg = sv_config(p=3, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=N)
+        arrays = feed.sv_base_arrays(obs, 1.0, float(N), F, K, fw)
+        fast = feed.sv_base_arrays(obs, 1.0, float(N), F, K, fw, exact_var=False)
+        for a, b in zip(arrays, fast):
+            assert np.allclose(a, b, rtol=1e-10, atol=1e-12)
+        pads = O.pad_series_sv(obs, -8.5, 1.0, float(N), N, F, K, fw)
+        idx = np.array([0, B, ((N - B - 1) // B) * B])
+        tf, mask, shift, d1 = O.gather_feed_sv(pads, idx, cfg.L0, cfg.B)
+        for r, i in enumerate(idx):
+            for c in range(cfg.Cf):
+                a = arrays[cfg.chan_array[c]]
+                off = cfg.chan_offset[c]
+                w = np.array([a[i + s + off] if 0 <= i + s + off < len(a) else 0. for s in range(cfg.L0)])
+                assert np.array_equal(w, tf[r, :, c]), (r, c)
+            assert np.array_equal(arrays[0][i + cfg.head_offset:i + cfg.head_offset + B + 1], d1[r])
+    want = np.array([np.var(obs[i:i + 50]) for i in range(len(obs) - 50)])
+    assert np.allclose(feed.rolling_var(obs, 50), want, rtol=1e-10)

@@ -210,3 +210,19 @@ def fhn_config(p=50, K=20, B=50, F=3, H=3, feat_window=10, target_dims=1000000, 
         scale=float(target_dims) / float(B), dt=dt, obs_std=0.1, x0=(0.0, 0.0), n_arrays=5,
         chan_array=[0] * fw + [1, 2, 3], chan_offset=[5 * i for i in range(fw)] + [0, 0, 0],
         obs_array=0, bin_array=4)
+
+
+def sv_config(p=200, K=50, B=52, F=5, H=3, feat_window=5, target_dims=1508, dt=1.0, x0=-8.5) -> NMAConfig:
+    """The stochastic-volatility model of SV_dense.py: a 1-D latent log-volatility flow with the observed price as a
+    second, fixed component (`dim_one`), delta-augmented features (SV_dense.py:53) and no observation term.
+
+    Base arrays (SV_dense.py:159-184): 0 = observations padded with no_flows*kernel_len zeros (NOT +1; look-ahead
+    channels at offsets 0, 5, ...; also the source of dim_one = obs[idx : idx+B+1], i.e. head_offset = F*K),
+    1 = time_pad, 2 = rolling variance, 3 = log rolling variance of the first differences.
+    Channel order SV_dense.py:312-320."""
+    fw = feat_window
+    return NMAConfig(
+        model=MODEL_SV, p=p, K=K, B=B, D=1, F=F, H=H, bn=1, Cf=fw + 3, feat_aug=1, dtheta=4,
+        scale=float(target_dims) / float(B), dt=dt, obs_std=1.0, x0=(x0, 0.0), n_arrays=4,
+        chan_array=[0] * fw + [1, 2, 3], chan_offset=[5 * i for i in range(fw)] + [0, 0, 0],
+        obs_array=0, bin_array=0, head_offset=F * K)

@@ -62,3 +62,38 @@ def fhn_base_arrays(obs, obs_bin, time_till, dt: float, T: float, target_dims: i
     lead = np.reshape(np.repeat(np.arange(np.round(P2 * (dt / D), 1), -dt, -dt), D), (D, -1), 'F')
     tt = np.reshape(np.concatenate((lead, np.asarray(time_till, dtype=np.float64)), 1), -1, 'F')
     return [obs_pad, bin_feats, time_pad, tt, np.asarray(obs_bin, dtype=np.float64).reshape(-1)]
+
+
+def rolling_var(x: np.ndarray, K: int) -> np.ndarray:
+    """[np.var(x[i:i+K]) for i in range(len(x) - K)] (SV_dense.py:159-161) from prefix sums in float64.
+    (A14 of SURVEY section 8a; the O(T*K) Python loop of the reference becomes O(T).)"""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0] - K
+    if n <= 0:
+        return np.zeros(0)
+    # centre first: var is shift invariant and the prefix-sum form cancels catastrophically otherwise
+    xc = x - x.mean()
+    c1 = np.concatenate(([0.0], np.cumsum(xc)))
+    c2 = np.concatenate(([0.0], np.cumsum(xc * xc)))
+    s1 = c1[K:K + n] - c1[:n]
+    s2 = c2[K:K + n] - c2[:n]
+    return np.maximum(s2 / K - (s1 / K) ** 2, 0.0)
+
+
+def sv_base_arrays(obs, dt: float, T: float, F: int, K: int, fw: int, exact_var: bool = True) -> List[np.ndarray]:
+    """Base arrays of the SV model in the order `config.sv_config` expects (SV_dense.py:159-184).
+    `exact_var=True` evaluates the rolling variances with the reference's own np.var loop (bit-exact);
+    False uses the O(T) prefix-sum form (agrees to ~1e-12 relative)."""
+    obs = np.asarray(obs, dtype=np.float64)
+    obs_pad = np.concatenate((np.zeros(F * K), obs, np.zeros(5 * max(fw - 1, 0))))
+    time_pad = np.concatenate((np.zeros(F * K + 1), np.arange(0.1, T + dt, dt)))
+    obs_diff = obs[1:] - obs[:-1]
+    if exact_var:
+        var_store = np.array([np.var(obs[i:i + K]) for i in range(0, obs.shape[0] - K)])
+        var_diff_store = np.array([np.var(obs_diff[i:i + K]) for i in range(0, obs_diff.shape[0] - K)])
+    else:
+        var_store = rolling_var(obs, K)
+        var_diff_store = rolling_var(obs_diff, K)
+    var_pad = np.concatenate((np.zeros((F + 1) * K), var_store))
+    var_diff_pad = np.concatenate((np.zeros((F + 1) * K), np.log(var_diff_store), np.zeros(1)))
+    return [obs_pad, time_pad, var_pad, var_diff_pad]
