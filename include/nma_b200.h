@@ -119,6 +119,10 @@ int nma_get_tensor_cores(nma_handle h);
 int nma_tc_conv_raw(const float* d_in, const float* d_w, int32_t mode, int32_t nacc, float* d_out, int64_t Q,
                     int32_t K, void* stream);
 
+/* Test hook: bare tensor-core weight gradient.  d_in, d_da [Q][56] fp32, d_gw [K][51][50] (accumulated into):
+ * gw[k][c][f] += sum_{q <= Q-K} in[q+k][c] * da[q][f]. */
+int nma_tc_wgrad_raw(const float* d_in, const float* d_da, float* d_gw, int64_t Q, int32_t K, void* stream);
+
 /* Measurement hooks (no reference counterpart): re-launch one stage of the last step on the workspace it
  * left behind (stage: 0 conv_fwd, 1 conv_dgrad, 2 conv_wgrad, 3 epi_bwd, 4 feat_fwd, 5 feat_bwd), and the
  * number of kernels this library has launched so far in this process. */

@@ -214,6 +214,25 @@ def test_tensor_core_contraction_matches_fp64(mode, nacc, K, Q):
     assert got[:nout, 51:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("K,Q", [(50, 3000), (10, 200), (7, 129), (1, 64), (64, 40000)])
+def test_tensor_core_weight_gradient_matches_fp64(K, Q):
+    """The bare tcgen05 weight-gradient reduction (spaced-position units, tap pairs, periodic drain) against fp64."""
+    from viforssms_b200.engine import tc_wgrad_raw
+    g = torch.Generator().manual_seed(K * 13 + Q)
+    x = torch.randn(Q, 56, generator=g)
+    da = torch.randn(Q, 56, generator=g) * torch.exp(torch.randn(Q, 1, generator=g))
+    x[:, 51:] = 0.0
+    da[:, 50:] = 0.0
+    got = tc_wgrad_raw(x.cuda(), da.cuda(), K).cpu().double()
+    nout = Q - K + 1
+    xd, dd = x.double(), da.double()
+    want = torch.stack([xd[k:k + nout, :51].T @ dd[:nout, :50] for k in range(K)])
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item()
+    print("tc wgrad: max abs err / max |value| = %.2e (K=%d, Q=%d)" % (err / scale, K, Q))
+    assert err <= 2e-5 * scale, (err, scale)
+
+
 @pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("shape", [
     dict(p=3, K=10, B=7, F=2, H=1, feat_window=3),      # tiny

@@ -271,7 +271,7 @@ extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float
     for (int i = h->cfg.F - 1; i >= 0; --i) {
         if ((rc = launch_epi_bwd(h, i, d_params, p, objective, d_grad_params, st))) return rc;
         if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, st) : launch_conv_dgrad(h, i, p, st)))) return rc;
-        if ((rc = launch_conv_wgrad(h, i, p, d_grad_params, st))) return rc;
+        if ((rc = (h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, st) : launch_conv_wgrad(h, i, p, d_grad_params, st)))) return rc;
         if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
     }
     if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, st))) return rc;
@@ -288,7 +288,7 @@ extern "C" int nma_launch_stage(nma_handle h, int32_t stage, int32_t flow, const
     switch (stage) {
         case 0: return launch_conv_fwd(h, flow, d_params, p, true, st);
         case 1: return h->use_tc ? launch_conv_dgrad_tc(h, flow, p, st) : launch_conv_dgrad(h, flow, p, st);
-        case 2: return launch_conv_wgrad(h, flow, p, d_grad_params, st);
+        case 2: return h->use_tc ? launch_conv_wgrad_tc(h, flow, p, d_grad_params, st) : launch_conv_wgrad(h, flow, p, d_grad_params, st);
         case 3: return launch_epi_bwd(h, flow, d_params, p, NMA_OBJ_ELBO, d_grad_params, st);
         case 4: return launch_feat_fwd_eps(h, d_params, d_idx, d_eps, p, true, st);
         case 5: return launch_feat_bwd(h, flow, d_params, p, d_grad_params, st);

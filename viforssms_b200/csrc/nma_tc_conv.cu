@@ -345,3 +345,286 @@ extern "C" int nma_tc_conv_raw(const float* d_in, const float* d_w, int32_t mode
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// weight gradient on the tensor cores:  dW[k][c][f] = sum_q inp_flat[q + k][c] * dA_flat[q][f]
+//
+// GEMM per pair of taps (t, t+1):  D[(j, c), f] += A[(j, c), q] * B[q, f]  with M = 2 taps x 64 channel slots,
+// N = 64 and the flattened positions as the reduction.  tf32 operands must be K-major here (the no-swizzle MN-major
+// form is not available for 32-bit types), i.e. 4 reduction indices per 16-byte unit.  The reduction order is free,
+// so a unit holds 4 positions SPACED by 8:  unit(w)[c] = { inp[P + w + 8e][c] : e = 0..3 }.  With units stored
+// [w][64 channel rows][16 B], tap t is again a start-address shift (w -> w + t, +1152 B), and the 128 M rows of a
+// tap pair are simply two consecutive units.  Worker warps build the units from the same [channel/4][position][4]
+// hi/lo tiles the forward pass reads (4x4 register transposes, conflict-free with an 8-row group stride of 144 B),
+// so no extra layout lives in HBM.
+//
+// 3xTF32 as in the forward pass: B rows are [64 hi | 64 lo], one N=128 MMA with a_hi gives the main and the first
+// correction sum, one N=64 MMA with a_lo the second.  The tensor core accumulates with truncation and this
+// reduction is millions long, so every WGT_FLUSH stages (256 positions, a 32-MMA chain) the accumulators are drained
+// TMEM -> registers and summed there in round-to-nearest fp32.
+// CTA = (group of <= 4 tap pairs, range of stages); warps 0-7 transform + drain, warp 8 TMA, warp 9 MMA issue.
+// ---------------------------------------------------------------------------
+#define WGT_KT 32                    // positions per stage
+#define WGT_AUNITS 16                // units of the A tile: 4 k-steps + 4 (second K chunk) + 7 (tap offsets) + 1
+#define WGT_BUNITS 8
+#define WGT_SBO 144                  // bytes between 8-row groups (128 + 16 pad: conflict-free transposes)
+#define WGT_AUNIT_F (8 * WGT_SBO / 4)     // floats per A unit (64 rows)  = 288
+#define WGT_BUNIT_F (16 * WGT_SBO / 4)    // floats per B unit (128 rows) = 576
+#define WGT_ASRC 41                  // source positions of the A tile (40 needed; odd pitch)
+#define WGT_BSRC 33
+#define WGT_FLUSH 8
+#define WGT_MAXPAIRS 4
+#define WGT_THREADS 320
+#define WGT_SRCA_F (TC_CCH * WGT_ASRC * 4)
+#define WGT_SRCB_F (TC_CCH * WGT_BSRC * 4)
+#define WGT_UA_F (WGT_AUNITS * WGT_AUNIT_F)
+#define WGT_UB_F (WGT_BUNITS * WGT_BUNIT_F)
+#define WGT_STAGE_F (2 * WGT_SRCA_F + 2 * WGT_SRCB_F + 2 * WGT_UA_F + WGT_UB_F)
+
+struct ConvWgradTcArgs {
+    const float* in_hi; const float* in_lo; long long in_Q;      // [14][in_Q][4]
+    const float* da_hi; const float* da_lo; long long da_Q;      // [14][da_Q][4], dA(q) at index q + K - 1
+    float* gW;                                                   // [K][51][50]
+    int K, npairs, ngroups, nstages_total, nq;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_tc(ConvWgradTcArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t src_full[2], src_empty[2], unit_full[2], unit_empty[2], acc_full, acc_free;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y;
+    const int base = a.npairs / a.ngroups, rem = a.npairs % a.ngroups;
+    const int np = base + (g < rem ? 1 : 0);                    // tap pairs of this CTA
+    const int k0 = 2 * (g * base + (g < rem ? g : rem));        // first tap
+    const int s_begin = (int)((long long)a.nstages_total * blockIdx.x / a.nq);
+    const int s_end = (int)((long long)a.nstages_total * (blockIdx.x + 1) / a.nq);
+    const int nst = s_end - s_begin;
+    const int nchunks = (nst + WGT_FLUSH - 1) / WGT_FLUSH;
+
+    // unit rows that no transform ever writes (channel slots 56..63) must hold finite values: zero everything once
+    for (int t = tid; t < 2 * WGT_STAGE_F; t += blockDim.x) smem[t] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&src_full[i], 1); mbar_init(&src_empty[i], 8);
+            mbar_init(&unit_full[i], 8); mbar_init(&unit_empty[i], 1);
+        }
+        mbar_init(&acc_full, 1); mbar_init(&acc_free, 8);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        for (int si = 0; si < nst; ++si) {
+            const int st = si & 1;
+            if (si >= 2) mbar_wait_backoff(&src_empty[st], (uint32_t)(((si >> 1) - 1) & 1));
+            if (elect_one()) {
+                float* sb = smem + (size_t)st * WGT_STAGE_F;
+                const long long q0 = (long long)(s_begin + si) * WGT_KT;
+                mbar_expect_tx(&src_full[st], (uint32_t)(2 * WGT_SRCA_F + 2 * WGT_SRCB_F) * 4u);
+                for (int c = 0; c < TC_CCH; ++c) {
+                    const size_t sa = ((size_t)c * a.in_Q + q0 + k0) * 4;
+                    bulk_g2s(sb + (size_t)c * WGT_ASRC * 4, a.in_hi + sa, WGT_ASRC * 16u, &src_full[st]);
+                    bulk_g2s(sb + WGT_SRCA_F + (size_t)c * WGT_ASRC * 4, a.in_lo + sa, WGT_ASRC * 16u, &src_full[st]);
+                    const size_t sd = ((size_t)c * a.da_Q + q0 + (a.K - 1)) * 4;
+                    bulk_g2s(sb + 2 * WGT_SRCA_F + (size_t)c * WGT_BSRC * 4, a.da_hi + sd, WGT_BSRC * 16u, &src_full[st]);
+                    bulk_g2s(sb + 2 * WGT_SRCA_F + WGT_SRCB_F + (size_t)c * WGT_BSRC * 4, a.da_lo + sd, WGT_BSRC * 16u,
+                             &src_full[st]);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc_n64 = umma_idesc_tf32(TC_M, TC_N, 0, 0);
+        constexpr uint32_t idesc_n128 = umma_idesc_tf32(TC_M, 2 * TC_N, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+        const uint32_t hi32 = desc_hi(WGT_SBO);
+        for (int si = 0; si < nst; ++si) {
+            const int st = si & 1;
+            const int ci = si / WGT_FLUSH;
+            const bool chunk_first = (si % WGT_FLUSH) == 0;
+            const bool chunk_last = ((si % WGT_FLUSH) == WGT_FLUSH - 1) || (si == nst - 1);
+            if (chunk_first && ci > 0) mbar_wait_backoff(&acc_free, (uint32_t)((ci - 1) & 1));
+            mbar_wait_backoff(&unit_full[st], (uint32_t)((si >> 1) & 1));
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ua_hi = sbase + (uint32_t)(st * WGT_STAGE_F + 2 * WGT_SRCA_F + 2 * WGT_SRCB_F) * 4u;
+                const uint32_t ua_lo = ua_hi + WGT_UA_F * 4u;
+                const uint32_t ub = ua_lo + WGT_UA_F * 4u;
+                const uint32_t ah0 = desc_lo(ua_hi, 4u * WGT_AUNIT_F * 4u), al0 = desc_lo(ua_lo, 4u * WGT_AUNIT_F * 4u);
+                const uint32_t b0 = desc_lo(ub, 4u * WGT_BUNIT_F * 4u);
+                for (int pr = 0; pr < np; ++pr) {
+                    const uint32_t d = tmem + (uint32_t)(pr * 2 * TC_N);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t aoff = (uint32_t)(u + 2 * pr) * (WGT_AUNIT_F * 4u / 16u);
+                        const uint64_t ah = desc_pack(ah0 + aoff, hi32), al = desc_pack(al0 + aoff, hi32);
+                        const uint64_t bw = desc_pack(b0 + (uint32_t)u * (WGT_BUNIT_F * 4u / 16u), hi32);
+                        umma_tf32(d, ah, bw, idesc_n128, (chunk_first && u == 0) ? 0u : 1u);
+                        umma_tf32(d + TC_N, al, bw, idesc_n64, 1u);
+                    }
+                }
+                tc_commit(&unit_empty[st]);
+                if (chunk_last) tc_commit(&acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== worker warps: build units, drain accumulators =====
+        const int quarter = warp & 3, colhalf = warp >> 2;
+        float acc[WGT_MAXPAIRS][32];
+#pragma unroll
+        for (int pr = 0; pr < WGT_MAXPAIRS; ++pr)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[pr][i] = 0.f;
+
+        auto drain = [&](int ci) {
+            mbar_wait_backoff(&acc_full, (uint32_t)(ci & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int pr = 0; pr < WGT_MAXPAIRS; ++pr) {
+                if (pr < np) {
+                    float v[32], c2[32];
+                    const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pr * 2 * TC_N + colhalf * 32);
+                    tmem_ld32(ta, v);
+                    tmem_ld32(ta + TC_N, c2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[pr][i] += v[i] + c2[i];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free);
+        };
+
+        const int oct = tid >> 3, l8 = tid & 7;           // 32 octets of 8 lanes; 96 octet-items per stage
+        for (int si = 0; si < nst; ++si) {
+            const int st = si & 1;
+            mbar_wait_backoff(&src_full[st], (uint32_t)((si >> 1) & 1));
+            if (si >= 2) mbar_wait_backoff(&unit_empty[st], (uint32_t)(((si >> 1) - 1) & 1));
+            float* sb = smem + (size_t)st * WGT_STAGE_F;
+#pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int o = oct + 32 * it;                 // 0..63: A (hl, w, grp); 64..95: B (hl, u, grp)
+                const bool isA = o < 64;
+                const int oo = isA ? o : o - 64;
+                const int grp = oo & 1;
+                const int w = isA ? ((oo >> 1) & 15) : ((oo >> 1) & 7);
+                const int hl = isA ? (oo >> 5) : (oo >> 4);
+                const int c4 = grp * 8 + l8;
+                if (c4 < TC_CCH) {
+                    const int spitch = isA ? WGT_ASRC : WGT_BSRC;
+                    const float* src = sb + (isA ? hl * WGT_SRCA_F : 2 * WGT_SRCA_F + hl * WGT_SRCB_F) + ((size_t)c4 * spitch + w) * 4;
+                    const float4 v0 = *reinterpret_cast<const float4*>(src);
+                    const float4 v1 = *reinterpret_cast<const float4*>(src + 8 * 4);
+                    const float4 v2 = *reinterpret_cast<const float4*>(src + 16 * 4);
+                    const float4 v3 = *reinterpret_cast<const float4*>(src + 24 * 4);
+                    // rows 4*c4 .. 4*c4+3 of the unit (B: + 64 for the lo half); group = row / 8, 36 floats per group
+                    const int row0 = 4 * c4 + (isA ? 0 : hl * 64);
+                    float* dst = sb + 2 * WGT_SRCA_F + 2 * WGT_SRCB_F +
+                                 (isA ? hl * WGT_UA_F + w * WGT_AUNIT_F : 2 * WGT_UA_F + w * WGT_BUNIT_F) +
+                                 (row0 >> 3) * (WGT_SBO / 4) + (row0 & 7) * 4;
+                    *reinterpret_cast<float4*>(dst + 0) = make_float4(v0.x, v1.x, v2.x, v3.x);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v0.y, v1.y, v2.y, v3.y);
+                    *reinterpret_cast<float4*>(dst + 8) = make_float4(v0.z, v1.z, v2.z, v3.z);
+                    *reinterpret_cast<float4*>(dst + 12) = make_float4(v0.w, v1.w, v2.w, v3.w);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&unit_full[st]); mbar_arrive(&src_empty[st]); }
+            if (si > 0 && (si % WGT_FLUSH) == 0) drain(si / WGT_FLUSH - 1);
+        }
+        drain(nchunks - 1);
+
+        // TMEM lane = M row = j*64 + channel slot
+        const int M = quarter * 32 + lane, j = M >> 6, c = M & 63;
+#pragma unroll
+        for (int pr = 0; pr < WGT_MAXPAIRS; ++pr) {
+            const int tap = k0 + 2 * pr + j;
+            if (pr < np && tap < a.K && c < NMA_C1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int f = colhalf * 32 + i;
+                    if (f < NMA_C) atomicAdd(a.gW + ((size_t)tap * NMA_C1 + c) * NMA_C + f, acc[pr][i]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void wgrad_tc_geometry(ConvWgradTcArgs& a, long long qtot, int sm_count) {
+    a.npairs = (a.K + 1) / 2;
+    a.ngroups = (a.npairs + WGT_MAXPAIRS - 1) / WGT_MAXPAIRS;
+    a.nstages_total = (int)((qtot + WGT_KT - 1) / WGT_KT);
+    int nq = (3 * sm_count) / a.ngroups;
+    if (nq < 1) nq = 1;
+    if (nq > a.nstages_total) nq = a.nstages_total;
+    a.nq = nq;
+}
+
+int launch_conv_wgrad_tc(nma_handle_s* h, int i, int p, float* gp, cudaStream_t st) {
+    const FlowDims& d = h->fd[i];
+    ConvWgradTcArgs a;
+    a.in_hi = h->ws[i].tin_hi; a.in_lo = h->ws[i].tin_lo; a.in_Q = h->ws[i].tin_Q;
+    a.da_hi = h->ws[i].dat_hi; a.da_lo = h->ws[i].dat_lo; a.da_Q = h->ws[i].dat_Q;
+    a.gW = gp + h->po[i].convw;
+    a.K = h->cfg.K;
+    wgrad_tc_geometry(a, (long long)p * d.Lin, h->sm_count);
+    const int smem = 2 * WGT_STAGE_F * 4;
+    static int configured = 0;
+    if (configured < smem) {
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    k_conv_wgrad_tc<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// test hook: bare tensor-core weight gradient.  d_in, d_da [Q][56] (channel-last fp32), d_gw [K][51][50]
+// (accumulated into; the caller zeroes it):  gw[k][c][f] += sum_{q <= Q-K} in[q+k][c] * da[q][f]
+extern "C" int nma_tc_wgrad_raw(const float* d_in, const float* d_da, float* d_gw, int64_t Q, int32_t K, void* stream) {
+    if (!d_in || !d_da || !d_gw || Q < K || K < 1) { nma_set_error("nma_tc_wgrad_raw: bad argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long Qalloc = (Q + 255) / 256 * 256 + 640 + K;
+    const size_t abytes = (size_t)TC_CCH * Qalloc * 16;
+    float *ih = nullptr, *il = nullptr, *dh = nullptr, *dl = nullptr;
+    NMA_CHECK_CUDA(cudaMalloc(&ih, abytes)); NMA_CHECK_CUDA(cudaMalloc(&il, abytes));
+    NMA_CHECK_CUDA(cudaMalloc(&dh, abytes)); NMA_CHECK_CUDA(cudaMalloc(&dl, abytes));
+    NMA_CHECK_CUDA(cudaMemsetAsync(ih, 0, abytes, st)); NMA_CHECK_CUDA(cudaMemsetAsync(il, 0, abytes, st));
+    NMA_CHECK_CUDA(cudaMemsetAsync(dh, 0, abytes, st)); NMA_CHECK_CUDA(cudaMemsetAsync(dl, 0, abytes, st));
+    k_tc_split_in<<<296, 256, 0, st>>>(d_in, Q, Qalloc, ih, il);
+    // dA(q) lives at index q + K - 1; only q <= Q-K contribute
+    k_tc_split_in<<<296, 256, 0, st>>>(d_da, Q - K + 1, Qalloc, dh + (size_t)(K - 1) * 4, dl + (size_t)(K - 1) * 4);
+    ConvWgradTcArgs a;
+    a.in_hi = ih; a.in_lo = il; a.in_Q = Qalloc; a.da_hi = dh; a.da_lo = dl; a.da_Q = Qalloc;
+    a.gW = d_gw; a.K = K;
+    wgrad_tc_geometry(a, Q, 4);
+    const int smem = 2 * WGT_STAGE_F * 4;
+    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) k_conv_wgrad_tc<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(ih); cudaFree(il); cudaFree(dh); cudaFree(dl);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        nma_set_error("nma_tc_wgrad_raw: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return -2;
+    }
+    return 0;
+}

@@ -161,6 +161,16 @@ def tc_conv_raw(x: torch.Tensor, w: torch.Tensor, mode: int = 0, nacc: int = 2) 
     return out
 
 
+def tc_wgrad_raw(x: torch.Tensor, da: torch.Tensor, K: int) -> torch.Tensor:
+    """Test hook: bare tensor-core weight gradient.  x, da [Q,56] fp32 -> [K,51,50] (see nma_b200.h)."""
+    lib = _lib.load()
+    assert x.is_cuda and da.is_cuda and x.shape == da.shape and x.shape[1] == 56
+    assert x.dtype == torch.float32 and da.dtype == torch.float32 and x.is_contiguous() and da.is_contiguous()
+    gw = torch.zeros(K, 51, 50, dtype=torch.float32, device=x.device)
+    _lib.check(lib.nma_tc_wgrad_raw(_ptr(x), _ptr(da), _ptr(gw), x.shape[0], K, _stream()), "nma_tc_wgrad_raw")
+    return gw
+
+
 def scan_ar1(z: torch.Tensor, x0: float, a: float, b: float, c: float) -> torch.Tensor:
     """x[0]=x0, x[i] = a*x[i-1] + b + c*z[i-1] on device (float64); AR_dat_gen.py:11-14."""
     lib = _lib.load()
