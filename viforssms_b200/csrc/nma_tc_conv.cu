@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_tc(ConvWgradTcArg
         // ===== TMA producer =====
         for (int si = 0; si < nst; ++si) {
             const int st = si & 1;
-            if (si >= 2) mbar_wait_backoff(&src_empty[st], (uint32_t)(((si >> 1) - 1) & 1));
+            if (si >= 2) mbar_wait_lane0(&src_empty[st], (uint32_t)(((si >> 1) - 1) & 1));
             if (elect_one()) {
                 float* sb = smem + (size_t)st * WGT_STAGE_F;
                 const long long q0 = (long long)(s_begin + si) * WGT_KT;
@@ -455,8 +455,8 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_tc(ConvWgradTcArg
             const int ci = si / WGT_FLUSH;
             const bool chunk_first = (si % WGT_FLUSH) == 0;
             const bool chunk_last = ((si % WGT_FLUSH) == WGT_FLUSH - 1) || (si == nst - 1);
-            if (chunk_first && ci > 0) mbar_wait_backoff(&acc_free, (uint32_t)((ci - 1) & 1));
-            mbar_wait_backoff(&unit_full[st], (uint32_t)((si >> 1) & 1));
+            if (chunk_first && ci > 0) mbar_wait_lane0(&acc_free, (uint32_t)((ci - 1) & 1));
+            mbar_wait_lane0(&unit_full[st], (uint32_t)((si >> 1) & 1));
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t ua_hi = sbase + (uint32_t)(st * WGT_STAGE_F + 2 * WGT_SRCA_F + 2 * WGT_SRCB_F) * 4u;
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_tc(ConvWgradTcArg
             }
             __syncwarp();
         }
-    } else {
+    } else if (warp < 8) {
         // ===== worker warps: build units, drain accumulators =====
         const int quarter = warp & 3, colhalf = warp >> 2;
         float acc[WGT_MAXPAIRS][32];
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_tc(ConvWgradTcArg
             for (int i = 0; i < 32; ++i) acc[pr][i] = 0.f;
 
         auto drain = [&](int ci) {
-            mbar_wait_backoff(&acc_full, (uint32_t)(ci & 1));
+            mbar_wait_lane0(&acc_full, (uint32_t)(ci & 1));
             tc_fence_after();
 #pragma unroll
             for (int pr = 0; pr < WGT_MAXPAIRS; ++pr) {
@@ -511,8 +511,8 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_tc(ConvWgradTcArg
         const int oct = tid >> 3, l8 = tid & 7;           // 32 octets of 8 lanes; 96 octet-items per stage
         for (int si = 0; si < nst; ++si) {
             const int st = si & 1;
-            mbar_wait_backoff(&src_full[st], (uint32_t)((si >> 1) & 1));
-            if (si >= 2) mbar_wait_backoff(&unit_empty[st], (uint32_t)(((si >> 1) - 1) & 1));
+            mbar_wait_lane0(&src_full[st], (uint32_t)((si >> 1) & 1));
+            if (si >= 2) mbar_wait_lane0(&unit_empty[st], (uint32_t)(((si >> 1) - 1) & 1));
             float* sb = smem + (size_t)st * WGT_STAGE_F;
 #pragma unroll
             for (int it = 0; it < 3; ++it) {
