@@ -304,9 +304,14 @@ def run_native(args):
             "flop_per_unit": fl["flop_step"] / B_DIMS,
             "achieved_tflops_step": fl["flop_step"] * args.rows * world * args.steps / (ms_total * 1e-3) / 1e12,
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)
+    # Leave without tearing NCCL down: the CUDA graph holds captured NCCL kernels, and destroying the communicator
+    # while such a graph is alive blocks forever (seen on 8 GPUs: the line was printed, the job never exited).
+    stepper.close()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

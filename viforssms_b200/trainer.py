@@ -330,4 +330,6 @@ class ARStepper:
 
     def close(self):
         self.feeder.close()
+        self.graph = None            # drop the captured graph (it references NCCL kernels when world > 1)
+        self._elbo_static = None
         self.eng.close()
