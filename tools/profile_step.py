@@ -1,4 +1,5 @@
-"""A few plain training steps at a fixed size: the command ncu wraps (tools/gpu_profile.sh)."""
+"""A few plain (eager, one launch per kernel) training steps at a fixed size; the LAST step is bracketed by
+cudaProfilerStart/Stop so `ncu --profile-from-start off` sees exactly one step (tools/gpu_profile.sh)."""
 import argparse
 import os
 import sys
@@ -10,12 +11,16 @@ from viforssms_b200.trainer import ARStepper  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=2048)
-ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--T", type=int, default=10 ** 6)
 a = ap.parse_args()
 st = ARStepper(T=a.T, rows=a.rows, device=torch.device("cuda", 0))
-for _ in range(a.steps):
+for _ in range(a.steps - 1):
     st.step_resident()
 torch.cuda.synchronize()
+torch.cuda.profiler.start()
+st.step_resident()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", float(st.last_elbo.item()))
 st.close()
