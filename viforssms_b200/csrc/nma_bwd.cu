@@ -591,77 +591,147 @@ int launch_conv_wgrad(nma_handle_s* h, int i, int p, float* gp, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------
-// k_feat_bwd: backward of 4x dense(C, elu) over the window positions of one row (persistent over rows)
+// k_feat_bwd: backward of 4x dense(C, elu) over the window positions (AR.py:53-56 differentiated).
+//
+// Layer-outer, rows-inner: a CTA owns a fixed set of rows and sweeps them once per layer (l = 3..0), so the
+// weight-gradient tile of ONE layer lives in registers for the whole sweep (5 inputs x 10 outputs per thread,
+// 15 shared-memory float4 loads per 200 FMAs) and the transposed weights are staged once per layer instead
+// of once per row.  The gradient w.r.t. the layer input overwrites the row's df slab in place (only this CTA
+// ever touches that row), and elu' is applied while the next sweep loads it.
 // ---------------------------------------------------------------------------
+#define FB_WPITCH 64         // transposed weights [g][4 output groups][16]: group fg holds outputs f = 4*i + fg
 struct FeatBwdArgs {
     const float* w[4];
     const float* act[5];     // a0 [p][Cf_in][LP], a1..a4 [p][50][LP]
-    const float* df;         // [p][50][LP]
+    float* df;               // [p][50][LP]  in: d objective / d a4;  overwritten layer by layer
     float* gw[4]; float* gb[4];
     int Lin, LP, Cf_in, p, tile_pitch;
 };
 
-__global__ void __launch_bounds__(BWD_THREADS) k_feat_bwd(FeatBwdArgs a) {
+__global__ void __launch_bounds__(BWD_THREADS, 2) k_feat_bwd(FeatBwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     const int tid = threadIdx.x, tp = a.tile_pitch;
-    float* E = smem;
-    float* G = E + NMA_C * tp;
-    float* Wsm = G + NMA_C * tp;
-    float* v1 = Wsm + NMA_C * PW_WPITCH;
-    const int f_own = tid % NMA_C, gg_own = tid / NMA_C;
-    const bool w_owner = tid < 5 * NMA_C;
-    float accW[4][10];
-#pragma unroll
-    for (int l = 0; l < 4; ++l)
-#pragma unroll
-        for (int g = 0; g < 10; ++g) accW[l][g] = 0.f;
-    float acc_b[4] = {0.f, 0.f, 0.f, 0.f};
-    const int np4 = tp / 4, n = a.Lin;
+    float* X = smem;                          // [50][tp] layer input a_l
+    float* G = X + NMA_C * tp;                // [50][tp] gradient w.r.t. the layer's pre-activation
+    float* Wt = G + NMA_C * tp;               // [50][FB_WPITCH]
+    float* v1 = Wt + NMA_C * FB_WPITCH;       // [64]
+    float* wred = v1 + 64;                    // [50][50] cross-slice reduction of the weight-gradient tiles
+    const int np4 = tp / 4, n = a.Lin, n4 = a.LP / 4;
+    // weight-gradient ownership: 50 (5 x 10) tiles x 5 position slices
+    const bool w_owner = tid < 250;
+    const int slice = tid / 50, wt_tile = tid % 50;
+    const int f0 = (wt_tile % 10) * 5, g0 = (wt_tile / 10) * 10;
+    const int j_lo = (np4 * slice) / 5, j_hi = (np4 * (slice + 1)) / 5;
+    // data-gradient work items: (4 columns mg) x (13 outputs f = 4*i + fg), 4 * np4 items per row; a window
+    // wider than 64 float4 columns (SV: 302 slots) needs more items than the CTA has threads, hence the loop
 
-    for (int t = tid; t < 2 * NMA_C * tp; t += blockDim.x) smem[t] = 0.f;
-    for (int r = blockIdx.x; r < a.p; r += gridDim.x) {
+    for (int t = tid; t < 2 * NMA_C * tp; t += blockDim.x) smem[t] = 0.f;     // pad columns stay zero
+    for (int l = 3; l >= 0; --l) {
+        const int nin = (l == 0) ? a.Cf_in : NMA_C;
         __syncthreads();
-        load_tile(G, tp, a.df + (size_t)r * NMA_C * a.LP, a.LP, NMA_C);
-        load_tile(E, tp, a.act[4] + (size_t)r * NMA_C * a.LP, a.LP, NMA_C);
-        __syncthreads();
-        for (int l = 3; l >= 0; --l) {
-            // E = a_{l+1}, G = grad w.r.t. a_{l+1}
-            for (int t = tid; t < NMA_C * n; t += blockDim.x) {
-                const int g = t / n, m = t - g * n;
-                G[g * tp + m] *= elu_grad_from_out(E[g * tp + m]);
+        if (l > 0) {    // Wt[g][fg][i] = W_l[f = 4i + fg][g]
+            for (int t = tid; t < NMA_C * FB_WPITCH; t += blockDim.x) {
+                const int g = t / FB_WPITCH, q = t - g * FB_WPITCH;
+                const int f = 4 * (q & 15) + (q >> 4);
+                Wt[t] = ((q & 15) < 13 && f < NMA_C) ? a.w[l][f * NMA_C + g] : 0.f;
             }
+        }
+        for (int t = tid; t < NMA_C * NMA_C; t += blockDim.x) wred[t] = 0.f;
+        float acc[5][10];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int g = 0; g < 10; ++g) acc[i][g] = 0.f;
+        float acc_b = 0.f;
+
+        for (int r = blockIdx.x; r < a.p; r += gridDim.x) {
             __syncthreads();
-            row_sums(G, nullptr, tp, n, v1, nullptr);
-            const int nin = (l == 0) ? a.Cf_in : NMA_C;
-            load_tile(E, tp, a.act[l] + (size_t)r * nin * a.LP, a.LP, nin);
-            if (l > 0) {
-                for (int t = tid; t < NMA_C * PW_WPITCH; t += blockDim.x) {
-                    const int g = t / PW_WPITCH, f = t - g * PW_WPITCH;
-                    Wsm[t] = (f < NMA_C) ? a.w[l][f * NMA_C + g] : 0.f;
+            // G = df * elu'(a_{l+1}),  X = a_l   (coalesced float4; columns >= Lin stay zero)
+            {
+                const float* gsrc = a.df + (size_t)r * NMA_C * a.LP;
+                const float* esrc = a.act[l + 1] + (size_t)r * NMA_C * a.LP;
+                for (int t = tid; t < NMA_C * n4; t += blockDim.x) {
+                    const int f = t / n4, j4 = t - f * n4;
+                    // plain load: df is rewritten by this kernel between sweeps, the read-only path is not coherent
+                    const float4 gv = *reinterpret_cast<const float4*>(gsrc + (size_t)f * a.LP + 4 * j4);
+                    const float4 ev = __ldg(reinterpret_cast<const float4*>(esrc + (size_t)f * a.LP + 4 * j4));
+                    float4 o;
+                    o.x = (4 * j4 + 0 < n) ? gv.x * elu_grad_from_out(ev.x) : 0.f;
+                    o.y = (4 * j4 + 1 < n) ? gv.y * elu_grad_from_out(ev.y) : 0.f;
+                    o.z = (4 * j4 + 2 < n) ? gv.z * elu_grad_from_out(ev.z) : 0.f;
+                    o.w = (4 * j4 + 3 < n) ? gv.w * elu_grad_from_out(ev.w) : 0.f;
+                    *reinterpret_cast<float4*>(G + f * tp + 4 * j4) = o;
+                }
+                const float* xsrc = a.act[l] + (size_t)r * nin * a.LP;
+                for (int t = tid; t < nin * n4; t += blockDim.x) {
+                    const int f = t / n4, j4 = t - f * n4;
+                    *reinterpret_cast<float4*>(X + f * tp + 4 * j4) =
+                        __ldg(reinterpret_cast<const float4*>(xsrc + (size_t)f * a.LP + 4 * j4));
                 }
             }
             __syncthreads();
-            if (tid < NMA_C) acc_b[l] += v1[tid];
-            if (w_owner && f_own < nin) wgrad_accum(E, G, tp, np4, f_own, gg_own, accW[l]);
-            __syncthreads();
-            if (l > 0) {
-                col_matvec_inplace(G, tp, n, Wsm);
-                __syncthreads();
+            row_sums(G, nullptr, tp, n, v1, nullptr);
+            // weight gradient: acc[i][g] += sum_m X[f0+i][m] * G[g0+g][m] over this thread's slice of positions
+            if (w_owner && f0 < nin) {
+                for (int jj = j_lo; jj < j_hi; ++jj) {
+                    float4 xv[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) xv[i] = *reinterpret_cast<const float4*>(X + (f0 + i) * tp + 4 * jj);
+#pragma unroll
+                    for (int g = 0; g < 10; ++g) {
+                        const float4 gv = *reinterpret_cast<const float4*>(G + (g0 + g) * tp + 4 * jj);
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            acc[i][g] = fmaf(xv[i].x, gv.x, acc[i][g]);
+                            acc[i][g] = fmaf(xv[i].y, gv.y, acc[i][g]);
+                            acc[i][g] = fmaf(xv[i].z, gv.z, acc[i][g]);
+                            acc[i][g] = fmaf(xv[i].w, gv.w, acc[i][g]);
+                        }
+                    }
+                }
             }
+            // data gradient (l > 0): d a_l[f][m] = sum_g G[g][m] * W_l[f][g]  -> overwrites df[r] in place
+            if (l > 0) for (int it = tid; it < 4 * np4; it += blockDim.x) {
+                const int mg = it % np4, fg = it / np4;
+                float4 d[13];
+#pragma unroll
+                for (int i = 0; i < 13; ++i) d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int g = 0; g < NMA_C; ++g) {
+                    const float4 gv = *reinterpret_cast<const float4*>(G + g * tp + 4 * mg);
+                    const float4* w4 = reinterpret_cast<const float4*>(Wt + g * FB_WPITCH + fg * 16);
+                    const float4 wa = w4[0], wb = w4[1], wc = w4[2], wd = w4[3];
+                    const float w[13] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w, wd.x};
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) {
+                        d[i].x = fmaf(gv.x, w[i], d[i].x);
+                        d[i].y = fmaf(gv.y, w[i], d[i].y);
+                        d[i].z = fmaf(gv.z, w[i], d[i].z);
+                        d[i].w = fmaf(gv.w, w[i], d[i].w);
+                    }
+                }
+                if (mg < n4) {
+                    float* dst = a.df + (size_t)r * NMA_C * a.LP + 4 * mg;
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) {
+                        const int f = 4 * i + fg;
+                        if (f < NMA_C) *reinterpret_cast<float4*>(dst + (size_t)f * a.LP) = d[i];
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < NMA_C) acc_b += v1[tid];
         }
-    }
-    if (w_owner) {
+        // combine the 5 position slices in shared memory, then one atomic per weight per CTA
+        if (w_owner && f0 < nin) {
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            const int nin = (l == 0) ? a.Cf_in : NMA_C;
-            if (f_own < nin)
+            for (int i = 0; i < 5; ++i)
 #pragma unroll
-                for (int g = 0; g < 10; ++g) atomicAdd(a.gw[l] + f_own * NMA_C + gg_own * 10 + g, accW[l][g]);
+                for (int g = 0; g < 10; ++g) atomicAdd(wred + (f0 + i) * NMA_C + g0 + g, acc[i][g]);
         }
+        __syncthreads();
+        for (int t = tid; t < nin * NMA_C; t += blockDim.x) atomicAdd(a.gw[l] + t, wred[t]);
+        if (tid < NMA_C) atomicAdd(a.gb[l] + tid, acc_b);
     }
-    if (tid < NMA_C)
-#pragma unroll
-        for (int l = 0; l < 4; ++l) atomicAdd(a.gb[l] + tid, acc_b[l]);
 }
 
 int launch_feat_bwd(nma_handle_s* h, int i, const float* params, int p, float* gp, cudaStream_t st) {
@@ -674,7 +744,7 @@ int launch_feat_bwd(nma_handle_s* h, int i, const float* params, int p, float* g
     }
     for (int l = 0; l < 5; ++l) a.act[l] = h->ws[i].a[l];
     a.df = h->ws[i].df; a.Lin = d.Lin; a.LP = d.LP; a.Cf_in = h->Cf_in; a.p = p; a.tile_pitch = d.LP | 4;
-    const size_t smem = ((size_t)2 * NMA_C * a.tile_pitch + NMA_C * PW_WPITCH + 64) * 4;
+    const size_t smem = ((size_t)2 * NMA_C * a.tile_pitch + NMA_C * FB_WPITCH + 64 + NMA_C * NMA_C) * 4;
     static size_t configured = 0;
     if (configured < smem) {
         NMA_CHECK_CUDA(cudaFuncSetAttribute(k_feat_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
