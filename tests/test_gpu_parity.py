@@ -151,7 +151,8 @@ def _check_step(cfg, T, seed, objective=0, path_target=0.0, tc=None):
                            path_target=path_target)
     eng = _engine(cfg, tc)
     if tc is not None:
-        assert eng.tensor_cores == tc
+        assert eng.tensor_cores == bool(tc)
+        assert eng.tensor_core_features == (tc is True)
     eng.set_series(arrays)
     dev = torch.device("cuda")
     out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev),
@@ -233,7 +234,8 @@ def test_tensor_core_weight_gradient_matches_fp64(K, Q):
     assert err <= 2e-5 * scale, (err, scale)
 
 
-@pytest.mark.parametrize("tc", [False, True])
+# tc: False = FP32 SIMT kernels, 1 = K-tap conv on tcgen05 (feature MLP SIMT), True = conv and feature MLP on tcgen05
+@pytest.mark.parametrize("tc", [False, 1, True])
 @pytest.mark.parametrize("shape", [
     dict(p=3, K=10, B=7, F=2, H=1, feat_window=3),      # tiny
     dict(p=5, K=20, B=13, F=3, H=3, feat_window=5),     # hidden stack, ragged block tails
@@ -246,7 +248,7 @@ def test_step_parity_small(shape, tc):
     _check_step(cfg, T, seed=3, tc=tc)
 
 
-@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("tc", [False, 1, True])
 def test_step_parity_ar_default(tc):
     """configs[0]: hyperparameters.txt on dat/AR_obs_partial.txt (p=50, K=50, B=50, 3 flows)."""
     cfg = ar_config()
@@ -430,7 +432,7 @@ def test_fhn_step_parity(shape, objective, target):
 # Stochastic volatility (configs[3]): delta-augmented features, fixed first component, mask/shift pin of x0
 # ---------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("tc", [False, 1, True])
 @pytest.mark.parametrize("objective,target", [(0, 0.0), (2, -7.0)])
 @pytest.mark.parametrize("shape", [
     dict(p=6, K=10, B=7, F=3, H=3, feat_window=2),
@@ -466,7 +468,7 @@ def test_sv_step_parity(shape, objective, target, tc):
                          torch.randn(cfg.p, generator=g) * 0.1 - 2.5, torch.randn(cfg.p, generator=g) * 0.1 - 0.7],
                         dim=1).float()
     eng = _engine(cfg, tc)
-    assert eng.tensor_cores == tc
+    assert eng.tensor_cores == bool(tc) and eng.tensor_core_features == (tc is True)
     eng.set_series(arrays)
     got_tf, got_mask, got_shift = eng.gather(idx)
     assert np.array_equal(got_tf.cpu().numpy(), tf64.astype(np.float32))

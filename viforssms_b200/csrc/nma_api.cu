@@ -111,6 +111,8 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     {
         const char* env = getenv("NMA_TC");
         h->use_tc = h->tc_ok && !(env && env[0] == '0');
+        const char* envf = getenv("NMA_TC_FEAT");
+        h->use_tc_feat = h->use_tc && !(envf && envf[0] == '0');
     }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
@@ -119,7 +121,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     const int64_t p = cfg->p;
     int64_t total = 0;
     auto reserve = [&](int64_t floats) { int64_t o = total; total += align_up(floats * 4, 256); return o; };
-    struct Off { int64_t x, dx, a[5], h[NMA_MAXH + 1], s, dA, df, tb, dtb, wpk, wdpk, tin_hi, tin_lo, dat_hi, dat_lo, wtc_f, wtc_d; } off[NMA_MAX_FLOWS + 1];
+    struct Off { int64_t x, dx, a[5], h[NMA_MAXH + 1], s, dA, df, tb, dtb, wpk, wdpk, tin_hi, tin_lo, dat_hi, dat_lo, wtc_f, wtc_d, wtc_feat; } off[NMA_MAX_FLOWS + 1];
     for (int i = 0; i <= cfg->F; ++i) {
         const FlowDims& d = h->fd[i];
         const int64_t XP = (d.L + 3) & ~3;
@@ -145,6 +147,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
             off[i].dat_lo = reserve((int64_t)TC_CCH * Q * 4);
             off[i].wtc_f = reserve((int64_t)cfg->K * TC_WSTAGE);
             off[i].wtc_d = reserve((int64_t)cfg->K * TC_WSTAGE);
+            off[i].wtc_feat = reserve((int64_t)8 * TC_CCH * 128 * 4);
         }
     }
     h->arena_bytes = total;
@@ -175,6 +178,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
             w.tin_hi = (float*)(base + off[i].tin_hi); w.tin_lo = (float*)(base + off[i].tin_lo);
             w.dat_hi = (float*)(base + off[i].dat_hi); w.dat_lo = (float*)(base + off[i].dat_lo);
             w.wtc_f = (float*)(base + off[i].wtc_f); w.wtc_d = (float*)(base + off[i].wtc_d);
+            w.wtc_feat = (float*)(base + off[i].wtc_feat);
         }
     }
     *out = h;
@@ -191,10 +195,11 @@ extern "C" int nma_destroy(nma_handle h) {
 extern "C" int nma_set_tensor_cores(nma_handle h, int32_t on) {
     if (!h) { nma_set_error("null handle"); return -1; }
     if (on && !h->tc_ok) { nma_set_error("the tensor-core conv does not support this configuration (flow_dims=%d, kernel_len=%d)", h->cfg.D, h->cfg.K); return -1; }
-    h->use_tc = on ? 1 : 0;
+    h->use_tc = (on & 1) ? 1 : 0;
+    h->use_tc_feat = ((on & 3) == 3) ? 1 : 0;
     return 0;
 }
-extern "C" int nma_get_tensor_cores(nma_handle h) { return h ? h->use_tc : -1; }
+extern "C" int nma_get_tensor_cores(nma_handle h) { return h ? (h->use_tc | (h->use_tc_feat << 1)) : -1; }
 
 extern "C" int64_t nma_param_count(nma_handle h) { return h ? h->n_params : -1; }
 extern "C" int64_t nma_workspace_bytes(nma_handle h) { return h ? h->arena_bytes : -1; }

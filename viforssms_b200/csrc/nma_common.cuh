@@ -49,6 +49,7 @@ struct FlowWs {
     float* dat_lo;
     float* wtc_f;    // [K][14][64 hi | 64 lo rows][4] packed taps of the forward conv
     float* wtc_d;    // same, data-gradient conv (flipped, transposed)
+    float* wtc_feat; // [8][14][64 hi | 64 lo rows][4] packed feature-MLP kernels: 4 forward, 4 transposed (nma_tc_feat.cu)
     long long tin_Q, dat_Q;
 };
 
@@ -68,6 +69,7 @@ struct nma_handle_s {
     int tc_ok;       // the tensor-core conv supports this configuration
     int use_tc;      // ... and is switched on (default; NMA_TC=0 or nma_set_tensor_cores(h, 0) selects the FP32 SIMT conv)
     int tc_nacc;     // 128-position accumulators per CTA (2 when the tile fits in shared memory, else 1)
+    int use_tc_feat; // feature MLP on the tensor cores as well (needs use_tc; NMA_TC_FEAT=0 keeps the FP32 SIMT kernels)
 };
 
 // device-side copy of what kernels need about the series and the channel table
@@ -102,6 +104,9 @@ int launch_conv_fwd_tc(nma_handle_s* h, int flow, const float* params, int p, bo
 int launch_conv_dgrad_tc(nma_handle_s* h, int flow, int p, cudaStream_t st);
 int launch_conv_wgrad_tc(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
+int launch_pack_feat_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
+int launch_feat_fwd_tc(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
+                       cudaStream_t st);
 struct FlowEpiArgs;
 void fill_flow_epi_args(nma_handle_s* h, int flow, const float* params, bool save, FlowEpiArgs& e);
 int launch_elbo(nma_handle_s* h, const float* theta, const float* eps, const int64_t* idx, int p, int objective,
@@ -124,6 +129,13 @@ __device__ __forceinline__ float elu_grad_from_out(float e) { return e > 0.f ? 1
 // tf.nn.softplus, numerically stable: max(x,0) + log1p(exp(-|x|))
 __device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// series access (A1): time_feats[r, slot, c] = base[chan_array[c]][win0 + slot + chan_offset[c]]
+__device__ __forceinline__ float series_val(const SeriesView& sv, int c, long long pos) {
+    const int a = sv.chan_array[c];
+    const long long q = pos + sv.chan_offset[c];
+    return (q >= 0 && q < sv.len[a]) ? __ldg(sv.base[a] + q) : 0.f;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

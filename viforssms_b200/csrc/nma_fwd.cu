@@ -5,15 +5,6 @@
 #include "nma_flow_epi.cuh"
 
 // ---------------------------------------------------------------------------
-// series access (A1): time_feats[r, slot, c] = base[chan_array[c]][win0 + slot + chan_offset[c]]
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float series_val(const SeriesView& sv, int c, long long pos) {
-    const int a = sv.chan_array[c];
-    const long long q = pos + sv.chan_offset[c];
-    return (q >= 0 && q < sv.len[a]) ? __ldg(sv.base[a] + q) : 0.f;
-}
-
-// ---------------------------------------------------------------------------
 // nma_gather: materialise the feed the reference builds on the host every iteration
 // ---------------------------------------------------------------------------
 __global__ void k_gather(SeriesView sv, const int64_t* __restrict__ idx, int p, int L0, int B, float x0a, float x0b,
@@ -290,6 +281,7 @@ static int feat_smem_bytes(const nma_handle_s* h) {
 // eps is passed through the handle-level wrapper (see nma_api.cu) via this file-scope pointer-free path
 int launch_feat_fwd_eps(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
                         cudaStream_t st) {
+    if (h->use_tc && h->use_tc_feat) return launch_feat_fwd_tc(h, params, idx, eps, p, save, st);
     FeatArgs fa;
     for (int i = 0; i < h->cfg.F; ++i) {
         for (int l = 0; l < 4; ++l) {

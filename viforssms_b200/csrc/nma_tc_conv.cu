@@ -53,6 +53,7 @@ int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, 
         }
     }
     NMA_CHECK_CUDA(cudaGetLastError());
+    if (h->use_tc_feat) return launch_pack_feat_tc(h, params, need_bwd, st);
     return 0;
 }
 

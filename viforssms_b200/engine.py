@@ -37,7 +37,10 @@ class NMAEngine:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.nma_create(ctypes.byref(ccfg), ctypes.byref(self._h)), "nma_create")
         if tensor_cores is not None:
-            _lib.check(self._lib.nma_set_tensor_cores(self._h, 1 if tensor_cores else 0), "nma_set_tensor_cores")
+            # bit 0: K-tap conv (forward, data and weight gradient) on tcgen05; bit 1: feature MLP as well.
+            # True selects everything, an int selects exactly those bits (1 = conv only).
+            mode = (3 if tensor_cores else 0) if isinstance(tensor_cores, bool) else int(tensor_cores)
+            _lib.check(self._lib.nma_set_tensor_cores(self._h, mode), "nma_set_tensor_cores")
         self.n_params = int(self._lib.nma_param_count(self._h))
         self.layout, n = param_layout(cfg)
         if n != self.n_params:
@@ -61,7 +64,12 @@ class NMAEngine:
     @property
     def tensor_cores(self) -> bool:
         """True when the conv and its data gradient run on the tcgen05 tensor cores (3xTF32)."""
-        return int(self._lib.nma_get_tensor_cores(self._h)) == 1
+        return (int(self._lib.nma_get_tensor_cores(self._h)) & 1) == 1
+
+    @property
+    def tensor_core_features(self) -> bool:
+        """True when the feature MLP runs on the tensor cores as well (nma_tc_feat.cu)."""
+        return (int(self._lib.nma_get_tensor_cores(self._h)) & 2) == 2
 
     @property
     def workspace_bytes(self) -> int:
