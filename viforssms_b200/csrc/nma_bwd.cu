@@ -735,6 +735,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) k_feat_bwd(FeatBwdArgs a) {
 }
 
 int launch_feat_bwd(nma_handle_s* h, int i, const float* params, int p, float* gp, cudaStream_t st) {
+    if (h->use_tc && h->use_tc_feat) return launch_feat_bwd_tc(h, i, params, p, gp, st);
     const FlowDims& d = h->fd[i];
     FeatBwdArgs a;
     for (int l = 0; l < 4; ++l) {

@@ -105,6 +105,7 @@ int launch_conv_dgrad_tc(nma_handle_s* h, int flow, int p, cudaStream_t st);
 int launch_conv_wgrad_tc(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
 int launch_pack_feat_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
+int launch_feat_bwd_tc(nma_handle_s* h, int flow, const float* params, int p, float* grad_params, cudaStream_t st);
 int launch_feat_fwd_tc(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
                        cudaStream_t st);
 struct FlowEpiArgs;

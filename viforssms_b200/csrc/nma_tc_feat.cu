@@ -96,6 +96,11 @@ struct FeatTcArgs {
     int XP0, p, L0, K, Cf_in, feat_off, save, F, ks0;
 };
 
+// ELU with ONE transcendental-pipe op: exp(z) - 1 through ex2.approx.  Absolute error <= ~1e-7 on outputs in (-1, 0]
+// (expm1f's relative accuracy near 0 is irrelevant downstream: the value is added to O(1) sums).  ncu showed the XU pipe
+// at 92 % with expm1f (its range reduction converts through the same pipe), i.e. the whole kernel waiting on it.
+__device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+
 __device__ __forceinline__ void ft_split_store(float* hi_dst, float* lo_dst, float a, float b, float c, float d) {
     const float4 h4 = make_float4(tf32_hi(a), tf32_hi(b), tf32_hi(c), tf32_hi(d));
     *reinterpret_cast<float4*>(hi_dst) = h4;
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_feat_fwd_tc(FeatTcArgs fa, Se
                 tmem_ld32(ta + TC_N, c2);
                 const float* b = bias_sm + l * 64 + half * 32;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] = valid ? elu_f(v[k] + c2[k] + b[k]) : 0.f;
+                for (int k = 0; k < 32; ++k) v[k] = valid ? elu_fast(v[k] + c2[k] + b[k]) : 0.f;
             }
             if (fa.save && valid) {
                 float* dst = fa.a[i][l + 1] + ((size_t)r * NMA_C + half * 32) * LP + j;
@@ -338,6 +343,256 @@ int launch_feat_fwd_tc(nma_handle_s* h, const float* params, const int64_t* idx,
     }
     SeriesView sv = nma_series_view(h);
     k_feat_fwd_tc<<<G, FT_THREADS, smem, st>>>(fa, sv, idx, eps);
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// backward of the feature MLP on the tensor cores (AR.py:53-56 differentiated; replaces k_feat_bwd, nma_bwd.cu)
+//
+// Per tile of 128 flattened positions, layers l = 3..0 (G_l = gradient w.r.t. the layer's pre-activation):
+//     G_3 = df (.) elu'(a_4);    G_{l-1} = dA_l (.) elu'(a_l)
+//     data gradient    dA_l[pos][f] = sum_g G_l[pos][g] W_l[f][g]      M = positions, N = 64, K = 56: the forward
+//                      layer's MMA sequence with the transposed packed kernel (streamed through one 28 KB buffer by
+//                      the TMA engine while the previous layer is being processed)
+//     weight gradient  gW_l[f][g]  += sum_pos a_l[pos][f] G_l[pos][g]  reduction over positions: both operands K-major
+//                      in 16-byte units of 4 consecutive positions, [position/4][row][4].  Rows are STACKED hi over lo:
+//                      A = [a_hi (64 rows); a_lo (64 rows)], B = [G_hi | G_lo], so ONE 128x128x8 MMA yields all four
+//                      products of the split; the drain adds the quadrants.  Row 50 of A is all ones: its
+//                      accumulator row is the bias gradient sum_pos G_l, for free.
+// The tensor core accumulates with truncation, so the weight-gradient chain is kept to the 16 MMAs of one tile:
+// after every tile-layer the accumulator is drained TMEM -> registers (16 per thread and layer) and summed there
+// in round-to-nearest fp32; one atomicAdd per weight and CTA at the end.
+// 512 threads: thread = (position, group of 16 channels); warp w owns TMEM lanes 32*(w%4).. and columns 16*(w/4)...
+// ---------------------------------------------------------------------------
+#define FB_LBO 2064                              // bytes between position chunks: 128 rows x 16 B + 16 (bank spread)
+#define FB_OPW_F (32 * FB_LBO / 4)               // floats of one weight-gradient operand tile
+#define FB_THREADS 512
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// sum of the main and the correction accumulator (64 columns to the right) for 16 columns, 8 at a time (register budget)
+template <typename F>
+__device__ __forceinline__ void tmem_sum16(uint32_t taddr, F&& consume) {
+#pragma unroll
+    for (int h8 = 0; h8 < 2; ++h8) {
+        float v[8], c2[8];
+        tmem_ld8(taddr + 8 * h8, v);
+        tmem_ld8(taddr + TC_N + 8 * h8, c2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) consume(8 * h8 + k, v[k] + c2[k]);
+    }
+}
+
+struct FeatBwdTcArgs {
+    const float* wpk;        // [8][FT_WLAYER_F]; slots 4..7 = transposed kernels of layers 0..3
+    const float* act[5];     // a0 [p][Cf_in][LP], a1..a4 [p][50][LP]
+    const float* df;         // [p][50][LP]  d objective / d a4
+    float* gw[4];
+    float* gb[4];
+    int Lin, LP, Cf_in, p;
+};
+
+__global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t dbar, wbar, wt_bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quarter = warp & 3, cg = warp >> 2;
+    const int pos = quarter * 32 + lane;
+    float* Ad_hi = smem;                         // data-gradient A operand [14][128][4]
+    float* Ad_lo = Ad_hi + FT_A_F;
+    float* Aw = Ad_lo + FT_A_F;                  // weight-gradient A operand: rows f (hi) / 64 + f (lo), K = positions
+    float* Bw = Aw + FB_OPW_F;                   // weight-gradient B operand: rows g (hi) / 64 + g (lo)
+    float* Wt = Bw + FB_OPW_F;                   // transposed packed kernel of the current layer
+
+    if (tid == 0) {
+        mbar_init(&dbar, 1);
+        mbar_init(&wbar, 1);
+        mbar_init(&wt_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, FT_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot, tmem_w = tmem_slot + 2 * TC_N;
+    const uint32_t td = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(16 * cg);
+    const uint32_t tw = tmem_w + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(16 * cg);
+    const uint32_t ad_hi_u = smem_u32(Ad_hi), ad_lo_u = smem_u32(Ad_lo), aw_u = smem_u32(Aw), bw_u = smem_u32(Bw),
+                   wt_u = smem_u32(Wt);
+
+    const int Lin = a.Lin, LP = a.LP;
+    const long long qtot = (long long)a.p * Lin;
+    const long long ntiles = (qtot + FT_M - 1) / FT_M;
+    uint32_t dph = 0, wph = 0, tph = 0;
+    float acc[4][16];
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[l][k] = 0.f;
+
+    auto load_wt = [&](int l) {     // one thread: stream the transposed kernel of layer l into Wt
+        mbar_expect_tx(&wt_bar, FT_WLAYER_F * 4u);
+        bulk_g2s(Wt, a.wpk + (size_t)(4 + l) * FT_WLAYER_F, FT_WLAYER_F * 4u, &wt_bar);
+    };
+    if (tid == 0 && (long long)blockIdx.x < ntiles) load_wt(3);
+
+    // this thread's 16 rows inside a weight-gradient operand tile (float offsets): hi row f, lo row 64 + f
+    const int wofs = (pos >> 2) * (FB_LBO / 4) + (pos & 3);
+    bool first_tile = true;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long q = tile * FT_M + pos;
+        const bool valid = q < qtot;
+        const int r = valid ? (int)(q / Lin) : 0;
+        const int j = valid ? (int)(q - (long long)r * Lin) : 0;
+        const bool more = tile + gridDim.x < ntiles;
+
+        float g[16];
+        {   // G_3 = df (.) elu'(a_4)
+            const float* dsrc = a.df + ((size_t)r * NMA_C + 16 * cg) * LP + j;
+            const float* esrc = a.act[4] + ((size_t)r * NMA_C + 16 * cg) * LP + j;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const bool ok = valid && (16 * cg + k < NMA_C);
+                g[k] = ok ? dsrc[(size_t)k * LP] * elu_grad_from_out(__ldg(esrc + (size_t)k * LP)) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int l = 3; l >= 0; --l) {
+            const int nin = (l == 0) ? a.Cf_in : NMA_C;
+            float al[16];
+            {
+                const float* asrc = a.act[l] + ((size_t)r * nin + 16 * cg) * LP + j;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    al[k] = (valid && (16 * cg + k < nin)) ? __ldg(asrc + (size_t)k * LP) : 0.f;
+            }
+            // the previous weight-gradient MMAs still read Aw / Bw: wait for them, then drain their accumulator
+            if (l < 3 || !first_tile) {
+                mbar_wait_backoff(&wbar, wph);
+                wph ^= 1u;
+                tc_fence_after();
+                tmem_sum16(tw, [&](int k, float x) { acc[(l + 1) & 3][k] += x; });
+            }
+            // ---- stage the operands of layer l ----
+            if (l > 0) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int ch = 4 * cg + cc;
+                    if (ch < TC_CCH) {
+                        const size_t o = ((size_t)ch * FT_M + pos) * 4;
+                        ft_split_store(Ad_hi + o, Ad_lo + o, g[4 * cc], g[4 * cc + 1], g[4 * cc + 2], g[4 * cc + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int row = 16 * cg + k;
+                const int o_hi = wofs + (row >> 3) * 32 + (row & 7) * 4;
+                const int o_lo = wofs + ((64 + row) >> 3) * 32 + (row & 7) * 4;
+                const float gh = tf32_hi(g[k]);
+                Bw[o_hi] = gh;
+                Bw[o_lo] = g[k] - gh;
+                const float av = (row == NMA_C) ? 1.f : al[k];       // row 50: ones -> bias gradient
+                const float ah = tf32_hi(av);
+                Aw[o_hi] = ah;
+                Aw[o_lo] = av - ah;
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) {
+                if (l > 0) {
+                    mbar_wait_backoff(&wt_bar, tph);
+                    tph ^= 1u;
+                    ft_issue_layer(ad_hi_u, ad_lo_u, wt_u, TC_CCH / 2, tmem_d, &dbar);
+                }
+                tc_fence_after();
+                if (elect_one()) {
+                    constexpr uint32_t idesc_wide = umma_idesc_tf32(FT_M, 2 * TC_N, 0, 0);
+                    const uint32_t a0 = desc_lo(aw_u, FB_LBO), b0 = desc_lo(bw_u, FB_LBO);
+                    const uint32_t hi32 = desc_hi(128u);
+#pragma unroll 4
+                    for (int ks = 0; ks < FT_M / 8; ++ks) {
+                        const uint32_t step = (uint32_t)ks * (2u * FB_LBO / 16u);
+                        umma_tf32(tmem_w, desc_pack(a0 + step, hi32), desc_pack(b0 + step, hi32), idesc_wide, ks ? 1u : 0u);
+                    }
+                    tc_commit(&wbar);
+                }
+                __syncwarp();
+            }
+            if (l > 0) {
+                mbar_wait_backoff(&dbar, dph);
+                dph ^= 1u;
+                tc_fence_after();
+                // the data-gradient MMAs are done with Wt: fetch the next layer's kernel (layer 3 of the next tile after layer 1)
+                if (tid == 0) {
+                    if (l > 1) load_wt(l - 1);
+                    else if (more) load_wt(3);
+                }
+                tmem_sum16(td, [&](int k, float x) { g[k] = x * elu_grad_from_out(al[k]); });
+            }
+        }
+        first_tile = false;
+    }
+    if (!first_tile) {   // drain the last tile's layer 0
+        mbar_wait_backoff(&wbar, wph);
+        tc_fence_after();
+        tmem_sum16(tw, [&](int k, float x) { acc[0][k] += x; });
+    }
+    // TMEM lane = operand row: f (hi rows 0..63) or 64 + f (lo rows); column 16*cg + k = output channel g
+    {
+        const int f = pos & 63;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int nin = (l == 0) ? a.Cf_in : NMA_C;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int gc = 16 * cg + k;
+                if (gc < NMA_C) {
+                    if (f < nin) atomicAdd(a.gw[l] + f * NMA_C + gc, acc[l][k]);
+                    else if (pos == NMA_C) atomicAdd(a.gb[l] + gc, acc[l][k]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, FT_TMEM_COLS);
+}
+
+int launch_feat_bwd_tc(nma_handle_s* h, int i, const float* params, int p, float* gp, cudaStream_t st) {
+    (void)params;
+    const FlowDims& d = h->fd[i];
+    FeatBwdTcArgs a;
+    a.wpk = h->ws[i].wtc_feat;
+    for (int l = 0; l < 5; ++l) a.act[l] = h->ws[i].a[l];
+    a.df = h->ws[i].df;
+    for (int l = 0; l < 4; ++l) {
+        a.gw[l] = gp + h->po[i].featw[l];
+        a.gb[l] = gp + h->po[i].featb[l];
+    }
+    a.Lin = d.Lin; a.LP = d.LP; a.Cf_in = h->Cf_in; a.p = p;
+    const long long ntiles = ((long long)p * d.Lin + FT_M - 1) / FT_M;
+    const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
+    const int smem = (2 * FT_A_F + 2 * FB_OPW_F + FT_WLAYER_F) * 4;
+    static int configured = 0;
+    if (configured < smem) {
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_feat_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    k_feat_bwd_tc<<<grid, FB_THREADS, smem, st>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
