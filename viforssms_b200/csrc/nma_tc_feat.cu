@@ -99,7 +99,11 @@ struct FeatTcArgs {
 // ELU with ONE transcendental-pipe op: exp(z) - 1 through ex2.approx.  Absolute error <= ~1e-7 on outputs in (-1, 0]
 // (expm1f's relative accuracy near 0 is irrelevant downstream: the value is added to O(1) sums).  ncu showed the XU pipe
 // at 92 % with expm1f (its range reduction converts through the same pipe), i.e. the whole kernel waiting on it.
-__device__ __forceinline__ float elu_fast(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+// Branch-free (a select, not a divergent branch per element).
+__device__ __forceinline__ float elu_fast(float z) {
+    const float e = __expf(fminf(z, 0.f)) - 1.f;
+    return z > 0.f ? z : e;
+}
 
 __device__ __forceinline__ void ft_split_store(float* hi_dst, float* lo_dst, float a, float b, float c, float d) {
     const float4 h4 = make_float4(tf32_hi(a), tf32_hi(b), tf32_hi(c), tf32_hi(d));
@@ -451,6 +455,28 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
     const int wofs = (pos >> 2) * (FB_LBO / 4) + (pos & 3);
     bool first_tile = true;
 
+    // 16 channels [16*cg, 16*cg + 16) of activation a_l at one position (zero outside the layer's width / the tile)
+    auto load_act = [&](float (&dst)[16], int l, bool ok, int r, int j) {
+        const int nin = (l == 0) ? a.Cf_in : NMA_C;
+        const float* src = a.act[l] + ((size_t)r * nin + 16 * cg) * LP + j;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dst[k] = (ok && (16 * cg + k < nin)) ? __ldg(src + (size_t)k * LP) : 0.f;
+    };
+    auto load_raw = [&](float (&dst)[16], const float* base, bool ok, int r, int j) {
+        const float* src = base + ((size_t)r * NMA_C + 16 * cg) * LP + j;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dst[k] = (ok && (16 * cg + k < NMA_C)) ? src[(size_t)k * LP] : 0.f;
+    };
+    float g[16], al[16];
+    {   // first tile: raw df and a_4
+        const long long q = (long long)blockIdx.x * FT_M + pos;
+        const bool ok = q < qtot;
+        const int r = ok ? (int)(q / Lin) : 0;
+        const int j = ok ? (int)(q - (long long)r * Lin) : 0;
+        load_raw(g, a.df, ok, r, j);
+        load_act(al, 4, ok, r, j);
+    }
+
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long q = tile * FT_M + pos;
         const bool valid = q < qtot;
@@ -458,26 +484,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
         const int j = valid ? (int)(q - (long long)r * Lin) : 0;
         const bool more = tile + gridDim.x < ntiles;
 
-        float g[16];
-        {   // G_3 = df (.) elu'(a_4)
-            const float* dsrc = a.df + ((size_t)r * NMA_C + 16 * cg) * LP + j;
-            const float* esrc = a.act[4] + ((size_t)r * NMA_C + 16 * cg) * LP + j;
+        // G_3 = df (.) elu'(a_4): the raw values were prefetched into g / al during layer 0 of the previous tile
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const bool ok = valid && (16 * cg + k < NMA_C);
-                g[k] = ok ? dsrc[(size_t)k * LP] * elu_grad_from_out(__ldg(esrc + (size_t)k * LP)) : 0.f;
-            }
-        }
+        for (int k = 0; k < 16; ++k) g[k] = (valid && (16 * cg + k < NMA_C)) ? g[k] * elu_grad_from_out(al[k]) : 0.f;
+        load_act(al, 3, valid, r, j);
 #pragma unroll
         for (int l = 3; l >= 0; --l) {
-            const int nin = (l == 0) ? a.Cf_in : NMA_C;
-            float al[16];
-            {
-                const float* asrc = a.act[l] + ((size_t)r * nin + 16 * cg) * LP + j;
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    al[k] = (valid && (16 * cg + k < nin)) ? __ldg(asrc + (size_t)k * LP) : 0.f;
-            }
             // the previous weight-gradient MMAs still read Aw / Bw: wait for them, then drain their accumulator
             if (l < 3 || !first_tile) {
                 mbar_wait_backoff(&wbar, wph);
@@ -485,7 +497,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
                 tc_fence_after();
                 tmem_sum16(tw, [&](int k, float x) { acc[(l + 1) & 3][k] += x; });
             }
-            // ---- stage the operands of layer l ----
+            // ---- stage the operands of layer l (al holds a_l, prefetched one layer ahead) ----
             if (l > 0) {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
@@ -500,7 +512,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
             for (int k = 0; k < 16; ++k) {
                 const int row = 16 * cg + k;
                 const int o_hi = wofs + (row >> 3) * 32 + (row & 7) * 4;
-                const int o_lo = wofs + ((64 + row) >> 3) * 32 + (row & 7) * 4;
+                const int o_lo = o_hi + 8 * 32;                    // row + 64
                 const float gh = tf32_hi(g[k]);
                 Bw[o_hi] = gh;
                 Bw[o_lo] = g[k] - gh;
@@ -532,6 +544,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
                 }
                 __syncwarp();
             }
+            // ---- prefetch while the MMAs run: a_{l-1}, or (after layer 0) the raw df / a_4 of the next tile ----
+            if (l > 0) {
+                load_act(al, l - 1, valid, r, j);
+            } else {
+                const long long qn = (tile + gridDim.x) * FT_M + pos;
+                const bool vn = qn < qtot;
+                const int rn = vn ? (int)(qn / Lin) : 0;
+                const int jn = vn ? (int)(qn - (long long)rn * Lin) : 0;
+                load_raw(g, a.df, vn, rn, jn);
+                load_act(al, 4, vn, rn, jn);
+            }
             if (l > 0) {
                 mbar_wait_backoff(&dbar, dph);
                 dph ^= 1u;
@@ -541,7 +564,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
                     if (l > 1) load_wt(l - 1);
                     else if (more) load_wt(3);
                 }
-                tmem_sum16(td, [&](int k, float x) { g[k] = x * elu_grad_from_out(al[k]); });
+                // G_{l-1} = dA_l (.) elu'(a_l); a_l is read back from the operand tile (hi + lo is exact), the
+                // registers that held it already carry the prefetch
+                tmem_sum16(td, [&](int k, float x) {
+                    const int row = 16 * cg + k;
+                    const int o_hi = wofs + (row >> 3) * 32 + (row & 7) * 4;
+                    const float e = Aw[o_hi] + Aw[o_hi + 8 * 32];
+                    g[k] = x * elu_grad_from_out(e);
+                });
             }
         }
         first_tile = false;
