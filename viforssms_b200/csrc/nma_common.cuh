@@ -124,7 +124,14 @@ int launch_theta_bwd(nma_handle_s* h, const float* params, const float* theta, i
 // ---------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float elu_f(float z) { return z > 0.f ? z : expm1f(z); }
+// ELU with ONE transcendental-pipe op: exp(z) - 1 through ex2.approx, as a select (no divergent branch per element).
+// Absolute error <= ~2e-7 on outputs in (-1, 0]; expm1f's relative accuracy near 0 is irrelevant downstream (the value
+// is added to O(1) sums) and costs ~15 XU-pipe operations per call: ncu showed that pipe at 92 % in every kernel
+// that applies an ELU per element (profiles/r01_feat_tc.md).
+__device__ __forceinline__ float elu_f(float z) {
+    const float e = __expf(fminf(z, 0.f)) - 1.f;
+    return z > 0.f ? z : e;
+}
 // derivative of ELU expressed through its output e = elu(z): z>0 -> 1, else e+1
 __device__ __forceinline__ float elu_grad_from_out(float e) { return e > 0.f ? 1.f : e + 1.f; }
 // tf.nn.softplus, numerically stable: max(x,0) + log1p(exp(-|x|))

@@ -96,15 +96,6 @@ struct FeatTcArgs {
     int XP0, p, L0, K, Cf_in, feat_off, save, F, ks0;
 };
 
-// ELU with ONE transcendental-pipe op: exp(z) - 1 through ex2.approx.  Absolute error <= ~1e-7 on outputs in (-1, 0]
-// (expm1f's relative accuracy near 0 is irrelevant downstream: the value is added to O(1) sums).  ncu showed the XU pipe
-// at 92 % with expm1f (its range reduction converts through the same pipe), i.e. the whole kernel waiting on it.
-// Branch-free (a select, not a divergent branch per element).
-__device__ __forceinline__ float elu_fast(float z) {
-    const float e = __expf(fminf(z, 0.f)) - 1.f;
-    return z > 0.f ? z : e;
-}
-
 __device__ __forceinline__ void ft_split_store(float* hi_dst, float* lo_dst, float a, float b, float c, float d) {
     const float4 h4 = make_float4(tf32_hi(a), tf32_hi(b), tf32_hi(c), tf32_hi(d));
     *reinterpret_cast<float4*>(hi_dst) = h4;
@@ -246,7 +237,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_feat_fwd_tc(FeatTcArgs fa, Se
                 tmem_ld32(ta + TC_N, c2);
                 const float* b = bias_sm + l * 64 + half * 32;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] = valid ? elu_fast(v[k] + c2[k] + b[k]) : 0.f;
+                for (int k = 0; k < 32; ++k) v[k] = valid ? elu_f(v[k] + c2[k] + b[k]) : 0.f;
             }
             if (fa.save && valid) {
                 float* dst = fa.a[i][l + 1] + ((size_t)r * NMA_C + half * 32) * LP + j;
