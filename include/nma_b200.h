@@ -32,6 +32,7 @@ extern "C" {
 #define NMA_MODEL_AR  0   /* AR.py:168-187 */
 #define NMA_MODEL_FHN 1   /* fitz_nag_NVP.py:232-266 */
 #define NMA_MODEL_SV  2   /* SV_dense.py:203-234 */
+#define NMA_MODEL_LV  3   /* lotka_volterra_partial_batch_fix_theta.py: nma_gather only; the step entry points return an error */
 
 /* objectives (which scalar is differentiated) */
 #define NMA_OBJ_ELBO    0 /* -sum_rows scale*(sde - logq + obs)   AR.py:184-185,228-229 */

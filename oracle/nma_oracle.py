@@ -12,6 +12,8 @@ numpy / torch-CPU ops, following the reference scripts line by line:
   pad_series_ar        AR.py:135-150           series padding (numpy, float64)
   sample_indices       AR.py:257-265           np.random.choice index draw
   gather_feed_ar       AR.py:267-288           window gather -> time_feats/mask/shift
+  pad_series_fhn/_sv/_lv, gather_feed_fhn/_sv/_lv  the same for fitz_nag_NVP.py:187-202,350-370, SV_dense.py:159-184,
+                       305-328 and lotka_volterra_partial_batch_fix_theta.py:203-222,478-503
   flow_forward         AR.py:24-35,44-110      base dist, IAF layer, Flow_Stack
                        fitz_nag_NVP.py:56-156  stride-2 head, interleave, Permute
                        SV_dense.py:37-89       delta-augmented features
@@ -19,9 +21,10 @@ numpy / torch-CPU ops, following the reference scripts line by line:
   adamax_step          optimisers/adamax.py:42-58 + AR.py:226-234 (global-norm clip)
 
 PARITY STATUS.  The numpy half (padding, index draw, gather, data generation) is
-PINNED: tests/golden/ar_golden.npz holds what the reference's own unmodified
-code fed to its session (tests/golden/make_golden.py runs AR.py's VI_SSM.train
-under a stub `tensorflow`).  The torch half (flow, ELBO, gradients, Adamax) is
+PINNED: tests/golden/{ar,fhn,sv,lv}_golden.npz hold what the reference's own
+unmodified code fed to its session (tests/golden/make_golden.py and
+make_golden_models.py run AR.py / fitz_nag_NVP.py / SV_dense.py /
+lotka_volterra_partial_batch_fix_theta.py under a stub `tensorflow`).  The torch half (flow, ELBO, gradients, Adamax) is
 "parity unpinned": the reference records no ELBO / gradient / parameter value
 anywhere and its TF graph cannot be executed here; it is pinned only by fp64
 autograd + gradcheck of this restatement (tests/test_oracle.py).
@@ -143,6 +146,37 @@ def gather_feed_sv(pads, batch_select, L0, B):
     shift = np.stack([pads["shift_vals"][0, i:i + B + 1] for i in batch_select], axis=0)
     dim_one = np.stack([pads["obs"][i:i + B + 1] for i in batch_select], axis=0)
     return time_feats, mask, shift, dim_one
+
+
+def pad_series_lv(obs, time_till, x0_mean, dt, T, target_dims, p_val, F, K, fw) -> Dict[str, object]:
+    """lotka_volterra_partial_batch_fix_theta.py:186,203-222 (flow_dims = 2).  Unlike the FHN script the time channel
+    starts at 0 and is repeated 2*p_val times, the lead of time_till stops before 0, and bin_feats is 0 on the pad and
+    1 on the series."""
+    D = 2
+    obs_flatten = np.reshape(obs, -1, 'F')
+    store = []
+    for i in range(0, fw * 5, 5):
+        store.append(np.concatenate((np.zeros(F * K + D - i), obs_flatten, np.zeros(i)), axis=0))
+    time_pad = np.concatenate((np.zeros(F * K + D), np.repeat(np.arange(0, T + dt, dt), D * p_val)), axis=0)
+    time_till_pad = np.reshape(np.repeat(np.arange(np.round((F * K + D) * (dt / D), 1), 0., -dt), D), (D, -1), 'F')
+    return {
+        "obs_pad_store": store,
+        "time_pad": time_pad,
+        "time_till": np.reshape(np.concatenate((time_till_pad, time_till), 1), -1, 'F'),
+        "bin_feats": np.float32(np.concatenate((np.zeros(F * K + D), np.ones(target_dims * D * p_val)), axis=0)),
+        "mask_vals": np.concatenate((np.zeros((2, p_val)), np.ones((D, target_dims * p_val))), axis=1),
+        "shift_vals": np.concatenate((np.repeat(np.expand_dims(x0_mean, 1), p_val, 1),
+                                      np.zeros((D, target_dims * p_val))), axis=1),
+    }
+
+
+def sample_indices_lv(target_dims, B, p_val, rng=np.random) -> np.ndarray:
+    """lotka_volterra_partial_batch_fix_theta.py:478-479: always without replacement, candidates over p_val series."""
+    return rng.choice(np.arange(0, target_dims * p_val, B), size=p_val, replace=False)
+
+
+# the LV window gather (lotka_volterra_partial_batch_fix_theta.py:481-503) is statement for statement the FHN one
+gather_feed_lv = gather_feed_fhn
 
 
 # ----------------------------------------------------------------------------

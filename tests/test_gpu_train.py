@@ -118,3 +118,73 @@ def test_stepper_sharded_series_matches_unsharded_windows():
         assert torch.equal(got, want)
     finally:
         st.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# FitzHugh-Nagumo and stochastic-volatility facades (fitz_nag_NVP.py / SV_dense.py surfaces)
+# ---------------------------------------------------------------------------------------------------
+
+def _fhn_model(N=2000, p=16, K=10, B=20, F=2, fw=3, pre_train=False, early_stopping=5):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import synth
+    from viforssms_b200.theta_flow import ThetaFlow
+    from fitz_nag_NVP import VI_SSM
+    obs, obs_bin, tt = synth.fhn_inputs(N)
+    np.random.seed(1)
+    theta_dist = ThetaFlow(5, 4, 0.0, 1.0, "elu")
+    m = VI_SSM(obs, obs_bin, tt, np.array([2.0, 3.0]), theta_dist, [(0., 10.)] * 5, 0.1, N * 0.1, p, K, B, [50] * 5, N,
+               F, fw, learn_rate=1e-4, pre_train=pre_train, early_stopping=early_stopping)
+    m.build_flow()
+    return m
+
+
+def test_fhn_facade_pretrains_trains_and_exports_paths(tmp_path):
+    m = _fhn_model()
+    w0 = m.blob.clone()
+    th0 = m.blob[m.n_nma:].clone()
+    for _ in range(3):                                   # the two pre-train optimisers in one step
+        assert m._iteration(m._draw(), pre_train=True)
+    assert not torch.equal(m.blob[:m.n_nma], w0[:m.n_nma]) and not torch.equal(m.blob[m.n_nma:], th0)
+    assert all(float(s[0].abs().sum()) > 0 for s in (m.slots["pre_path"], m.slots["pre_theta"]))
+    assert float(m.slots["pre_theta"][0][:m.n_nma].abs().sum()) == 0.0     # t2 touches the theta flow only
+    m.train(str(tmp_path / "train"), str(tmp_path / "model_saves" / "fhn.ckpt"))
+    assert torch.isfinite(m.blob).all()
+    assert set(m.scalars) == {"loss/ELBO", "loss/SDE_log_prob", "loss/theta_log_prob", "loss/obs_log_prob",
+                              "loss/path_log_prob", "optimize/global_norm"}
+    assert all(np.isfinite(float(v)) for v in m.scalars.values())
+    paths = m.save_paths(str(tmp_path / "paths.txt"))
+    assert paths.shape == (m.p, 2, 2000) and np.isfinite(paths).all()
+    assert np.loadtxt(tmp_path / "paths.txt").shape == (m.p, 4000)
+    m.save(str(tmp_path / "ck.pt"))
+    w1 = m.blob.clone()
+    m.blob.zero_()
+    m.load(str(tmp_path / "ck.pt"))
+    assert torch.equal(m.blob, w1)
+
+
+def test_sv_facade_pretrains_trains_and_exports_paths(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import synth
+    from viforssms_b200.theta_flow import ThetaFlow
+    from SV_dense import VI_SSM
+    obs = synth.sv_prices(686)[100:]                     # 586 prices: T = 585 = 45 * 13, every window fits the series
+    T = obs.shape[0] - 1                                 # (as 1508 = 29 * 52 does in the script, SV_dense.py:404-413)
+    np.random.seed(1)
+    theta_dist = ThetaFlow(4, 5, 0.0, 1.0, "relu")
+    m = VI_SSM(obs, -8.5, theta_dist, [(0., 10.0)] * 4, 1.0, T, 24, 10, 13, [50] * 5, T, 3, 2, learn_rate=1e-4,
+               pre_train=False, early_stopping=5)
+    m.build_flow()
+    assert m.eng.tensor_cores
+    for _ in range(3):
+        m._iteration(m._draw(), pre_train=True)
+    m.train(str(tmp_path / "train"), str(tmp_path / "model_saves" / "sv.ckpt"))
+    assert torch.isfinite(m.blob).all()
+    assert set(m.scalars) == {"loss/ELBO", "loss/SDE_log_prob", "loss/theta_log_prob", "loss/path_log_prob",
+                              "optimize/global_norm"}
+    paths = m.save_paths(str(tmp_path / "paths.txt"))
+    n = len(np.arange(0, T, 13)) * 13
+    assert paths.shape == (m.p, 2, n) and np.isfinite(paths).all()
+    # component 0 is the observed price itself, component 1 the latent log-volatility
+    assert np.allclose(paths[0, 0, :T - 1], obs[1:T], rtol=1e-6)

@@ -18,6 +18,7 @@ from typing import Dict, List, Tuple
 MODEL_AR = 0
 MODEL_FHN = 1
 MODEL_SV = 2
+MODEL_LV = 3      # Lotka-Volterra: feed (A0/A1) only so far; the flow and its ELBO are not built
 
 MAX_CHAN = 32
 MAX_ARRAYS = 8
@@ -226,3 +227,19 @@ def sv_config(p=200, K=50, B=52, F=5, H=3, feat_window=5, target_dims=1508, dt=1
         scale=float(target_dims) / float(B), dt=dt, obs_std=1.0, x0=(x0, 0.0), n_arrays=4,
         chan_array=[0] * fw + [1, 2, 3], chan_offset=[5 * i for i in range(fw)] + [0, 0, 0],
         obs_array=0, bin_array=0, head_offset=F * K)
+
+
+def lv_config(p=1, K=20, B=151, F=3, H=3, feat_window=10, target_dims=151, dt=0.2, x0=(91.0, 99.0)) -> NMAConfig:
+    """The Lotka-Volterra model of lotka_volterra_partial_batch_fix_theta.py (p_val = 1: one subsequence that is the
+    whole series).  Only the feed is built for this model: `NMAEngine.gather` reproduces time_feats / mask / shift
+    bit-exactly; the flow (transposed feature MLP, 364-channel conv) and the bivariate ELBO are the next widening
+    step, and `elbo_fwd_bwd` fails loudly for MODEL_LV.
+
+    Base arrays (ibid. :203-222): as the FHN model, except that bin_feats is 0 on the pad and 1 on the series, the
+    time channel starts at 0, and the lead of time_till stops before 0.  Channel order :497-498."""
+    fw = feat_window
+    return NMAConfig(
+        model=MODEL_LV, p=p, K=K, B=B, D=2, F=F, H=H, bn=1, Cf=fw + 3, feat_aug=0, dtheta=4,
+        scale=float(target_dims) / float(B), dt=dt, obs_std=1.0, x0=(float(x0[0]), float(x0[1])), n_arrays=5,
+        chan_array=[0] * fw + [1, 2, 3], chan_offset=[5 * i for i in range(fw)] + [0, 0, 0],
+        obs_array=0, bin_array=4)

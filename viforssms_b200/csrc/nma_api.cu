@@ -241,6 +241,14 @@ static int check_step_args(nma_handle h, int p, const void* a, const void* b, co
     if (!h->base[0]) { nma_set_error("nma_set_series has not been called"); return -1; }
     return 0;
 }
+static int check_model_built(nma_handle h) {
+    if (h->cfg.model < NMA_MODEL_AR || h->cfg.model > NMA_MODEL_SV) {
+        nma_set_error("model %d: only the feed (nma_gather) is built for this model; the Lotka-Volterra flow "
+                      "(transposed feature MLP, 364-channel conv) and its bivariate ELBO are not", h->cfg.model);
+        return -3;
+    }
+    return 0;
+}
 
 extern "C" int nma_gather(nma_handle h, const int64_t* d_idx, int32_t p, float* d_tf, float* d_mask, float* d_shift,
                           void* stream) {
@@ -264,6 +272,7 @@ extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float
                                 float* d_lf, float* d_grad_params, float* d_grad_theta, uint32_t* d_flags,
                                 void* stream) {
     if (check_step_args(h, p, d_params, d_eps, d_theta, d_idx)) return -1;
+    if (check_model_built(h)) return -3;
     if (!d_terms || !d_grad_params || !d_grad_theta) { nma_set_error("null output pointer"); return -1; }
     if (objective < 0 || objective > 2) { nma_set_error("unknown objective %d", objective); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -308,6 +317,7 @@ extern "C" int64_t nma_launch_count(void) { return g_launches; }
 extern "C" int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
                                  const int64_t* d_idx, int32_t p, float* d_terms, float* d_lf, void* stream) {
     if (check_step_args(h, p, d_params, d_eps, d_theta, d_idx)) return -1;
+    if (check_model_built(h)) return -3;
     if (!d_terms) { nma_set_error("null output pointer"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     int rc;

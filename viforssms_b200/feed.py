@@ -84,16 +84,41 @@ def sv_base_arrays(obs, dt: float, T: float, F: int, K: int, fw: int, exact_var:
     """Base arrays of the SV model in the order `config.sv_config` expects (SV_dense.py:159-184).
     `exact_var=True` evaluates the rolling variances with the reference's own np.var loop (bit-exact);
     False uses the O(T) prefix-sum form (agrees to ~1e-12 relative)."""
-    obs = np.asarray(obs, dtype=np.float64)
+    obs_in = np.asarray(obs)                 # the script keeps the series in float32 (NP_DTYPE, SV_dense.py:404) and
+    obs = obs_in.astype(np.float64)          # np.var / the first differences run in THAT precision (pinned by sv_golden.npz)
     obs_pad = np.concatenate((np.zeros(F * K), obs, np.zeros(5 * max(fw - 1, 0))))
     time_pad = np.concatenate((np.zeros(F * K + 1), np.arange(0.1, T + dt, dt)))
     obs_diff = obs[1:] - obs[:-1]
     if exact_var:
-        var_store = np.array([np.var(obs[i:i + K]) for i in range(0, obs.shape[0] - K)])
-        var_diff_store = np.array([np.var(obs_diff[i:i + K]) for i in range(0, obs_diff.shape[0] - K)])
+        diff_in = obs_in[1:] - obs_in[:-1]
+        var_store = np.array([np.var(obs_in[i:i + K]) for i in range(0, obs_in.shape[0] - K)])
+        var_diff_store = np.array([np.var(diff_in[i:i + K]) for i in range(0, diff_in.shape[0] - K)])   # log below too
     else:
         var_store = rolling_var(obs, K)
         var_diff_store = rolling_var(obs_diff, K)
     var_pad = np.concatenate((np.zeros((F + 1) * K), var_store))
     var_diff_pad = np.concatenate((np.zeros((F + 1) * K), np.log(var_diff_store), np.zeros(1)))
     return [obs_pad, time_pad, var_pad, var_diff_pad]
+
+
+def lv_base_arrays(obs, obs_bin, time_till, dt: float, T: float, target_dims: int, F: int, K: int, fw: int,
+                   p_val: int = 1) -> List[np.ndarray]:
+    """Base arrays of the Lotka-Volterra model in the order `config.lv_config` expects
+    (lotka_volterra_partial_batch_fix_theta.py:186,203-222).  obs, obs_bin, time_till: [2, target_dims * p_val];
+    unobserved entries of obs already replaced by 1 + softplus(-2) (ibid. :661-663)."""
+    D = 2
+    P2 = F * K + D
+    obs_flat = np.reshape(np.asarray(obs, dtype=np.float64), -1, 'F')
+    obs_pad = np.concatenate((np.zeros(P2), obs_flat, np.zeros(5 * max(fw - 1, 0))))
+    bin_feats = np.concatenate((np.zeros(P2), np.ones(target_dims * D * p_val)))
+    time_pad = np.concatenate((np.zeros(P2), np.repeat(np.arange(0, T + dt, dt), D * p_val)))
+    lead = np.reshape(np.repeat(np.arange(np.round(P2 * (dt / D), 1), 0., -dt), D), (D, -1), 'F')
+    tt = np.reshape(np.concatenate((lead, np.asarray(time_till, dtype=np.float64)), 1), -1, 'F')
+    return [obs_pad, bin_feats, time_pad, tt, np.asarray(obs_bin, dtype=np.float64).reshape(-1)]
+
+
+def sample_indices_lv(target_dims: int, B: int, p_val: int, rng=None) -> np.ndarray:
+    """p_val subsequence starts from arange(0, target_dims * p_val, B), never with replacement
+    (lotka_volterra_partial_batch_fix_theta.py:471,478-479)."""
+    rng = np.random if rng is None else rng
+    return rng.choice(np.arange(0, target_dims * p_val, B), size=p_val, replace=False).astype(np.int64)

@@ -1,0 +1,314 @@
+"""`VI_SSM` facades of the FitzHugh-Nagumo (fitz_nag_NVP.py:158-448) and stochastic-volatility (SV_dense.py:139-402)
+scripts, re-hosted on the B200 library.
+
+Each class keeps the constructor arguments and the methods of the reference class of the same script
+(`build_flow`, `train`, `save`, `load`, `save_paths`) and the same side effects (TensorBoard scalars under the same
+tags, a checkpoint every 1000 iterations, posterior paths written with `np.savetxt` in the script's layout).  What
+`sess.run([train_step, merged], feed_dict)` does in the reference (fitz_nag_NVP.py:389-390, SV_dense.py:341-342)
+happens in `nma_elbo_fwd_bwd` + `nma_adamax_step`; the numpy window gather of every iteration is replaced by the
+device gather, fed only the subsequence starts, which are still drawn with the reference's own `np.random.choice`
+call on numpy's global legacy stream.
+
+Pre-training runs the scripts' TWO optimisers in the same step (fitz_nag_NVP.py:286-292,372-374;
+SV_dense.py:251-254,330-332): `(lf_sample - c)^2` over every variable and `(theta - theta*)^2` over the
+theta-flow variables, each with its own Adamax slots, both gradients taken at the pre-update values.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from datetime import datetime
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import feed
+from .config import OBJ_ELBO, OBJ_PATH_SQ, NMAConfig, fhn_config, param_layout, sv_config
+from .engine import NMAEngine
+from .theta_flow import ThetaFlow, prior_log_prob, prior_tensors
+from .trainer import glorot_blob
+
+
+class _ModelVISSM:
+    """Shared mechanics; the subclasses supply the configuration, the base arrays and the path layout."""
+
+    grad_clip = 2.5e11
+    pretrain_path_target = 0.0
+    theta_star: Sequence[float] = ()
+    theta_pos_index: Sequence[bool] = ()
+    has_obs_term = True
+
+    def _common(self, theta_dist: ThetaFlow, priors, p, kernel_len, batch_dims, network_dims, target_dims, no_flows,
+                feat_window, learn_rate, pre_train, device, seed, early_stopping):
+        if len(set(network_dims)) != 1:
+            raise ValueError("all network_dims must be equal (the reference only ever uses [50]*n)")
+        self.theta_dist = theta_dist
+        self.priors = list(priors)
+        self.p = int(p)
+        self.kernel_len = int(kernel_len)
+        self.batch_dims = int(batch_dims)
+        self.network_dims = list(network_dims)
+        self.target_dims = int(target_dims)
+        self.no_flows = int(no_flows)
+        self.feat_window = int(feat_window)
+        self.learn_rate = learn_rate
+        self.pre_train = pre_train
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.seed = seed
+        self.early_stopping = early_stopping
+        self.eng: Optional[NMAEngine] = None
+        self.scalars = {}
+        self.pre_train_count = 0
+
+    # supplied by the subclass -------------------------------------------------
+    cfg: NMAConfig
+
+    def _base_arrays(self):
+        raise NotImplementedError
+
+    def _paths_from_lf(self, lf: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------
+    def build_flow(self) -> None:
+        cfg = self.cfg
+        self.eng = NMAEngine(cfg, self.device)
+        self.eng.set_series(self._base_arrays())
+        g = torch.Generator().manual_seed(self.seed)
+        _, self.n_nma = param_layout(cfg)
+        self.blob = torch.cat([glorot_blob(cfg, g), self.theta_dist.init_values(g)]).to(self.device)
+        self.n_total = self.blob.numel()
+        zeros = lambda: (torch.zeros_like(self.blob), torch.zeros_like(self.blob))
+        self.slots = {"pre_path": zeros(), "pre_theta": zeros(), "main": zeros()}
+        self.grad = torch.zeros_like(self.blob)
+        self.grad2 = torch.zeros_like(self.blob)
+        self.theta_leaf = self.blob[self.n_nma:].detach().requires_grad_(True)
+        self.theta_dist.bind(self.theta_leaf)
+        self.out = self.eng.alloc_outputs(self.p)
+        self.out["grad_params"] = self.grad[:self.n_nma]
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(self.seed)
+        self.idx_dev = torch.empty(self.p, dtype=torch.int64, device=self.device)
+        self.prior_t = prior_tensors(self.priors, self.device)
+        self.theta_star_t = torch.tensor(list(self.theta_star), dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------
+    def _iteration(self, batch_select: np.ndarray, pre_train: bool) -> bool:
+        """One sess.run of the reference.  Returns False when the step met a non-finite transition density
+        (the FHN script restarts its pre-train counter on that, fitz_nag_NVP.py:378-381)."""
+        cfg = self.cfg
+        self.idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(batch_select, dtype=np.int64)))
+        z0 = self.theta_dist.base_sample(self.p, self.gen, self.device)
+        theta, logq_theta = self.theta_dist.sample_and_log_prob(z0)
+        eps = torch.randn(self.p, cfg.L0, device=self.device, generator=self.gen)
+        if pre_train:
+            out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), self.idx_dev,
+                                        objective=OBJ_PATH_SQ, path_target=self.pretrain_path_target, out=self.out)
+            # t1: (lf_sample - c)^2 reaches the theta-flow variables through the theta-bias of every flow layer
+            self.theta_leaf.grad = None
+            (out["grad_theta"] * theta).sum().backward(retain_graph=True)
+            self.grad[self.n_nma:].copy_(self.theta_leaf.grad)
+            # t2: (theta - theta*)^2, theta-flow variables only
+            self.theta_leaf.grad = None
+            ((theta - self.theta_star_t) ** 2).sum().backward()
+            self.grad2.zero_()
+            self.grad2[self.n_nma:].copy_(self.theta_leaf.grad)
+            m, v = self.slots["pre_path"]
+            self.eng.adamax_step(self.blob, self.grad, m, v, 1e-3, 0.9, clip=0.0)
+            m, v = self.slots["pre_theta"]
+            tail = slice(self.n_nma, self.n_total)
+            self.eng.adamax_step(self.blob[tail], self.grad2[tail], m[tail], v[tail], 1e-3, 0.9, clip=0.0)
+            return bool(torch.isfinite(out["terms"][:, 0]).all().item())
+        out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), self.idx_dev,
+                                    objective=OBJ_ELBO, out=self.out)
+        prior = prior_log_prob(theta, self.prior_t)
+        host_loss = (out["grad_theta"] * theta).sum() - (prior - logq_theta).sum()
+        self.theta_leaf.grad = None
+        host_loss.backward()
+        self.grad[self.n_nma:].copy_(self.theta_leaf.grad)
+        m, v = self.slots["main"]
+        norm = self.eng.adamax_step(self.blob, self.grad, m, v, self.learn_rate, 0.95, clip=self.grad_clip)
+        t = out["terms"]
+        scale = float(cfg.scale)
+        obs = t[:, 1] if self.has_obs_term else torch.zeros_like(t[:, 1])
+        elbo = scale * (t[:, 0] - t[:, 2] + obs) + prior.detach() - logq_theta.detach()
+        self.scalars = {"loss/ELBO": elbo.mean(), "loss/SDE_log_prob": scale * t[:, 0].mean(),
+                        "loss/theta_log_prob": logq_theta.detach().mean(),
+                        "loss/path_log_prob": scale * t[:, 2].mean(), "optimize/global_norm": norm.clone()[0]}
+        if self.has_obs_term:
+            self.scalars["loss/obs_log_prob"] = scale * t[:, 1].mean()
+        self._theta_last = theta.detach()
+        return True
+
+    def _draw(self) -> np.ndarray:
+        replace_bool = bool(self.batch_dims * self.p >= self.target_dims)
+        return np.random.choice(np.arange(0, self.target_dims, self.batch_dims), size=self.p, replace=replace_bool)
+
+    def _pretrain_done(self, run: int, finite: bool) -> bool:
+        raise NotImplementedError
+
+    def train(self, tensorboard_path, save_path, log_every: int = 1):
+        for d in (tensorboard_path, os.path.dirname(save_path)):
+            if d and not os.path.exists(d):
+                os.makedirs(d)
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter('%s/%s' % (tensorboard_path, datetime.now().strftime("%d:%m:%y-%H:%M:%S")))
+        except Exception:       # tensorboard not installed: train without event files
+            writer = None
+        run = 0
+        print("Training model...")
+        t_start = time.time()
+        while True:
+            batch_select = self._draw()
+            if self.pre_train:
+                if run == 0:
+                    print("Pre-training...")
+                finite = self._iteration(batch_select, pre_train=True)
+                if self._pretrain_done(run, finite):
+                    self.pre_train = False
+                    run = 0
+                    print("Finished pre-training...")
+                    self.save(save_path)
+            else:
+                self._iteration(batch_select, pre_train=False)
+                if writer is not None and run % log_every == 0:
+                    for tag, val in self.scalars.items():
+                        writer.add_scalar(tag, float(val), run)
+                    th = self._theta_last
+                    for i, pos in enumerate(self.theta_pos_index):
+                        writer.add_histogram("parameters/%d" % i, (th[:, i].exp() if pos else th[:, i]).cpu(), run)
+                if run >= self.early_stopping:
+                    break
+            if run % 1000 == 0:
+                self.save(save_path)
+            run += 1
+        if writer is not None:
+            writer.close()
+        self.train_seconds = time.time() - t_start
+
+    # ------------------------------------------------------------------
+    def save(self, PATH):
+        torch.save({"blob": self.blob.cpu(), "slots": {k: (m.cpu(), v.cpu()) for k, (m, v) in self.slots.items()},
+                    "numpy_rng": np.random.get_state(), "perms": [p.tolist() for p in self.theta_dist.perms]}, PATH)
+        print("Model saved")
+
+    def load(self, PATH):
+        self.pre_train = False
+        ck = torch.load(PATH, weights_only=False)
+        self.blob.copy_(ck["blob"].to(self.device))
+        for k, (m, v) in ck["slots"].items():
+            self.slots[k][0].copy_(m.to(self.device))
+            self.slots[k][1].copy_(v.to(self.device))
+        print("Model restored")
+
+    def sample_paths(self, temp_index: int) -> torch.Tensor:
+        """lf_sample [p, 2, batch_dims + 1] of p posterior samples of the subsequence starting at `temp_index`."""
+        cfg = self.cfg
+        idx = torch.full((self.p,), int(temp_index), dtype=torch.int64, device=self.device)
+        with torch.no_grad():
+            z0 = self.theta_dist.base_sample(self.p, self.gen, self.device)
+            theta, _ = self.theta_dist.sample_and_log_prob(z0)
+        eps = torch.randn(self.p, cfg.L0, device=self.device, generator=self.gen)
+        _, lf = self.eng.forward_paths(self.blob[:self.n_nma], eps, theta.contiguous(), idx)
+        return self._paths_from_lf(lf, idx)
+
+    def save_paths(self, PATH_obs):
+        """fitz_nag_NVP.py:409-448 / SV_dense.py:363-402: every row evaluates the same subsequence, the windows are
+        concatenated along time, the [p, 2, target_dims] tensor is written as [p, 2*target_dims]."""
+        path_store = []
+        for index_temp in np.arange(0, self.target_dims, self.batch_dims):
+            path_store.append(self.sample_paths(int(index_temp))[:, :, 1:].cpu().numpy())
+        paths = np.concatenate(path_store, axis=2)
+        with open(PATH_obs, 'w') as f:
+            np.savetxt(f, np.reshape(paths, (self.p, -1)))
+        return paths
+
+
+class FHN_VI_SSM(_ModelVISSM):
+    """fitz_nag_NVP.py:158-448 (class VI_SSM there)."""
+
+    grad_clip = 2.5e11                                                   # fitz_nag_NVP.py:321
+    pretrain_path_target = 0.0                                           # :288-289
+    theta_star = (math.log(2.0), 1.0, 1.5, math.log(0.5), math.log(0.3))  # :291-292
+    theta_pos_index = (True, False, False, True, True)                   # :307
+    has_obs_term = True
+
+    def __init__(self, obs, obs_bin, time_till, x0, theta_dist: ThetaFlow, priors, dt, T, p, kernel_len, batch_dims,
+                 network_dims, target_dims, no_flows, feat_window, learn_rate=1e-3, pre_train=True, train_paths=True,
+                 device: Optional[torch.device] = None, seed: int = 1, early_stopping=1e99):
+        self._common(theta_dist, priors, p, kernel_len, batch_dims, network_dims, target_dims, no_flows, feat_window,
+                     learn_rate, pre_train, device, seed, early_stopping)
+        self.flow_dims = 2
+        self.dt, self.T = float(dt), float(T)
+        self.kernel_ext = self.kernel_len * self.no_flows + self.flow_dims * self.batch_dims + 2
+        self._series = (np.asarray(obs), np.asarray(obs_bin), np.asarray(time_till))
+        self.cfg = fhn_config(p=self.p, K=self.kernel_len, B=self.batch_dims, F=self.no_flows,
+                              H=len(self.network_dims) - 2, feat_window=self.feat_window,
+                              target_dims=self.target_dims, dt=self.dt)
+        self.cfg.x0 = (float(x0[0]), float(x0[1]))
+
+    def _base_arrays(self):
+        obs, obs_bin, tt = self._series
+        return feed.fhn_base_arrays(obs, obs_bin, tt, self.dt, self.T, self.target_dims, self.no_flows,
+                                    self.kernel_len, self.feat_window)
+
+    def _paths_from_lf(self, lf, idx):
+        # lf_sample = transpose(reshape(lf_sample_init, [p, -1, 2]), [0, 2, 1])  (fitz_nag_NVP.py:283-284)
+        return lf.reshape(self.p, -1, 2).transpose(1, 2)
+
+    def _pretrain_done(self, run, finite):
+        self.pre_train_count = self.pre_train_count + 1 if finite else 0      # fitz_nag_NVP.py:378-381
+        return self.pre_train_count == 500
+
+
+class SV_VI_SSM(_ModelVISSM):
+    """SV_dense.py:139-402 (class VI_SSM there)."""
+
+    grad_clip = 1e7                                                      # SV_dense.py:283
+    pretrain_path_target = -7.0                                          # :251-252
+    theta_star = (0.001, -0.6, math.log(0.08), math.log(0.5))             # :253-254
+    theta_pos_index = (False, False, True, True)                         # :257
+    has_obs_term = False
+
+    def __init__(self, obs, x0, theta_dist: ThetaFlow, priors, dt, T, p, kernel_len, batch_dims, network_dims,
+                 target_dims, no_flows, feat_window, learn_rate=1e-3, pre_train=False,
+                 device: Optional[torch.device] = None, seed: int = 1, early_stopping=1e99, exact_var: bool = True):
+        self._common(theta_dist, priors, p, kernel_len, batch_dims, network_dims, target_dims, no_flows, feat_window,
+                     learn_rate, pre_train, device, seed, early_stopping)
+        self.dt, self.T, self.x0 = float(dt), float(T), float(x0)
+        self.kernel_ext = self.kernel_len * self.no_flows + self.batch_dims + 1
+        self.obs = np.asarray(obs)
+        last = ((self.target_dims - 1) // self.batch_dims) * self.batch_dims
+        if last + self.batch_dims + 1 > self.obs.shape[0]:
+            # the reference's np.concatenate of obs[index : index + batch_dims + 1] slices (SV_dense.py:327-328) raises
+            # on the ragged last window; say why instead
+            raise ValueError("the last subsequence (start %d, %d + 1 prices) runs past the series (%d prices): "
+                             "choose batch_dims dividing target_dims" % (last, self.batch_dims, self.obs.shape[0]))
+        self.exact_var = exact_var
+        self.cfg = sv_config(p=self.p, K=self.kernel_len, B=self.batch_dims, F=self.no_flows,
+                             H=len(self.network_dims) - 2, feat_window=self.feat_window,
+                             target_dims=self.target_dims, dt=self.dt, x0=self.x0)
+
+    def _base_arrays(self):
+        return feed.sv_base_arrays(self.obs, self.dt, self.T, self.no_flows, self.kernel_len, self.feat_window,
+                                   exact_var=self.exact_var)
+
+    def build_flow(self) -> None:
+        super().build_flow()
+        self._obs_dev = torch.from_numpy(self.obs.astype(np.float32)).to(self.device)
+
+    def _paths_from_lf(self, lf, idx):
+        # lf_sample = [dim_one, lf_sample_temp * mask + shift]  (SV_dense.py:243-245): the observed price and the
+        # latent log-volatility whose very first value is pinned to x0
+        B1 = self.batch_dims + 1
+        t = idx[:, None] + torch.arange(B1, device=self.device)[None, :]
+        dim_one = self._obs_dev[t.clamp(max=self._obs_dev.numel() - 1)]
+        first = (t == 0)
+        latent = torch.where(first, torch.full_like(lf[:, :B1], self.x0), lf[:, :B1])
+        return torch.stack([dim_one, latent], dim=1)
+
+    def _pretrain_done(self, run, finite):
+        return run == 1000                                               # SV_dense.py:335-338
