@@ -124,10 +124,10 @@ int launch_theta_bwd(nma_handle_s* h, const float* params, const float* theta, i
 // ---------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------
-// ELU with ONE transcendental-pipe op: exp(z) - 1 through ex2.approx, as a select (no divergent branch per element).
-// Absolute error <= ~2e-7 on outputs in (-1, 0]; expm1f's relative accuracy near 0 is irrelevant downstream (the value
-// is added to O(1) sums) and costs ~15 XU-pipe operations per call: ncu showed that pipe at 92 % in every kernel
-// that applies an ELU per element (profiles/r01_feat_tc.md).
+// ELU as exp(z) - 1 through ex2.approx (one MUFU) and a select: no divergent branch per element, ~6 instructions
+// instead of expm1f's ~30.  Absolute error <= ~2e-7 on outputs in (-1, 0]; expm1f's relative accuracy near 0 is
+// irrelevant downstream (the value is added to O(1) sums).  The fused feature kernel went from 314 M to 220 M warp
+// instructions per 2048 rows with this change alone (profiles/r01_feat_tc.md).
 __device__ __forceinline__ float elu_f(float z) {
     const float e = __expf(fminf(z, 0.f)) - 1.f;
     return z > 0.f ? z : e;
