@@ -205,13 +205,23 @@ def flow_forward(cfg, P: Dict[str, torch.Tensor], eps: torch.Tensor, theta: torc
     # init_dist.slp: sum over the last S slots of log N(eps; 0, 1)            (AR.py:33-34)
     logq = (-0.5 * eps[:, -S:] ** 2 - 0.5 * LOG2PI).sum(dim=1)
     for i in range(cfg.F):
-        ts = time_feats[:, i * K:, :]                                         # AR.py:192-193
-        if cfg.feat_aug:                                                      # SV_dense.py:53
-            f = torch.cat([ts[:, 1:, :], ts[:, 1:, :-2] - ts[:, :-1, :-2]], dim=2)
+        if cfg.model == 3:
+            # lotka_volterra_partial_batch_fix_theta.py:343-344,71-76: EVERY flow reads the whole window
+            # (ts_feats = self.time_feats, no i*K slice); 3 x dense(50) + dense(feat_dims = L_i - 1), then the
+            # [window position, unit] matrix is TRANSPOSED: unit m becomes the conv position, window position w a
+            # conv input channel
+            f = time_feats[:, :-1, :]
+            for l in range(4):
+                f = Fnn.elu(f @ P[f"f{i}.feat{l}.w"] + P[f"f{i}.feat{l}.b"])
+            f = f.transpose(1, 2)
         else:
-            f = ts[:, :-1, :]                                                 # AR.py:53
-        for l in range(4):                                                    # AR.py:54-56
-            f = Fnn.elu(f @ P[f"f{i}.feat{l}.w"] + P[f"f{i}.feat{l}.b"])
+            ts = time_feats[:, i * K:, :]                                     # AR.py:192-193
+            if cfg.feat_aug:                                                  # SV_dense.py:53
+                f = torch.cat([ts[:, 1:, :], ts[:, 1:, :-2] - ts[:, :-1, :-2]], dim=2)
+            else:
+                f = ts[:, :-1, :]                                             # AR.py:53
+            for l in range(4):                                                # AR.py:54-56
+                f = Fnn.elu(f @ P[f"f{i}.feat{l}.w"] + P[f"f{i}.feat{l}.b"])
         inp = torch.cat([x[:, :-1, None], f], dim=2)                          # AR.py:58-59
         W = P[f"f{i}.conv.w"]                                                 # [K, Cin, Cout]
         A = Fnn.conv1d(inp.transpose(1, 2), W.permute(2, 1, 0), P[f"f{i}.conv.b"]).transpose(1, 2)  # AR.py:61-62
@@ -290,7 +300,59 @@ def elbo_terms(cfg, x_final: torch.Tensor, theta: torch.Tensor, time_feats: torc
         s2 = math.sqrt(dt) * torch.exp(th[3]).expand_as(x1)
         sde_lp = (normal_logpdf(diff[:, 0, :], dt * d1, s1) + normal_logpdf(diff[:, 1, :], dt * d2, s2)).sum(dim=1)
         return sde_lp, torch.zeros_like(sde_lp), lf
+    if cfg.model == 3:      # lotka_volterra_partial_batch_fix_theta.py:265-332,346-371
+        sde_lp, obs_lp, _, lf = lv_terms(cfg, x_final, theta, time_feats, extra)
+        return sde_lp, obs_lp, lf
     raise ValueError("unknown model")
+
+
+def lv_terms(cfg, x_final, theta, time_feats, extra):
+    """Lotka-Volterra (fixed theta).  Returns (sde_log_prob incl. the x0 term, obs_log_prob, the log-det term that
+    lf_log_prob receives on top of the flow's own logq, lf_sample [p,2,B+1]).
+
+    Bijector conventions (SURVEY Appendix D): Chain composes right to left; Softplus.ildj(y) = -log(1 - exp(-y));
+    the chains' log-det is summed over the two components of each state ("event").  theta = softplus of the script's
+    constants, constant across rows (ibid. :190)."""
+    B, dt, p = cfg.B, cfg.dt, x_final.shape[0]
+    neg = x_final.reshape(p, -1, 2).transpose(1, 2)                           # :350-351  [p,2,B+1]
+    lf = (Fnn.softplus(neg) + 1.0) * extra["mask"] + extra["shift"]           # :355-358,367
+
+    def ildj(y):            # of z -> 1 + softplus(z [- 1]) evaluated at y: -log(1 - exp(-(y - 1)))
+        return -torch.log(-torch.expm1(-(y - 1.0)))
+
+    def inv(y):             # inverse of Chain([Affine(+1), Softplus, Affine(-1)]): 1 + softplus^-1(y - 1)   (:307-314)
+        return y + torch.log(-torch.expm1(-(y - 1.0)))      # = 1 + log(exp(y - 1) - 1), without the overflow
+    extra_logq = ildj(lf[:, :, 1:]).reshape(p, -1).sum(dim=1)                 # :369-370
+    th = [theta[:, k:k + 1] for k in range(4)]
+    # observations (:266-272): y ~ 1 + softplus(N(x, theta3 x) - 1)
+    obs_eval = time_feats[:, -2 * B:, 0].reshape(p, -1, 2).transpose(1, 2)
+    loc = lf[:, :, 1:]
+    y_lp = normal_logpdf(inv(obs_eval), loc, th[3][:, None, :] * loc) + ildj(obs_eval)
+    obs_lp = (y_lp * extra["bin_feed"]).reshape(p, -1).sum(dim=1)
+    # transitions (:274-314) between the states 1..B ("flow_head = lf_sample[:, :, 1:-1]")
+    head, nxt = lf[:, :, 1:-1], lf[:, :, 2:]
+    x1, x2 = head[:, 0, :], head[:, 1, :]
+    a1 = th[0] * x1 - th[1] * x1 * x2
+    a2 = th[1] * x1 * x2 - th[2] * x2
+    ca = torch.sqrt(th[0] * x1 + th[1] * x1 * x2)
+    cb = -th[1] * x1 * x2 / ca
+    cc = torch.sqrt(th[1] * x1 * x2 + th[2] * x2 - cb ** 2)
+    sq = math.sqrt(dt)
+    L11, L21, L22 = sq * ca, sq * cb, sq * cc                                 # chol = sqrt(dt) [[a,0],[b,c]]
+    d1 = inv(nxt[:, 0, :]) - (x1 + dt * a1)
+    d2 = inv(nxt[:, 1, :]) - (x2 + dt * a2)
+    # Bivariate_Normal.normal_log_prob (:54-58): det = prod(diag(chol))^2, cov_inv = inverse(chol chol^T), both from the
+    # un-jittered chol (the +1e-6 copy is stored but never used)
+    w1 = d1 / L11
+    w2 = (d2 - L21 * w1) / L22
+    log_det = 2.0 * (torch.log(L11) + torch.log(L22))
+    n_lp = -0.5 * log_det - 0.5 * (w1 ** 2 + w2 ** 2) - LOG2PI
+    sde_lp = (n_lp + ildj(nxt[:, 0, :]) + ildj(nxt[:, 1, :])).sum(dim=1)
+    # p(x0) (:316-326): transformed diagonal Gaussian on the first retained state lf[:, :, 1]
+    x0s = lf[:, :, 1]
+    mean = torch.as_tensor(cfg.x0, dtype=x_final.dtype)
+    x0_lp = (normal_logpdf(inv(x0s), mean, cfg.obs_std) + ildj(x0s)).sum(dim=1)   # x0_std rides in cfg.obs_std
+    return sde_lp + x0_lp, obs_lp, extra_logq, lf
 
 
 def objective(cfg, obj: int, P, eps, theta, time_feats, extra=None, path_target: float = 0.0):
@@ -301,7 +363,11 @@ def objective(cfg, obj: int, P, eps, theta, time_feats, extra=None, path_target:
     obj 2: sum (lf_sample - path_target)^2       [fitz_nag_NVP.py:288-289; SV_dense.py:251-252]
     """
     x_final, logq = flow_forward(cfg, P, eps, theta, time_feats)
-    sde, obs, lf = elbo_terms(cfg, x_final, theta, time_feats, extra)
+    if cfg.model == 3:
+        sde, obs, extra_logq, lf = lv_terms(cfg, x_final, theta, time_feats, extra)
+        logq = logq + extra_logq                                              # lf_log_prob, LV fix-theta :369-370
+    else:
+        sde, obs, lf = elbo_terms(cfg, x_final, theta, time_feats, extra)
     base = (-0.5 * eps[:, -cfg.S:] ** 2 - 0.5 * LOG2PI).sum(dim=1)
     terms = torch.stack([sde, obs, logq, base], dim=1)
     if obj == 0:

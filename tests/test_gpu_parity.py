@@ -497,3 +497,94 @@ def test_sv_step_parity(shape, objective, target, tc):
         assert err <= RTOL * max(want.norm().item(), 1e-6 * gn_all), (name, err, want.norm().item())
     gth = out["grad_theta"].cpu().double()
     assert (gth - ref["grad_theta"]).norm().item() <= RTOL * max(ref["grad_theta"].norm().item(), 1e-6 * gn_all)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Lotka-Volterra, fixed theta (configs[1]): transposed feature MLP (the conv sees 1 + window input channels), coupling
+# flow as FHN, softplus-transformed path with mask/shift, bivariate Euler-Maruyama density with a state-dependent
+# covariance, transformed-Gaussian observation term
+# ---------------------------------------------------------------------------------------------------
+
+def _lv_case(cfg, n_series_steps, dt, seed):
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    fw = cfg.Cf - 3
+    N = n_series_steps                       # target_dims * p_val: the rows' windows tile the concatenated series
+    T = (N - 1) * dt
+    t = np.arange(N, dtype=np.float64)
+    obs = np.stack([12.0 + 4.0 * np.sin(0.3 * t) + 0.3 * rs.standard_normal(N),
+                    9.0 + 3.0 * np.cos(0.3 * t) + 0.3 * rs.standard_normal(N)])
+    obs_bin = (rs.uniform(size=(2, N)) < 0.7).astype(np.float64)
+    obs = np.where(obs_bin > 0, obs, np.log1p(np.exp(-2.0)) + 1.0)      # unobserved -> 1 + softplus(-2) (:661-663)
+    tt = rs.uniform(0.0, 1.0, size=(2, N)).round(1)
+    x0 = np.array(cfg.x0)
+    arrays = feed.lv_base_arrays(obs, obs_bin, tt, dt, T, N, cfg.F, cfg.K, fw, p_val=1)
+    pads = O.pad_series_lv(obs, tt, x0, dt, T, N, 1, cfg.F, cfg.K, fw)
+    idx = np.arange(cfg.p, dtype=np.int64) * cfg.B
+    tf64, mask, shift, bin_feed = O.gather_feed_lv(pads, obs_bin, idx, cfg.L0, cfg.B)
+    layout, n = param_layout(cfg)
+    params = O.glorot_init(layout, n, g, torch.float32)
+    for name, (off, shape) in layout.items():
+        k = int(np.prod(shape))
+        if name.endswith(".b") or name.endswith(".beta"):
+            params[off:off + k] = 0.05 * torch.randn(k, generator=g)
+        if name.endswith(".gamma"):
+            params[off:off + k] = 1.0 + 0.1 * torch.randn(k, generator=g)
+    for i in range(cfg.F):                   # a head bias that puts the path near the populations (as pre-training does)
+        off, _ = layout[f"f{i}.head.b"]
+        params[off] = 3.0
+    eps = torch.randn(cfg.p, cfg.L0, generator=g)
+    theta = torch.tensor(np.log1p(np.exp([-1.0, -6.0, -1.0, -2.0])), dtype=torch.float32).repeat(cfg.p, 1)
+    return arrays, idx, layout, params, eps, theta, tf64, mask, shift, bin_feed
+
+
+@pytest.mark.parametrize("objective,target", [(0, 0.0), (2, 7.5)])
+@pytest.mark.parametrize("shape", [
+    dict(p=3, K=4, B=6, F=2, H=2, feat_window=2),
+    dict(p=2, K=20, B=31, F=3, H=3, feat_window=10),       # the script's kernel_len / depth / look-ahead, shorter series
+    dict(p=1, K=20, B=151, F=3, H=3, feat_window=10),      # the script's exact shape (:616-626): 364-slot window
+])
+def test_lv_step_parity(shape, objective, target):
+    from viforssms_b200.config import lv_config
+    dt = 0.2
+    N = shape["p"] * shape["B"]
+    cfg = lv_config(target_dims=shape["B"], dt=dt, x0=(11.0, 9.5), **shape)
+    arrays, idx, layout, params, eps, theta, tf64, mask, shift, bin_feed = _lv_case(cfg, N, dt, seed=13)
+    eng = _engine(cfg)
+    assert not eng.tensor_cores
+    assert eng.n_params == sum(int(np.prod(s)) for _, s in layout.values())
+    eng.set_series(arrays)
+    got_tf, got_mask, got_shift = eng.gather(idx)
+    assert np.array_equal(got_tf.cpu().numpy(), tf64.astype(np.float32))
+    assert np.array_equal(got_mask.cpu().numpy(), mask.astype(np.float32))
+    assert np.array_equal(got_shift.cpu().numpy(), shift.astype(np.float32))
+    f32 = lambda a: torch.from_numpy(a.astype(np.float32)).double()
+    extra = {"mask": f32(mask), "shift": f32(shift), "bin_feed": f32(bin_feed)}
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), f32(tf64), obj=objective,
+                           extra=extra, path_target=target)
+    dev = torch.device("cuda")
+    out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev),
+                           objective=objective, path_target=target)
+    torch.cuda.synchronize()
+    terms = out["terms"].cpu().double()
+    for k, name in enumerate(("sde", "obs", "logq", "base")):
+        want = ref["terms"][:, k]
+        tol = RTOL * max(1.0, want.abs().max().item())
+        assert (terms[:, k] - want).abs().max().item() <= tol, (name, terms[:, k], want)
+    # lf of this model is the transformed state lf_sample[d][t] at [2t + d]
+    want_lf = ref["lf"].transpose(1, 2).reshape(cfg.p, -1)
+    assert _rel(out["lf"].cpu(), want_lf) < RTOL
+    gp = out["grad_params"].cpu()
+    gn_all = ref["grad_params"].norm().item()
+    worst = 0.0
+    for name, (off, shape_) in layout.items():
+        k = int(np.prod(shape_))
+        want = ref["grad_params"][off:off + k]
+        err = (gp[off:off + k].double() - want).norm().item()
+        scale = max(want.norm().item(), 1e-6 * gn_all)
+        worst = max(worst, err / scale)
+        assert err <= RTOL * scale, (name, err, want.norm().item())
+    print("lv step parity: worst per-variable grad rel err %.2e" % worst)
+    # theta is a constant of this model (:190): no gradient flows to it in the reference; the library returns only the
+    # part through the theta-bias MLP, which the oracle isolates by differentiating the flow alone
+    eng.close()

@@ -163,10 +163,13 @@ def param_layout(cfg: NMAConfig) -> Tuple[Dict[str, Tuple[int, Tuple[int, ...]]]
         off += n
 
     for i in range(cfg.F):
+        # LV (lotka_volterra_partial_batch_fix_theta.py:71-82): the 4th feature layer is as wide as the flow's conv
+        # input (feat_dims = L_i - 1) and its TRANSPOSE feeds the conv, whose input channels are then 1 + (L0 - 1)
+        lv = cfg.model == MODEL_LV
         for l in range(4):
-            add(f"f{i}.feat{l}.w", (cfg.Cf_in if l == 0 else C, C))
-            add(f"f{i}.feat{l}.b", (C,))
-        add(f"f{i}.conv.w", (cfg.K, C + 1, C))
+            add(f"f{i}.feat{l}.w", (cfg.Cf_in if l == 0 else C, cfg.Lin(i) if (lv and l == 3) else C))
+            add(f"f{i}.feat{l}.b", (cfg.Lin(i) if (lv and l == 3) else C,))
+        add(f"f{i}.conv.w", (cfg.K, cfg.L0 if lv else C + 1, C))
         add(f"f{i}.conv.b", (C,))
         for l in range(3):
             add(f"f{i}.th{l}.w", (cfg.dtheta if l == 0 else C, C))

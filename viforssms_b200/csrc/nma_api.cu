@@ -45,10 +45,11 @@ static void compute_layout(nma_handle_s* h) {
     for (int i = 0; i < c.F; ++i) {
         FlowParamOff& po = h->po[i];
         for (int l = 0; l < 4; ++l) {
-            po.featw[l] = off; off += (int64_t)(l == 0 ? h->Cf_in : NMA_C) * NMA_C;
-            po.featb[l] = off; off += NMA_C;
+            const int nout = (l == 3) ? h->feat_out[i] : NMA_C;
+            po.featw[l] = off; off += (int64_t)(l == 0 ? h->Cf_in : NMA_C) * nout;
+            po.featb[l] = off; off += nout;
         }
-        po.convw = off; off += (int64_t)c.K * NMA_C1 * NMA_C;
+        po.convw = off; off += (int64_t)c.K * h->conv_cin * NMA_C;
         po.convb = off; off += NMA_C;
         for (int l = 0; l < 3; ++l) {
             po.thw[l] = off; off += (int64_t)(l == 0 ? c.dtheta : NMA_C) * NMA_C;
@@ -104,6 +105,12 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         d.NP = (d.N + 3) & ~3;
         if (i < cfg->F && d.N < 1) { delete h; nma_set_error("nma_create: window too short"); return -1; }
     }
+    h->is_lv = (cfg->model == NMA_MODEL_LV) ? 1 : 0;
+    h->LW = h->L0 - 1;
+    h->LWP = (h->LW + 3) & ~3;
+    h->conv_cin = h->is_lv ? 1 + h->LW : NMA_C1;
+    for (int i = 0; i < cfg->F; ++i) h->feat_out[i] = h->is_lv ? h->fd[i].Lin : NMA_C;
+    if (h->is_lv && cfg->D != 2) { delete h; nma_set_error("nma_create: the Lotka-Volterra model has flow_dims = 2"); return -1; }
     compute_layout(h);
     // tensor-core conv (nma_tc_conv.cu): 1-D flows whose operand tile fits in shared memory
     h->tc_ok = (cfg->D == 1 && cfg->K <= 190) ? 1 : 0;
@@ -121,22 +128,30 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     const int64_t p = cfg->p;
     int64_t total = 0;
     auto reserve = [&](int64_t floats) { int64_t o = total; total += align_up(floats * 4, 256); return o; };
-    struct Off { int64_t x, dx, a[5], h[NMA_MAXH + 1], s, dA, df, tb, dtb, wpk, wdpk, tin_hi, tin_lo, dat_hi, dat_lo, wtc_f, wtc_d, wtc_feat; } off[NMA_MAX_FLOWS + 1];
+    struct Off { int64_t x, dx, a[5], h[NMA_MAXH + 1], s, dA, df, df3, tb, dtb, wpk, wdpk, tin_hi, tin_lo, dat_hi, dat_lo, wtc_f, wtc_d, wtc_feat; } off[NMA_MAX_FLOWS + 1];
     for (int i = 0; i <= cfg->F; ++i) {
         const FlowDims& d = h->fd[i];
         const int64_t XP = (d.L + 3) & ~3;
         off[i].x = reserve(p * XP);
         off[i].dx = reserve(p * XP);
         if (i == cfg->F) break;
-        off[i].a[0] = reserve(p * cf_in * d.LP);
-        for (int l = 1; l < 5; ++l) off[i].a[l] = reserve(p * NMA_C * d.LP);
+        if (h->is_lv) {
+            off[i].a[0] = reserve(p * cf_in * h->LWP);
+            for (int l = 1; l < 4; ++l) off[i].a[l] = reserve(p * NMA_C * h->LWP);
+            off[i].a[4] = reserve(p * h->LW * d.LP);            // [window position w][unit m]: conv channel 1 + w
+            off[i].df3 = reserve(p * NMA_C * h->LWP);
+        } else {
+            off[i].a[0] = reserve(p * cf_in * d.LP);
+            for (int l = 1; l < 5; ++l) off[i].a[l] = reserve(p * NMA_C * d.LP);
+            off[i].df3 = 0;
+        }
         for (int l = 0; l <= cfg->H; ++l) off[i].h[l] = reserve(p * NMA_C * d.NP);
         off[i].s = reserve(p * d.NP);
         off[i].dA = reserve(p * NMA_C * d.NP);
-        off[i].df = reserve(p * NMA_C * d.LP);
+        off[i].df = reserve(p * (h->is_lv ? h->LW : NMA_C) * d.LP);
         off[i].tb = reserve(p * 3 * NMA_C);
         off[i].dtb = reserve(p * NMA_C);
-        off[i].wpk = reserve((int64_t)NMA_C1 * 5 * h->KP * 12);
+        off[i].wpk = reserve((int64_t)h->conv_cin * 5 * h->KP * 12);
         off[i].wdpk = reserve((int64_t)NMA_C * 6 * h->KP * 12);
         if (h->tc_ok) {
             const int64_t Q = (p * d.Lin + 255) / 256 * 256 + 640 + cfg->K;
@@ -170,6 +185,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         w.s = (float*)(base + off[i].s);
         w.dA = (float*)(base + off[i].dA);
         w.df = (float*)(base + off[i].df);
+        w.df3 = h->is_lv ? (float*)(base + off[i].df3) : nullptr;
         w.tb = (float*)(base + off[i].tb);
         w.dtb = (float*)(base + off[i].dtb);
         w.wpk = (float*)(base + off[i].wpk);
@@ -242,9 +258,8 @@ static int check_step_args(nma_handle h, int p, const void* a, const void* b, co
     return 0;
 }
 static int check_model_built(nma_handle h) {
-    if (h->cfg.model < NMA_MODEL_AR || h->cfg.model > NMA_MODEL_SV) {
-        nma_set_error("model %d: only the feed (nma_gather) is built for this model; the Lotka-Volterra flow "
-                      "(transposed feature MLP, 364-channel conv) and its bivariate ELBO are not", h->cfg.model);
+    if (h->cfg.model < NMA_MODEL_AR || h->cfg.model > NMA_MODEL_LV) {
+        nma_set_error("unknown model %d", h->cfg.model);
         return -3;
     }
     return 0;
@@ -261,7 +276,9 @@ static int forward_all(nma_handle_s* h, const float* params, const float* eps, c
     int rc;
     if ((rc = launch_pack_weights(h, params, save, st))) return rc;
     if ((rc = launch_theta_fwd(h, params, theta, p, st))) return rc;
-    if ((rc = launch_feat_fwd_eps(h, params, idx, eps, p, save, st))) return rc;
+    if ((rc = (h->is_lv ? launch_lv_feat_fwd(h, params, idx, eps, p, save, st)
+                        : launch_feat_fwd_eps(h, params, idx, eps, p, save, st))))
+        return rc;
     for (int i = 0; i < h->cfg.F; ++i)
         if ((rc = launch_conv_fwd(h, i, params, p, save, st))) return rc;
     return 0;
@@ -284,6 +301,13 @@ extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float
         return rc;
     for (int i = h->cfg.F - 1; i >= 0; --i) {
         if ((rc = launch_epi_bwd(h, i, d_params, p, objective, d_grad_params, st))) return rc;
+        if (h->is_lv) {
+            if ((rc = launch_lv_conv_dgrad(h, i, d_params, p, st))) return rc;
+            if ((rc = launch_lv_conv_wgrad(h, i, p, d_grad_params, st))) return rc;
+            if ((rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
+            if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
+            continue;
+        }
         if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, st) : launch_conv_dgrad(h, i, p, st)))) return rc;
         if ((rc = (h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, st) : launch_conv_wgrad(h, i, p, d_grad_params, st)))) return rc;
         if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;

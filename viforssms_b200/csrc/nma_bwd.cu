@@ -606,6 +606,7 @@ struct FeatBwdArgs {
     float* df;               // [p][50][LP]  in: d objective / d a4;  overwritten layer by layer
     float* gw[4]; float* gb[4];
     int Lin, LP, Cf_in, p, tile_pitch;
+    int top;                 // last dense(50) layer: 3; Lotka-Volterra: 2 (its 4th layer is the wide one, nma_lv.cu)
 };
 
 __global__ void __launch_bounds__(BWD_THREADS, 2) k_feat_bwd(FeatBwdArgs a) {
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) k_feat_bwd(FeatBwdArgs a) {
     // wider than 64 float4 columns (SV: 302 slots) needs more items than the CTA has threads, hence the loop
 
     for (int t = tid; t < 2 * NMA_C * tp; t += blockDim.x) smem[t] = 0.f;     // pad columns stay zero
-    for (int l = 3; l >= 0; --l) {
+    for (int l = a.top; l >= 0; --l) {
         const int nin = (l == 0) ? a.Cf_in : NMA_C;
         __syncthreads();
         if (l > 0) {    // Wt[g][fg][i] = W_l[f = 4i + fg][g]
@@ -745,6 +746,10 @@ int launch_feat_bwd(nma_handle_s* h, int i, const float* params, int p, float* g
     }
     for (int l = 0; l < 5; ++l) a.act[l] = h->ws[i].a[l];
     a.df = h->ws[i].df; a.Lin = d.Lin; a.LP = d.LP; a.Cf_in = h->Cf_in; a.p = p; a.tile_pitch = d.LP | 4;
+    a.top = 3;
+    if (h->is_lv) {          // three dense(50) layers over the whole window; df3 = d objective / d a3 (nma_lv.cu)
+        a.df = h->ws[i].df3; a.Lin = h->LW; a.LP = h->LWP; a.tile_pitch = h->LWP | 4; a.top = 2;
+    }
     const size_t smem = ((size_t)2 * NMA_C * a.tile_pitch + NMA_C * FB_WPITCH + 64 + NMA_C * NMA_C) * 4;
     static size_t configured = 0;
     if (configured < smem) {

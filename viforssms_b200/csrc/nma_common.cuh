@@ -38,6 +38,7 @@ struct FlowWs {
     float* s;        // [p][NP]     pre-softplus scale logits
     float* dA;       // [p][C][NP]  gradient w.r.t. the conv pre-activation
     float* df;       // [p][C][LP]  gradient w.r.t. the feature channels of the conv input
+    float* df3;      // LV only: [p][C][LWP] gradient w.r.t. the third feature activation (input of the wide 4th layer)
     float* tb;       // [p][3][C]   theta-MLP activations t1, t2, b(+conv bias)
     float* dtb;      // [p][C]      sum_m dA
     float* wpk;      // packed conv weights for the forward conv  [Cin=51][5][KP][12]
@@ -70,6 +71,11 @@ struct nma_handle_s {
     int use_tc;      // ... and is switched on (default; NMA_TC=0 or nma_set_tensor_cores(h, 0) selects the FP32 SIMT conv)
     int tc_nacc;     // 128-position accumulators per CTA (2 when the tile fits in shared memory, else 1)
     int use_tc_feat; // feature MLP on the tensor cores as well (needs use_tc; NMA_TC_FEAT=0 keeps the FP32 SIMT kernels)
+    // Lotka-Volterra (lotka_volterra_partial_batch_fix_theta.py:71-82): every flow's feature MLP runs over the whole
+    // window (LW = L0 - 1 positions), ends in a dense layer as wide as the flow's conv input and is transposed, so the
+    // conv has 1 + LW input channels.  For the other models conv_cin = 51 and feat_out[i] = 50.
+    int is_lv, conv_cin, LW, LWP;
+    int feat_out[NMA_MAX_FLOWS];
 };
 
 // device-side copy of what kernels need about the series and the channel table
@@ -120,6 +126,12 @@ int launch_conv_wgrad(nma_handle_s* h, int flow, int p, float* grad_params, cuda
 int launch_feat_bwd(nma_handle_s* h, int flow, const float* params, int p, float* grad_params, cudaStream_t st);
 int launch_theta_bwd(nma_handle_s* h, const float* params, const float* theta, int p, float* grad_params,
                      float* grad_theta, cudaStream_t st);
+// Lotka-Volterra instances (nma_lv.cu)
+int launch_lv_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
+                       cudaStream_t st);
+int launch_lv_conv_dgrad(nma_handle_s* h, int flow, const float* params, int p, cudaStream_t st);
+int launch_lv_conv_wgrad(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
+int launch_lv_feat4_bwd(nma_handle_s* h, int flow, const float* params, int p, float* grad_params, cudaStream_t st);
 
 // ---------------------------------------------------------------------------
 // small device helpers

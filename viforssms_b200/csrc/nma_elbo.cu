@@ -2,6 +2,7 @@
 // entropy term) as one warp-per-row segmented reduction, fused with the gradient of the chosen
 // objective w.r.t. the final flow sample and theta.
 //   AR  : AR.py:168-187            FHN : fitz_nag_NVP.py:232-266            SV : SV_dense.py:203-246
+//   LV  : lotka_volterra_partial_batch_fix_theta.py:265-371
 #include "nma_common.cuh"
 
 #define LOG2PI_F 1.8378770664093453f
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
     const long long win0 = (long long)a.sv.D * i0;
     float* dx = a.dxF + (size_t)r * a.XPF;
 
-    float sde = 0.f, obs = 0.f, base = 0.f;
+    float sde = 0.f, obs = 0.f, base = 0.f, lq_extra = 0.f;
     float gth[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d sde / d theta
     // coefficients of d objective / d (sde, obs) and the path-square objective
     float c_sde = 0.f, c_obs = 0.f, c_sq = 0.f;
@@ -140,6 +141,93 @@ __global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
             if (a.want_grad) { dx[2 * j] = g1; dx[2 * j + 1] = g2; }
             if (a.lf) { a.lf[(size_t)r * a.LF + 2 * j] = x1; a.lf[(size_t)r * a.LF + 2 * j + 1] = x2; }
         }
+    } else if (a.model == NMA_MODEL_LV) {
+        // Lotka-Volterra, fixed theta (lotka_volterra_partial_batch_fix_theta.py:265-371).  z[d][t] = x[2t+d] is the raw
+        // flow output, lf[d][t] = (softplus(z) + 1) * mask + shift the state (:355-358,367).  For t >= 1 (mask = 1)
+        // the inverse of the transition / x0 bijector chain at the state is simply z + 1 and every chain's
+        // inverse-log-det at the state is softplus(-z) per component.
+        //   terms[0] = sum_{t=1..B-1} log N2(z_{t+1} + 1; lf_t + dt alpha(lf_t), dt S(lf_t)) + ildj(lf_{t+1})  +  log p(x0 = lf_1)
+        //   terms[1] = sum_{t=1..B} bin * [log N(u_t; lf_t, theta3 lf_t) + ildj_obs],  u = 1 + softplus^-1(obs - 1)
+        //   logq    += sum_{t=1..B} softplus(-z_t)   (collected in `base`-independent `lq_extra`)
+        const float t0 = th[0], t1 = th[1], t2 = th[2], t3 = th[3];
+        const float dt = a.dt;
+        const long long tlen = a.sv.len[a.bin_array] / 2;
+        const float cq = (a.objective == NMA_OBJ_ELBO) ? a.scale : 0.f;     // d objective / d logq
+        for (int j = lane; j <= B; j += 32) {
+            const bool first = (i0 + j) == 0;
+            const float z1 = x[2 * j], z2 = x[2 * j + 1];
+            const float u1 = first ? a.x0a : softplus_f(z1) + 1.f;
+            const float u2 = first ? a.x0b : softplus_f(z2) + 1.f;
+            float g1 = 0.f, g2 = 0.f;        // d objective / d lf (chain to z below)
+            float h1 = 0.f, h2 = 0.f;        // d objective / d z directly (the z + 1 arguments and the log-dets)
+            if (j >= 1) {
+                // entropy correction and observation
+                lq_extra += softplus_f(-z1) + softplus_f(-z2);
+                h1 += cq * (-sigmoid_f(-z1));
+                h2 += cq * (-sigmoid_f(-z2));
+                const long long slot = win0 + (a.L0 - 2 * B) + 2 * (j - 1);
+                const float y1 = series_chan(a.sv, 0, slot), y2 = series_chan(a.sv, 0, slot + 1);
+                const float w1 = series_raw(a.sv, a.bin_array, i0 + (j - 1));
+                const float w2 = series_raw(a.sv, a.bin_array, tlen + i0 + (j - 1));
+                // u = 1 + softplus^-1(y - 1) = y + log(1 - exp(-(y - 1))) = y - ildj   (no exp of a population of ~100)
+                const float j1 = -logf(-expm1f(-(y1 - 1.f))), j2 = -logf(-expm1f(-(y2 - 1.f)));
+                const float v1 = y1 - j1, v2 = y2 - j2;
+                const float s1 = t3 * u1, s2 = t3 * u2;
+                const float q1 = (v1 - u1) / s1, q2 = (v2 - u2) / s2;
+                obs += w1 * (-0.5f * q1 * q1 - 0.5f * LOG2PI_F - logf(s1) + j1) +
+                       w2 * (-0.5f * q2 * q2 - 0.5f * LOG2PI_F - logf(s2) + j2);
+                // d/d loc with scale = theta3 * loc:  q * v / (theta3 loc^2) - 1 / loc
+                g1 += c_obs * w1 * (q1 * v1 / (s1 * u1) - 1.f / u1);
+                g2 += c_obs * w2 * (q2 * v2 / (s2 * u2) - 1.f / u2);
+            }
+            if (j == 1) {   // p(x0) on the first retained state: N(z + 1; x0_mean, x0_std) + softplus(-z)
+                const G1 p1 = gauss(z1 + 1.f, a.x0a, a.obs_std), p2 = gauss(z2 + 1.f, a.x0b, a.obs_std);
+                sde += p1.lp + p2.lp + softplus_f(-z1) + softplus_f(-z2);
+                h1 += c_sde * (-p1.dz - sigmoid_f(-z1));
+                h2 += c_sde * (-p2.dz - sigmoid_f(-z2));
+            }
+            if (j >= 2) {   // this state as the TARGET of the transition from t = j - 1
+                const float pz1 = x[2 * j - 2], pz2 = x[2 * j - 1];
+                const float p1 = softplus_f(pz1) + 1.f, p2 = softplus_f(pz2) + 1.f;     // j - 1 >= 1: never the pinned state
+                const float s11 = t0 * p1 + t1 * p1 * p2, s12 = -t1 * p1 * p2, s22 = t1 * p1 * p2 + t2 * p2;
+                const float Dd = s11 * s22 - s12 * s12;
+                const float d1 = (z1 + 1.f) - (p1 + dt * (t0 * p1 - t1 * p1 * p2));
+                const float d2 = (z2 + 1.f) - (p2 + dt * (t1 * p1 * p2 - t2 * p2));
+                const float gm1 = (s22 * d1 - s12 * d2) / (dt * Dd), gm2 = (-s12 * d1 + s11 * d2) / (dt * Dd);   // Sigma^-1 delta
+                h1 += c_sde * (-gm1 - sigmoid_f(-z1));
+                h2 += c_sde * (-gm2 - sigmoid_f(-z2));
+            }
+            if (j >= 1 && j < B) {   // this state as the SOURCE of the transition to t = j + 1
+                const float nz1 = x[2 * j + 2], nz2 = x[2 * j + 3];
+                const float s11 = t0 * u1 + t1 * u1 * u2, s12 = -t1 * u1 * u2, s22 = t1 * u1 * u2 + t2 * u2;
+                const float Dd = s11 * s22 - s12 * s12;
+                const float d1 = (nz1 + 1.f) - (u1 + dt * (t0 * u1 - t1 * u1 * u2));
+                const float d2 = (nz2 + 1.f) - (u2 + dt * (t1 * u1 * u2 - t2 * u2));
+                const float Qf = s22 * d1 * d1 - 2.f * s12 * d1 * d2 + s11 * d2 * d2;
+                // log N2 = -log dt - 1/2 log D - Qf / (2 dt D) - log 2 pi   (det = (dt a c)^2 = dt^2 D, :50-58)
+                sde += -logf(dt) - 0.5f * logf(Dd) - 0.5f * Qf / (dt * Dd) - LOG2PI_F + softplus_f(-nz1) + softplus_f(-nz2);
+                const float gm1 = (s22 * d1 - s12 * d2) / (dt * Dd), gm2 = (-s12 * d1 + s11 * d2) / (dt * Dd);
+                // through the mean: d mu / d u = I + dt J_alpha
+                float e1 = gm1 * (1.f + dt * (t0 - t1 * u2)) + gm2 * (dt * t1 * u2);
+                float e2 = gm1 * (-dt * t1 * u1) + gm2 * (1.f + dt * (t1 * u1 - t2));
+                // through the covariance: dL/dv = -1/2 D_v / D - (Qf_v D - Qf D_v) / (2 dt D^2)
+                const float i2 = 1.f / (2.f * dt * Dd * Dd);
+                const float L11 = -0.5f * s22 / Dd - (d2 * d2 * Dd - Qf * s22) * i2;
+                const float L22 = -0.5f * s11 / Dd - (d1 * d1 * Dd - Qf * s11) * i2;
+                const float L12 = s12 / Dd - (-2.f * d1 * d2 * Dd + 2.f * Qf * s12) * i2;
+                e1 += L11 * (t0 + t1 * u2) + L12 * (-t1 * u2) + L22 * (t1 * u2);
+                e2 += L11 * (t1 * u1) + L12 * (-t1 * u1) + L22 * (t1 * u1 + t2);
+                g1 += c_sde * e1;
+                g2 += c_sde * e2;
+            }
+            g1 += c_sq * 2.f * (u1 - a.path_target);
+            g2 += c_sq * 2.f * (u2 - a.path_target);
+            if (a.want_grad) {
+                dx[2 * j] = first ? 0.f : fmaf(g1, sigmoid_f(z1), h1);
+                dx[2 * j + 1] = first ? 0.f : fmaf(g2, sigmoid_f(z2), h2);
+            }
+            if (a.lf) { a.lf[(size_t)r * a.LF + 2 * j] = u1; a.lf[(size_t)r * a.LF + 2 * j + 1] = u2; }
+        }
     } else {   // NMA_MODEL_SV
         // lf[0][t] = dim_one = obs[idx+t]; lf[1][t] = x*mask + shift  (SV_dense.py:245-246,327-328)
         const float t0 = th[0], t1 = th[1], e2 = expf(th[2]), s2 = sqrtf(a.dt) * expf(th[3]);
@@ -191,7 +279,7 @@ __global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
     sde = warp_sum(sde);
     obs = warp_sum(obs);
     base = warp_sum(base);
-    lsig = warp_sum(lsig);
+    lsig = warp_sum(lsig) - warp_sum(lq_extra);      // LV: lf_log_prob also carries the softplus log-det (:369-370)
 #pragma unroll
     for (int k = 0; k < 6; ++k) gth[k] = warp_sum(gth[k]);
     if (lane == 0) {

@@ -1,6 +1,7 @@
 // Forward kernels of the NMA ELBO step: weight packing, theta-bias MLP (AR.py:63-68), window gather +
 // feature MLP (AR.py:53-56, 267-283), fused conv + head + affine flow layer (AR.py:58-89), ELBO terms
 // (AR.py:168-187).  sm_100a only.
+#include <string.h>
 #include "nma_conv_core.cuh"
 #include "nma_flow_epi.cuh"
 
@@ -37,16 +38,16 @@ int launch_gather(nma_handle_s* h, const int64_t* idx, int p, float* tf, float* 
 // ---------------------------------------------------------------------------
 // weight packing: conv kernel [K][51][50] -> per input channel slabs [groups][KP][12]
 // ---------------------------------------------------------------------------
-__global__ void k_pack_fwd(const float* __restrict__ W, int K, int KP, float* __restrict__ out) {
-    // out[c][g][k][12], c<51, g<5
-    const int n = NMA_C1 * 5 * KP * CONV_WPAD;
+__global__ void k_pack_fwd(const float* __restrict__ W, int K, int KP, int cin, float* __restrict__ out) {
+    // out[c][g][k][12], c < cin (51; 1 + window for the Lotka-Volterra conv), g<5
+    const int n = cin * 5 * KP * CONV_WPAD;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         int q = t % CONV_WPAD;
         int k = (t / CONV_WPAD) % KP;
         int g = (t / (CONV_WPAD * KP)) % 5;
         int c = t / (CONV_WPAD * KP * 5);
         float v = 0.f;
-        if (q < 10 && k < K) v = W[((size_t)k * NMA_C1 + c) * NMA_C + g * 10 + q];
+        if (q < 10 && k < K) v = W[((size_t)k * cin + c) * NMA_C + g * 10 + q];
         out[t] = v;
     }
 }
@@ -71,9 +72,9 @@ __global__ void k_pack_dgrad(const float* __restrict__ W, int K, int KP, float* 
 int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
     if (h->use_tc) return launch_pack_weights_tc(h, params, need_bwd, st);
     for (int i = 0; i < h->cfg.F; ++i) {
-        k_pack_fwd<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->ws[i].wpk);
+        k_pack_fwd<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->conv_cin, h->ws[i].wpk);
         nma_count_launch(1);
-        if (need_bwd) k_pack_dgrad<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->ws[i].wdpk);
+        if (need_bwd && !h->is_lv) k_pack_dgrad<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->ws[i].wdpk);
     }
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -329,7 +330,7 @@ struct ConvFwdArgs {
     const float* wpk;
     const float* tb;         // [p][3][50]; slot 2 = theta bias + conv bias
     FlowEpiArgs e;
-    int KP, rcmax, npb, row_pitch, p;
+    int KP, rcmax, npb, row_pitch, p, cin;
     long long items_total;
 };
 
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(CONVF_THREADS, 2) k_conv_fwd(ConvFwdArgs a) {
     const int rc = (int)(last_item / a.npb) - row_first + 1;
 
     ConvRing rg;
-    rg.cin = NMA_C1; rg.ngroups = 5; rg.KP = a.KP; rg.rc = rc; rg.row_pitch = a.row_pitch;
+    rg.cin = a.cin; rg.ngroups = 5; rg.KP = a.KP; rg.rc = rc; rg.row_pitch = a.row_pitch;
     rg.stage_floats = 5 * a.KP * CONV_WPAD + a.rcmax * a.row_pitch;
 
     // zero the ring once: the tail of every input row must read as 0 (finite) under the padded taps
@@ -442,10 +443,12 @@ int launch_conv_fwd(nma_handle_s* h, int i, const float* params, int p, bool sav
     if (rp < d.LP) rp = d.LP;
     a.row_pitch = (rp + 3) & ~3;
     a.src.chan0 = h->ws[i].x; a.src.row_stride0 = a.e.XP;
-    a.src.rest = h->ws[i].a[4]; a.src.row_stride = (long long)NMA_C * d.LP; a.src.chan_stride = d.LP;
+    // channels 1.. : the feature activations [50][LP]; Lotka-Volterra: the transposed 4th layer, [window][LP]
+    a.src.rest = h->ws[i].a[4]; a.src.row_stride = (long long)(h->conv_cin - 1) * d.LP; a.src.chan_stride = d.LP;
     a.src.copy_floats = d.LP; a.src.dst_off = 0;
     a.wpk = h->ws[i].wpk;
     a.tb = h->ws[i].tb;
+    a.cin = h->conv_cin;
 
     const size_t ring = (size_t)CONV_STAGES * (5 * h->KP * CONV_WPAD + a.rcmax * a.row_pitch);
     const size_t epi = flow_epi_smem_floats<ITEM_COLS>();
@@ -457,6 +460,93 @@ int launch_conv_fwd(nma_handle_s* h, int i, const float* params, int p, bool sav
     }
     const long long grid = (a.items_total + 31) / 32;
     k_conv_fwd<<<(unsigned)grid, CONVF_THREADS, smem, st>>>(a);
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Lotka-Volterra feature MLP (lotka_volterra_partial_batch_fix_theta.py:71-76): every flow reads the WHOLE window
+// (LW = L0 - 1 positions, no i*K offset, :343-344), runs 3 x dense(50, elu) and a 4th dense layer as wide as the
+// flow's conv input (feat_dims = L_i - 1 units), and the [window position w][unit m] result is transposed: it is
+// stored exactly like that, a4[r][w][m], which makes w the conv's input channel 1 + w and m its position.
+// p = 1 in the script (one series per iteration): one CTA per (row, flow), no tiling beyond that.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FEAT_THREADS) k_lv_feat_fwd(FeatArgs fa, SeriesView sv, const int64_t* __restrict__ idx,
+                                                              const float* __restrict__ eps, int L0, int Cf_in, int LW,
+                                                              int LWP, int save) {
+    extern __shared__ __align__(128) float smem[];
+    const int r = blockIdx.x, i = blockIdx.y;
+    const int Fd = fa.Lin[i], LP = fa.LP[i];
+    float* T0 = smem;
+    float* T1 = T0 + NMA_C * LWP;
+    float* Wsm = T1 + NMA_C * LWP;
+    float* bsm = Wsm + NMA_C * FEAT_WPITCH;
+    const long long win0 = (long long)sv.D * idx[r];
+    if (i == 0) {
+        for (int t = threadIdx.x; t < fa.XP0; t += blockDim.x)
+            fa.x0[(size_t)r * fa.XP0 + t] = (t < L0) ? eps[(size_t)r * L0 + t] : 0.f;
+    }
+    float* ga0 = save ? fa.a[i][0] + (size_t)r * Cf_in * LWP : nullptr;
+    for (int t = threadIdx.x; t < Cf_in * LWP; t += blockDim.x) {
+        const int c = t / LWP, w = t - c * LWP;
+        const float v = (w < LW) ? series_val(sv, c, win0 + w) : 0.f;
+        T0[t] = v;
+        if (ga0) ga0[t] = v;
+    }
+    float* cur = T0;
+    float* nxt = T1;
+    for (int l = 0; l < 3; ++l) {
+        __syncthreads();
+        const int nin = (l == 0) ? Cf_in : NMA_C;
+        stage_dense_w(fa.w[i][l], fa.b[i][l], nin, Wsm, bsm);
+        __syncthreads();
+        float* gout = save ? fa.a[i][l + 1] + (size_t)r * NMA_C * LWP : nullptr;
+        dense_tile_elu(cur, LWP, nin, Wsm, bsm, nxt, LWP, LWP / 4, gout, LWP, LW);
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    __syncthreads();
+    // 4th layer: a4[w][m] = elu(b[m] + sum_f a3[f][w] W4[f][m]), lanes along the units m (kernel rows are read coalesced)
+    const float* __restrict__ W4 = fa.w[i][3];
+    const float* __restrict__ b4 = fa.b[i][3];
+    float* out = fa.a[i][4] + (size_t)r * LW * LP;
+    for (int t = threadIdx.x; t < LW * LP; t += blockDim.x) {
+        const int w = t / LP, m = t - w * LP;
+        float v = 0.f;
+        if (m < Fd) {
+            float acc = b4[m];
+            for (int f = 0; f < NMA_C; ++f) acc = fmaf(cur[f * LWP + w], __ldg(W4 + (size_t)f * Fd + m), acc);
+            v = elu_f(acc);
+        }
+        out[t] = v;
+    }
+}
+
+int launch_lv_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
+                       cudaStream_t st) {
+    FeatArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    for (int i = 0; i < h->cfg.F; ++i) {
+        for (int l = 0; l < 4; ++l) {
+            fa.w[i][l] = params + h->po[i].featw[l];
+            fa.b[i][l] = params + h->po[i].featb[l];
+        }
+        for (int l = 0; l < 5; ++l) fa.a[i][l] = h->ws[i].a[l];
+        fa.Lin[i] = h->fd[i].Lin;
+        fa.LP[i] = h->fd[i].LP;
+    }
+    fa.x0 = h->ws[0].x;
+    fa.XP0 = (h->fd[0].L + 3) & ~3;
+    const int smem = (2 * NMA_C * h->LWP + NMA_C * FEAT_WPITCH + 64) * 4;
+    if (smem > 227 * 1024) { nma_set_error("Lotka-Volterra window of %d positions does not fit in shared memory", h->LW); return -1; }
+    static int configured = 0;
+    if (configured < smem) {
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_lv_feat_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    SeriesView sv = nma_series_view(h);
+    k_lv_feat_fwd<<<dim3(p, h->cfg.F), FEAT_THREADS, smem, st>>>(fa, sv, idx, eps, h->L0, h->Cf_in, h->LW, h->LWP,
+                                                                  save ? 1 : 0);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
