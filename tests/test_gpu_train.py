@@ -188,3 +188,23 @@ def test_sv_facade_pretrains_trains_and_exports_paths(tmp_path):
     assert paths.shape == (m.p, 2, n) and np.isfinite(paths).all()
     # component 0 is the observed price itself, component 1 the latent log-volatility
     assert np.allclose(paths[0, 0, :T - 1], obs[1:T], rtol=1e-6)
+
+
+def test_lv_facade_script_pretrains_trains_and_exports_paths(tmp_path, monkeypatch):
+    """lotka_volterra_partial_batch_fix_theta.py surface at the script's own shape (p_val = 1, 151 steps, 364-slot
+    window): generate two synthetic series, run the script body for a few epochs."""
+    monkeypatch.chdir(tmp_path)
+    import lotka_volterra_partial_batch_fix_theta as lv
+    obs = lv.generate(n_series=2)
+    assert obs.shape == (2, 302) and (obs > 1.0).all()
+    models = lv.main(n_series=2, num_epochs=12, pre_train_epochs=6)
+    assert len(models) == 2
+    for m in models:
+        assert not m.pre_train                                   # 6 finite pre-train steps, then 6 ELBO steps
+        assert torch.isfinite(m.blob).all()
+        assert all(np.isfinite(float(v)) for v in m.scalars.values())
+        assert m.lf_sample.shape == (1, 2, 152)
+        assert float(m.lf_sample[0, 0, 0]) == 91.0 and float(m.lf_sample[0, 1, 0]) == 99.0     # pinned by mask/shift
+        assert (m.lf_sample[:, :, 1:] > 1.0).all()               # 1 + softplus(.)
+    assert np.loadtxt(tmp_path / "locally_variant/fix_theta/LV_obs_paths_series_dense_1.txt").shape == (302,)
+    assert os.path.exists(tmp_path / "model_saves/fix_theta/LV_model_series_151_3_dense_0.ckpt")

@@ -312,3 +312,164 @@ class SV_VI_SSM(_ModelVISSM):
 
     def _pretrain_done(self, run, finite):
         return run == 1000                                               # SV_dense.py:335-338
+
+
+class LV_VI_SSM:
+    """lotka_volterra_partial_batch_fix_theta.py:181-613 (class VI_SSM there): the Lotka-Volterra model with the
+    parameters fixed at `priors` (theta is a constant tiled over the rows, :190 - there is no theta posterior, no
+    prior term and no second optimiser), p_val subsequences per iteration drawn without replacement from
+    arange(0, target_dims * p_val, batch_dims) (:478-479), pre-training on (lf_sample - 75)^2 until
+    `pre_train_epochs` consecutive finite steps (:505-516), then the ELBO with clip_by_global_norm(1e9) (:450-458).
+
+    The committed script runs p_val = 1 with batch_dims = target_dims = 151: every iteration evaluates the one
+    subsequence that is the whole series.  The mask/shift pin of the first state is reproduced for that case
+    (`mask_vals = zeros((2, p_val)) ++ ones`, :216-219, coincides with "index 0 only" when p_val = 1)."""
+
+    grad_clip = 1e9
+    pretrain_path_target = 75.0
+
+    def __init__(self, obs, obs_bin, time_till, x0_mean, x0_std, priors, dt, T, p_val, kernel_len, batch_dims,
+                 network_dims, target_dims, no_flows, feat_window, learn_rate=1e-3, pre_train=True,
+                 device: Optional[torch.device] = None, seed: int = 1):
+        from .config import lv_config
+        if len(set(network_dims)) != 1:
+            raise ValueError("all network_dims must be equal (the reference only ever uses [50]*n)")
+        if int(p_val) != 1:
+            raise ValueError("p_val > 1 changes which states are pinned to x0 (mask_vals, :216-219); only the "
+                             "script's p_val = 1 is reproduced")
+        x0_std = np.asarray(x0_std, dtype=np.float64)
+        if not np.all(x0_std == x0_std[0]):
+            raise ValueError("x0_std must be the same for both components")
+        self.p_val = int(p_val)
+        self.priors = np.asarray(priors, dtype=np.float64)
+        self.kernel_len, self.batch_dims = int(kernel_len), int(batch_dims)
+        self.network_dims, self.no_flows = list(network_dims), int(no_flows)
+        self.target_dims, self.feat_window = int(target_dims), int(feat_window)
+        self.dt, self.T = float(dt), float(T)
+        self.learn_rate, self.pre_train = learn_rate, pre_train
+        self.flow_dims = 2
+        self.kernel_ext = self.kernel_len * self.no_flows + self.flow_dims * self.batch_dims + 2
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.seed = seed
+        self._series = (np.asarray(obs), np.asarray(obs_bin), np.asarray(time_till))
+        self.cfg = lv_config(p=self.p_val, K=self.kernel_len, B=self.batch_dims, F=self.no_flows,
+                             H=len(self.network_dims) - 2, feat_window=self.feat_window,
+                             target_dims=self.target_dims, dt=self.dt, x0=np.asarray(x0_mean, dtype=np.float64))
+        self.cfg.obs_std = float(x0_std[0])          # this model's only use of the field: the scale of p(x0)
+        self.eng: Optional[NMAEngine] = None
+        self.scalars = {}
+
+    def build_flow(self) -> None:
+        cfg = self.cfg
+        self.eng = NMAEngine(cfg, self.device)
+        obs, obs_bin, tt = self._series
+        self.eng.set_series(feed.lv_base_arrays(obs, obs_bin, tt, self.dt, self.T, self.target_dims, self.no_flows,
+                                                self.kernel_len, self.feat_window, p_val=self.p_val))
+        g = torch.Generator().manual_seed(self.seed)
+        self.blob = glorot_blob(cfg, g).to(self.device)
+        self.n_nma = self.n_total = self.blob.numel()
+        zeros = lambda: (torch.zeros_like(self.blob), torch.zeros_like(self.blob))
+        self.slots = {"pre_path": zeros(), "main": zeros()}
+        self.grad = torch.zeros_like(self.blob)
+        self.out = self.eng.alloc_outputs(self.p_val)
+        self.out["grad_params"] = self.grad
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(self.seed)
+        self.idx_dev = torch.empty(self.p_val, dtype=torch.int64, device=self.device)
+        self.theta = torch.tensor(self.priors, dtype=torch.float32, device=self.device).repeat(self.p_val, 1).contiguous()
+
+    def _iteration(self, batch_select: np.ndarray, pre_train: bool) -> bool:
+        cfg = self.cfg
+        self.idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(batch_select, dtype=np.int64)))
+        eps = torch.randn(self.p_val, cfg.L0, device=self.device, generator=self.gen)
+        if pre_train:
+            out = self.eng.elbo_fwd_bwd(self.blob, eps, self.theta, self.idx_dev, objective=OBJ_PATH_SQ,
+                                        path_target=self.pretrain_path_target, out=self.out)
+            m, v = self.slots["pre_path"]
+            self.eng.adamax_step(self.blob, self.grad, m, v, 1e-3, 0.9, clip=0.0)
+            self.lf_sample = out["lf"].reshape(self.p_val, -1, 2).transpose(1, 2)
+            return bool(torch.isfinite(out["terms"][:, 2]).all().item())      # `test = lf_log_prob`, :507-510
+        out = self.eng.elbo_fwd_bwd(self.blob, eps, self.theta, self.idx_dev, objective=OBJ_ELBO, out=self.out)
+        m, v = self.slots["main"]
+        norm = self.eng.adamax_step(self.blob, self.grad, m, v, self.learn_rate, 0.95, clip=self.grad_clip)
+        t = out["terms"]
+        scale = float(cfg.scale)
+        elbo = scale * (t[:, 0] - t[:, 2] + t[:, 1])
+        self.scalars = {"loss/NELBO": -elbo.mean(), "loss/ELBO": elbo.mean(),
+                        "loss/SDE_log_prob p(x)": scale * t[:, 0].mean(),
+                        "loss/obs_log_prob p(y|x)": scale * t[:, 1].mean(),
+                        "loss/path_log_prob q(x)": scale * t[:, 2].mean(), "optimize/global_norm": norm.clone()[0]}
+        self.lf_sample = out["lf"].reshape(self.p_val, -1, 2).transpose(1, 2)
+        return True
+
+    def _draw(self) -> np.ndarray:
+        return feed.sample_indices_lv(self.target_dims, self.batch_dims, self.p_val)
+
+    def train(self, tensorboard_path, save_path, num_epochs, pre_train_epochs, series_idx=None):
+        series_idx_str = 'series_' + str(series_idx) + '_' if series_idx is not None else ''
+        for d in (tensorboard_path, os.path.dirname(save_path)):
+            if d and not os.path.exists(d):
+                os.makedirs(d)
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter('%s/%s' % (tensorboard_path,
+                                              series_idx_str + datetime.now().strftime("%d:%m:%y-%H:%M:%S")))
+        except Exception:
+            writer = None
+        run, pre_train_count = 0, 0
+        t_start = time.time()
+        self.epoch_times = []
+        for epoch in range(num_epochs):
+            batch_select = self._draw()
+            if self.pre_train:
+                if run == 0:
+                    print("Initialising paths and parameters...")
+                pre_train_count = pre_train_count + 1 if self._iteration(batch_select, pre_train=True) else 0
+                if pre_train_count == pre_train_epochs:
+                    self.pre_train = False
+                    print("Finished pre-training...")
+                    run = 0
+            else:
+                self._iteration(batch_select, pre_train=False)
+                if writer is not None:
+                    for tag, val in self.scalars.items():
+                        writer.add_scalar(tag, float(val), run)
+                    writer.add_scalar("elapsed_time", time.time() - t_start, epoch)
+            if run % 1000 == 0:
+                self.save(save_path)
+            run += 1
+            self.epoch_times.append(time.time() - t_start)
+        if writer is not None:
+            writer.close()
+        return self.lf_sample
+
+    def save(self, PATH):
+        torch.save({"blob": self.blob.cpu(), "slots": {k: (m.cpu(), v.cpu()) for k, (m, v) in self.slots.items()},
+                    "numpy_rng": np.random.get_state()}, PATH)
+        print("Model saved")
+
+    def load(self, PATH):
+        self.pre_train = False
+        ck = torch.load(PATH, weights_only=False)
+        self.blob.copy_(ck["blob"].to(self.device))
+        for k, (m, v) in ck["slots"].items():
+            self.slots[k][0].copy_(m.to(self.device))
+            self.slots[k][1].copy_(v.to(self.device))
+        print("Model restored")
+
+    def sample_paths(self, temp_index: int) -> torch.Tensor:
+        """lf_sample [p_val, 2, batch_dims + 1] (softplus-transformed, first state pinned) of one posterior draw."""
+        idx = torch.full((self.p_val,), int(temp_index), dtype=torch.int64, device=self.device)
+        eps = torch.randn(self.p_val, self.cfg.L0, device=self.device, generator=self.gen)
+        _, lf = self.eng.forward_paths(self.blob, eps, self.theta, idx)
+        return lf.reshape(self.p_val, -1, 2).transpose(1, 2)
+
+    def save_paths(self, PATH_obs):
+        """:571-613: windows at 0, batch_dims, ... < batch_dims * p_val, concatenated along time, written [p_val, 2T]."""
+        path_store = []
+        for index_temp in np.arange(0, self.batch_dims * self.p_val, self.batch_dims):
+            path_store.append(self.sample_paths(int(index_temp))[:, :, 1:].cpu().numpy())
+        paths = np.concatenate(path_store, axis=2)
+        with open(PATH_obs, 'w') as f:
+            np.savetxt(f, np.reshape(paths, (self.p_val, -1)))
+        return paths
