@@ -162,7 +162,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
             off[i].dat_lo = reserve((int64_t)TC_CCH * Q * 4);
             off[i].wtc_f = reserve((int64_t)cfg->K * TC_WSTAGE);
             off[i].wtc_d = reserve((int64_t)cfg->K * TC_WSTAGE);
-            off[i].wtc_feat = reserve((int64_t)8 * TC_CCH * 128 * 4);
+            off[i].wtc_feat = reserve((int64_t)9 * TC_CCH * 128 * 4);
         }
     }
     h->arena_bytes = total;

@@ -5,6 +5,7 @@
 //   k_conv_wgrad : weight gradient of the K-tap conv, reduction over rows x positions
 //   k_feat_bwd   : feature-MLP backward (4 dense+ELU layers)
 //   k_theta_bwd  : theta-bias MLP backward -> d/dtheta and its weight gradients
+#include <stdlib.h>
 #include "nma_conv_core.cuh"
 
 #include "nma_flow_epi.cuh"
@@ -311,6 +312,10 @@ static int persistent_grid(const nma_handle_s* h, int p, int per_sm) {
 }
 
 int launch_epi_bwd(nma_handle_s* h, int i, const float* params, int p, int objective, float* gp, cudaStream_t st) {
+    {
+        const char* env = getenv("NMA_TC_EPI");
+        if (epi_bwd_tc_supported(h) && !(env && env[0] == '0')) return launch_epi_bwd_tc(h, i, params, p, objective, gp, st);
+    }
     const FlowDims& d = h->fd[i];
     EpiBwdArgs a;
     for (int l = 0; l < NMA_MAXH; ++l) {

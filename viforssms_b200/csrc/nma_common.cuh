@@ -50,7 +50,7 @@ struct FlowWs {
     float* dat_lo;
     float* wtc_f;    // [K][14][64 hi | 64 lo rows][4] packed taps of the forward conv
     float* wtc_d;    // same, data-gradient conv (flipped, transposed)
-    float* wtc_feat; // [8][14][64 hi | 64 lo rows][4] packed feature-MLP kernels: 4 forward, 4 transposed (nma_tc_feat.cu)
+    float* wtc_feat; // [9][14][64 hi | 64 lo rows][4] packed feature-MLP kernels: 4 forward, 4 transposed, + the transposed hidden 1x1 kernel (nma_tc_feat.cu)
     long long tin_Q, dat_Q;
 };
 
@@ -111,6 +111,9 @@ int launch_conv_dgrad_tc(nma_handle_s* h, int flow, int p, cudaStream_t st);
 int launch_conv_wgrad_tc(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
 int launch_pack_feat_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
+int epi_bwd_tc_supported(const nma_handle_s* h);
+int launch_epi_bwd_tc(nma_handle_s* h, int flow, const float* params, int p, int objective, float* grad_params,
+                      cudaStream_t st);
 int launch_feat_bwd_tc(nma_handle_s* h, int flow, const float* params, int p, float* grad_params, cudaStream_t st);
 int launch_feat_fwd_tc(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
                        cudaStream_t st);

@@ -618,3 +618,297 @@ int launch_feat_bwd_tc(nma_handle_s* h, int i, const float* params, int p, float
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// backward of the flow layer's head and hidden 1x1 layer on the tensor cores (replaces k_epi_bwd, nma_bwd.cu, for the
+// configuration of the AR scripts: one hidden layer, no batch-norm, flow_dims = 1; AR.py:74-89 differentiated).
+//
+// Per position (r, m) of the conv output: the affine flow layer and the softplus head give d objective / d (mu, s)
+// (SIMT, a handful of flops); G = gradient w.r.t. the hidden layer's pre-activation = (dmu hw[.,0] + ds hw[.,1]) elu'(e_1);
+// then exactly one layer of k_feat_bwd_tc: data gradient G W^T on tcgen05 (-> dA = . elu'(e_0), written straight
+// into the conv gradient operand `dat`, hi/lo split), weight gradient e_0^T G as one stacked 128x128x8 MMA per 8
+// positions, bias gradient through the ones row.  Head weight gradients are register partial sums per thread,
+// flushed once.  The per-row sums of dA the theta-bias backward needs are taken from `dat` by k_dtb_from_dat.
+// ---------------------------------------------------------------------------
+struct EpiBwdTcArgs {
+    const float* wpk;        // transposed packed hidden kernel [14][128][4] (k_tc_pack_w1x1)
+    const float* headw;      // [50][2]
+    const float* e0;         // [p][50][NP]  elu(conv + theta-bias)
+    const float* e1;         // [p][50][NP]  output of the hidden layer
+    const float* s;          // [p][NP]
+    const float* x_in;       // [p][XP]
+    const float* dx_next;    // [p][XPn]
+    float* dx;               // [p][XP]
+    float* dat_hi;           // [14][dat_Q][4], dA(r, m) at q = K-1 + r*Lin + m
+    float* dat_lo;
+    long long dat_Q;
+    float* g_hidw; float* g_hidb; float* g_headw; float* g_headb;
+    int XP, XPn, N, NP, K, S, Lin, p;
+    float cq;
+};
+
+__global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t dbar, wbar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float hw[2 * 64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quarter = warp & 3, cg = warp >> 2;
+    const int pos = quarter * 32 + lane;
+    float* Ad_hi = smem;
+    float* Ad_lo = Ad_hi + FT_A_F;
+    float* Aw = Ad_lo + FT_A_F;
+    float* Bw = Aw + FB_OPW_F;
+    float* Wt = Bw + FB_OPW_F;
+
+    // dx[r][0..K) = 0 (the affine layer only touches slots >= K); positions of `dat` past the last row read as zero
+    for (long long t = (long long)blockIdx.x * blockDim.x + tid; t < (long long)a.p * a.K; t += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(t / a.K), j = (int)(t - (long long)r * a.K);
+        a.dx[(size_t)r * a.XP + j] = 0.f;
+    }
+    if (blockIdx.x == 0) {
+        const long long q_lo = (long long)a.p * a.Lin + (a.K - 1);
+        for (int t = tid; t < TC_CCH * 128; t += blockDim.x) {
+            const int fch = t / 128, q = t - fch * 128;
+            if (q_lo + q < a.dat_Q) {
+                const size_t o = ((size_t)fch * a.dat_Q + q_lo + q) * 4;
+                *reinterpret_cast<float4*>(a.dat_hi + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(a.dat_lo + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.wpk);
+        float4* dst = reinterpret_cast<float4*>(Wt);
+        for (int t = tid; t < FT_WLAYER_F / 4; t += blockDim.x) dst[t] = __ldg(src + t);
+        if (tid < 128) hw[tid] = (tid < 2 * NMA_C) ? a.headw[tid] : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(&dbar, 1);
+        mbar_init(&wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, FT_TMEM_COLS);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot, tmem_w = tmem_slot + 2 * TC_N;
+    const uint32_t td = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(16 * cg);
+    const uint32_t tw = tmem_w + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(16 * cg);
+    const uint32_t ad_hi_u = smem_u32(Ad_hi), ad_lo_u = smem_u32(Ad_lo), aw_u = smem_u32(Aw), bw_u = smem_u32(Bw),
+                   wt_u = smem_u32(Wt);
+
+    const int N = a.N, NP = a.NP;
+    const long long qtot = (long long)a.p * N;
+    const long long ntiles = (qtot + FT_M - 1) / FT_M;
+    uint32_t dph = 0, wph = 0;
+    float acc[16], hacc0[16], hacc1[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { acc[k] = 0.f; hacc0[k] = 0.f; hacc1[k] = 0.f; }
+    float hb0 = 0.f, hb1 = 0.f;
+    const int wofs = (pos >> 2) * (FB_LBO / 4) + (pos & 3);
+    bool first_tile = true;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long q = tile * FT_M + pos;
+        const bool valid = q < qtot;
+        const int r = valid ? (int)(q / N) : 0;
+        const int m = valid ? (int)(q - (long long)r * N) : 0;
+        // ---- affine flow layer + softplus head (AR.py:83-88) ----
+        float dmu = 0.f, dsr = 0.f;
+        if (valid) {
+            const float dxo = a.dx_next[(size_t)r * a.XPn + m];
+            const float sr = a.s[(size_t)r * NP + m];
+            const float sigma = softplus_f(sr) + 1e-10f;
+            const float xin = a.x_in[(size_t)r * a.XP + m + a.K];
+            float dsig = dxo * xin;
+            if (m >= N - a.S) dsig -= a.cq / sigma;        // logq -= log sigma over the last S slots
+            dmu = dxo;
+            dsr = dsig * sigmoid_f(sr);
+            if (cg == 0) a.dx[(size_t)r * a.XP + m + a.K] = dxo * sigma;
+        }
+        float g[16], e0v[16];
+        {
+            const float* p1 = a.e1 + ((size_t)r * NMA_C + 16 * cg) * NP + m;
+            const float* p0 = a.e0 + ((size_t)r * NMA_C + 16 * cg) * NP + m;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int ch = 16 * cg + k;
+                const bool ok = valid && ch < NMA_C;
+                const float eh = ok ? __ldg(p1 + (size_t)k * NP) : 0.f;
+                e0v[k] = ok ? __ldg(p0 + (size_t)k * NP) : 0.f;
+                hacc0[k] = fmaf(eh, dmu, hacc0[k]);
+                hacc1[k] = fmaf(eh, dsr, hacc1[k]);
+                g[k] = ok ? fmaf(dmu, hw[2 * ch], dsr * hw[2 * ch + 1]) * elu_grad_from_out(eh) : 0.f;
+            }
+        }
+        if (cg == 0) { hb0 += dmu; hb1 += dsr; }
+        if (!first_tile) {
+            mbar_wait_backoff(&wbar, wph);
+            wph ^= 1u;
+            tc_fence_after();
+            tmem_sum16(tw, [&](int k, float x) { acc[k] += x; });
+        }
+        // ---- operands: data gradient A = G [g/4][pos][4]; weight gradient A = [e_0; ones], B = G, K = positions ----
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int ch = 4 * cg + cc;
+            if (ch < TC_CCH) {
+                const size_t o = ((size_t)ch * FT_M + pos) * 4;
+                ft_split_store(Ad_hi + o, Ad_lo + o, g[4 * cc], g[4 * cc + 1], g[4 * cc + 2], g[4 * cc + 3]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int row = 16 * cg + k;
+            const int o_hi = wofs + (row >> 3) * 32 + (row & 7) * 4;
+            const int o_lo = o_hi + 8 * 32;
+            const float gh = tf32_hi(g[k]);
+            Bw[o_hi] = gh;
+            Bw[o_lo] = g[k] - gh;
+            const float av = (row == NMA_C) ? 1.f : e0v[k];
+            const float ah = tf32_hi(av);
+            Aw[o_hi] = ah;
+            Aw[o_lo] = av - ah;
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            ft_issue_layer(ad_hi_u, ad_lo_u, wt_u, TC_CCH / 2, tmem_d, &dbar);
+            tc_fence_after();
+            if (elect_one()) {
+                constexpr uint32_t idesc_wide = umma_idesc_tf32(FT_M, 2 * TC_N, 0, 0);
+                const uint32_t a0 = desc_lo(aw_u, FB_LBO), b0 = desc_lo(bw_u, FB_LBO);
+                const uint32_t hi32 = desc_hi(128u);
+#pragma unroll 4
+                for (int ks = 0; ks < FT_M / 8; ++ks) {
+                    const uint32_t step = (uint32_t)ks * (2u * FB_LBO / 16u);
+                    umma_tf32(tmem_w, desc_pack(a0 + step, hi32), desc_pack(b0 + step, hi32), idesc_wide, ks ? 1u : 0u);
+                }
+                tc_commit(&wbar);
+            }
+            __syncwarp();
+        }
+        mbar_wait_backoff(&dbar, dph);
+        dph ^= 1u;
+        tc_fence_after();
+        // dA = (G W^T) (.) elu'(e_0) -> the conv gradient operand, channels 16*cg .. +15 of this position
+        tmem_sum16(td, [&](int k, float x) { g[k] = x * elu_grad_from_out(e0v[k]); });
+        if (valid) {
+            const long long qd = (long long)(a.K - 1) + (long long)r * a.Lin + m;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int ch = 4 * cg + cc;
+                if (ch < TC_CCH) {
+                    const size_t o = ((size_t)ch * a.dat_Q + qd) * 4;
+                    ft_split_store(a.dat_hi + o, a.dat_lo + o, g[4 * cc], g[4 * cc + 1], g[4 * cc + 2], g[4 * cc + 3]);
+                }
+            }
+        }
+        first_tile = false;
+    }
+    if (!first_tile) {
+        mbar_wait_backoff(&wbar, wph);
+        tc_fence_after();
+        tmem_sum16(tw, [&](int k, float x) { acc[k] += x; });
+    }
+    {
+        const int f = pos & 63;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int gc = 16 * cg + k;
+            if (gc < NMA_C) {
+                if (f < NMA_C) atomicAdd(a.g_hidw + f * NMA_C + gc, acc[k]);
+                else if (pos == NMA_C) atomicAdd(a.g_hidb + gc, acc[k]);
+                // head kernel gradient [50][2]: partial sums of this thread's positions, reduced over the warp first
+                const float s0 = warp_sum(hacc0[k]), s1 = warp_sum(hacc1[k]);
+                if (lane == 0) { atomicAdd(a.g_headw + 2 * gc, s0); atomicAdd(a.g_headw + 2 * gc + 1, s1); }
+            }
+        }
+        if (cg == 0) {
+            hb0 = warp_sum(hb0);
+            hb1 = warp_sum(hb1);
+            if (lane == 0) { atomicAdd(a.g_headb, hb0); atomicAdd(a.g_headb + 1, hb1); }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, FT_TMEM_COLS);
+}
+
+// dtb[r][f] = sum_m dA[r][f][m] (upstream of the theta-bias MLP, AR.py:63-72) and the conv bias gradient, from the
+// hi + lo parts of the gradient operand: one CTA per row, warp w owns channel chunk w, lanes along the positions
+__global__ void __launch_bounds__(TC_CCH * 32) k_dtb_from_dat(const float* __restrict__ dat_hi,
+                                                             const float* __restrict__ dat_lo, long long Q, int K,
+                                                             int Lin, int N, float* __restrict__ dtb,
+                                                             float* __restrict__ g_convb) {
+    const int r = blockIdx.x, c4 = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t base = ((size_t)c4 * Q + (size_t)(K - 1) + (size_t)r * Lin) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = lane; m < N; m += 32) {
+        const float4 h4 = __ldg(reinterpret_cast<const float4*>(dat_hi + base + (size_t)m * 4));
+        const float4 l4 = __ldg(reinterpret_cast<const float4*>(dat_lo + base + (size_t)m * 4));
+        acc.x += h4.x + l4.x; acc.y += h4.y + l4.y; acc.z += h4.z + l4.z; acc.w += h4.w + l4.w;
+    }
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+    if (lane == 0) {
+        const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int f = 4 * c4 + e;
+            if (f < NMA_C) {
+                dtb[(size_t)r * NMA_C + f] = v[e];
+                atomicAdd(g_convb + f, v[e]);
+            }
+        }
+    }
+}
+
+// transposed pack of ONE 1x1 kernel [50][50] (same element map as the feature kernels' transposed slots)
+__global__ void k_tc_pack_w1x1_t(const float* __restrict__ W, float* __restrict__ out) {
+    for (int t = threadIdx.x; t < FT_WLAYER_F; t += blockDim.x) {
+        const int e = t & 3, row = (t >> 2) & 127, cch = t >> 9;
+        const int n = row & 63, c = 4 * cch + e;
+        const float v = (c < NMA_C && n < NMA_C) ? W[n * NMA_C + c] : 0.f;
+        const float hi = tf32_hi(v);
+        out[t] = (row < 64) ? hi : v - hi;
+    }
+}
+
+int epi_bwd_tc_supported(const nma_handle_s* h) {
+    return h->use_tc && h->use_tc_feat && h->cfg.H == 1 && !h->cfg.bn && h->cfg.D == 1;
+}
+
+int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int objective, float* gp, cudaStream_t st) {
+    const FlowDims& d = h->fd[i];
+    // slot 8 of the flow's pack buffer: the transposed hidden kernel (weights are constant during a step)
+    float* wt = h->ws[i].wtc_feat + (size_t)8 * FT_WLAYER_F;
+    k_tc_pack_w1x1_t<<<1, 256, 0, st>>>(params + h->po[i].hidw[0], wt);
+    EpiBwdTcArgs a;
+    a.wpk = wt;
+    a.headw = params + h->po[i].headw;
+    a.e0 = h->ws[i].h[0]; a.e1 = h->ws[i].h[1];
+    a.s = h->ws[i].s; a.x_in = h->ws[i].x; a.dx_next = h->ws[i + 1].dx; a.dx = h->ws[i].dx;
+    a.dat_hi = h->ws[i].dat_hi; a.dat_lo = h->ws[i].dat_lo; a.dat_Q = h->ws[i].dat_Q;
+    a.g_hidw = gp + h->po[i].hidw[0]; a.g_hidb = gp + h->po[i].hidb[0];
+    a.g_headw = gp + h->po[i].headw; a.g_headb = gp + h->po[i].headb;
+    a.XP = (d.L + 3) & ~3; a.XPn = (h->fd[i + 1].L + 3) & ~3; a.N = d.N; a.NP = d.NP; a.K = h->cfg.K; a.S = h->S;
+    a.Lin = d.Lin; a.p = p;
+    a.cq = (objective == NMA_OBJ_ELBO) ? (float)h->cfg.scale : 0.f;
+    const long long ntiles = ((long long)p * d.N + FT_M - 1) / FT_M;
+    const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
+    const int smem = (2 * FT_A_F + 2 * FB_OPW_F + FT_WLAYER_F) * 4;
+    static int configured = 0;
+    if (configured < smem) {
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_epi_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    k_epi_bwd_tc<<<grid, FB_THREADS, smem, st>>>(a);
+    k_dtb_from_dat<<<p, TC_CCH * 32, 0, st>>>(h->ws[i].dat_hi, h->ws[i].dat_lo, h->ws[i].dat_Q, h->cfg.K, d.Lin, d.N,
+                                             h->ws[i].dtb, gp + h->po[i].convb);
+    nma_count_launch(3);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
