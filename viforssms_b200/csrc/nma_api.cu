@@ -118,6 +118,8 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     {
         const char* env = getenv("NMA_TC");
         h->use_tc = h->tc_ok && !(env && env[0] == '0');
+        const char* envp = getenv("NMA_TC_PERSIST");
+        h->use_tc_persist = !(envp && envp[0] == '0');
         const char* envf = getenv("NMA_TC_FEAT");
         h->use_tc_feat = h->use_tc && !(envf && envf[0] == '0');
     }
@@ -162,7 +164,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
             off[i].dat_lo = reserve((int64_t)TC_CCH * Q * 4);
             off[i].wtc_f = reserve((int64_t)cfg->K * TC_WSTAGE);
             off[i].wtc_d = reserve((int64_t)cfg->K * TC_WSTAGE);
-            off[i].wtc_feat = reserve((int64_t)9 * TC_CCH * 128 * 4);
+            off[i].wtc_feat = reserve((int64_t)10 * TC_CCH * 128 * 4);
         }
     }
     h->arena_bytes = total;

@@ -50,7 +50,7 @@ struct FlowWs {
     float* dat_lo;
     float* wtc_f;    // [K][14][64 hi | 64 lo rows][4] packed taps of the forward conv
     float* wtc_d;    // same, data-gradient conv (flipped, transposed)
-    float* wtc_feat; // [9][14][64 hi | 64 lo rows][4] packed feature-MLP kernels: 4 forward, 4 transposed, + the transposed hidden 1x1 kernel (nma_tc_feat.cu)
+    float* wtc_feat; // [10][14][64 hi | 64 lo rows][4] packed feature-MLP kernels: 4 forward, 4 transposed, + the hidden 1x1 kernel transposed / forward
     long long tin_Q, dat_Q;
 };
 
@@ -70,6 +70,7 @@ struct nma_handle_s {
     int tc_ok;       // the tensor-core conv supports this configuration
     int use_tc;      // ... and is switched on (default; NMA_TC=0 or nma_set_tensor_cores(h, 0) selects the FP32 SIMT conv)
     int tc_nacc;     // 128-position accumulators per CTA (2 when the tile fits in shared memory, else 1)
+    int use_tc_persist;  // persistent warp-specialised conv kernels (nma_tc_conv2.cu); NMA_TC_PERSIST=0 keeps one tile per CTA
     int use_tc_feat; // feature MLP on the tensor cores as well (needs use_tc; NMA_TC_FEAT=0 keeps the FP32 SIMT kernels)
     // Lotka-Volterra (lotka_volterra_partial_batch_fix_theta.py:71-82): every flow's feature MLP runs over the whole
     // window (LW = L0 - 1 positions), ends in a dense layer as wide as the flow's conv input and is transposed, so the
@@ -109,6 +110,9 @@ int launch_conv_fwd(nma_handle_s* h, int flow, const float* params, int p, bool 
 int launch_conv_fwd_tc(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
 int launch_conv_dgrad_tc(nma_handle_s* h, int flow, int p, cudaStream_t st);
 int launch_conv_wgrad_tc(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
+int launch_conv_dgrad_tcp(nma_handle_s* h, int flow, int p, cudaStream_t st);
+int conv_fwd_tcp_supported(const nma_handle_s* h);
+int launch_conv_fwd_tcp(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
 int launch_pack_feat_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
 int epi_bwd_tc_supported(const nma_handle_s* h);

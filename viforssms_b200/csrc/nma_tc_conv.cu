@@ -126,6 +126,7 @@ static int tc_smem_bytes(int nacc, int K, size_t epi_floats) {
 }
 
 int launch_conv_fwd_tc(nma_handle_s* h, int i, const float* params, int p, bool save, cudaStream_t st) {
+    if (conv_fwd_tcp_supported(h)) return launch_conv_fwd_tcp(h, i, params, p, save, st);
     const FlowDims& d = h->fd[i];
     ConvFwdTcArgs a;
     const int nacc = h->tc_nacc;
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_dgrad_tc(ConvDgradTcArgs
 }
 
 int launch_conv_dgrad_tc(nma_handle_s* h, int i, int p, cudaStream_t st) {
+    if (h->use_tc_persist && h->tc_nacc == 2) return launch_conv_dgrad_tcp(h, i, p, st);
     const FlowDims& d = h->fd[i];
     ConvDgradTcArgs a;
     const int nacc = h->tc_nacc;
