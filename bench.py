@@ -165,8 +165,8 @@ def workload_config(args, rows_note=None):
 
 STAGE_NAMES = {0: "conv_fwd", 1: "conv_dgrad", 2: "conv_wgrad", 3: "epi_bwd", 5: "feat_bwd"}
 # dram__bytes_read.sum + dram__bytes_write.sum per ROW of the flow-0 launch of each tcgen05 conv kernel, from the
-# ncu --set full capture in profiles/r01_tc_path.md (2048 rows: 303.1 / 243.8 / 1327.4 MB); scaled by rows below
-NCU_DRAM_BYTES_PER_ROW = {"conv_fwd[0]": 303.1e6 / 2048, "conv_dgrad[0]": 243.8e6 / 2048, "conv_wgrad[0]": 1327.4e6 / 2048}
+# ncu --set full capture in profiles/r01_final.md (2048 rows: 301.2 / 239.0 / 1346.5 MB); scaled by rows below
+NCU_DRAM_BYTES_PER_ROW = {"conv_fwd[0]": 301.2e6 / 2048, "conv_dgrad[0]": 239.0e6 / 2048, "conv_wgrad[0]": 1346.5e6 / 2048}
 
 
 def roofline_report(stepper, peaks, ms_step):
@@ -197,7 +197,7 @@ def roofline_report(stepper, peaks, ms_step):
             "frac": achieved / tf32_peak,
             "traffic": (NCU_DRAM_BYTES_PER_ROW[name] * stepper.rows
                         if (name in NCU_DRAM_BYTES_PER_ROW and stepper.eng.tensor_cores and cfg.K == 50) else None),
-            "traffic_note": "dram bytes of this launch: ncu --set full at 2048 rows (profiles/r01_tc_path.md) scaled by rows",
+            "traffic_note": "dram bytes of this launch: ncu --set full at 2048 rows (profiles/r01_final.md) scaled by rows",
             "peak_source": "0.5 x bf16_tflops (%s) of MEASURED_PEAKS.json = TF32 dense" % peaks.get("source", "measured"),
             "ms_per_launch": ms, "flop_per_launch": flop,
             "conv_share_of_step": conv_ms / ms_step if ms_step > 0 else None}
