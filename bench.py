@@ -140,7 +140,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, rows_note="bounded sample of %d rows per step on the host" % rows),
+        "config": workload_config(args),      # the native arm's config, key for key; the bounded sample is described below
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d rows x %d steps of the same AR(1) K=50 B=50 3-flow step (torch-CPU fp32 oracle, "
                                    "the reference's TensorFlow 1.8 cannot be installed)" % (rows, args.steps)},
@@ -154,7 +154,8 @@ def workload_config(args, rows_note=None):
     c = {"workload": "AR(1) synthetic T=%d, kernel_len=50, batch_dims=50, no_flows=3, network_dims=50,50,50, "
                      "feat_window=10 (BASELINE.json configs[4])" % args.T,
          "rows_per_gpu_per_step": args.rows, "units_per_row": B_DIMS,
-         "l2": "per-step working set (activations %.1f GB at these rows) far exceeds the 126 MB L2; no flush needed",
+         "l2": "per-step working set (saved activations and tensor-core operands, ~1.1 MB per row: %.1f GB at these rows) far "
+               "exceeds the 126 MB L2; no flush needed" % (args.rows * 1.075e6 / 1e9),
          "parallelism": "time-sharded series, rows sharded %d-way, NCCL gradient all-reduce" % args.gpus,
          "launch": "eager" if args.no_graph else "one CUDA graph per step"}
     if rows_note:
@@ -297,11 +298,11 @@ def run_native(args):
         units_total = units_step_rank * world * args.steps
         value = units_total / (ms_total * 1e-3)
         wc = workload_config(args)
-        wc["l2"] = wc["l2"] % (stepper.eng.workspace_bytes / 1e9)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": wc, "clocks": clocks,
+            "dtype": "f32", "data": "synthetic", "config": wc, "workspace_bytes": int(stepper.eng.workspace_bytes),
+            "clocks": clocks,
             "e2e": {"value": units_total / (e2e_ms_total * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes,
                     "ms_per_step": e2e_ms_total / args.steps},
