@@ -219,7 +219,13 @@ def run_native(args):
         raise SystemExit("bench.py --impl native needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NCCL announces itself on stdout when its communicator is created ("NCCL version ..."); stdout must carry exactly one
+    # JSON line, so file descriptor 1 points at stderr until the communicators exist (restored before the timed region)
+    saved_stdout = None
     if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
 
@@ -246,6 +252,10 @@ def run_native(args):
     for _ in range(args.warmup):
         stepper.step_resident()
     barrier()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
