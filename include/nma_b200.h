@@ -146,6 +146,11 @@ int nma_scan_ar1(const double* d_z, double* d_x, int64_t n, double x0, double a,
 int nma_time_till(const double* d_obs, int64_t n, int32_t impute, double* d_obs_fill, double* d_obs_binary,
                   double* d_time_till, void* stream);
 
+/* A14 - rolling variances of the stochastic-volatility features (SV_dense.py:159-170):
+ * d_var[i] = np.var(x[i : i+K]) for i in [0, n-K), on the float32 series, bit-exact with numpy's float32 np.var
+ * (pairwise sums, two passes). */
+int nma_rolling_var(const float* d_x, int64_t n, int32_t K, float* d_var, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

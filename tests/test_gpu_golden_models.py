@@ -74,3 +74,26 @@ def test_lv_device_gather_matches_reference_feed():
     cfg = lv_config(p=p, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=N, dt=dt, x0=g["x0_mean"])
     arrays = feed.lv_base_arrays(obs[:, :B], obs_bin[:, :B], tt[:, :B], dt, T, N, F, K, fw, p_val=p)
     _gather_check(cfg, arrays, g, ("paths0", "train0", "train1"), lambda n: (n, 2, B + 1))
+
+
+def test_rolling_variance_kernel_is_bit_exact_with_numpy_float32():
+    """A14 (SV_dense.py:159-170): nma_rolling_var reproduces np.var on the float32 series bit for bit - for the window of
+    the script (50), below numpy's 8-wide unroll, and above its 128-element pairwise block - and yields the golden
+    var_pad / var_diff_pad of the reference script."""
+    from viforssms_b200.engine import rolling_var
+    g = _golden("sv_golden.npz")
+    obs = synth.sv_prices()[300:]
+    dev = torch.device("cuda")
+
+    def dev_var(x, K):
+        return rolling_var(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev), K).cpu().numpy()
+    for K in (50, 5, 8, 9, 129, 300):
+        want = np.array([np.var(obs[i:i + K]) for i in range(obs.shape[0] - K)], dtype=np.float32)
+        assert np.array_equal(dev_var(obs, K), want), K
+    rs = np.random.RandomState(4)
+    x = (rs.standard_normal(5000) * 37.0 - 11.0).astype(np.float32)
+    want = np.array([np.var(x[i:i + 50]) for i in range(x.shape[0] - 50)], dtype=np.float32)
+    assert np.array_equal(dev_var(x, 50), want)
+    p, K, B, F, N, fw = (int(v) for v in g["hyper"])
+    arrays = feed.sv_base_arrays(obs, float(g["dt"]), float(g["T"]), F, K, fw, var_fn=dev_var)
+    assert np.array_equal(arrays[2], g["var_pad"]) and np.array_equal(arrays[3], g["var_diff_pad"])

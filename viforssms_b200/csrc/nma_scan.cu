@@ -141,3 +141,58 @@ extern "C" int nma_time_till(const double* d_obs, int64_t n, int32_t impute, dou
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// A14 - rolling variances of the stochastic-volatility features (SV_dense.py:159-170):
+//     var_store[i] = np.var(obs[i : i + K])      on the script's float32 series.
+// Bit-exact with numpy: np.var is sum -> /K -> (x - mean)^2 -> sum -> /K, every step in float32, and numpy's float32
+// sum is the pairwise scheme of loops_utils.h (8 interleaved accumulators over blocks of 8, combined as a balanced
+// tree, remainder added sequentially; halves of at most 128 elements above that).  One thread per window; windows
+// overlap, so the loads hit L1.  No FMA contraction (explicit _rn intrinsics): a fused (x - m)^2 + acc would round
+// differently.
+// ---------------------------------------------------------------------------
+template <typename F>
+__device__ float np_pairwise_sum(F elem, int64_t lo, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, elem(lo + i));
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = elem(lo + j);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], elem(lo + i + j));
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, elem(lo + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise_sum(elem, lo, n2), np_pairwise_sum(elem, lo + n2, n - n2));
+}
+
+__global__ void k_rolling_var(const float* __restrict__ x, int64_t nout, int K, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nout; i += (int64_t)gridDim.x * blockDim.x) {
+        const float s = np_pairwise_sum([&](int64_t j) { return __ldg(x + j); }, i, K);
+        const float mean = (float)((double)s / (double)K);
+        const float s2 = np_pairwise_sum([&](int64_t j) { const float d = __fsub_rn(__ldg(x + j), mean); return __fmul_rn(d, d); }, i, K);
+        out[i] = (float)((double)s2 / (double)K);
+    }
+}
+
+extern "C" int nma_rolling_var(const float* d_x, int64_t n, int32_t K, float* d_var, void* stream) {
+    if (!d_x || !d_var || K < 1 || n <= K) { nma_set_error("nma_rolling_var: bad argument"); return -1; }
+    const int64_t nout = n - K;
+    int64_t blocks = (nout + 127) / 128;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_rolling_var<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(d_x, nout, K, d_var);
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -204,3 +204,12 @@ def time_till(obs: torch.Tensor, impute: int):
     _lib.check(lib.nma_time_till(_ptr(obs), n, impute, _ptr(fill), _ptr(binary), _ptr(till), _stream()),
                "nma_time_till")
     return fill, binary, till
+
+
+def rolling_var(x: torch.Tensor, K: int) -> torch.Tensor:
+    """[np.var(x[i:i+K]) for i in range(len(x) - K)] on the device, float32, bit-exact with numpy (SV_dense.py:159-170)."""
+    lib = _lib.load()
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 1
+    out = torch.empty(x.numel() - K, dtype=torch.float32, device=x.device)
+    _lib.check(lib.nma_rolling_var(_ptr(x), x.numel(), int(K), _ptr(out), _stream()), "nma_rolling_var")
+    return out

@@ -80,7 +80,8 @@ def rolling_var(x: np.ndarray, K: int) -> np.ndarray:
     return np.maximum(s2 / K - (s1 / K) ** 2, 0.0)
 
 
-def sv_base_arrays(obs, dt: float, T: float, F: int, K: int, fw: int, exact_var: bool = True) -> List[np.ndarray]:
+def sv_base_arrays(obs, dt: float, T: float, F: int, K: int, fw: int, exact_var: bool = True,
+                   var_fn=None) -> List[np.ndarray]:
     """Base arrays of the SV model in the order `config.sv_config` expects (SV_dense.py:159-184).
     `exact_var=True` evaluates the rolling variances with the reference's own np.var loop (bit-exact);
     False uses the O(T) prefix-sum form (agrees to ~1e-12 relative)."""
@@ -89,7 +90,11 @@ def sv_base_arrays(obs, dt: float, T: float, F: int, K: int, fw: int, exact_var:
     obs_pad = np.concatenate((np.zeros(F * K), obs, np.zeros(5 * max(fw - 1, 0))))
     time_pad = np.concatenate((np.zeros(F * K + 1), np.arange(0.1, T + dt, dt)))
     obs_diff = obs[1:] - obs[:-1]
-    if exact_var:
+    if var_fn is not None:       # e.g. the device kernel nma_rolling_var (engine.rolling_var): same float32 values
+        diff_in = obs_in[1:] - obs_in[:-1]
+        var_store = np.asarray(var_fn(obs_in, K))
+        var_diff_store = np.asarray(var_fn(diff_in, K))
+    elif exact_var:
         diff_in = obs_in[1:] - obs_in[:-1]
         var_store = np.array([np.var(obs_in[i:i + K]) for i in range(0, obs_in.shape[0] - K)])
         var_diff_store = np.array([np.var(diff_in[i:i + K]) for i in range(0, diff_in.shape[0] - K)])   # log below too

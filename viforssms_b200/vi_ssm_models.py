@@ -293,8 +293,16 @@ class SV_VI_SSM(_ModelVISSM):
                              target_dims=self.target_dims, dt=self.dt, x0=self.x0)
 
     def _base_arrays(self):
+        var_fn = None
+        if self.exact_var and self.obs.dtype == np.float32:
+            # A14 on the device: nma_rolling_var is bit-exact with the script's float32 np.var loop (SV_dense.py:159-170)
+            from .engine import rolling_var
+
+            def var_fn(x, K):
+                x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+                return rolling_var(x, K).cpu().numpy()
         return feed.sv_base_arrays(self.obs, self.dt, self.T, self.no_flows, self.kernel_len, self.feat_window,
-                                   exact_var=self.exact_var)
+                                   exact_var=self.exact_var, var_fn=var_fn)
 
     def build_flow(self) -> None:
         super().build_flow()
