@@ -109,20 +109,27 @@ int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, c
 /* The K-tap conv (AR.py:61-62) and its data gradient run on the tcgen05 tensor cores (3xTF32 split, fp32
  * accumulate) whenever the configuration allows it (flow_dims = 1, kernel_len <= 190); the FP32 SIMT kernels
  * remain as the correctness anchor.  on = 0 selects the SIMT conv, on = 1 the tensor-core conv (error if the
- * configuration does not support it).  The environment variable NMA_TC=0 sets the default to SIMT. */
+ * configuration does not support it).  The environment variable NMA_TC=0 sets the default to SIMT.
+ * `on` is a bit set: bit 0 the conv, bit 1 the feature MLP and the head backward on tcgen05 as well, bit 2 the conv
+ * GEMMs (forward, data gradient, weight gradient) in the 2-term bfloat16 split on kind::f16 - twice the tensor rate,
+ * 16 instead of 22 significand bits per operand, measured 4e-6..8e-6 on the step's gradients (bar 1e-4); it needs
+ * bits 0 and 1 and an AR-type model (flow_dims = 1, one hidden layer, no batch-norm), error otherwise.
+ * NMA_TC_BF16=1 makes it the default where supported.  nma_get_tensor_cores returns the same bit set. */
 int nma_set_tensor_cores(nma_handle h, int32_t on);
 int nma_get_tensor_cores(nma_handle h);
 
 /* Test hook: the bare tensor-core contraction on caller data.  d_in [Q][56] fp32, d_w [K][51][50] (conv1d kernel
  * layout), d_out [Q][64].  mode 0: out[q][n] = sum_k sum_c in[q+k][c] w[k][c][n]; mode 1 (data gradient):
  * out[q][n] = sum_k sum_f in[q+k][f] w[K-1-k][n][f].  nacc = 1 or 2 accumulators of 128 positions per CTA.
- * Synchronises the stream; allocates its own scratch. */
+ * mode + 2: the same contraction in the bf16 split.  Synchronises the stream; allocates its own scratch. */
 int nma_tc_conv_raw(const float* d_in, const float* d_w, int32_t mode, int32_t nacc, float* d_out, int64_t Q,
                     int32_t K, void* stream);
 
 /* Test hook: bare tensor-core weight gradient.  d_in, d_da [Q][56] fp32, d_gw [K][51][50] (accumulated into):
  * gw[k][c][f] += sum_{q <= Q-K} in[q+k][c] * da[q][f]. */
 int nma_tc_wgrad_raw(const float* d_in, const float* d_da, float* d_gw, int64_t Q, int32_t K, void* stream);
+/* ... and in the bf16 split (MN-major operands straight from the conv operand layout) */
+int nma_tc_wgrad_raw_bf(const float* d_in, const float* d_da, float* d_gw, int64_t Q, int32_t K, void* stream);
 
 /* Measurement hooks (no reference counterpart): re-launch one stage of the last step on the workspace it
  * left behind (stage: 0 conv_fwd, 1 conv_dgrad, 2 conv_wgrad, 3 epi_bwd, 4 feat_fwd, 5 feat_bwd), and the

@@ -151,8 +151,10 @@ def _check_step(cfg, T, seed, objective=0, path_target=0.0, tc=None):
                            path_target=path_target)
     eng = _engine(cfg, tc)
     if tc is not None:
-        assert eng.tensor_cores == bool(tc)
-        assert eng.tensor_core_features == (tc is True)
+        mode = (3 if tc else 0) if isinstance(tc, bool) else int(tc)
+        assert eng.tensor_cores == bool(mode & 1)
+        assert eng.tensor_core_features == bool(mode & 2)
+        assert eng.bf16_split == bool(mode & 4)
     eng.set_series(arrays)
     dev = torch.device("cuda")
     out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev),

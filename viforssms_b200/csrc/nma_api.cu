@@ -70,6 +70,8 @@ static void compute_layout(nma_handle_s* h) {
     h->n_params = off;
 }
 
+static int bf16_path_ok(const nma_handle_s* h);
+
 extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     if (!cfg || !out) { nma_set_error("nma_create: null argument"); return -1; }
     if (cfg->C != NMA_C) { nma_set_error("nma_create: network_dims[0] must be %d (got %d)", NMA_C, cfg->C); return -1; }
@@ -122,6 +124,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         h->use_tc_persist = !(envp && envp[0] == '0');
         const char* envf = getenv("NMA_TC_FEAT");
         h->use_tc_feat = h->use_tc && !(envf && envf[0] == '0');
+        h->use_bf16 = 0;            // decided below, once the kernels that understand the format are known to run
     }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
@@ -199,6 +202,11 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
             w.wtc_feat = (float*)(base + off[i].wtc_feat);
         }
     }
+    {
+        const char* envb = getenv("NMA_TC_BF16");
+        h->bf16_ok = bf16_path_ok(h);
+        h->use_bf16 = (h->bf16_ok && envb && envb[0] == '1') ? 1 : 0;
+    }
     *out = h;
     return 0;
 }
@@ -210,14 +218,43 @@ extern "C" int nma_destroy(nma_handle h) {
     return 0;
 }
 
+// The bf16-split conv operands are produced by k_feat_fwd_tc / k_conv_fwd_tcp / k_epi_bwd_tc only: the format is
+// available exactly when those kernels are the ones that run (AR-type model, one hidden layer, no batch-norm).
+static int bf16_path_ok(const nma_handle_s* h) {
+    const char* enve = getenv("NMA_TC_EPI");
+    return h->use_tc && h->use_tc_feat && conv_fwd_tcp_supported(h) && epi_bwd_tc_supported(h) &&
+           !(enve && enve[0] == '0');
+}
+
+// bit 0: conv on tcgen05; bit 1: feature MLP and head backward on tcgen05 as well; bit 2: the conv GEMMs in the
+// 2-term bf16 split (kind::f16) instead of 3xTF32 - needs bits 0 and 1 and a configuration the persistent kernels cover.
 extern "C" int nma_set_tensor_cores(nma_handle h, int32_t on) {
     if (!h) { nma_set_error("null handle"); return -1; }
     if (on && !h->tc_ok) { nma_set_error("the tensor-core conv does not support this configuration (flow_dims=%d, kernel_len=%d)", h->cfg.D, h->cfg.K); return -1; }
+    const int was_bf = h->use_bf16;
     h->use_tc = (on & 1) ? 1 : 0;
     h->use_tc_feat = ((on & 3) == 3) ? 1 : 0;
+    h->bf16_ok = bf16_path_ok(h);
+    if ((on & 4) && !h->bf16_ok) {
+        h->use_bf16 = 0;
+        nma_set_error("the bf16-split conv needs the tensor-core feature/head kernels and the persistent conv kernels "
+                      "(AR-type model: flow_dims=1, one hidden layer, no batch-norm)");
+        return -1;
+    }
+    h->use_bf16 = (on & 4) ? 1 : 0;
+    if (h->use_bf16 != was_bf && h->tc_ok) {
+        // the operand buffers change format: pad slots and the gaps between rows must read as zero in the new one
+        for (int i = 0; i < h->cfg.F; ++i) {
+            const size_t bytes = (size_t)TC_CCH * h->ws[i].tin_Q * 16;
+            NMA_CHECK_CUDA(cudaMemset(h->ws[i].tin_hi, 0, bytes));
+            NMA_CHECK_CUDA(cudaMemset(h->ws[i].tin_lo, 0, bytes));
+            NMA_CHECK_CUDA(cudaMemset(h->ws[i].dat_hi, 0, bytes));
+            NMA_CHECK_CUDA(cudaMemset(h->ws[i].dat_lo, 0, bytes));
+        }
+    }
     return 0;
 }
-extern "C" int nma_get_tensor_cores(nma_handle h) { return h ? (h->use_tc | (h->use_tc_feat << 1)) : -1; }
+extern "C" int nma_get_tensor_cores(nma_handle h) { return h ? (h->use_tc | (h->use_tc_feat << 1) | (h->use_bf16 << 2)) : -1; }
 
 extern "C" int64_t nma_param_count(nma_handle h) { return h ? h->n_params : -1; }
 extern "C" int64_t nma_workspace_bytes(nma_handle h) { return h ? h->arena_bytes : -1; }
@@ -311,7 +348,10 @@ extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float
             continue;
         }
         if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, st) : launch_conv_dgrad(h, i, p, st)))) return rc;
-        if ((rc = (h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, st) : launch_conv_wgrad(h, i, p, d_grad_params, st)))) return rc;
+        if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, st)
+                   : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, st)
+                               : launch_conv_wgrad(h, i, p, d_grad_params, st))))
+            return rc;
         if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
     }
     if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, st))) return rc;
@@ -328,7 +368,9 @@ extern "C" int nma_launch_stage(nma_handle h, int32_t stage, int32_t flow, const
     switch (stage) {
         case 0: return launch_conv_fwd(h, flow, d_params, p, true, st);
         case 1: return h->use_tc ? launch_conv_dgrad_tc(h, flow, p, st) : launch_conv_dgrad(h, flow, p, st);
-        case 2: return h->use_tc ? launch_conv_wgrad_tc(h, flow, p, d_grad_params, st) : launch_conv_wgrad(h, flow, p, d_grad_params, st);
+        case 2: return h->use_bf16 ? launch_conv_wgrad_bf(h, flow, p, d_grad_params, st)
+                     : h->use_tc ? launch_conv_wgrad_tc(h, flow, p, d_grad_params, st)
+                                 : launch_conv_wgrad(h, flow, p, d_grad_params, st);
         case 3: return launch_epi_bwd(h, flow, d_params, p, NMA_OBJ_ELBO, d_grad_params, st);
         case 4: return launch_feat_fwd_eps(h, d_params, d_idx, d_eps, p, true, st);
         case 5: return launch_feat_bwd(h, flow, d_params, p, d_grad_params, st);

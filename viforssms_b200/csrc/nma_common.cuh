@@ -44,6 +44,7 @@ struct FlowWs {
     float* wpk;      // packed conv weights for the forward conv  [Cin=51][5][KP][12]
     float* wdpk;     // packed conv weights for the data-gradient conv [Cin=50][6][KP][12]
     // ---- tensor-core path (nma_tc.cuh): flattened interleaved operands, q = row*Lin + slot ----
+    // (bf16 mode: the same buffers hold [8][Q][8 x bf16] units, see TcP<true>)
     float* tin_hi;   // [14][tin_Q][4]  conv input (channel 0 = x^(i), 1..50 = feature activations), 3xTF32 hi part
     float* tin_lo;   //                 lo part
     float* dat_hi;   // [14][dat_Q][4]  dA (gradient w.r.t. the conv pre-activation) at q = K-1 + row*Lin + m
@@ -72,6 +73,9 @@ struct nma_handle_s {
     int tc_nacc;     // 128-position accumulators per CTA (2 when the tile fits in shared memory, else 1)
     int use_tc_persist;  // persistent warp-specialised conv kernels (nma_tc_conv2.cu); NMA_TC_PERSIST=0 keeps one tile per CTA
     int use_tc_feat; // feature MLP on the tensor cores as well (needs use_tc; NMA_TC_FEAT=0 keeps the FP32 SIMT kernels)
+    int bf16_ok;     // the bf16-split conv path covers this configuration (persistent conv kernels + tensor-core head backward)
+    int use_bf16;    // conv GEMMs (forward, data gradient, weight gradient) in the 2-term bf16 split on kind::f16
+                     // (nma_tc.cuh); NMA_TC_BF16=1 or bit 2 of nma_set_tensor_cores
     // Lotka-Volterra (lotka_volterra_partial_batch_fix_theta.py:71-82): every flow's feature MLP runs over the whole
     // window (LW = L0 - 1 positions), ends in a dense layer as wide as the flow's conv input and is transposed, so the
     // conv has 1 + LW input channels.  For the other models conv_cin = 51 and feat_out[i] = 50.
@@ -111,6 +115,7 @@ int launch_conv_fwd_tc(nma_handle_s* h, int flow, const float* params, int p, bo
 int launch_conv_dgrad_tc(nma_handle_s* h, int flow, int p, cudaStream_t st);
 int launch_conv_wgrad_tc(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
 int launch_conv_dgrad_tcp(nma_handle_s* h, int flow, int p, cudaStream_t st);
+int launch_conv_wgrad_bf(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
 int conv_fwd_tcp_supported(const nma_handle_s* h);
 int launch_conv_fwd_tcp(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);

@@ -11,7 +11,16 @@
 // Precision: the contraction is 2550 deep over un-normalised activations and must hold 1e-4 on
 // gradients, so every product is the 3xTF32 split  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi
 // (hi = top 19 bits, lo = a - hi, both exact in fp32; fp32 accumulation in TMEM).
+//
+// Second operand format ("BF", TcP<true>): the 2-term bfloat16 split  a ~= a_hi + a_lo  (both round-to-nearest bf16,
+// 16 significand bits together) with the same three products on kind::f16, which runs at twice the kind::tf32 rate
+// and packs 8 channels into a 16-byte unit: 4 k-steps of 16 channels per tap instead of 7 k-steps of 8.  The layout
+// is byte-for-byte analogous - [channel/8][position][8 x bf16], one 16-byte unit per position and chunk - so every
+// descriptor below is shared; only the chunk count, the instruction descriptor and the MMA kind differ.
+// Measured on the fp64 oracle (tools/split_precision.py): worst per-variable gradient error of the whole step
+// 4e-6 .. 8e-6 with this split on all three conv GEMMs (bar 1e-4; 3xTF32: 4e-7).
 #pragma once
+#include <cuda_bf16.h>
 #include "nma_conv_core.cuh"
 
 #define TC_CCH 14                 // reduction chunks of 4 channels: 56 >= 51 (fwd) / 50 (dgrad)
@@ -23,6 +32,32 @@
 #define TC_STAGES 3
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// operand format traits: BF = false 3xTF32 (4 channels per 16-byte unit), BF = true 2-term bf16 split (8 channels)
+template <bool BF>
+struct TcP {
+    static constexpr int CCH = BF ? 8 : TC_CCH;        // 16-byte channel chunks per position (64 / 56 channel slots)
+    static constexpr int CPU = BF ? 8 : 4;             // channels per 16-byte unit
+    static constexpr int WHALF = CCH * TC_N * 4;       // floats (= 4-byte words) of the hi or lo part of one tap
+    static constexpr int WSTAGE = 2 * WHALF;           // one tap: [CCH][64 hi rows | 64 lo rows][16 B]
+};
+
+// 2-term bf16 split, both parts round-to-nearest
+__device__ __forceinline__ void bf_split(float v, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi = (uint32_t)__bfloat16_as_ushort(h);
+    lo = (uint32_t)__bfloat16_as_ushort(l);
+}
+// 8 consecutive channels of one position -> the 16-byte hi unit and the 16-byte lo unit
+__device__ __forceinline__ void bf_split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bf_split(v[e], h[e], l[e]);
+    hi = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    lo = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+}
+__device__ __forceinline__ float bf_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
 
 // ---- mbarrier extras ----
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
@@ -98,6 +133,26 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// instruction descriptor for kind::f16 with bf16 operands, fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool BF>
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return BF ? umma_idesc_bf16(M, N, a_mn_major, b_mn_major) : umma_idesc_tf32(M, N, a_mn_major, b_mn_major);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -108,6 +163,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+template <bool BF>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (BF) umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+    else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 
 // ---------------------------------------------------------------------------
@@ -124,14 +185,15 @@ struct TcConvSmem {
     uint32_t* tmem_slot;
 };
 __host__ __device__ inline int tc_conv_npos(int nacc, int K) { return (nacc * TC_M + K - 1 + 7) & ~7; }
-__host__ __device__ inline size_t tc_conv_smem_floats(int nacc, int K) {
-    return (size_t)2 * TC_CCH * tc_conv_npos(nacc, K) * 4 + (size_t)TC_STAGES * TC_WSTAGE;
+__host__ __device__ inline size_t tc_conv_smem_floats(int nacc, int K, int cch = TC_CCH) {
+    return (size_t)2 * cch * tc_conv_npos(nacc, K) * 4 + (size_t)TC_STAGES * (2 * cch * TC_N * 4);
 }
-__device__ __forceinline__ TcConvSmem tc_conv_carve(float* smem, int npos, uint64_t* bars, uint32_t* tmem_slot) {
+__device__ __forceinline__ TcConvSmem tc_conv_carve(float* smem, int npos, uint64_t* bars, uint32_t* tmem_slot,
+                                                    int cch = TC_CCH) {
     TcConvSmem s;
     s.a_hi = smem;
-    s.a_lo = s.a_hi + (size_t)TC_CCH * npos * 4;
-    s.wring = s.a_lo + (size_t)TC_CCH * npos * 4;
+    s.a_lo = s.a_hi + (size_t)cch * npos * 4;
+    s.wring = s.a_lo + (size_t)cch * npos * 4;
     s.full = bars;
     s.empty = bars + TC_STAGES;
     s.a_bar = bars + 2 * TC_STAGES;
@@ -142,10 +204,10 @@ __device__ __forceinline__ TcConvSmem tc_conv_carve(float* smem, int npos, uint6
 #define TC_NBARS (2 * TC_STAGES + 2)
 
 struct TcConvSrc {
-    const float* a_hi;     // [14][Qalloc][4]   hi parts of the flattened input (position q = row*Lin + slot)
+    const float* a_hi;     // [CCH][Qalloc][16 B]   hi parts of the flattened input (position q = row*Lin + slot)
     const float* a_lo;
     long long Qalloc;
-    const float* wt;       // [K][14][128][4] packed taps (rows 0-63 hi parts, rows 64-127 lo parts)
+    const float* wt;       // [K][CCH][128][16 B] packed taps (rows 0-63 hi parts, rows 64-127 lo parts)
     int K;
 };
 
@@ -180,16 +242,18 @@ __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_b
 // accumulators are readable with tcgen05.ld: accumulator a holds the main sum in columns [128a, 128a+64) and
 // the 3xTF32 correction terms in [128a+64, 128a+128) of tmem_base (lane = position); their sum is the result.
 // Barriers and TMEM must have been set up by tc_conv_setup().
-template <int NACC>
+template <int NACC, bool BF = false>
 __device__ __forceinline__ void tc_conv_mainloop(const TcConvSmem& s, const TcConvSrc& src, long long q0, int npos,
                                                  uint32_t tmem_base) {
+    constexpr int CCH = TcP<BF>::CCH;
+    constexpr int WSTAGE = TcP<BF>::WSTAGE;
     const int warp = threadIdx.x >> 5;
     if (warp == 0) {
         // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
         const uint32_t slab_bytes = (uint32_t)npos * 16u;
         if (elect_one()) {
-            mbar_expect_tx(s.a_bar, 2u * TC_CCH * slab_bytes);
-            for (int c = 0; c < TC_CCH; ++c) {
+            mbar_expect_tx(s.a_bar, 2u * CCH * slab_bytes);
+            for (int c = 0; c < CCH; ++c) {
                 bulk_g2s(s.a_hi + (size_t)c * npos * 4, src.a_hi + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, s.a_bar);
                 bulk_g2s(s.a_lo + (size_t)c * npos * 4, src.a_lo + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, s.a_bar);
             }
@@ -199,34 +263,34 @@ __device__ __forceinline__ void tc_conv_mainloop(const TcConvSmem& s, const TcCo
             const int st = k % TC_STAGES;
             if (k >= TC_STAGES) mbar_wait_lane0(&s.empty[st], (uint32_t)(((k / TC_STAGES) - 1) & 1));
             if (elect_one()) {
-                mbar_expect_tx(&s.full[st], TC_WSTAGE * 4u);
-                bulk_g2s(s.wring + (size_t)st * TC_WSTAGE, src.wt + (size_t)k * TC_WSTAGE, TC_WSTAGE * 4u, &s.full[st]);
+                mbar_expect_tx(&s.full[st], WSTAGE * 4u);
+                bulk_g2s(s.wring + (size_t)st * WSTAGE, src.wt + (size_t)k * WSTAGE, WSTAGE * 4u, &s.full[st]);
             }
             __syncwarp();
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = umma_idesc_tf32(TC_M, TC_N, 0, 0);
+        constexpr uint32_t idesc = umma_idesc<BF>(TC_M, TC_N, 0, 0);
         const uint32_t a_lbo = (uint32_t)npos * 16u;          // between channel chunks
         const uint32_t ah_lo0 = desc_lo(smem_u32(s.a_hi), a_lbo), al_lo0 = desc_lo(smem_u32(s.a_lo), a_lbo);
         const uint32_t a_hi32 = desc_hi(128u), b_hi32 = desc_hi(128u);
         const uint32_t w_lo0 = desc_lo(smem_u32(s.wring), TC_WROWS * 16u);
         const uint32_t ks_step_a = 2u * (uint32_t)npos;       // (2 channel chunks) >> 4
         constexpr uint32_t ks_step_b = 2u * TC_WROWS;         // 2 chunks of 128 rows x 16 B, >> 4
-        constexpr uint32_t idesc_wide = umma_idesc_tf32(TC_M, 2 * TC_N, 0, 0);
+        constexpr uint32_t idesc_wide = umma_idesc<BF>(TC_M, 2 * TC_N, 0, 0);
         mbar_wait_lane0(s.a_bar, 0);
         for (int k = 0; k < src.K; ++k) {
             const int st = k % TC_STAGES;
             mbar_wait_lane0(&s.full[st], (uint32_t)((k / TC_STAGES) & 1));
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t wb = w_lo0 + (uint32_t)st * (TC_WSTAGE * 4u / 16u);
+                const uint32_t wb = w_lo0 + (uint32_t)st * (WSTAGE * 4u / 16u);
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) {
                     const uint32_t row = (uint32_t)(a * TC_M + k);     // 16-byte units
                     const uint32_t d = tmem_base + (uint32_t)(a * 2 * TC_N);
 #pragma unroll
-                    for (int ks = 0; ks < TC_CCH / 2; ++ks) {
+                    for (int ks = 0; ks < CCH / 2; ++ks) {
                         const uint64_t ah = desc_pack(ah_lo0 + row + (uint32_t)ks * ks_step_a, a_hi32);
                         const uint64_t al = desc_pack(al_lo0 + row + (uint32_t)ks * ks_step_a, a_hi32);
                         const uint64_t bw = desc_pack(wb + (uint32_t)ks * ks_step_b, b_hi32);
@@ -235,8 +299,8 @@ __device__ __forceinline__ void tc_conv_mainloop(const TcConvSmem& s, const TcCo
                         // for a single read of A; a_lo*b_hi (N=64) then lands on the correction columns.
                         // The tensor core accumulates with truncation: keeping the 2^-11 smaller correction terms in
                         // their own accumulator makes the main chain 3x shorter; the epilogue adds the two in fp32.
-                        umma_tf32(d, ah, bw, idesc_wide, (k | ks) ? 1u : 0u);
-                        umma_tf32(d + TC_N, al, bw, idesc, 1u);
+                        umma<BF>(d, ah, bw, idesc_wide, (k | ks) ? 1u : 0u);
+                        umma<BF>(d + TC_N, al, bw, idesc, 1u);
                     }
                 }
                 tc_commit(&s.empty[st]);      // frees the weight stage once these MMAs have read it

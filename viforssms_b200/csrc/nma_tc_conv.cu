@@ -43,8 +43,37 @@ __global__ void k_tc_pack_w(const float* __restrict__ W, int K, int mode, float*
     }
 }
 
+// the same two packs in the 2-term bf16 split: [K][8][64 hi rows | 64 lo rows][8 x bf16]
+__global__ void k_tc_pack_w_bf(const float* __restrict__ W, int K, int mode, uint16_t* __restrict__ out) {
+    const int n_half = K * 8 * TC_N * 8;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_half; t += gridDim.x * blockDim.x) {
+        const int e = t & 7;
+        const int n = (t >> 3) & (TC_N - 1);
+        const int cch = (t >> 9) & 7;
+        const int k = t >> 12;
+        const int c = 8 * cch + e;
+        float v = 0.f;
+        if (mode == 0) {
+            if (c < NMA_C1 && n < NMA_C) v = W[((size_t)k * NMA_C1 + c) * NMA_C + n];
+        } else {
+            if (c < NMA_C && n < NMA_C1) v = W[((size_t)(K - 1 - k) * NMA_C1 + n) * NMA_C + c];
+        }
+        uint32_t hi, lo;
+        bf_split(v, hi, lo);
+        const size_t o = (size_t)k * (8 * TC_WROWS * 8) + ((size_t)cch * TC_WROWS + n) * 8 + e;
+        out[o] = (uint16_t)hi;
+        out[o + TC_N * 8] = (uint16_t)lo;
+    }
+}
+
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
     for (int i = 0; i < h->cfg.F; ++i) {
+        if (h->use_bf16) {
+            k_tc_pack_w_bf<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 0, (uint16_t*)h->ws[i].wtc_f);
+            if (need_bwd) k_tc_pack_w_bf<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 1, (uint16_t*)h->ws[i].wtc_d);
+            nma_count_launch(need_bwd ? 2 : 1);
+            continue;
+        }
         k_tc_pack_w<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 0, h->ws[i].wtc_f);
         nma_count_launch(1);
         if (need_bwd) {
@@ -281,17 +310,34 @@ __global__ void k_tc_split_in(const float* __restrict__ in, long long Q, long lo
     }
 }
 
-template <int NACC>
+// channel-last fp32 [Q][56] -> the bf16 split operand [8][Qalloc][8 x bf16] (hi and lo)
+__global__ void k_tc_split_in_bf(const float* __restrict__ in, long long Q, long long Qalloc, uint4* __restrict__ hi,
+                                 uint4* __restrict__ lo) {
+    const long long n = Q * 7;                  // chunk 7 (channels 56..63) stays zero
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long q = t / 7;
+        const int cch = (int)(t - q * 7);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = in[q * 56 + 8 * cch + e];
+        uint4 h4, l4;
+        bf_split8(v, h4, l4);
+        hi[(size_t)cch * Qalloc + q] = h4;
+        lo[(size_t)cch * Qalloc + q] = l4;
+    }
+}
+
+template <int NACC, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv_raw(TcConvSrc src, int npos, long long Q, float* __restrict__ out) {
     extern __shared__ __align__(128) float smem[];
     __shared__ uint64_t bars[TC_NBARS];
     __shared__ uint32_t tmem_slot;
     constexpr int NCOLS = NACC * TC_M;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TcConvSmem s = tc_conv_carve(smem, npos, bars, &tmem_slot);
+    const TcConvSmem s = tc_conv_carve(smem, npos, bars, &tmem_slot, TcP<BF>::CCH);
     const uint32_t tmem = tc_conv_setup(s, NACC * 2 * TC_N);
     const long long q0 = (long long)blockIdx.x * NCOLS;
-    tc_conv_mainloop<NACC>(s, src, q0, npos, tmem);
+    tc_conv_mainloop<NACC, BF>(s, src, q0, npos, tmem);
     if (warp < 4 * NACC) {
         const int acc = warp >> 2, quarter = warp & 3;
         const long long q = q0 + acc * TC_M + quarter * 32 + lane;
@@ -307,37 +353,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_conv_raw(TcConvSrc src, in
     tc_conv_teardown(tmem, NACC * 2 * TC_N);
 }
 
+template <int NACC, bool BF>
+static cudaError_t raw_launch(const TcConvSrc& src, int npos, long long Q, float* d_out, int smem, unsigned grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv_raw<NACC, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) k_tc_conv_raw<NACC, BF><<<grid, TC_THREADS, smem, st>>>(src, npos, Q, d_out);
+    return e;
+}
+
+// mode bit 0: 0 forward / 1 data-gradient orientation of the kernel; mode bit 1: operand format, 0 3xTF32 / 1 bf16 split
 extern "C" int nma_tc_conv_raw(const float* d_in, const float* d_w, int32_t mode, int32_t nacc, float* d_out, int64_t Q,
                                int32_t K, void* stream) {
-    if (!d_in || !d_w || !d_out || Q < 1 || K < 1 || (nacc != 1 && nacc != 2) || (mode != 0 && mode != 1)) {
+    if (!d_in || !d_w || !d_out || Q < 1 || K < 1 || (nacc != 1 && nacc != 2) || mode < 0 || mode > 3) {
         nma_set_error("nma_tc_conv_raw: bad argument");
         return -1;
     }
+    const bool bf = (mode & 2) != 0;
+    mode &= 1;
+    const int cch = bf ? TcP<true>::CCH : TcP<false>::CCH;
     cudaStream_t st = (cudaStream_t)stream;
     const int npos = tc_conv_npos(nacc, K);
     const int ncols = nacc * TC_M;
     const long long Qalloc = (Q + ncols - 1) / ncols * ncols + npos;
     float *hi = nullptr, *lo = nullptr, *wt = nullptr;
-    const size_t abytes = (size_t)TC_CCH * Qalloc * 16;
+    const size_t abytes = (size_t)cch * Qalloc * 16;
     NMA_CHECK_CUDA(cudaMalloc(&hi, abytes));
     NMA_CHECK_CUDA(cudaMalloc(&lo, abytes));
     NMA_CHECK_CUDA(cudaMalloc(&wt, (size_t)K * TC_WSTAGE * 4));
     NMA_CHECK_CUDA(cudaMemsetAsync(hi, 0, abytes, st));
     NMA_CHECK_CUDA(cudaMemsetAsync(lo, 0, abytes, st));
-    k_tc_split_in<<<296, 256, 0, st>>>(d_in, Q, Qalloc, hi, lo);
-    k_tc_pack_w<<<148, 256, 0, st>>>(d_w, K, mode, wt);
+    if (bf) {
+        k_tc_split_in_bf<<<296, 256, 0, st>>>(d_in, Q, Qalloc, (uint4*)hi, (uint4*)lo);
+        k_tc_pack_w_bf<<<148, 256, 0, st>>>(d_w, K, mode, (uint16_t*)wt);
+    } else {
+        k_tc_split_in<<<296, 256, 0, st>>>(d_in, Q, Qalloc, hi, lo);
+        k_tc_pack_w<<<148, 256, 0, st>>>(d_w, K, mode, wt);
+    }
     TcConvSrc src;
     src.a_hi = hi; src.a_lo = lo; src.Qalloc = Qalloc; src.wt = wt; src.K = K;
-    const int smem = (int)(tc_conv_smem_floats(nacc, K) * 4);
+    const int smem = (int)(tc_conv_smem_floats(nacc, K, cch) * 4);
     const unsigned grid = (unsigned)((Q + ncols - 1) / ncols);
     cudaError_t e;
-    if (nacc == 2) {
-        e = cudaFuncSetAttribute(k_tc_conv_raw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) k_tc_conv_raw<2><<<grid, TC_THREADS, smem, st>>>(src, npos, Q, d_out);
-    } else {
-        e = cudaFuncSetAttribute(k_tc_conv_raw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) k_tc_conv_raw<1><<<grid, TC_THREADS, smem, st>>>(src, npos, Q, d_out);
-    }
+    if (nacc == 2) e = bf ? raw_launch<2, true>(src, npos, Q, d_out, smem, grid, st) : raw_launch<2, false>(src, npos, Q, d_out, smem, grid, st);
+    else e = bf ? raw_launch<1, true>(src, npos, Q, d_out, smem, grid, st) : raw_launch<1, false>(src, npos, Q, d_out, smem, grid, st);
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(st);
     cudaFree(hi); cudaFree(lo); cudaFree(wt);
@@ -627,6 +684,232 @@ extern "C" int nma_tc_wgrad_raw(const float* d_in, const float* d_da, float* d_g
     cudaFree(ih); cudaFree(il); cudaFree(dh); cudaFree(dl);
     if (e != cudaSuccess || e2 != cudaSuccess) {
         nma_set_error("nma_tc_wgrad_raw: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return -2;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// weight gradient in the bf16 split:  dW[k][c][f] = sum_q inp_flat[q + k][c] * dA_flat[q][f]   on kind::f16
+//
+// 16-bit operands may be MN-major, and the conv operand layout [channel/8][position][8 x bf16] IS the no-swizzle
+// MN-major canonical layout of a (channels x positions) matrix with the positions as the reduction: 8 consecutive
+// positions of one channel chunk are one 128-byte core matrix, the next 8 positions follow at +128 B (leading byte
+// offset), the next channel chunk at the slab stride (stride byte offset).  So both operands are fed to the tensor
+// core exactly as the forward pass and the head backward wrote them: no transposes, no unit building - the TMA engine
+// copies slabs, one thread issues MMAs.  Tap t is, again, a +16t-byte start address.
+//   A (M = 128): rows 0-63 = the 64 channel slots at tap t, rows 64-127 = the same at tap t+1: the slabs are staged
+//                twice, the second copy read from one position further on, so that all 16 chunk slabs of a tap pair
+//                lie at one stride.  hi and lo parts are separate tiles.
+//   B (N = 128): 64 hi | 64 lo channel slots of dA: the dat_hi slabs followed by the dat_lo slabs.
+//   D[pair]:     128 TMEM columns: A_hi x [B_hi | B_lo] -> main | correction, A_lo x B_hi (N = 64) -> correction.
+// K = 16 positions per MMA; a stage is 64 positions; the accumulators are drained TMEM -> registers every 4 stages
+// (16-MMA chains: the tensor core accumulates with truncation) and summed in round-to-nearest fp32.
+// CTA = (group of <= 4 tap pairs, range of stages); warps 0-7 drain, warp 8 TMA (all lanes issue), warp 9 MMA.
+// ---------------------------------------------------------------------------
+#define WB_KT 64
+#define WB_APOS (WB_KT + 8)                 // tap offsets 0..6 inside a group of 4 pairs
+#define WB_STAGES 4
+#define WB_FLUSH 4
+#define WB_A_UNITS (16 * WB_APOS)           // 16-byte units of A_hi (or A_lo): 16 chunk slabs
+#define WB_B_UNITS (16 * WB_KT)
+#define WB_STAGE_UNITS (2 * WB_A_UNITS + WB_B_UNITS)
+#define WB_NCOPY 42                         // bulk copies per stage: 2 x 2 x 7 A slabs + 2 x 7 B slabs (chunk 7 is all zero)
+#define WB_STAGE_TX ((28 * WB_APOS + 14 * WB_KT) * 16)
+
+struct ConvWgradBfArgs {
+    const uint4* in_hi; const uint4* in_lo; long long in_Q;      // [8][in_Q] 16-byte units
+    const uint4* da_hi; const uint4* da_lo; long long da_Q;      // dA(q) at unit q + K - 1
+    float* gW;                                                   // [K][51][50]
+    int K, npairs, ngroups, nstages_total, nq;
+};
+
+__global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArgs a) {
+    extern __shared__ __align__(128) uint4 smem_u[];
+    __shared__ uint64_t full[WB_STAGES], empty[WB_STAGES], acc_full, acc_free;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y;
+    const int base = a.npairs / a.ngroups, rem = a.npairs % a.ngroups;
+    const int np = base + (g < rem ? 1 : 0);                    // tap pairs of this CTA
+    const int k0 = 2 * (g * base + (g < rem ? g : rem));        // first tap
+    const int s_begin = (int)((long long)a.nstages_total * blockIdx.x / a.nq);
+    const int s_end = (int)((long long)a.nstages_total * (blockIdx.x + 1) / a.nq);
+    const int nst = s_end - s_begin;
+    const int nchunks = (nst + WB_FLUSH - 1) / WB_FLUSH;
+
+    // slabs of chunk 7 (channel slots 56..63) are never loaded: zero everything once
+    for (int t = tid; t < WB_STAGES * WB_STAGE_UNITS; t += blockDim.x) smem_u[t] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        for (int i = 0; i < WB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(&acc_full, 1); mbar_init(&acc_free, 8);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer: every lane issues its share of the stage's 42 slab copies =====
+        for (int si = 0; si < nst; ++si) {
+            const int st = si % WB_STAGES;
+            if (si >= WB_STAGES) mbar_wait_backoff(&empty[st], (uint32_t)(((si / WB_STAGES) - 1) & 1));
+            if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)WB_STAGE_TX);
+            __syncwarp();
+            uint4* sb = smem_u + (size_t)st * WB_STAGE_UNITS;
+            const long long q0 = (long long)(s_begin + si) * WB_KT;
+            for (int idx = lane; idx < WB_NCOPY; idx += 32) {
+                if (idx < 28) {
+                    const int hl = idx / 14, r2 = idx - hl * 14, copy = r2 / 7, c = r2 - copy * 7;
+                    const uint4* src = (hl ? a.in_lo : a.in_hi) + (size_t)c * a.in_Q + q0 + k0 + copy;
+                    bulk_g2s(sb + hl * WB_A_UNITS + (copy * 8 + c) * WB_APOS, src, WB_APOS * 16u, &full[st]);
+                } else {
+                    const int j = idx - 28, hl = j / 7, c = j - hl * 7;
+                    const uint4* src = (hl ? a.da_lo : a.da_hi) + (size_t)c * a.da_Q + q0 + (a.K - 1);
+                    bulk_g2s(sb + 2 * WB_A_UNITS + (hl * 8 + c) * WB_KT, src, WB_KT * 16u, &full[st]);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc_n64 = umma_idesc_bf16(TC_M, TC_N, 1, 1);
+        constexpr uint32_t idesc_n128 = umma_idesc_bf16(TC_M, 2 * TC_N, 1, 1);
+        const uint32_t sbase = smem_u32(smem_u);
+        const uint32_t a_hi32 = desc_hi(WB_APOS * 16u), b_hi32 = desc_hi(WB_KT * 16u);    // stride offset: next channel chunk
+        for (int si = 0; si < nst; ++si) {
+            const int st = si % WB_STAGES;
+            const int ci = si / WB_FLUSH;
+            const bool chunk_first = (si % WB_FLUSH) == 0;
+            const bool chunk_last = ((si % WB_FLUSH) == WB_FLUSH - 1) || (si == nst - 1);
+            if (chunk_first && ci > 0) mbar_wait_backoff(&acc_free, (uint32_t)((ci - 1) & 1));
+            mbar_wait_backoff(&full[st], (uint32_t)((si / WB_STAGES) & 1));
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ua_hi = sbase + (uint32_t)(st * WB_STAGE_UNITS) * 16u;
+                const uint32_t ua_lo = ua_hi + WB_A_UNITS * 16u;
+                const uint32_t ub = ua_lo + WB_A_UNITS * 16u;
+                const uint32_t ah0 = desc_lo(ua_hi, 128u), al0 = desc_lo(ua_lo, 128u), b0 = desc_lo(ub, 128u);   // leading offset: next 8 positions
+                for (int pr = 0; pr < np; ++pr) {
+                    const uint32_t d = tmem + (uint32_t)(pr * 2 * TC_N);
+#pragma unroll
+                    for (int ks = 0; ks < WB_KT / 16; ++ks) {
+                        const uint32_t aoff = (uint32_t)(2 * pr + 16 * ks);          // 16-byte units = positions
+                        const uint64_t ah = desc_pack(ah0 + aoff, a_hi32), al = desc_pack(al0 + aoff, a_hi32);
+                        const uint64_t bw = desc_pack(b0 + (uint32_t)(16 * ks), b_hi32);
+                        umma_bf16(d, ah, bw, idesc_n128, (chunk_first && ks == 0) ? 0u : 1u);
+                        umma_bf16(d + TC_N, al, bw, idesc_n64, 1u);
+                    }
+                }
+                tc_commit(&empty[st]);
+                if (chunk_last) tc_commit(&acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== drain warps =====
+        const int quarter = warp & 3, colhalf = warp >> 2;
+        float acc[WGT_MAXPAIRS][32];
+#pragma unroll
+        for (int pr = 0; pr < WGT_MAXPAIRS; ++pr)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[pr][i] = 0.f;
+        for (int ci = 0; ci < nchunks; ++ci) {
+            mbar_wait_backoff(&acc_full, (uint32_t)(ci & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int pr = 0; pr < WGT_MAXPAIRS; ++pr) {
+                if (pr < np) {
+                    float v[32], c2[32];
+                    const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pr * 2 * TC_N + colhalf * 32);
+                    tmem_ld32(ta, v);
+                    tmem_ld32(ta + TC_N, c2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[pr][i] += v[i] + c2[i];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free);
+        }
+        // TMEM lane = M row = j*64 + channel slot
+        const int M = quarter * 32 + lane, j = M >> 6, c = M & 63;
+#pragma unroll
+        for (int pr = 0; pr < WGT_MAXPAIRS; ++pr) {
+            const int tap = k0 + 2 * pr + j;
+            if (pr < np && tap < a.K && c < NMA_C1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int f = colhalf * 32 + i;
+                    if (f < NMA_C) atomicAdd(a.gW + ((size_t)tap * NMA_C1 + c) * NMA_C + f, acc[pr][i]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void wgrad_bf_geometry(ConvWgradBfArgs& a, long long qtot, int sm_count) {
+    a.npairs = (a.K + 1) / 2;
+    a.ngroups = (a.npairs + WGT_MAXPAIRS - 1) / WGT_MAXPAIRS;
+    a.nstages_total = (int)((qtot + WB_KT - 1) / WB_KT);
+    int nq = (3 * sm_count) / a.ngroups;
+    if (nq < 1) nq = 1;
+    if (nq > a.nstages_total) nq = a.nstages_total;
+    a.nq = nq;
+}
+
+int launch_conv_wgrad_bf(nma_handle_s* h, int i, int p, float* gp, cudaStream_t st) {
+    const FlowDims& d = h->fd[i];
+    ConvWgradBfArgs a;
+    a.in_hi = (const uint4*)h->ws[i].tin_hi; a.in_lo = (const uint4*)h->ws[i].tin_lo; a.in_Q = h->ws[i].tin_Q;
+    a.da_hi = (const uint4*)h->ws[i].dat_hi; a.da_lo = (const uint4*)h->ws[i].dat_lo; a.da_Q = h->ws[i].dat_Q;
+    a.gW = gp + h->po[i].convw;
+    a.K = h->cfg.K;
+    wgrad_bf_geometry(a, (long long)p * d.Lin, h->sm_count);
+    const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
+    static int configured = 0;
+    if (configured < smem) {
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    k_conv_wgrad_bf<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// test hook: the bare bf16-split weight gradient, same contract as nma_tc_wgrad_raw
+extern "C" int nma_tc_wgrad_raw_bf(const float* d_in, const float* d_da, float* d_gw, int64_t Q, int32_t K, void* stream) {
+    if (!d_in || !d_da || !d_gw || Q < K || K < 1) { nma_set_error("nma_tc_wgrad_raw_bf: bad argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long Qalloc = (Q + 255) / 256 * 256 + 640 + K;
+    const size_t abytes = (size_t)8 * Qalloc * 16;
+    uint4 *ih = nullptr, *il = nullptr, *dh = nullptr, *dl = nullptr;
+    NMA_CHECK_CUDA(cudaMalloc(&ih, abytes)); NMA_CHECK_CUDA(cudaMalloc(&il, abytes));
+    NMA_CHECK_CUDA(cudaMalloc(&dh, abytes)); NMA_CHECK_CUDA(cudaMalloc(&dl, abytes));
+    NMA_CHECK_CUDA(cudaMemsetAsync(ih, 0, abytes, st)); NMA_CHECK_CUDA(cudaMemsetAsync(il, 0, abytes, st));
+    NMA_CHECK_CUDA(cudaMemsetAsync(dh, 0, abytes, st)); NMA_CHECK_CUDA(cudaMemsetAsync(dl, 0, abytes, st));
+    k_tc_split_in_bf<<<296, 256, 0, st>>>(d_in, Q, Qalloc, ih, il);
+    // dA(q) lives at unit q + K - 1; only q <= Q-K contribute
+    k_tc_split_in_bf<<<296, 256, 0, st>>>(d_da, Q - K + 1, Qalloc, dh + (K - 1), dl + (K - 1));
+    ConvWgradBfArgs a;
+    a.in_hi = ih; a.in_lo = il; a.in_Q = Qalloc; a.da_hi = dh; a.da_lo = dl; a.da_Q = Qalloc;
+    a.gW = d_gw; a.K = K;
+    wgrad_bf_geometry(a, Q, 4);
+    const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
+    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) k_conv_wgrad_bf<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(ih); cudaFree(il); cudaFree(dh); cudaFree(dl);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        nma_set_error("nma_tc_wgrad_raw_bf: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
         return -2;
     }
     return 0;

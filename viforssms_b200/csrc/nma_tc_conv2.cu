@@ -28,9 +28,11 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
 }
 
 // producer and MMA-issuer roles, shared by both kernels.  NST = ring stages in use (<= TC_STAGES).
-template <int NST>
+template <int NST, bool BF>
 __device__ __forceinline__ void p_producer(PBars& b, float* a_hi, float* a_lo, float* wring, const TcConvSrc& src,
                                            int npos, long long ntiles) {
+    constexpr int CCH = TcP<BF>::CCH;
+    constexpr int WSTAGE = TcP<BF>::WSTAGE;
     const uint32_t slab_bytes = (uint32_t)npos * 16u;
     uint32_t g = 0;
     int it = 0;
@@ -38,8 +40,8 @@ __device__ __forceinline__ void p_producer(PBars& b, float* a_hi, float* a_lo, f
         const long long q0 = tile * (2 * TC_M);
         if (it > 0) mbar_wait_backoff(&b.a_free, (uint32_t)((it - 1) & 1));
         if (elect_one()) {
-            mbar_expect_tx(&b.a_full, 2u * TC_CCH * slab_bytes);
-            for (int c = 0; c < TC_CCH; ++c) {
+            mbar_expect_tx(&b.a_full, 2u * CCH * slab_bytes);
+            for (int c = 0; c < CCH; ++c) {
                 bulk_g2s(a_hi + (size_t)c * npos * 4, src.a_hi + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, &b.a_full);
                 bulk_g2s(a_lo + (size_t)c * npos * 4, src.a_lo + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, &b.a_full);
             }
@@ -49,19 +51,21 @@ __device__ __forceinline__ void p_producer(PBars& b, float* a_hi, float* a_lo, f
             const uint32_t st = g % NST;
             if (g >= NST) mbar_wait_backoff(&b.empty[st], ((g / NST) - 1u) & 1u);
             if (elect_one()) {
-                mbar_expect_tx(&b.full[st], TC_WSTAGE * 4u);
-                bulk_g2s(wring + (size_t)st * TC_WSTAGE, src.wt + (size_t)k * TC_WSTAGE, TC_WSTAGE * 4u, &b.full[st]);
+                mbar_expect_tx(&b.full[st], WSTAGE * 4u);
+                bulk_g2s(wring + (size_t)st * WSTAGE, src.wt + (size_t)k * WSTAGE, WSTAGE * 4u, &b.full[st]);
             }
             __syncwarp();
         }
     }
 }
 
-template <int NST>
+template <int NST, bool BF>
 __device__ __forceinline__ void p_mma(PBars& b, const float* a_hi, const float* a_lo, const float* wring, int K, int npos,
                                       uint32_t tmem_base, long long ntiles) {
-    constexpr uint32_t idesc = umma_idesc_tf32(TC_M, TC_N, 0, 0);
-    constexpr uint32_t idesc_wide = umma_idesc_tf32(TC_M, 2 * TC_N, 0, 0);
+    constexpr int CCH = TcP<BF>::CCH;
+    constexpr int WSTAGE = TcP<BF>::WSTAGE;
+    constexpr uint32_t idesc = umma_idesc<BF>(TC_M, TC_N, 0, 0);
+    constexpr uint32_t idesc_wide = umma_idesc<BF>(TC_M, 2 * TC_N, 0, 0);
     const uint32_t a_lbo = (uint32_t)npos * 16u;
     const uint32_t ah_lo0 = desc_lo(smem_u32(a_hi), a_lbo), al_lo0 = desc_lo(smem_u32(a_lo), a_lbo);
     const uint32_t hi32 = desc_hi(128u);
@@ -79,18 +83,18 @@ __device__ __forceinline__ void p_mma(PBars& b, const float* a_hi, const float* 
             mbar_wait_backoff(&b.full[st], (g / NST) & 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t wb = w_lo0 + st * (TC_WSTAGE * 4u / 16u);
+                const uint32_t wb = w_lo0 + st * (WSTAGE * 4u / 16u);
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
                     const uint32_t row = (uint32_t)(a * TC_M + k);
                     const uint32_t d = tmem_base + set * (4u * TC_N) + (uint32_t)(a * 2 * TC_N);
 #pragma unroll
-                    for (int ks = 0; ks < TC_CCH / 2; ++ks) {
+                    for (int ks = 0; ks < CCH / 2; ++ks) {
                         const uint64_t ah = desc_pack(ah_lo0 + row + (uint32_t)ks * ks_step_a, hi32);
                         const uint64_t al = desc_pack(al_lo0 + row + (uint32_t)ks * ks_step_a, hi32);
                         const uint64_t bw = desc_pack(wb + (uint32_t)ks * ks_step_b, hi32);
-                        umma_tf32(d, ah, bw, idesc_wide, (k | ks) ? 1u : 0u);
-                        umma_tf32(d + TC_N, al, bw, idesc, 1u);
+                        umma<BF>(d, ah, bw, idesc_wide, (k | ks) ? 1u : 0u);
+                        umma<BF>(d + TC_N, al, bw, idesc, 1u);
                     }
                 }
                 tc_commit(&b.empty[st]);
@@ -139,22 +143,23 @@ struct ConvDgradP {
     int Lin, LP, XP, p, npos, need_dx;
 };
 
+template <bool BF>
 __global__ void __launch_bounds__(P_THREADS, 1) k_conv_dgrad_tcp(ConvDgradP a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ PBars bars;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* a_hi = smem;
-    float* a_lo = a_hi + (size_t)TC_CCH * a.npos * 4;
-    float* wring = a_lo + (size_t)TC_CCH * a.npos * 4;
+    float* a_lo = a_hi + (size_t)TcP<BF>::CCH * a.npos * 4;
+    float* wring = a_lo + (size_t)TcP<BF>::CCH * a.npos * 4;
     const long long qtot = (long long)a.p * a.Lin;
     const long long ntiles = (qtot + 2 * TC_M - 1) / (2 * TC_M);
     const uint32_t tmem = p_setup(bars, &tmem_slot, 1);
 
     if (warp == 8) {
-        p_producer<TC_STAGES>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
+        p_producer<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
     } else if (warp == 9) {
-        p_mma<TC_STAGES>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
+        p_mma<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
     } else {
         const int acc = warp >> 2, quarter = warp & 3;
         int it = 0;
@@ -201,13 +206,25 @@ int launch_conv_dgrad_tcp(nma_handle_s* h, int i, int p, cudaStream_t st) {
     a.need_dx = i > 0 ? 1 : 0;
     const long long ntiles = ((long long)p * d.Lin + 2 * TC_M - 1) / (2 * TC_M);
     const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
+    if (h->use_bf16) {
+        const int smem = (int)(tc_conv_smem_floats(2, h->cfg.K, TcP<true>::CCH) * 4);
+        static int configured = 0;
+        if (configured < smem) {
+            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tcp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = smem;
+        }
+        k_conv_dgrad_tcp<true><<<grid, P_THREADS, smem, st>>>(a);
+        nma_count_launch(1);
+        NMA_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     const int smem = (int)(tc_conv_smem_floats(2, h->cfg.K) * 4);
     static int configured = 0;
     if (configured < smem) {
-        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tcp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tcp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    k_conv_dgrad_tcp<<<grid, P_THREADS, smem, st>>>(a);
+    k_conv_dgrad_tcp<false><<<grid, P_THREADS, smem, st>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -240,11 +257,12 @@ struct ConvFwdP {
     float* nx_hi;            // channel 0 of the next flow's conv operand (may be null)
     float* nx_lo;
     int nx_Lin;
-    int Lin, p, npos, N, NP, XP, XPn, K, save;
+    int Lin, p, npos, N, NP, XP, XPn, K, save, ring_off;
 };
 
 #define PF_E_F (TC_CCH * 2 * TC_M * 4)          // floats of E_hi (or E_lo): [14][256][4]
 
+template <bool BF>
 __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ PBars bars;
@@ -252,9 +270,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
     __shared__ uint32_t tmem_slot;
     __shared__ float hb_sm[64], hw_sm[128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // operand region: the conv operand tile (hi | lo) during the mainloop, E_hi | E_lo | hidden kernel (3xTF32, 140 KB)
+    // during the epilogue; the weight ring follows the larger of the two (a.ring_off floats)
     float* a_hi = smem;
-    float* a_lo = a_hi + (size_t)TC_CCH * a.npos * 4;
-    float* wring = a_lo + (size_t)TC_CCH * a.npos * 4;
+    float* a_lo = a_hi + (size_t)TcP<BF>::CCH * a.npos * 4;
+    float* wring = smem + a.ring_off;
     float* E_hi = smem;                          // epilogue view of the operand buffer
     float* E_lo = E_hi + PF_E_F;
     float* Wh = E_lo + PF_E_F;
@@ -266,9 +286,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
     const uint32_t tmem = p_setup(bars, &tmem_slot, 1 + P_EPI_WARPS);
 
     if (warp == 8) {
-        p_producer<TC_STAGES>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
+        p_producer<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
     } else if (warp == 9) {
-        p_mma<TC_STAGES>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
+        p_mma<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
     } else {
         const int acc = warp >> 2, quarter = warp & 3;
         const int col = acc * TC_M + quarter * 32 + lane;
@@ -383,10 +403,18 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
                 a.s[(size_t)r * a.NP + m] = sr;
                 a.x_out[(size_t)r * a.XPn + m] = xo;
                 if (a.nx_hi && m < a.nx_Lin) {                          // channel 0 of the next flow's conv operand
-                    const size_t qn = ((size_t)r * a.nx_Lin + m) * 4;
-                    const float hi = tf32_hi(xo);
-                    a.nx_hi[qn] = hi;
-                    a.nx_lo[qn] = xo - hi;
+                    if (BF) {
+                        const size_t qn = ((size_t)r * a.nx_Lin + m) * 8;    // bf16 elements: unit q of chunk 0, slot 0
+                        uint32_t hi, lo;
+                        bf_split(xo, hi, lo);
+                        reinterpret_cast<uint16_t*>(a.nx_hi)[qn] = (uint16_t)hi;
+                        reinterpret_cast<uint16_t*>(a.nx_lo)[qn] = (uint16_t)lo;
+                    } else {
+                        const size_t qn = ((size_t)r * a.nx_Lin + m) * 4;
+                        const float hi = tf32_hi(xo);
+                        a.nx_hi[qn] = hi;
+                        a.nx_lo[qn] = xo - hi;
+                    }
                 }
             }
             tc_fence_before();
@@ -421,7 +449,7 @@ static int fwd_p_npos(int K) {
 int conv_fwd_tcp_supported(const nma_handle_s* h) {
     if (!(h->use_tc && h->use_tc_persist && h->tc_nacc == 2 && h->cfg.H == 1 && !h->cfg.bn && h->cfg.D == 1)) return 0;
     const size_t smem = (size_t)2 * TC_CCH * fwd_p_npos(h->cfg.K) * 16 + (size_t)TC_STAGES * TC_WSTAGE * 4;
-    return smem + 1024 <= 227 * 1024;
+    return smem + 1024 <= 227 * 1024;      // (the bf16 operand tile is smaller: same bound)
 }
 
 int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool save, cudaStream_t st) {
@@ -442,13 +470,30 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
     a.XP = (d.L + 3) & ~3; a.XPn = (h->fd[i + 1].L + 3) & ~3; a.K = h->cfg.K; a.save = save ? 1 : 0;
     const long long ntiles = ((long long)p * d.Lin + 2 * TC_M - 1) / (2 * TC_M);
     const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
+    // operand region = max(conv operand tile, epilogue view E_hi | E_lo | hidden kernel); the ring follows it
+    const int epi_f = 2 * PF_E_F + TC_WSTAGE;
+    if (h->use_bf16) {
+        const int op_f = 2 * TcP<true>::CCH * a.npos * 4;
+        a.ring_off = op_f > epi_f ? op_f : epi_f;
+        const int smem = (a.ring_off + TC_STAGES * TcP<true>::WSTAGE) * 4;
+        static int configured = 0;
+        if (configured < smem) {
+            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tcp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = smem;
+        }
+        k_conv_fwd_tcp<true><<<grid, P_THREADS, smem, st>>>(a);
+        nma_count_launch(2);
+        NMA_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    a.ring_off = 2 * TC_CCH * a.npos * 4;
     const int smem = 2 * TC_CCH * a.npos * 16 + TC_STAGES * TC_WSTAGE * 4;
     static int configured = 0;
     if (configured < smem) {
-        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tcp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tcp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    k_conv_fwd_tcp<<<grid, P_THREADS, smem, st>>>(a);
+    k_conv_fwd_tcp<false><<<grid, P_THREADS, smem, st>>>(a);
     nma_count_launch(2);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -94,6 +94,7 @@ struct FeatTcArgs {
     int cta_begin[NMA_MAX_FLOWS + 1];         // CTAs [cta_begin[i], cta_begin[i+1]) work on flow i
     float* x0;                                // ws[0].x: aligned copy of eps
     int XP0, p, L0, K, Cf_in, feat_off, save, F, ks0;
+    int bf;                                   // conv operand in the bf16 split [8][tin_Q][8 x bf16] (TcP<true>)
 };
 
 __device__ __forceinline__ void ft_split_store(float* hi_dst, float* lo_dst, float a, float b, float c, float d) {
@@ -269,6 +270,23 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_feat_fwd_tc(FeatTcArgs fa, Se
                     float* th = fa.tin_hi[i];
                     float* tl = fa.tin_lo[i];
                     const long long Q = fa.tin_Q[i];
+                    if (fa.bf) {
+                        // channel 32*half + 8*c8 + e: e0 = `first` for the half's first channel, else feature (channel - 1)
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            if (half == 0 || c8 < 3) {
+                                float w8[8];
+                                w8[0] = (c8 == 0) ? first : v[8 * c8 - 1 + (c8 == 0)];
+#pragma unroll
+                                for (int e = 1; e < 8; ++e) w8[e] = v[8 * c8 + e - 1];
+                                uint4 h4, l4;
+                                bf_split8(w8, h4, l4);
+                                const size_t o = (size_t)(half * 4 + c8) * Q + q;
+                                reinterpret_cast<uint4*>(th)[o] = h4;
+                                reinterpret_cast<uint4*>(tl)[o] = l4;
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int cc = 0; cc < 8; ++cc) {
                         if (half == 0 || cc < 6) {
@@ -330,6 +348,7 @@ int launch_feat_fwd_tc(nma_handle_s* h, const float* params, const int64_t* idx,
     fa.XP0 = (h->fd[0].L + 3) & ~3;
     fa.p = p; fa.L0 = h->L0; fa.K = h->cfg.K; fa.Cf_in = h->Cf_in; fa.feat_off = h->feat_off;
     fa.save = save ? 1 : 0; fa.F = F; fa.ks0 = (h->Cf_in + 7) / 8;
+    fa.bf = h->use_bf16;
     const int smem = (3 * FT_WLAYER_F + 2 * fa.ks0 * FT_CHUNK_F + FT_SLOTS * 2 * FT_A_F + 256 + FT_SLOTS * FT_M) * 4;
     static int configured = 0;
     if (configured < smem) {
@@ -645,6 +664,7 @@ struct EpiBwdTcArgs {
     float* g_hidw; float* g_hidb; float* g_headw; float* g_headb;
     int XP, XPn, N, NP, K, S, Lin, p;
     float cq;
+    int bf;                  // `dat` in the bf16 split [8][dat_Q][8 x bf16]
 };
 
 __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
@@ -668,7 +688,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
     }
     if (blockIdx.x == 0) {
         const long long q_lo = (long long)a.p * a.Lin + (a.K - 1);
-        for (int t = tid; t < TC_CCH * 128; t += blockDim.x) {
+        for (int t = tid; t < (a.bf ? 8 : TC_CCH) * 128; t += blockDim.x) {      // same 16-byte units in both formats
             const int fch = t / 128, q = t - fch * 128;
             if (q_lo + q < a.dat_Q) {
                 const size_t o = ((size_t)fch * a.dat_Q + q_lo + q) * 4;
@@ -798,6 +818,20 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
         tmem_sum16(td, [&](int k, float x) { g[k] = x * elu_grad_from_out(e0v[k]); });
         if (valid) {
             const long long qd = (long long)(a.K - 1) + (long long)r * a.Lin + m;
+            if (a.bf) {
+                // channels 16*cg .. +15 = chunks 2*cg, 2*cg + 1 of 8 channels (channels >= 50 are exact zeros)
+#pragma unroll
+                for (int c8 = 0; c8 < 2; ++c8) {
+                    float w8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) w8[e] = g[8 * c8 + e];
+                    uint4 h4, l4;
+                    bf_split8(w8, h4, l4);
+                    const size_t o = (size_t)(2 * cg + c8) * a.dat_Q + qd;
+                    reinterpret_cast<uint4*>(a.dat_hi)[o] = h4;
+                    reinterpret_cast<uint4*>(a.dat_lo)[o] = l4;
+                }
+            } else
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const int ch = 4 * cg + cc;
@@ -866,6 +900,38 @@ __global__ void __launch_bounds__(TC_CCH * 32) k_dtb_from_dat(const float* __res
     }
 }
 
+// the same from the bf16-split operand [8][Q][8 x bf16]: warp w owns the 8 channels of chunk w
+__global__ void __launch_bounds__(8 * 32) k_dtb_from_dat_bf(const uint4* __restrict__ dat_hi, const uint4* __restrict__ dat_lo,
+                                                            long long Q, int K, int Lin, int N, float* __restrict__ dtb,
+                                                            float* __restrict__ g_convb) {
+    const int r = blockIdx.x, c8 = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t base = (size_t)c8 * Q + (size_t)(K - 1) + (size_t)r * Lin;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int m = lane; m < N; m += 32) {
+        const uint4 h4 = __ldg(dat_hi + base + m), l4 = __ldg(dat_lo + base + m);
+        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            acc[2 * e] += bf_to_float(hw[e] & 0xffffu) + bf_to_float(lw[e] & 0xffffu);
+            acc[2 * e + 1] += bf_to_float(hw[e] >> 16) + bf_to_float(lw[e] >> 16);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = warp_sum(acc[e]);
+    if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int f = 8 * c8 + e;
+            if (f < NMA_C) {
+                dtb[(size_t)r * NMA_C + f] = acc[e];
+                atomicAdd(g_convb + f, acc[e]);
+            }
+        }
+    }
+}
+
 // transposed pack of ONE 1x1 kernel [50][50] (same element map as the feature kernels' transposed slots)
 __global__ void k_tc_pack_w1x1_t(const float* __restrict__ W, float* __restrict__ out) {
     for (int t = threadIdx.x; t < FT_WLAYER_F; t += blockDim.x) {
@@ -897,6 +963,7 @@ int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int ob
     a.XP = (d.L + 3) & ~3; a.XPn = (h->fd[i + 1].L + 3) & ~3; a.N = d.N; a.NP = d.NP; a.K = h->cfg.K; a.S = h->S;
     a.Lin = d.Lin; a.p = p;
     a.cq = (objective == NMA_OBJ_ELBO) ? (float)h->cfg.scale : 0.f;
+    a.bf = h->use_bf16;
     const long long ntiles = ((long long)p * d.N + FT_M - 1) / FT_M;
     const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
     const int smem = (2 * FT_A_F + 2 * FB_OPW_F + FT_WLAYER_F) * 4;
@@ -906,8 +973,12 @@ int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int ob
         configured = smem;
     }
     k_epi_bwd_tc<<<grid, FB_THREADS, smem, st>>>(a);
-    k_dtb_from_dat<<<p, TC_CCH * 32, 0, st>>>(h->ws[i].dat_hi, h->ws[i].dat_lo, h->ws[i].dat_Q, h->cfg.K, d.Lin, d.N,
-                                             h->ws[i].dtb, gp + h->po[i].convb);
+    if (h->use_bf16)
+        k_dtb_from_dat_bf<<<p, 8 * 32, 0, st>>>((const uint4*)h->ws[i].dat_hi, (const uint4*)h->ws[i].dat_lo, h->ws[i].dat_Q,
+                                               h->cfg.K, d.Lin, d.N, h->ws[i].dtb, gp + h->po[i].convb);
+    else
+        k_dtb_from_dat<<<p, TC_CCH * 32, 0, st>>>(h->ws[i].dat_hi, h->ws[i].dat_lo, h->ws[i].dat_Q, h->cfg.K, d.Lin, d.N,
+                                                 h->ws[i].dtb, gp + h->po[i].convb);
     nma_count_launch(3);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;

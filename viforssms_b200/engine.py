@@ -72,6 +72,15 @@ class NMAEngine:
         return (int(self._lib.nma_get_tensor_cores(self._h)) & 2) == 2
 
     @property
+    def bf16_split(self) -> bool:
+        """True when the conv GEMMs run in the 2-term bf16 split on kind::f16 (mode bit 2 / NMA_TC_BF16=1)."""
+        return (int(self._lib.nma_get_tensor_cores(self._h)) & 4) == 4
+
+    def set_tensor_cores(self, mode: int) -> None:
+        """Bit set of nma_set_tensor_cores: 1 conv, 2 feature MLP + head backward, 4 bf16 split of the conv GEMMs."""
+        _lib.check(self._lib.nma_set_tensor_cores(self._h, int(mode)), "nma_set_tensor_cores")
+
+    @property
     def workspace_bytes(self) -> int:
         return int(self._lib.nma_workspace_bytes(self._h))
 
@@ -169,13 +178,15 @@ def tc_conv_raw(x: torch.Tensor, w: torch.Tensor, mode: int = 0, nacc: int = 2) 
     return out
 
 
-def tc_wgrad_raw(x: torch.Tensor, da: torch.Tensor, K: int) -> torch.Tensor:
-    """Test hook: bare tensor-core weight gradient.  x, da [Q,56] fp32 -> [K,51,50] (see nma_b200.h)."""
+def tc_wgrad_raw(x: torch.Tensor, da: torch.Tensor, K: int, bf16: bool = False) -> torch.Tensor:
+    """Test hook: bare tensor-core weight gradient.  x, da [Q,56] fp32 -> [K,51,50] (see nma_b200.h);
+    bf16=True: the 2-term bf16 split kernel."""
     lib = _lib.load()
     assert x.is_cuda and da.is_cuda and x.shape == da.shape and x.shape[1] == 56
     assert x.dtype == torch.float32 and da.dtype == torch.float32 and x.is_contiguous() and da.is_contiguous()
     gw = torch.zeros(K, 51, 50, dtype=torch.float32, device=x.device)
-    _lib.check(lib.nma_tc_wgrad_raw(_ptr(x), _ptr(da), _ptr(gw), x.shape[0], K, _stream()), "nma_tc_wgrad_raw")
+    fn = lib.nma_tc_wgrad_raw_bf if bf16 else lib.nma_tc_wgrad_raw
+    _lib.check(fn(_ptr(x), _ptr(da), _ptr(gw), x.shape[0], K, _stream()), "nma_tc_wgrad_raw")
     return gw
 
 
