@@ -157,7 +157,9 @@ def workload_config(args, rows_note=None):
          "l2": "per-step working set (saved activations and tensor-core operands, ~1.1 MB per row: %.1f GB at these rows) far "
                "exceeds the 126 MB L2; no flush needed" % (args.rows * 1.075e6 / 1e9),
          "parallelism": "time-sharded series, rows sharded %d-way, NCCL gradient all-reduce" % args.gpus,
-         "launch": "eager" if args.no_graph else "one CUDA graph per step"}
+         "launch": "eager" if args.no_graph else "one CUDA graph per step",
+         "conv_operands": {"bf16": "2-term bf16 split (3 products, kind::f16), fp32 accumulate",
+                           "tf32": "3xTF32 split (kind::tf32), fp32 accumulate"}[args.conv_split]}
     if rows_note:
         c["note"] = rows_note
     return c
@@ -168,6 +170,8 @@ STAGE_NAMES = {0: "conv_fwd", 1: "conv_dgrad", 2: "conv_wgrad", 3: "epi_bwd", 5:
 # dram__bytes_read.sum + dram__bytes_write.sum per ROW of the flow-0 launch of each tcgen05 conv kernel, from the
 # ncu --set full capture in profiles/r01_final.md (2048 rows: 301.2 / 239.0 / 1346.5 MB); scaled by rows below
 NCU_DRAM_BYTES_PER_ROW = {"conv_fwd[0]": 301.2e6 / 2048, "conv_dgrad[0]": 239.0e6 / 2048, "conv_wgrad[0]": 1346.5e6 / 2048}
+# the same for the bf16-split kernels (profiles/r01_bf16.md: 119.6+90.5 / 105.7+43.6 / 552.7+14.4 MB at 2048 rows)
+NCU_DRAM_BYTES_PER_ROW_BF16 = {"conv_fwd[0]": 210.1e6 / 2048, "conv_dgrad[0]": 149.3e6 / 2048, "conv_wgrad[0]": 567.1e6 / 2048}
 
 
 def roofline_report(stepper, peaks, ms_step):
@@ -191,15 +195,19 @@ def roofline_report(stepper, peaks, ms_step):
                     best = (ms, "%s[%d]" % (name, i), flop)
     stages["feat_fwd[all]"] = round(stepper.time_stage(4, 0), 4)
     ms, name, flop = best
-    tf32_peak = 0.5 * float(peaks["bf16_tflops"])
+    bf = bool(stepper.eng.bf16_split)
+    # kind::f16 (the bf16 split) runs at the measured bf16 figure, kind::tf32 at half of it
+    tf32_peak = (1.0 if bf else 0.5) * float(peaks["bf16_tflops"])
     achieved = flop / (ms * 1e-3) / 1e12
     conv_ms = sum(v for k, v in stages.items() if k.startswith("conv_"))
     roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
             "frac": achieved / tf32_peak,
-            "traffic": (NCU_DRAM_BYTES_PER_ROW[name] * stepper.rows
+            "traffic": ((NCU_DRAM_BYTES_PER_ROW_BF16 if bf else NCU_DRAM_BYTES_PER_ROW)[name] * stepper.rows
                         if (name in NCU_DRAM_BYTES_PER_ROW and stepper.eng.tensor_cores and cfg.K == 50) else None),
-            "traffic_note": "dram bytes of this launch: ncu --set full at 2048 rows (profiles/r01_final.md) scaled by rows",
-            "peak_source": "0.5 x bf16_tflops (%s) of MEASURED_PEAKS.json = TF32 dense" % peaks.get("source", "measured"),
+            "traffic_note": "dram bytes of this launch: ncu --set full at 2048 rows (profiles/%s) scaled by rows"
+                            % ("r01_bf16.md" if bf else "r01_final.md"),
+            "peak_source": ("bf16_tflops (%s) of MEASURED_PEAKS.json: the kernel issues kind::f16 MMAs, 3 per algorithmic MAC"
+                            if bf else "0.5 x bf16_tflops (%s) of MEASURED_PEAKS.json = TF32 dense") % peaks.get("source", "measured"),
             "ms_per_launch": ms, "flop_per_launch": flop,
             "conv_share_of_step": conv_ms / ms_step if ms_step > 0 else None}
     return roof, stages
@@ -230,7 +238,8 @@ def run_native(args):
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
 
     stepper = ARStepper(T=args.T, rows=args.rows, K=K_LEN, B=B_DIMS, F=FLOWS, H=HID, fw=FW, theta=THETA_TRUE,
-                        x0=10.0, obs_std=1.0, device=dev, rank=rank, world=world, seed=1)
+                        x0=10.0, obs_std=1.0, device=dev, rank=rank, world=world, seed=1,
+                        tensor_cores=7 if args.conv_split == "bf16" else 3)
     cfg = stepper.cfg
     fl = flops_per_row(cfg)
     units_step_rank = args.rows * B_DIMS
@@ -342,6 +351,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=100)
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--conv-split", default="bf16", choices=["tf32", "bf16"],
+                    help="operand split of the conv GEMMs: 3xTF32 (kind::tf32) or 2-term bf16 (kind::f16, twice the rate)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.warmup < 3:

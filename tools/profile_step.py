@@ -13,8 +13,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=2048)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--T", type=int, default=10 ** 6)
+ap.add_argument("--tc", type=int, default=3, help="bit set of nma_set_tensor_cores (7 = bf16 split of the conv GEMMs)")
 a = ap.parse_args()
-st = ARStepper(T=a.T, rows=a.rows, device=torch.device("cuda", 0))
+st = ARStepper(T=a.T, rows=a.rows, device=torch.device("cuda", 0), tensor_cores=a.tc)
 for _ in range(a.steps - 1):
     st.step_resident()
 torch.cuda.synchronize()

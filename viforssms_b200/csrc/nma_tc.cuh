@@ -209,6 +209,7 @@ struct TcConvSrc {
     long long Qalloc;
     const float* wt;       // [K][CCH][128][16 B] packed taps (rows 0-63 hi parts, rows 64-127 lo parts)
     int K;
+    int diag;              // timing experiments only (NMA_DIAG), 0 in every product path
 };
 
 // one lane of a converged warp; the surrounding control flow stays warp-uniform so descriptors live in

@@ -4,6 +4,7 @@
 //   k_conv_fwd_tc    : conv + theta-bias + ELU (TMEM -> smem tile) + flow_epilogue (hidden 1x1, head, affine update)
 //   k_conv_dgrad_tc  : full correlation of dA with the flipped kernel -> df (feature channels) and dx (channel 0)
 //   nma_tc_conv_raw  : test hook, the bare contraction on caller-provided data
+#include <stdlib.h>
 #include "nma_tc.cuh"
 #include "nma_flow_epi.cuh"
 
@@ -160,7 +161,7 @@ int launch_conv_fwd_tc(nma_handle_s* h, int i, const float* params, int p, bool 
     ConvFwdTcArgs a;
     const int nacc = h->tc_nacc;
     a.src.a_hi = h->ws[i].tin_hi; a.src.a_lo = h->ws[i].tin_lo; a.src.Qalloc = h->ws[i].tin_Q;
-    a.src.wt = h->ws[i].wtc_f; a.src.K = h->cfg.K;
+    a.src.wt = h->ws[i].wtc_f; a.src.K = h->cfg.K; a.src.diag = 0;
     a.tb = h->ws[i].tb;
     fill_flow_epi_args(h, i, params, save, a.e);
     a.Lin = d.Lin; a.p = p; a.npos = tc_conv_npos(nacc, h->cfg.K);
@@ -261,7 +262,7 @@ int launch_conv_dgrad_tc(nma_handle_s* h, int i, int p, cudaStream_t st) {
     ConvDgradTcArgs a;
     const int nacc = h->tc_nacc;
     a.src.a_hi = h->ws[i].dat_hi; a.src.a_lo = h->ws[i].dat_lo; a.src.Qalloc = h->ws[i].dat_Q;
-    a.src.wt = h->ws[i].wtc_d; a.src.K = h->cfg.K;
+    a.src.wt = h->ws[i].wtc_d; a.src.K = h->cfg.K; a.src.diag = 0;
     a.df = h->ws[i].df; a.dx = h->ws[i].dx;
     a.Lin = d.Lin; a.LP = d.LP; a.XP = (d.L + 3) & ~3; a.p = p; a.npos = tc_conv_npos(nacc, h->cfg.K);
     a.need_dx = i > 0 ? 1 : 0;
@@ -389,7 +390,7 @@ extern "C" int nma_tc_conv_raw(const float* d_in, const float* d_w, int32_t mode
         k_tc_pack_w<<<148, 256, 0, st>>>(d_w, K, mode, wt);
     }
     TcConvSrc src;
-    src.a_hi = hi; src.a_lo = lo; src.Qalloc = Qalloc; src.wt = wt; src.K = K;
+    src.a_hi = hi; src.a_lo = lo; src.Qalloc = Qalloc; src.wt = wt; src.K = K; src.diag = 0;
     const int smem = (int)(tc_conv_smem_floats(nacc, K, cch) * 4);
     const unsigned grid = (unsigned)((Q + ncols - 1) / ncols);
     cudaError_t e;
@@ -703,14 +704,14 @@ extern "C" int nma_tc_wgrad_raw(const float* d_in, const float* d_da, float* d_g
 //                lie at one stride.  hi and lo parts are separate tiles.
 //   B (N = 128): 64 hi | 64 lo channel slots of dA: the dat_hi slabs followed by the dat_lo slabs.
 //   D[pair]:     128 TMEM columns: A_hi x [B_hi | B_lo] -> main | correction, A_lo x B_hi (N = 64) -> correction.
-// K = 16 positions per MMA; a stage is 64 positions; the accumulators are drained TMEM -> registers every 4 stages
-// (16-MMA chains: the tensor core accumulates with truncation) and summed in round-to-nearest fp32.
+// K = 16 positions per MMA; a stage is 64 positions; the accumulators are drained TMEM -> registers every 8 stages
+// (32-MMA chains: the tensor core accumulates with truncation) and summed in round-to-nearest fp32.
 // CTA = (group of <= 4 tap pairs, range of stages); warps 0-7 drain, warp 8 TMA (all lanes issue), warp 9 MMA.
 // ---------------------------------------------------------------------------
 #define WB_KT 64
 #define WB_APOS (WB_KT + 8)                 // tap offsets 0..6 inside a group of 4 pairs
 #define WB_STAGES 4
-#define WB_FLUSH 4
+#define WB_FLUSH 8
 #define WB_A_UNITS (16 * WB_APOS)           // 16-byte units of A_hi (or A_lo): 16 chunk slabs
 #define WB_B_UNITS (16 * WB_KT)
 #define WB_STAGE_UNITS (2 * WB_A_UNITS + WB_B_UNITS)
@@ -722,6 +723,8 @@ struct ConvWgradBfArgs {
     const uint4* da_hi; const uint4* da_lo; long long da_Q;      // dA(q) at unit q + K - 1
     float* gW;                                                   // [K][51][50]
     int K, npairs, ngroups, nstages_total, nq;
+    int flush;                                                   // stages per accumulator drain (WB_FLUSH)
+    int diag;                                                    // NMA_DIAG timing experiments (results invalid): 1 no A loads, 2 no B loads, 8 / 16 see the MMA loop
 };
 
 __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArgs a) {
@@ -736,7 +739,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
     const int s_begin = (int)((long long)a.nstages_total * blockIdx.x / a.nq);
     const int s_end = (int)((long long)a.nstages_total * (blockIdx.x + 1) / a.nq);
     const int nst = s_end - s_begin;
-    const int nchunks = (nst + WB_FLUSH - 1) / WB_FLUSH;
+    const int nchunks = (nst + a.flush - 1) / a.flush;
 
     // slabs of chunk 7 (channel slots 56..63) are never loaded: zero everything once
     for (int t = tid; t < WB_STAGES * WB_STAGE_UNITS; t += blockDim.x) smem_u[t] = make_uint4(0u, 0u, 0u, 0u);
@@ -757,11 +760,13 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
         for (int si = 0; si < nst; ++si) {
             const int st = si % WB_STAGES;
             if (si >= WB_STAGES) mbar_wait_backoff(&empty[st], (uint32_t)(((si / WB_STAGES) - 1) & 1));
-            if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)WB_STAGE_TX);
+            if (lane == 0)
+                mbar_expect_tx(&full[st], (uint32_t)(((a.diag & 1) ? 0 : 28 * WB_APOS * 16) + ((a.diag & 2) ? 0 : 14 * WB_KT * 16)));
             __syncwarp();
             uint4* sb = smem_u + (size_t)st * WB_STAGE_UNITS;
             const long long q0 = (long long)(s_begin + si) * WB_KT;
             for (int idx = lane; idx < WB_NCOPY; idx += 32) {
+                if ((idx < 28 && (a.diag & 1)) || (idx >= 28 && (a.diag & 2))) continue;
                 if (idx < 28) {
                     const int hl = idx / 14, r2 = idx - hl * 14, copy = r2 / 7, c = r2 - copy * 7;
                     const uint4* src = (hl ? a.in_lo : a.in_hi) + (size_t)c * a.in_Q + q0 + k0 + copy;
@@ -782,9 +787,9 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
         const uint32_t a_hi32 = desc_hi(WB_APOS * 16u), b_hi32 = desc_hi(WB_KT * 16u);    // stride offset: next channel chunk
         for (int si = 0; si < nst; ++si) {
             const int st = si % WB_STAGES;
-            const int ci = si / WB_FLUSH;
-            const bool chunk_first = (si % WB_FLUSH) == 0;
-            const bool chunk_last = ((si % WB_FLUSH) == WB_FLUSH - 1) || (si == nst - 1);
+            const int ci = si / a.flush;
+            const bool chunk_first = (si % a.flush) == 0;
+            const bool chunk_last = ((si % a.flush) == a.flush - 1) || (si == nst - 1);
             if (chunk_first && ci > 0) mbar_wait_backoff(&acc_free, (uint32_t)((ci - 1) & 1));
             mbar_wait_backoff(&full[st], (uint32_t)((si / WB_STAGES) & 1));
             tc_fence_after();
@@ -801,7 +806,9 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
                         const uint64_t ah = desc_pack(ah0 + aoff, a_hi32), al = desc_pack(al0 + aoff, a_hi32);
                         const uint64_t bw = desc_pack(b0 + (uint32_t)(16 * ks), b_hi32);
                         umma_bf16(d, ah, bw, idesc_n128, (chunk_first && ks == 0) ? 0u : 1u);
-                        umma_bf16(d + TC_N, al, bw, idesc_n64, 1u);
+                        if (a.diag & 16) continue;                                        // timing experiment: no correction MMA
+                        if (a.diag & 8) umma_bf16(d, al, bw, idesc_n128, 1u);             // timing experiment: N = 128 instead of 64
+                        else umma_bf16(d + TC_N, al, bw, idesc_n64, 1u);
                     }
                 }
                 tc_commit(&empty[st]);
@@ -858,10 +865,15 @@ static void wgrad_bf_geometry(ConvWgradBfArgs& a, long long qtot, int sm_count) 
     a.npairs = (a.K + 1) / 2;
     a.ngroups = (a.npairs + WGT_MAXPAIRS - 1) / WGT_MAXPAIRS;
     a.nstages_total = (int)((qtot + WB_KT - 1) / WB_KT);
-    int nq = (3 * sm_count) / a.ngroups;
+    const char* ew = getenv("NMA_WB_WAVES");
+    int nq = (((ew && atoi(ew) > 0) ? atoi(ew) : 3) * sm_count) / a.ngroups;
     if (nq < 1) nq = 1;
     if (nq > a.nstages_total) nq = a.nstages_total;
     a.nq = nq;
+    const char* ef = getenv("NMA_WB_FLUSH");
+    a.flush = (ef && atoi(ef) > 0) ? atoi(ef) : WB_FLUSH;
+    const char* ed = getenv("NMA_DIAG");
+    a.diag = ed ? atoi(ed) : 0;
 }
 
 int launch_conv_wgrad_bf(nma_handle_s* h, int i, int p, float* gp, cudaStream_t st) {

@@ -150,7 +150,8 @@ class ARStepper:
     def __init__(self, T: int, rows: int, K: int = 50, B: int = 50, F: int = 3, H: int = 1, fw: int = 10,
                  theta: Sequence[float] = (5.0, 0.5, 3.0), x0: float = 10.0, obs_std: float = 1.0,
                  device: Optional[torch.device] = None, rank: int = 0, world: int = 1, seed: int = 1,
-                 lr: float = 1e-3, clip: float = 2.5e8, priors=((0.0, 10.0),) * 3, series=None, impute: int = 1):
+                 lr: float = 1e-3, clip: float = 2.5e8, priors=((0.0, 10.0),) * 3, series=None, impute: int = 1,
+                 tensor_cores: Optional[int] = None):
         self.T, self.rows, self.rank, self.world = int(T), int(rows), rank, world
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.lr, self.clip, self.priors = lr, clip, priors
@@ -158,7 +159,7 @@ class ARStepper:
         cfg = self.cfg
         self.t0, self.t1 = shard_bounds(self.T, B, world, rank)
         P = F * K + 1
-        self.eng = NMAEngine(cfg, self.device)
+        self.eng = NMAEngine(cfg, self.device, tensor_cores=tensor_cores)   # None: library default; bit set of nma_set_tensor_cores
         if series is None:
             obs_ext, bin_ext, till_ext, tt0 = self._generate_shard(theta, x0, obs_std, seed, P, fw, impute)
         else:
