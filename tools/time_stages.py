@@ -8,7 +8,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from viforssms_b200.trainer import ARStepper  # noqa: E402
 
-rows = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+rows = int(args[0]) if args else 16384
+quick = "--quick" in sys.argv          # default settings only (e.g. under NMA_DGRAD_WIDE=0/1 set by the caller)
 st = ARStepper(T=10 ** 6, rows=rows, device=torch.device("cuda", 0), tensor_cores=7)
 for _ in range(2):
     st.step_resident()
@@ -22,6 +24,8 @@ CASES = [
     ("DIAG wgrad no loads, no drain, no correction MMA", {"NMA_DIAG": "19", "NMA_WB_FLUSH": "100000"}, (2,)),
     ("DIAG wgrad with loads, no drain, no correction MMA", {"NMA_DIAG": "16", "NMA_WB_FLUSH": "100000"}, (2,)),
 ]
+if quick:
+    CASES = CASES[:1]
 for name, env, stages in CASES:
     for k in ("NMA_WB_FLUSH", "NMA_WB_WAVES", "NMA_DIAG"):
         os.environ.pop(k, None)

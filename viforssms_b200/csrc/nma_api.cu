@@ -125,6 +125,8 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         const char* envf = getenv("NMA_TC_FEAT");
         h->use_tc_feat = h->use_tc && !(envf && envf[0] == '0');
         h->use_bf16 = 0;            // decided below, once the kernels that understand the format are known to run
+        const char* envw = getenv("NMA_DGRAD_WIDE");
+        h->dgrad_wide = (envw && envw[0] == '0') ? 0 : 1;
     }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));

@@ -45,7 +45,9 @@ __global__ void k_tc_pack_w(const float* __restrict__ W, int K, int mode, float*
 }
 
 // the same two packs in the 2-term bf16 split: [K][8][64 hi rows | 64 lo rows][8 x bf16]
-__global__ void k_tc_pack_w_bf(const float* __restrict__ W, int K, int mode, uint16_t* __restrict__ out) {
+// interleave = 1: hi and lo part of output n in rows 2n, 2n+1 (the tile is then the stacked A operand of the
+// position-wide kernels, nma_tc_conv2.cu) instead of rows n, 64 + n
+__global__ void k_tc_pack_w_bf(const float* __restrict__ W, int K, int mode, uint16_t* __restrict__ out, int interleave) {
     const int n_half = K * 8 * TC_N * 8;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_half; t += gridDim.x * blockDim.x) {
         const int e = t & 7;
@@ -61,17 +63,17 @@ __global__ void k_tc_pack_w_bf(const float* __restrict__ W, int K, int mode, uin
         }
         uint32_t hi, lo;
         bf_split(v, hi, lo);
-        const size_t o = (size_t)k * (8 * TC_WROWS * 8) + ((size_t)cch * TC_WROWS + n) * 8 + e;
-        out[o] = (uint16_t)hi;
-        out[o + TC_N * 8] = (uint16_t)lo;
+        const size_t tile = (size_t)k * (8 * TC_WROWS * 8) + (size_t)cch * TC_WROWS * 8 + e;
+        out[tile + (size_t)(interleave ? 2 * n : n) * 8] = (uint16_t)hi;
+        out[tile + (size_t)(interleave ? 2 * n + 1 : n + TC_N) * 8] = (uint16_t)lo;
     }
 }
 
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
     for (int i = 0; i < h->cfg.F; ++i) {
         if (h->use_bf16) {
-            k_tc_pack_w_bf<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 0, (uint16_t*)h->ws[i].wtc_f);
-            if (need_bwd) k_tc_pack_w_bf<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 1, (uint16_t*)h->ws[i].wtc_d);
+            k_tc_pack_w_bf<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 0, (uint16_t*)h->ws[i].wtc_f, 0);
+            if (need_bwd) k_tc_pack_w_bf<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 1, (uint16_t*)h->ws[i].wtc_d, h->dgrad_wide);
             nma_count_launch(need_bwd ? 2 : 1);
             continue;
         }
@@ -384,7 +386,7 @@ extern "C" int nma_tc_conv_raw(const float* d_in, const float* d_w, int32_t mode
     NMA_CHECK_CUDA(cudaMemsetAsync(lo, 0, abytes, st));
     if (bf) {
         k_tc_split_in_bf<<<296, 256, 0, st>>>(d_in, Q, Qalloc, (uint4*)hi, (uint4*)lo);
-        k_tc_pack_w_bf<<<148, 256, 0, st>>>(d_w, K, mode, (uint16_t*)wt);
+        k_tc_pack_w_bf<<<148, 256, 0, st>>>(d_w, K, mode, (uint16_t*)wt, 0);
     } else {
         k_tc_split_in<<<296, 256, 0, st>>>(d_in, Q, Qalloc, hi, lo);
         k_tc_pack_w<<<148, 256, 0, st>>>(d_w, K, mode, wt);

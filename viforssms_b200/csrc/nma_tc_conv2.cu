@@ -201,6 +201,125 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_dgrad_tcp(ConvDgradP a) {
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------
+// data gradient, position-wide form (bf16 split):  D^T[c][q] = sum_k' sum_f Wd[k'][c][f] * dA_flat[q + k'][f]
+//
+// Measured (profiles/r01_bf16.md): an M = 128 MMA re-fetches its 128-row A operand from shared memory per instruction
+// and that fetch, not the math, sets its duration (~116 cycles at N = 128, ~100 at N = 64, against 64 / 32 of math).
+// Here the SMALL matrix is A - the tap kernel, hi and lo part of output channel c stacked in rows 2c, 2c+1 (M = 128) -
+// and the 256 positions of the tile are N, the tap being a start-address shift of the B descriptor: two N = 256
+// instructions per k-step (B = dA_hi, B = dA_lo) give all FOUR products of the split for 256 positions, against four
+// instructions (two of them N = 64) for three products before.  The accumulator arrives channel-major - TMEM lane =
+// 2c + {hi, lo} row, column = position - which is the layout of df [row][channel][slot]: one shuffle adds the two
+// lanes of a channel, then every even lane stores consecutive slots of its channel.
+// ---------------------------------------------------------------------------
+template <int NST>
+__device__ __forceinline__ void q_mma(PBars& b, const float* a_hi, const float* a_lo, const float* wring, int K, int npos,
+                                      uint32_t tmem_base, long long ntiles) {
+    constexpr int WSTAGE = TcP<true>::WSTAGE;
+    constexpr uint32_t idesc = umma_idesc_bf16(TC_M, 2 * TC_M, 0, 0);       // M = 128 stacked kernel rows, N = 256 positions
+    const uint32_t in_lbo = (uint32_t)npos * 16u;                           // between the two 8-channel chunks of a k-step
+    const uint32_t bh_lo0 = desc_lo(smem_u32(a_hi), in_lbo), bl_lo0 = desc_lo(smem_u32(a_lo), in_lbo);
+    const uint32_t hi32 = desc_hi(128u);
+    const uint32_t w_lo0 = desc_lo(smem_u32(wring), TC_WROWS * 16u);
+    const uint32_t ks_step_in = 2u * (uint32_t)npos;
+    constexpr uint32_t ks_step_w = 2u * TC_WROWS;
+    uint32_t g = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t set = (uint32_t)(it & 1);
+        mbar_wait_backoff(&b.a_full, (uint32_t)(it & 1));
+        if (it >= 2) mbar_wait_backoff(&b.acc_free[set], (uint32_t)(((it >> 1) - 1) & 1));
+        for (int k = 0; k < K; ++k, ++g) {
+            const uint32_t st = g % NST;
+            mbar_wait_backoff(&b.full[st], (g / NST) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t wb = w_lo0 + st * (WSTAGE * 4u / 16u);
+                const uint32_t d = tmem_base + set * (2u * TC_M);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t aw = desc_pack(wb + (uint32_t)ks * ks_step_w, hi32);
+                    const uint64_t bh = desc_pack(bh_lo0 + (uint32_t)k + (uint32_t)ks * ks_step_in, hi32);
+                    const uint64_t bl = desc_pack(bl_lo0 + (uint32_t)k + (uint32_t)ks * ks_step_in, hi32);
+                    umma_bf16(d, aw, bh, idesc, (k | ks) ? 1u : 0u);
+                    umma_bf16(d, aw, bl, idesc, 1u);
+                }
+                tc_commit(&b.empty[st]);
+                if (k == K - 1) {
+                    tc_commit(&b.acc_full[set]);
+                    tc_commit(&b.a_free);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(P_THREADS, 1) k_conv_dgrad_tcq(ConvDgradP a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ PBars bars;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* a_hi = smem;
+    float* a_lo = a_hi + (size_t)TcP<true>::CCH * a.npos * 4;
+    float* wring = a_lo + (size_t)TcP<true>::CCH * a.npos * 4;
+    const long long qtot = (long long)a.p * a.Lin;
+    const long long ntiles = (qtot + 2 * TC_M - 1) / (2 * TC_M);
+    const uint32_t tmem = p_setup(bars, &tmem_slot, 1);
+
+    if (warp == 8) {
+        p_producer<TC_STAGES, true>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
+    } else if (warp == 9) {
+        q_mma<TC_STAGES>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
+    } else {
+        const int quarter = warp & 3, colhalf = warp >> 2;
+        const int c = (quarter * 32 + lane) >> 1;                  // output channel of this TMEM lane (rows 2c, 2c+1)
+        const bool writer = ((lane & 1) == 0) && c < NMA_C1;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t set = (uint32_t)(it & 1);
+            mbar_wait_backoff(&bars.acc_full[set], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + set * (2u * TC_M) + (uint32_t)(colhalf * TC_M);
+#pragma unroll 1
+            for (int blk = 0; blk < 4; ++blk) {
+                float v[32];
+                tmem_ld32(ta + (uint32_t)(blk * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+                const long long q = tile * (2 * TC_M) + colhalf * TC_M + blk * 32;
+                if (writer && q < qtot) {
+                    int r = (int)(q / a.Lin);
+                    int j = (int)(q - (long long)r * a.Lin);
+                    const int nvalid = (qtot - q < 32) ? (int)(qtot - q) : 32;
+                    if (c >= 1) {
+                        float* dst = a.df + ((size_t)r * NMA_C + (c - 1)) * a.LP;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < nvalid) dst[j] = v[i];
+                            if (++j == a.Lin) { j = 0; dst += (size_t)NMA_C * a.LP; }
+                        }
+                    } else if (a.need_dx) {
+                        float* dst = a.dx + (size_t)r * a.XP;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (i < nvalid) dst[j] += v[i];
+                            if (++j == a.Lin) { j = 0; dst += a.XP; }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&bars.acc_free[set]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int launch_conv_dgrad_tcp(nma_handle_s* h, int i, int p, cudaStream_t st) {
     const FlowDims& d = h->fd[i];
     ConvDgradP a;
@@ -212,6 +331,18 @@ int launch_conv_dgrad_tcp(nma_handle_s* h, int i, int p, cudaStream_t st) {
     a.need_dx = i > 0 ? 1 : 0;
     const long long ntiles = ((long long)p * d.Lin + 2 * TC_M - 1) / (2 * TC_M);
     const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
+    if (h->use_bf16 && h->dgrad_wide) {
+        const int smem = (int)(tc_conv_smem_floats(2, h->cfg.K, TcP<true>::CCH) * 4);
+        static int configured = 0;
+        if (configured < smem) {
+            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tcq, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = smem;
+        }
+        k_conv_dgrad_tcq<<<grid, P_THREADS, smem, st>>>(a);
+        nma_count_launch(1);
+        NMA_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (h->use_bf16) {
         const int smem = (int)(tc_conv_smem_floats(2, h->cfg.K, TcP<true>::CCH) * 4);
         static int configured = 0;
