@@ -394,7 +394,7 @@ struct ConvFwdP {
     float* nx_hi;            // channel 0 of the next flow's conv operand (may be null)
     float* nx_lo;
     int nx_Lin;
-    int Lin, p, npos, N, NP, XP, XPn, K, save, ring_off;
+    int Lin, p, npos, N, NP, XP, XPn, K, save, ring_off, e_off;
 };
 
 #define PF_E_F (TC_CCH * 2 * TC_M * 4)          // floats of E_hi (or E_lo): [14][256][4]
@@ -412,15 +412,27 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
     float* a_hi = smem;
     float* a_lo = a_hi + (size_t)TcP<BF>::CCH * a.npos * 4;
     float* wring = smem + a.ring_off;
-    float* E_hi = smem;                          // epilogue view of the operand buffer
-    float* E_lo = E_hi + PF_E_F;
-    float* Wh = E_lo + PF_E_F;
+    // 3xTF32: the epilogue's E_hi | E_lo | hidden kernel alias the operand buffer (e_off = 0), so the next tile's operand
+    // load waits for the epilogue.  bf16 split: the operand tile is 80 KB and the epilogue operands - bf16 as well,
+    // [8][256][16 B] hi and lo + the 16 KB kernel - have their own 80 KB behind it (e_off): the next tile's load starts
+    // the moment the last MMA of the mainloop has retired, and the hidden kernel is fetched once.
+    constexpr int E_F = BF ? (TcP<true>::CCH * 2 * TC_M * 4) : PF_E_F;
+    float* E_hi = smem + a.e_off;
+    float* E_lo = E_hi + E_F;
+    float* Wh = E_lo + E_F;
     const long long qtot = (long long)a.p * a.Lin;
     const long long ntiles = (qtot + 2 * TC_M - 1) / (2 * TC_M);
     if (tid < 64) hb_sm[tid] = (tid < NMA_C) ? a.hidb[tid] : 0.f;
     if (tid < 128) hw_sm[tid] = (tid < 2 * NMA_C) ? a.headw[tid] : 0.f;
     if (tid == 0) mbar_init(&wh_bar, 1);
-    const uint32_t tmem = p_setup(bars, &tmem_slot, 1 + P_EPI_WARPS);
+    if (BF) {
+        // chunk 7 (channels 56..63) of E is never written: zero it once
+        uint4* z = reinterpret_cast<uint4*>(E_hi);
+        for (int t = tid; t < 2 * 2 * TC_M; t += blockDim.x)
+            z[(t < 2 * TC_M ? 7 * 2 * TC_M + t : E_F / 4 + 7 * 2 * TC_M + (t - 2 * TC_M))] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+    }
+    const uint32_t tmem = p_setup(bars, &tmem_slot, BF ? 1 : 1 + P_EPI_WARPS);
 
     if (warp == 8) {
         p_producer<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
@@ -436,10 +448,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
             mbar_wait_backoff(&bars.acc_full[set], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             // the mainloop is done with the operand buffer: fetch the packed hidden kernel into its tail
-            if (warp == 0) {
+            // (bf16 split: own region, fetched once)
+            if (warp == 0 && (!BF || it == 0)) {
                 if (elect_one()) {
-                    mbar_expect_tx(&wh_bar, TC_WSTAGE * 4u);
-                    bulk_g2s(Wh, a.whid, TC_WSTAGE * 4u, &wh_bar);
+                    mbar_expect_tx(&wh_bar, (uint32_t)TcP<BF>::WSTAGE * 4u);
+                    bulk_g2s(Wh, a.whid, (uint32_t)TcP<BF>::WSTAGE * 4u, &wh_bar);
                 }
                 __syncwarp();
             }
@@ -466,6 +479,21 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
                     for (int i = 0; i < 32; ++i)
                         if (half * 32 + i < NMA_C) dst[(size_t)i * a.NP] = v[i];
                 }
+                if (BF) {
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        if (half == 0 || c8 < 3) {
+                            float w8[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) w8[e] = v[8 * c8 + e];
+                            uint4 h4, l4;
+                            bf_split8(w8, h4, l4);
+                            const size_t o = (size_t)(half * 4 + c8) * (2 * TC_M) + col;
+                            reinterpret_cast<uint4*>(E_hi)[o] = h4;
+                            reinterpret_cast<uint4*>(E_lo)[o] = l4;
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
                     if (half == 0 || cc < 6) {
@@ -483,11 +511,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             // ---- hidden 1x1 layer (AR.py:74-76) on the tensor cores, both 128-position accumulators ----
             if (warp == 0) {
-                mbar_wait_backoff(&wh_bar, (uint32_t)(it & 1));
+                if (!BF || it == 0) mbar_wait_backoff(&wh_bar, BF ? 0u : (uint32_t)(it & 1));
                 tc_fence_after();
                 if (elect_one()) {
-                    constexpr uint32_t idesc = umma_idesc_tf32(TC_M, TC_N, 0, 0);
-                    constexpr uint32_t idesc_wide = umma_idesc_tf32(TC_M, 2 * TC_N, 0, 0);
+                    constexpr uint32_t idesc = umma_idesc<BF>(TC_M, TC_N, 0, 0);
+                    constexpr uint32_t idesc_wide = umma_idesc<BF>(TC_M, 2 * TC_N, 0, 0);
                     constexpr uint32_t e_lbo = 2u * TC_M * 16u;                 // between channel chunks: 256 positions
                     const uint32_t eh0 = desc_lo(smem_u32(E_hi), e_lbo), el0 = desc_lo(smem_u32(E_lo), e_lbo);
                     const uint32_t w0 = desc_lo(smem_u32(Wh), TC_WROWS * 16u);
@@ -497,12 +525,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
                         const uint32_t d = tmem + set * (4u * TC_N) + (uint32_t)(a2 * 2 * TC_N);
                         const uint32_t row = (uint32_t)(a2 * TC_M);             // 16-byte units
 #pragma unroll
-                        for (int ks = 0; ks < TC_CCH / 2; ++ks) {
+                        for (int ks = 0; ks < TcP<BF>::CCH / 2; ++ks) {
                             const uint64_t eh = desc_pack(eh0 + row + (uint32_t)ks * (2u * e_lbo / 16u), hi32);
                             const uint64_t el = desc_pack(el0 + row + (uint32_t)ks * (2u * e_lbo / 16u), hi32);
                             const uint64_t bw = desc_pack(w0 + (uint32_t)ks * (2u * TC_WROWS), hi32);
-                            umma_tf32(d, eh, bw, idesc_wide, ks ? 1u : 0u);
-                            umma_tf32(d + TC_N, el, bw, idesc, 1u);
+                            umma<BF>(d, eh, bw, idesc_wide, ks ? 1u : 0u);
+                            umma<BF>(d + TC_N, el, bw, idesc, 1u);
                         }
                     }
                     tc_commit(&bars.hid);
@@ -558,7 +586,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive1(&bars.acc_free[set]);
-                mbar_arrive1(&bars.a_free);
+                if (!BF) mbar_arrive1(&bars.a_free);
             }
         }
     }
@@ -578,6 +606,19 @@ __global__ void k_tc_pack_w1x1(const float* __restrict__ W, float* __restrict__ 
     }
 }
 
+// the same in the bf16 split: [8][64 hi | 64 lo rows][8 x bf16], element (cch, n, e) = W[8*cch + e][n]
+__global__ void k_tc_pack_w1x1_bf(const float* __restrict__ W, uint16_t* __restrict__ out) {
+    for (int t = threadIdx.x; t < 8 * TC_N * 8; t += blockDim.x) {
+        const int e = t & 7, n = (t >> 3) & (TC_N - 1), cch = t >> 9;
+        const int c = 8 * cch + e;
+        const float v = (c < NMA_C && n < NMA_C) ? W[c * NMA_C + n] : 0.f;
+        uint32_t hi, lo;
+        bf_split(v, hi, lo);
+        out[((size_t)cch * TC_WROWS + n) * 8 + e] = (uint16_t)hi;
+        out[((size_t)cch * TC_WROWS + n + TC_N) * 8 + e] = (uint16_t)lo;
+    }
+}
+
 static int fwd_p_npos(int K) {
     const int n = tc_conv_npos(2, K);
     return n < 320 ? 320 : n;       // the epilogue needs E_hi | E_lo | hidden kernel = 140 KB inside the operand buffer
@@ -592,7 +633,8 @@ int conv_fwd_tcp_supported(const nma_handle_s* h) {
 int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool save, cudaStream_t st) {
     const FlowDims& d = h->fd[i];
     float* whid = h->ws[i].wtc_feat + (size_t)9 * TC_WSTAGE;     // slot 9 of the flow's pack buffer
-    k_tc_pack_w1x1<<<1, 256, 0, st>>>(params + h->po[i].hidw[0], whid);
+    if (h->use_bf16) k_tc_pack_w1x1_bf<<<1, 256, 0, st>>>(params + h->po[i].hidw[0], (uint16_t*)whid);
+    else k_tc_pack_w1x1<<<1, 256, 0, st>>>(params + h->po[i].hidw[0], whid);
     ConvFwdP a;
     a.src.a_hi = h->ws[i].tin_hi; a.src.a_lo = h->ws[i].tin_lo; a.src.Qalloc = h->ws[i].tin_Q;
     a.src.wt = h->ws[i].wtc_f; a.src.K = h->cfg.K;
@@ -611,8 +653,9 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
     // operand region = max(conv operand tile, epilogue view E_hi | E_lo | hidden kernel); the ring follows it
     const int epi_f = 2 * PF_E_F + TC_WSTAGE;
     if (h->use_bf16) {
-        const int op_f = 2 * TcP<true>::CCH * a.npos * 4;
-        a.ring_off = op_f > epi_f ? op_f : epi_f;
+        // [operand tile hi | lo][E_hi | E_lo | hidden kernel, all bf16][ring]
+        a.e_off = 2 * TcP<true>::CCH * a.npos * 4;
+        a.ring_off = a.e_off + 2 * (TcP<true>::CCH * 2 * TC_M * 4) + TcP<true>::WSTAGE;
         const int smem = (a.ring_off + TC_STAGES * TcP<true>::WSTAGE) * 4;
         static int configured = 0;
         if (configured < smem) {
@@ -625,6 +668,8 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
         return 0;
     }
     a.ring_off = 2 * TC_CCH * a.npos * 4;
+    a.e_off = 0;
+    (void)epi_f;
     const int smem = 2 * TC_CCH * a.npos * 16 + TC_STAGES * TC_WSTAGE * 4;
     static int configured = 0;
     if (configured < smem) {
