@@ -718,13 +718,17 @@ extern "C" int nma_tc_wgrad_raw(const float* d_in, const float* d_da, float* d_g
 #define WB_B_UNITS (16 * WB_KT)
 #define WB_STAGE_UNITS (2 * WB_A_UNITS + WB_B_UNITS)
 #define WB_NCOPY 42                         // bulk copies per stage: 2 x 2 x 7 A slabs + 2 x 7 B slabs (chunk 7 is all zero)
-#define WB_STAGE_TX ((28 * WB_APOS + 14 * WB_KT) * 16)
 
 struct ConvWgradBfArgs {
     const uint4* in_hi; const uint4* in_lo; long long in_Q;      // [8][in_Q] 16-byte units
     const uint4* da_hi; const uint4* da_lo; long long da_Q;      // dA(q) at unit q + K - 1
     float* gW;                                                   // [K][51][50]
     int K, npairs, ngroups, nstages_total, nq;
+    // stages walk the VALID dA positions only: row r contributes positions [r*Lin, r*Lin + Nv) in spr stages of 64 (the
+    // last one of a row with fewer k-steps); the K-1 slots between rows hold dA = 0 and would be wasted reduction steps
+    // (24 % / 33 % / 49 % of the flattened positions of the three flows of the AR configuration)
+    long long Lin, Nv;
+    int spr;
     int flush;                                                   // stages per accumulator drain (WB_FLUSH)
     int diag;                                                    // NMA_DIAG timing experiments (results invalid): 1 no A loads, 2 no B loads, 8 / 16 see the MMA loop
 };
@@ -762,21 +766,26 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
         for (int si = 0; si < nst; ++si) {
             const int st = si % WB_STAGES;
             if (si >= WB_STAGES) mbar_wait_backoff(&empty[st], (uint32_t)(((si / WB_STAGES) - 1) & 1));
-            if (lane == 0)
-                mbar_expect_tx(&full[st], (uint32_t)(((a.diag & 1) ? 0 : 28 * WB_APOS * 16) + ((a.diag & 2) ? 0 : 14 * WB_KT * 16)));
-            __syncwarp();
             uint4* sb = smem_u + (size_t)st * WB_STAGE_UNITS;
-            const long long q0 = (long long)(s_begin + si) * WB_KT;
+            const long long gs = s_begin + si, row = gs / a.spr;
+            const long long q0 = row * a.Lin + (gs - row * a.spr) * WB_KT;
+            // the last stage of a row has fewer k-steps: copy only the positions they read
+            const long long left = a.Nv - (gs - row * a.spr) * WB_KT;
+            const uint32_t npos_b = left >= WB_KT ? (uint32_t)WB_KT : (uint32_t)((left + 15) / 16) * 16u;
+            const uint32_t npos_a = npos_b + 8u;
+            if (lane == 0)
+                mbar_expect_tx(&full[st], ((a.diag & 1) ? 0u : 28u * npos_a * 16u) + ((a.diag & 2) ? 0u : 14u * npos_b * 16u));
+            __syncwarp();
             for (int idx = lane; idx < WB_NCOPY; idx += 32) {
                 if ((idx < 28 && (a.diag & 1)) || (idx >= 28 && (a.diag & 2))) continue;
                 if (idx < 28) {
                     const int hl = idx / 14, r2 = idx - hl * 14, copy = r2 / 7, c = r2 - copy * 7;
                     const uint4* src = (hl ? a.in_lo : a.in_hi) + (size_t)c * a.in_Q + q0 + k0 + copy;
-                    bulk_g2s(sb + hl * WB_A_UNITS + (copy * 8 + c) * WB_APOS, src, WB_APOS * 16u, &full[st]);
+                    bulk_g2s(sb + hl * WB_A_UNITS + (copy * 8 + c) * WB_APOS, src, npos_a * 16u, &full[st]);
                 } else {
                     const int j = idx - 28, hl = j / 7, c = j - hl * 7;
                     const uint4* src = (hl ? a.da_lo : a.da_hi) + (size_t)c * a.da_Q + q0 + (a.K - 1);
-                    bulk_g2s(sb + 2 * WB_A_UNITS + (hl * 8 + c) * WB_KT, src, WB_KT * 16u, &full[st]);
+                    bulk_g2s(sb + 2 * WB_A_UNITS + (hl * 8 + c) * WB_KT, src, npos_b * 16u, &full[st]);
                 }
             }
             __syncwarp();
@@ -795,6 +804,9 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
             if (chunk_first && ci > 0) mbar_wait_backoff(&acc_free, (uint32_t)((ci - 1) & 1));
             mbar_wait_backoff(&full[st], (uint32_t)((si / WB_STAGES) & 1));
             tc_fence_after();
+            const long long gs = s_begin + si;
+            const long long left = a.Nv - (gs % a.spr) * WB_KT;                  // valid positions from this stage's start
+            const int nks = left >= WB_KT ? WB_KT / 16 : (int)((left + 15) / 16);
             if (elect_one()) {
                 const uint32_t ua_hi = sbase + (uint32_t)(st * WB_STAGE_UNITS) * 16u;
                 const uint32_t ua_lo = ua_hi + WB_A_UNITS * 16u;
@@ -802,8 +814,7 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
                 const uint32_t ah0 = desc_lo(ua_hi, 128u), al0 = desc_lo(ua_lo, 128u), b0 = desc_lo(ub, 128u);   // leading offset: next 8 positions
                 for (int pr = 0; pr < np; ++pr) {
                     const uint32_t d = tmem + (uint32_t)(pr * 2 * TC_N);
-#pragma unroll
-                    for (int ks = 0; ks < WB_KT / 16; ++ks) {
+                    for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t aoff = (uint32_t)(2 * pr + 16 * ks);          // 16-byte units = positions
                         const uint64_t ah = desc_pack(ah0 + aoff, a_hi32), al = desc_pack(al0 + aoff, a_hi32);
                         const uint64_t bw = desc_pack(b0 + (uint32_t)(16 * ks), b_hi32);
@@ -863,10 +874,15 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-static void wgrad_bf_geometry(ConvWgradBfArgs& a, long long qtot, int sm_count) {
+// rows of Lin flattened positions each, the first Nv of which carry dA (rows = 1, Lin = Nv = Q: plain flattened walk)
+static void wgrad_bf_geometry(ConvWgradBfArgs& a, long long rows, long long Lin, long long Nv, int sm_count) {
     a.npairs = (a.K + 1) / 2;
     a.ngroups = (a.npairs + WGT_MAXPAIRS - 1) / WGT_MAXPAIRS;
-    a.nstages_total = (int)((qtot + WB_KT - 1) / WB_KT);
+    // the last k-step of a row reads up to 15 positions past Nv: they must fall into the zero gap of K-1 slots
+    if (rows > 1 && ((16 - Nv % 16) % 16) > a.K - 1) { Nv = Lin = rows * Lin; rows = 1; }
+    a.Lin = Lin; a.Nv = Nv;
+    a.spr = (int)((Nv + WB_KT - 1) / WB_KT);
+    a.nstages_total = (int)(rows * a.spr);
     const char* ew = getenv("NMA_WB_WAVES");
     int nq = (((ew && atoi(ew) > 0) ? atoi(ew) : 3) * sm_count) / a.ngroups;
     if (nq < 1) nq = 1;
@@ -885,7 +901,7 @@ int launch_conv_wgrad_bf(nma_handle_s* h, int i, int p, float* gp, cudaStream_t 
     a.da_hi = (const uint4*)h->ws[i].dat_hi; a.da_lo = (const uint4*)h->ws[i].dat_lo; a.da_Q = h->ws[i].dat_Q;
     a.gW = gp + h->po[i].convw;
     a.K = h->cfg.K;
-    wgrad_bf_geometry(a, (long long)p * d.Lin, h->sm_count);
+    wgrad_bf_geometry(a, p, d.Lin, d.N, h->sm_count);
     const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
     static int configured = 0;
     if (configured < smem) {
@@ -915,7 +931,7 @@ extern "C" int nma_tc_wgrad_raw_bf(const float* d_in, const float* d_da, float* 
     ConvWgradBfArgs a;
     a.in_hi = ih; a.in_lo = il; a.in_Q = Qalloc; a.da_hi = dh; a.da_lo = dl; a.da_Q = Qalloc;
     a.gW = d_gw; a.K = K;
-    wgrad_bf_geometry(a, Q, 4);
+    wgrad_bf_geometry(a, 1, Q, Q, 4);
     const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
     cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) k_conv_wgrad_bf<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
