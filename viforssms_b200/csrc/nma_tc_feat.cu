@@ -19,6 +19,7 @@
 // the epilogue time).  Per slot: 8 warps; warp w reads TMEM lanes 32*(w%4).. (positions) and columns 32*(w/4)..
 // (output channels).
 #include <string.h>
+#include <stdlib.h>
 #include "nma_tc.cuh"
 
 #define FT_SLOTS 2
@@ -665,6 +666,7 @@ struct EpiBwdTcArgs {
     int XP, XPn, N, NP, K, S, Lin, p;
     float cq;
     int bf;                  // `dat` in the bf16 split [8][dat_Q][8 x bf16]
+    float* dtb;              // [p][50] per-row sums of dA, accumulated here when non-null (zeroed by the launcher)
 };
 
 __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
@@ -816,6 +818,29 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
         tc_fence_after();
         // dA = (G W^T) (.) elu'(e_0) -> the conv gradient operand, channels 16*cg .. +15 of this position
         tmem_sum16(td, [&](int k, float x) { g[k] = x * elu_grad_from_out(e0v[k]); });
+        if (a.dtb) {
+            // per-row sums of dA for the theta-bias backward (AR.py:63-72): a warp holds 32 consecutive flattened
+            // positions, i.e. one row or the end of one and the start of the next; anything else (rows shorter than a
+            // warp) falls back to one atomic per lane
+            const int rk = valid ? r : -1;
+            const int r0 = __shfl_sync(0xffffffffu, rk, 0), r1 = __shfl_sync(0xffffffffu, rk, 31);
+            const bool two = __all_sync(0xffffffffu, rk == r0 || rk == r1);
+            if (two) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float s0 = warp_sum(rk == r0 ? g[k] : 0.f);
+                    const float s1 = warp_sum((rk == r1 && r1 != r0) ? g[k] : 0.f);
+                    if (lane == 0 && 16 * cg + k < NMA_C) {
+                        if (r0 >= 0) atomicAdd(a.dtb + (size_t)r0 * NMA_C + 16 * cg + k, s0);
+                        if (r1 >= 0 && r1 != r0) atomicAdd(a.dtb + (size_t)r1 * NMA_C + 16 * cg + k, s1);
+                    }
+                }
+            } else if (valid) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (16 * cg + k < NMA_C) atomicAdd(a.dtb + (size_t)r * NMA_C + 16 * cg + k, g[k]);
+            }
+        }
         if (valid) {
             const long long qd = (long long)(a.K - 1) + (long long)r * a.Lin + m;
             if (a.bf) {
@@ -932,6 +957,18 @@ __global__ void __launch_bounds__(8 * 32) k_dtb_from_dat_bf(const uint4* __restr
     }
 }
 
+// conv bias gradient from the per-row sums: g_convb[f] += sum_r dtb[r][f]
+__global__ void __launch_bounds__(256) k_convb_from_dtb(const float* __restrict__ dtb, int p, float* __restrict__ g_convb) {
+    __shared__ float part[4][64];
+    const int f = threadIdx.x & 63, rl = threadIdx.x >> 6;
+    float acc = 0.f;
+    if (f < NMA_C)
+        for (int r = blockIdx.x * 4 + rl; r < p; r += gridDim.x * 4) acc += __ldg(dtb + (size_t)r * NMA_C + f);
+    part[rl][f] = acc;
+    __syncthreads();
+    if (rl == 0 && f < NMA_C) atomicAdd(g_convb + f, part[0][f] + part[1][f] + part[2][f] + part[3][f]);
+}
+
 // transposed pack of ONE 1x1 kernel [50][50] (same element map as the feature kernels' transposed slots)
 __global__ void k_tc_pack_w1x1_t(const float* __restrict__ W, float* __restrict__ out) {
     for (int t = threadIdx.x; t < FT_WLAYER_F; t += blockDim.x) {
@@ -964,6 +1001,11 @@ int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int ob
     a.Lin = d.Lin; a.p = p;
     a.cq = (objective == NMA_OBJ_ELBO) ? (float)h->cfg.scale : 0.f;
     a.bf = h->use_bf16;
+    {
+        const char* env = getenv("NMA_DTB_FUSED");           // 0: per-row sums by k_dtb_from_dat from the operand instead
+        a.dtb = (env && env[0] == '0') ? nullptr : h->ws[i].dtb;
+    }
+    if (a.dtb) NMA_CHECK_CUDA(cudaMemsetAsync(a.dtb, 0, (size_t)p * NMA_C * 4, st));
     const long long ntiles = ((long long)p * d.N + FT_M - 1) / FT_M;
     const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
     const int smem = (2 * FT_A_F + 2 * FB_OPW_F + FT_WLAYER_F) * 4;
@@ -973,7 +1015,11 @@ int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int ob
         configured = smem;
     }
     k_epi_bwd_tc<<<grid, FB_THREADS, smem, st>>>(a);
-    if (h->use_bf16)
+    if (a.dtb) {
+        int g = (p + 3) / 4;
+        if (g > h->sm_count) g = h->sm_count;
+        k_convb_from_dtb<<<g, 256, 0, st>>>(a.dtb, p, gp + h->po[i].convb);
+    } else if (h->use_bf16)
         k_dtb_from_dat_bf<<<p, 8 * 32, 0, st>>>((const uint4*)h->ws[i].dat_hi, (const uint4*)h->ws[i].dat_lo, h->ws[i].dat_Q,
                                                h->cfg.K, d.Lin, d.N, h->ws[i].dtb, gp + h->po[i].convb);
     else
