@@ -24,10 +24,18 @@ PARITY STATUS.  The numpy half (padding, index draw, gather, data generation) is
 PINNED: tests/golden/{ar,fhn,sv,lv}_golden.npz hold what the reference's own
 unmodified code fed to its session (tests/golden/make_golden.py and
 make_golden_models.py run AR.py / fitz_nag_NVP.py / SV_dense.py /
-lotka_volterra_partial_batch_fix_theta.py under a stub `tensorflow`).  The torch half (flow, ELBO, gradients, Adamax) is
-"parity unpinned": the reference records no ELBO / gradient / parameter value
-anywhere and its TF graph cannot be executed here; it is pinned only by fp64
-autograd + gradcheck of this restatement (tests/test_oracle.py).
+lotka_volterra_partial_batch_fix_theta.py under a stub `tensorflow`).  The torch half:
+  * AR model (flow, ELBO terms, gradients of -ELBO and of the pre-training objective, clip + Adamax): PINNED TO THE
+    REFERENCE'S OWN CLASSES.  tests/golden/make_golden_step.py imports AR.py and optimisers/adamax.py unmodified and
+    executes init_dist, IAF._create_flow, Flow_Stack, VI_SSM._ELBO / build_flow and AdamaxOptimizer over
+    tests/golden/tf_shim.py, a torch float64 stand-in for the ~30 TensorFlow-1.8 LIBRARY ops they call; this
+    restatement agrees with what they return to 1e-10 (terms, path) and 1e-9 (every gradient entry)
+    (tests/test_step_golden.py; the CUDA path is held to 1e-4 against the same file, tests/test_gpu_step_golden.py).
+    Pinned: the composition - slices, terms, signs, scales, variable creation order, slot arithmetic.  Not pinned:
+    TensorFlow's own op kernels (the shim restates their documented behaviour) - the real TF cannot run here.
+  * FHN / SV / LV models and the theta posterior (tf.contrib bijectors): still "parity unpinned" - pinned only by fp64
+    autograd + gradcheck of this restatement (tests/test_oracle.py); their scripts build the graph at module level
+    around constructs the shim does not cover yet (Permute via scatter_nd is covered, the bijector chains are not).
 """
 from __future__ import annotations
 
