@@ -33,9 +33,12 @@ lotka_volterra_partial_batch_fix_theta.py under a stub `tensorflow`).  The torch
     (tests/test_step_golden.py; the CUDA path is held to 1e-4 against the same file, tests/test_gpu_step_golden.py).
     Pinned: the composition - slices, terms, signs, scales, variable creation order, slot arithmetic.  Not pinned:
     TensorFlow's own op kernels (the shim restates their documented behaviour) - the real TF cannot run here.
-  * FHN / SV / LV models and the theta posterior (tf.contrib bijectors): still "parity unpinned" - pinned only by fp64
-    autograd + gradcheck of this restatement (tests/test_oracle.py); their scripts build the graph at module level
-    around constructs the shim does not cover yet (Permute via scatter_nd is covered, the bijector chains are not).
+  * FHN and SV models: the same, from the class sections of fitz_nag_NVP.py and SV_dense.py exec'd verbatim
+    (tests/golden/make_golden_step_models.py -> models_step_golden.npz; tests/test_step_golden_models.py): terms, path,
+    ELBO, gradients of -ELBO and of the scripts' pre-training objective, 1e-10 / 1e-9.
+  * LV (fixed theta) model and the theta posterior (tf.contrib bijector chains): still "parity unpinned" - pinned only
+    by fp64 autograd + gradcheck of this restatement (tests/test_oracle.py); the shim does not cover
+    tfd.TransformedDistribution / tfb.Chain / tfb.Softplus(event_ndims=2) yet.
 """
 from __future__ import annotations
 

@@ -111,9 +111,13 @@ class Var:
 # ------------------------------------------------------------------------------------------------------------
 # tf.layers  (TF 1.8 defaults: use_bias=True, kernel created before bias, channels_last, 'valid' padding)
 # ------------------------------------------------------------------------------------------------------------
+def _only_trainable(kw):
+    assert set(kw) <= {"trainable"} and kw.get("trainable", True), kw      # the scripts pass trainable=True at most
+
+
 def dense(inputs, units, activation=None, **kw):
     """tf.layers.dense: outputs = activation(inputs . kernel + bias) on the LAST axis; kernel [in, units]."""
-    assert not kw, kw
+    _only_trainable(kw)
     x = _t(inputs)
     k = STATE.new_variable((x.shape[-1], units), "dense_kernel")
     b = STATE.new_variable((units,), "dense_bias")
@@ -124,7 +128,7 @@ def dense(inputs, units, activation=None, **kw):
 def conv1d(inputs, filters, kernel_size, strides=1, padding="valid", activation=None, **kw):
     """tf.layers.conv1d, channels_last: out[n, m, f] = sum_k sum_c in[n, m*s + k, c] kernel[k, c, f] + bias[f]
     (cross-correlation, no kernel flip), kernel [kernel_size, in_channels, filters], 'valid': no padding."""
-    assert not kw, kw
+    _only_trainable(kw)
     assert padding.lower() == "valid"
     x = _t(inputs)
     k = STATE.new_variable((kernel_size, x.shape[-1], filters), "conv_kernel")
@@ -242,8 +246,9 @@ def name_scope(*a, **k):
     yield
 
 
-def placeholder(shape=None, dtype=None, **kw):
-    return STATE.next_placeholder(shape)
+def placeholder(dtype=None, shape=None, name=None):
+    """tf.placeholder(dtype, shape): the next injected feed value."""
+    return STATE.next_placeholder([shape] if isinstance(shape, int) else shape)
 
 
 def split(value, num_or_size_splits, axis=0):
@@ -267,7 +272,13 @@ def scatter_nd(indices, updates, shape):
 def install():
     """Registers the stand-in as `tensorflow` (+ the submodules the reference imports) in sys.modules."""
     tf = types.ModuleType("tensorflow")
-    tf.float32, tf.float16 = float32, float16
+    tf.float32, tf.float16, tf.int32 = float32, float16, _DType("int32")
+    tf.shape = lambda x, **k: [int(d) for d in _t(x).shape]
+    tf.zeros = lambda shape, dtype=None, **k: torch.zeros([int(d) for d in shape], dtype=DT)
+    tf.ones = lambda shape, dtype=None, **k: torch.ones([int(d) for d in shape], dtype=DT)
+    tf.reduce_prod = lambda x, axis=None, **k: _t(x).prod() if axis is None else _t(x).prod(dim=axis)
+    tf.matrix_inverse = lambda x, **k: torch.linalg.inv(_t(x))
+    tf.matrix_diag_part = lambda x, **k: torch.diagonal(_t(x), dim1=-2, dim2=-1)
     tf.set_random_seed = lambda *a, **k: None
     tf.InteractiveSession = lambda *a, **k: mock.MagicMock(name="session")
     tf.Session = tf.InteractiveSession
@@ -299,7 +310,12 @@ def install():
     tf.train = mock.MagicMock(name="train")
     bij = mock.MagicMock(name="bijectors")
     tf.contrib = types.SimpleNamespace(distributions=types.SimpleNamespace(
-        Normal=Normal, MultivariateNormalDiag=MultivariateNormalDiag, bijectors=bij))
+        Normal=Normal, MultivariateNormalDiag=MultivariateNormalDiag, bijectors=bij,
+        TransformedDistribution=mock.MagicMock(name="TransformedDistribution")))
+    client = types.ModuleType("tensorflow.python.client")
+    client.timeline = mock.MagicMock(name="timeline")
+    sys.modules.setdefault("matplotlib", mock.MagicMock(name="matplotlib"))          # imported by the scripts, unused here
+    sys.modules.setdefault("matplotlib.pyplot", mock.MagicMock(name="matplotlib.pyplot"))
 
     py = types.ModuleType("tensorflow.python")
     opsm = types.ModuleType("tensorflow.python.ops")
@@ -320,12 +336,13 @@ def install():
     tr_opt.Optimizer = Optimizer
     opsm.clip_ops, opsm.control_flow_ops, opsm.math_ops, opsm.state_ops = clip_ops, control_flow_ops, math_ops, state_ops
     fw.ops, tr.optimizer = fw_ops, tr_opt
-    py.ops, py.framework, py.training = opsm, fw, tr
+    py.ops, py.framework, py.training, py.client = opsm, fw, tr, client
     tf.python = py
     mods = {"tensorflow": tf, "tensorflow.python": py, "tensorflow.python.ops": opsm,
             "tensorflow.python.ops.clip_ops": clip_ops, "tensorflow.python.ops.control_flow_ops": control_flow_ops,
             "tensorflow.python.ops.math_ops": math_ops, "tensorflow.python.ops.state_ops": state_ops,
             "tensorflow.python.framework": fw, "tensorflow.python.framework.ops": fw_ops,
-            "tensorflow.python.training": tr, "tensorflow.python.training.optimizer": tr_opt}
+            "tensorflow.python.training": tr, "tensorflow.python.training.optimizer": tr_opt,
+            "tensorflow.python.client": client}
     sys.modules.update(mods)
     return tf

@@ -88,3 +88,51 @@ def test_cuda_adamax_matches_the_reference_optimizer(G):
     big = torch.from_numpy(np.abs(G["small_grad"]) > 1e-3)
     upd = (w.cpu().double() - params.double())[big]
     assert (upd.abs() - lr * 0.05).abs().max().item() <= 1e-4 * lr
+
+
+# ---------------------------------------------------------------------------------------------------
+# FitzHugh-Nagumo and stochastic volatility: the CUDA path against the reference's own classes
+# (tests/golden/models_step_golden.npz, tests/golden/make_golden_step_models.py)
+# ---------------------------------------------------------------------------------------------------
+from test_step_golden_models import GM, check_grads, fhn_inputs, sv_inputs  # noqa: E402,F401
+
+
+def _check_model(GM, prefix, inputs, term_keys, tc, objective=0, path_target=0.0, gprefix=None):
+    from viforssms_b200.engine import NMAEngine
+    cfg, layout, n, params, eps, theta, idx, tf, extra, arrays = inputs
+    eng = NMAEngine(cfg, tensor_cores=tc)
+    eng.set_series(arrays)
+    dev = torch.device("cuda")
+    out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(np.asarray(idx)).to(dev),
+                           objective=objective, path_target=path_target)
+    torch.cuda.synchronize()
+    gp = out["grad_params"].cpu().double().numpy()
+    worst = check_grads(gp, layout, GM, gprefix or prefix, RTOL, 1e-6)
+    if objective == 0:
+        t = out["terms"].cpu().double().numpy()
+        for k, key in term_keys:
+            want = GM[prefix + key]
+            assert np.abs(t[:, k] - want).max() <= RTOL * max(1.0, np.abs(want).max()), key
+        gth = out["grad_theta"].cpu().double().numpy()
+        want = GM[prefix + "grad_theta"]
+        assert np.linalg.norm(gth - want) <= RTOL * np.linalg.norm(want)
+    return out, worst
+
+
+def test_cuda_fhn_step_matches_the_reference_classes(GM):
+    inputs = fhn_inputs(GM)
+    out, worst = _check_model(GM, "fhn_", inputs, [(0, "sde"), (1, "obs_lp"), (2, "logq")], None)
+    p, B = inputs[0].p, inputs[0].B
+    lf = out["lf"].cpu().double().numpy().reshape(p, -1, 2).transpose(0, 2, 1)      # fitz_nag_NVP.py:282-283
+    want = GM["fhn_lf_sample"]
+    assert np.linalg.norm(lf - want) <= RTOL * np.linalg.norm(want)
+    _, worst2 = _check_model(GM, "fhn_", inputs, [], None, objective=2, path_target=0.0, gprefix="fhn_pre_")
+    print("CUDA vs reference classes (FHN): worst gradient slice error %.2e (ELBO), %.2e (pre-training)" % (worst, worst2))
+
+
+@pytest.mark.parametrize("tc", [0, 3])
+def test_cuda_sv_step_matches_the_reference_classes(GM, tc):
+    inputs = sv_inputs(GM)
+    out, worst = _check_model(GM, "sv_", inputs, [(0, "sde"), (2, "logq")], tc)
+    _, worst2 = _check_model(GM, "sv_", inputs, [], tc, objective=2, path_target=-7.0, gprefix="sv_pre_")
+    print("CUDA vs reference classes (SV, mode %d): worst gradient slice error %.2e (ELBO), %.2e (pre-training)" % (tc, worst, worst2))

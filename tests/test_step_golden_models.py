@@ -1,0 +1,137 @@
+"""FitzHugh-Nagumo and stochastic-volatility models: the oracle's flow / ELBO / gradient restatement against values
+produced by the reference's OWN classes (tests/golden/models_step_golden.npz, made by
+tests/golden/make_golden_step_models.py: the class sections of fitz_nag_NVP.py and SV_dense.py exec'd verbatim over
+tests/golden/tf_shim.py).  See tests/test_step_golden.py for what such a fixture pins and what it does not.
+CPU only; the GPU leg is tests/test_gpu_step_golden.py."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nma_oracle as O
+from viforssms_b200 import feed
+from viforssms_b200.config import fhn_config, param_layout, sv_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def GM():
+    return np.load(os.path.join(ROOT, "tests", "golden", "models_step_golden.npz"))
+
+
+def _params(cfg, layout, n, g, time_row, T):
+    params = O.glorot_init(layout, n, g, torch.float32)
+    for name, (off, shape) in layout.items():
+        k = int(np.prod(shape))
+        if name.endswith(".b") or name.endswith(".beta"):
+            params[off:off + k] = 0.05 * torch.randn(k, generator=g)
+        if name.endswith(".gamma"):
+            params[off:off + k] = 1.0 + 0.1 * torch.randn(k, generator=g)
+    if time_row is not None:
+        for i in range(cfg.F):
+            off, shape = layout[f"f{i}.feat0.w"]
+            params[off:off + shape[0] * shape[1]].reshape(shape)[time_row, :] *= 10.0 / T
+    return params
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def fhn_inputs(GM):
+    p, K, B, F, fw, target_dims, seed = (int(v) for v in GM["fhn_hyper"])
+    dt = float(GM["fhn_dt"])
+    T = target_dims * dt
+    cfg = fhn_config(p=p, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=target_dims, dt=dt)
+    layout, n = param_layout(cfg)
+    g = torch.Generator().manual_seed(seed)
+    params = _params(cfg, layout, n, g, None, T)
+    assert _sha(params.numpy()) == str(GM["fhn_params_sha_f32"])
+    obs, obs_bin, tt, idx = GM["fhn_obs"], GM["fhn_obs_bin"], GM["fhn_time_till"], GM["fhn_idx"]
+    pads = O.pad_series_fhn(obs, tt, np.array([2.0, 3.0]), dt, T, target_dims, F, K, fw)
+    tf64, _, _, bin_feed = O.gather_feed_fhn(pads, obs_bin, idx, cfg.L0, B)
+    f32 = lambda a: torch.from_numpy(np.asarray(a).astype(np.float32)).double()
+    arrays = feed.fhn_base_arrays(obs, obs_bin, tt, dt, T, target_dims, F, K, fw)
+    return (cfg, layout, n, params, torch.from_numpy(GM["fhn_eps"]), torch.from_numpy(GM["fhn_theta"]), idx, f32(tf64),
+            {"bin_feed": f32(bin_feed)}, arrays)
+
+
+def sv_inputs(GM):
+    p, K, B, F, fw, N, seed = (int(v) for v in GM["sv_hyper"])
+    dt, x0 = float(GM["sv_dt"]), float(GM["sv_x0"])
+    T = float(N)
+    cfg = sv_config(p=p, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=N, dt=dt, x0=x0)
+    layout, n = param_layout(cfg)
+    g = torch.Generator().manual_seed(seed)
+    params = _params(cfg, layout, n, g, fw, N)
+    assert _sha(params.numpy()) == str(GM["sv_params_sha_f32"])
+    obs, idx = GM["sv_obs"], GM["sv_idx"]
+    pads = O.pad_series_sv(obs, x0, dt, T, N, F, K, fw)
+    tf64, mask, shift, dim_one = O.gather_feed_sv(pads, idx, cfg.L0, B)
+    f32 = lambda a: torch.from_numpy(np.asarray(a).astype(np.float32)).double()
+    arrays = feed.sv_base_arrays(obs, dt, T, F, K, fw)
+    return (cfg, layout, n, params, torch.from_numpy(GM["sv_eps"]), torch.from_numpy(GM["sv_theta"]), idx, f32(tf64),
+            {"mask": f32(mask), "shift": f32(shift), "dim_one": f32(dim_one)}, arrays)
+
+
+def _close(got, want, rtol):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    return np.abs(got - want).max() <= rtol * max(1.0, np.abs(want).max())
+
+
+def check_grads(got, layout, GM, prefix, rtol, floor):
+    """per-variable norms and leading entries; returns the worst relative error seen"""
+    heads = GM[prefix + "grad_heads"]
+    gn = float(GM[prefix + "global_norm"])
+    pos, worst = 0, 0.0
+    for nm, want_norm in zip([str(s) for s in GM[prefix + "var_names"]], GM[prefix + "grad_norms"]):
+        off, shape = layout[nm]
+        k = int(np.prod(shape))
+        scale = max(want_norm, floor * gn)
+        assert abs(np.linalg.norm(got[off:off + k]) - want_norm) <= rtol * scale, (prefix, nm)
+        h = min(k, 16)
+        hs = max(np.linalg.norm(heads[pos:pos + h]), floor * gn)
+        err = np.linalg.norm(got[off:off + h] - heads[pos:pos + h])
+        worst = max(worst, err / hs)
+        assert err <= rtol * hs, (prefix, nm)
+        pos += h
+    assert abs(np.linalg.norm(got) - gn) <= rtol * gn
+    return worst
+
+
+def test_fhn_oracle_matches_the_reference_classes(GM):
+    cfg, layout, n, params, eps, theta, idx, tf, extra, _ = fhn_inputs(GM)
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, extra=extra)
+    t = ref["terms"].numpy()
+    assert _close(t[:, 0], GM["fhn_sde"], 1e-10)              # fitz_nag_NVP.py:236-255
+    assert _close(t[:, 1], GM["fhn_obs_lp"], 1e-10)           # :232-233
+    assert _close(t[:, 2], GM["fhn_logq"], 1e-10)             # base log-density minus the coupling layers' log sigma
+    assert _close(ref["lf"].numpy(), GM["fhn_lf_sample"], 1e-10)          # [p, 2, B+1] (:282-283)
+    th = theta.double().numpy()
+    prior = sum(-0.5 * (th[:, k] / 10.0) ** 2 - 0.5 * np.log(2 * np.pi) - np.log(10.0) for k in range(5))
+    assert _close(cfg.scale * (t[:, 0] - t[:, 2] + t[:, 1]) + prior, GM["fhn_elbo"], 1e-10)      # :265-268
+    assert _close(ref["grad_theta"].numpy(), GM["fhn_grad_theta"], 1e-9)
+    check_grads(ref["grad_params"].numpy(), layout, GM, "fhn_", 1e-9, 1e-12)
+    pre = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, obj=2, extra=extra,
+                           path_target=0.0)
+    check_grads(pre["grad_params"].numpy(), layout, GM, "fhn_pre_", 1e-9, 1e-12)                # :288-289
+
+
+def test_sv_oracle_matches_the_reference_classes(GM):
+    cfg, layout, n, params, eps, theta, idx, tf, extra, _ = sv_inputs(GM)
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, extra=extra)
+    t = ref["terms"].numpy()
+    assert _close(t[:, 0], GM["sv_sde"], 1e-10)               # SV_dense.py:203-226
+    assert _close(t[:, 2], GM["sv_logq"], 1e-10)
+    assert _close(ref["lf"].numpy(), GM["sv_lf_sample"], 1e-10)           # [p, 2, B+1]: price, masked log-volatility
+    th = theta.double().numpy()
+    prior = sum(-0.5 * (th[:, k] / 10.0) ** 2 - 0.5 * np.log(2 * np.pi) - np.log(10.0) for k in range(4))
+    assert _close(cfg.scale * (t[:, 0] - t[:, 2]) + prior, GM["sv_elbo"], 1e-10)                 # :231-232
+    assert _close(ref["grad_theta"].numpy(), GM["sv_grad_theta"], 1e-9)
+    check_grads(ref["grad_params"].numpy(), layout, GM, "sv_", 1e-9, 1e-12)
+    pre = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, obj=2, extra=extra,
+                           path_target=-7.0)
+    check_grads(pre["grad_params"].numpy(), layout, GM, "sv_pre_", 1e-9, 1e-12)                 # :251-252
