@@ -127,6 +127,10 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         h->use_bf16 = 0;            // decided below, once the kernels that understand the format are known to run
         const char* envw = getenv("NMA_DGRAD_WIDE");
         h->dgrad_wide = (envw && envw[0] == '0') ? 0 : 1;
+        const char* envp2 = getenv("NMA_TAP_PAIRS");
+        // default for even kernel_len (every reference script); the zero-kernel pairing of an odd last tap is written but
+        // has not been run on hardware yet, so odd kernel_len keeps the tap-by-tap kernels unless NMA_TAP_PAIRS=1 insists
+        h->tap_pairs = (h->dgrad_wide && !(envp2 && envp2[0] == '0') && ((cfg->K % 2 == 0) || (envp2 && envp2[0] == '1'))) ? 1 : 0;
     }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));

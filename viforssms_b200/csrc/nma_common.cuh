@@ -76,6 +76,8 @@ struct nma_handle_s {
     int bf16_ok;     // the bf16-split conv path covers this configuration (persistent conv kernels + tensor-core head backward)
     int dgrad_wide;  // bf16 split only: data gradient as N = 256 instructions with the stacked kernel as A (k_conv_dgrad_tcq);
                      // (default) NMA_DGRAD_WIDE=0 selects the M = 128 positions form k_conv_dgrad_tcp<true>
+    int tap_pairs;   // bf16 split only: forward / data-gradient taps in pairs, 7 instead of 8 instructions per pair
+                     // (nma_tc_conv2.cu); default for even kernel_len, NMA_TAP_PAIRS=0 / 1 forces it off / on; needs dgrad_wide
     int use_bf16;    // conv GEMMs (forward, data gradient, weight gradient) in the 2-term bf16 split on kind::f16
                      // (nma_tc.cuh); NMA_TC_BF16=1 or bit 2 of nma_set_tensor_cores
     // Lotka-Volterra (lotka_volterra_partial_batch_fix_theta.py:71-82): every flow's feature MLP runs over the whole

@@ -69,8 +69,42 @@ __global__ void k_tc_pack_w_bf(const float* __restrict__ W, int K, int mode, uin
     }
 }
 
+// tap pairs (nma_tc_conv2.cu): one tile per pair, chunks [tap a: 0-5][tap b: 0-5][a: 6][b: 6]; a tap >= K packs zeros
+__global__ void k_tc_pack_w_bf_pair(const float* __restrict__ W, int K, int mode, uint16_t* __restrict__ out, int interleave) {
+    const int npairs = (K + 1) / 2;
+    const int n_half = npairs * 14 * TC_N * 8;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_half; t += gridDim.x * blockDim.x) {
+        const int e = t & 7;
+        const int n = (t >> 3) & (TC_N - 1);
+        const int u = (t >> 9) % 14;
+        const int pr = t / (14 * TC_N * 8);
+        const int k = 2 * pr + (u < 6 ? 0 : u < 12 ? 1 : u - 12);
+        const int cch = u < 6 ? u : u < 12 ? u - 6 : 6;
+        const int c = 8 * cch + e;
+        float v = 0.f;
+        if (k < K) {
+            if (mode == 0) {
+                if (c < NMA_C1 && n < NMA_C) v = W[((size_t)k * NMA_C1 + c) * NMA_C + n];
+            } else {
+                if (c < NMA_C && n < NMA_C1) v = W[((size_t)(K - 1 - k) * NMA_C1 + n) * NMA_C + c];
+            }
+        }
+        uint32_t hi, lo;
+        bf_split(v, hi, lo);
+        const size_t tile = (size_t)pr * (14 * TC_WROWS * 8) + (size_t)u * TC_WROWS * 8 + e;
+        out[tile + (size_t)(interleave ? 2 * n : n) * 8] = (uint16_t)hi;
+        out[tile + (size_t)(interleave ? 2 * n + 1 : n + TC_N) * 8] = (uint16_t)lo;
+    }
+}
+
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
     for (int i = 0; i < h->cfg.F; ++i) {
+        if (h->use_bf16 && h->tap_pairs) {
+            k_tc_pack_w_bf_pair<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 0, (uint16_t*)h->ws[i].wtc_f, 0);
+            if (need_bwd) k_tc_pack_w_bf_pair<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 1, (uint16_t*)h->ws[i].wtc_d, 1);
+            nma_count_launch(need_bwd ? 2 : 1);
+            continue;
+        }
         if (h->use_bf16) {
             k_tc_pack_w_bf<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 0, (uint16_t*)h->ws[i].wtc_f, 0);
             if (need_bwd) k_tc_pack_w_bf<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 1, (uint16_t*)h->ws[i].wtc_d, h->dgrad_wide);

@@ -113,6 +113,159 @@ __device__ __forceinline__ void p_mma(PBars& b, const float* a_hi, const float* 
     }
 }
 
+// ---------------------------------------------------------------------------
+// bf16 split, taps in PAIRS (NMA_TAP_PAIRS=1).  51 (50) reduction channels fill 6.4 (6.25) of the 8-channel chunks, and a
+// K = 16 instruction eats two chunks: four instructions per tap, the last one for 3 (2) channels.  The 7th chunk of tap
+// k can instead share an instruction with the 7th chunk of tap k+1: on the input side the two K-chunks of that
+// instruction are the same channel chunk one position apart - a leading byte offset of 16 in the descriptor - and the
+// tap kernels are packed to match ([tap a: chunks 0-5][tap b: chunks 0-5][a: chunk 6][b: chunk 6], 14 x 128 rows x 16 B
+// = one ring stage per pair).  Seven instructions per pair instead of eight, and the all-zero 8th chunk of the operand
+// tile is no longer loaded.  An odd last tap is paired with a zero kernel.
+// ---------------------------------------------------------------------------
+#define PW_CH 14
+#define PW_STAGE (PW_CH * TC_WROWS * 4)          // floats of one pair stage: 28672 B
+
+template <int NST>
+__device__ __forceinline__ void pp_producer(PBars& b, float* a_hi, float* a_lo, float* wring, const TcConvSrc& src,
+                                            int npos, long long ntiles) {
+    const uint32_t slab_bytes = (uint32_t)npos * 16u;
+    const int npairs = (src.K + 1) / 2;
+    uint32_t g = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const long long q0 = tile * (2 * TC_M);
+        if (it > 0) mbar_wait_backoff(&b.a_free, (uint32_t)((it - 1) & 1));
+        if (elect_one()) {
+            mbar_expect_tx(&b.a_full, 2u * 7u * slab_bytes);
+            for (int c = 0; c < 7; ++c) {
+                bulk_g2s(a_hi + (size_t)c * npos * 4, src.a_hi + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, &b.a_full);
+                bulk_g2s(a_lo + (size_t)c * npos * 4, src.a_lo + ((size_t)c * src.Qalloc + q0) * 4, slab_bytes, &b.a_full);
+            }
+        }
+        __syncwarp();
+        for (int pr = 0; pr < npairs; ++pr, ++g) {
+            const uint32_t st = g % NST;
+            if (g >= NST) mbar_wait_backoff(&b.empty[st], ((g / NST) - 1u) & 1u);
+            if (elect_one()) {
+                mbar_expect_tx(&b.full[st], PW_STAGE * 4u);
+                bulk_g2s(wring + (size_t)st * PW_STAGE, src.wt + (size_t)pr * PW_STAGE, PW_STAGE * 4u, &b.full[st]);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// M = 128 positions form (forward): per pair and accumulator 7 x (N=128 with a_hi, N=64 with a_lo)
+template <int NST>
+__device__ __forceinline__ void pp_mma(PBars& b, const float* a_hi, const float* a_lo, const float* wring, int K, int npos,
+                                       uint32_t tmem_base, long long ntiles) {
+    constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N, 0, 0);
+    constexpr uint32_t idesc_wide = umma_idesc_bf16(TC_M, 2 * TC_N, 0, 0);
+    const uint32_t a_lbo = (uint32_t)npos * 16u;
+    const uint32_t ah_lo0 = desc_lo(smem_u32(a_hi), a_lbo), al_lo0 = desc_lo(smem_u32(a_lo), a_lbo);
+    // the shared instruction: chunk 6 at tap a, then one position further on (tap b)
+    const uint32_t ah_lo6 = desc_lo(smem_u32(a_hi) + 6u * a_lbo, 16u), al_lo6 = desc_lo(smem_u32(a_lo) + 6u * a_lbo, 16u);
+    const uint32_t hi32 = desc_hi(128u);
+    const uint32_t w_lo0 = desc_lo(smem_u32(wring), TC_WROWS * 16u);
+    const uint32_t ks_step_a = 2u * (uint32_t)npos;
+    constexpr uint32_t ks_step_b = 2u * TC_WROWS;
+    const int npairs = (K + 1) / 2;
+    uint32_t g = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t set = (uint32_t)(it & 1);
+        mbar_wait_backoff(&b.a_full, (uint32_t)(it & 1));
+        if (it >= 2) mbar_wait_backoff(&b.acc_free[set], (uint32_t)(((it >> 1) - 1) & 1));
+        for (int pr = 0; pr < npairs; ++pr, ++g) {
+            const uint32_t st = g % NST;
+            mbar_wait_backoff(&b.full[st], (g / NST) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t wb = w_lo0 + st * (PW_STAGE * 4u / 16u);
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const uint32_t row = (uint32_t)(a * TC_M + 2 * pr);
+                    const uint32_t d = tmem_base + set * (4u * TC_N) + (uint32_t)(a * 2 * TC_N);
+#pragma unroll
+                    for (int ks = 0; ks < 7; ++ks) {
+                        uint64_t ah, al;
+                        if (ks < 6) {
+                            const uint32_t off = row + (uint32_t)(ks >= 3 ? 1 : 0) + (uint32_t)(ks % 3) * ks_step_a;
+                            ah = desc_pack(ah_lo0 + off, hi32);
+                            al = desc_pack(al_lo0 + off, hi32);
+                        } else {
+                            ah = desc_pack(ah_lo6 + row, hi32);
+                            al = desc_pack(al_lo6 + row, hi32);
+                        }
+                        const uint64_t bw = desc_pack(wb + (uint32_t)ks * ks_step_b, hi32);
+                        umma_bf16(d, ah, bw, idesc_wide, (pr | ks) ? 1u : 0u);
+                        umma_bf16(d + TC_N, al, bw, idesc, 1u);
+                    }
+                }
+                tc_commit(&b.empty[st]);
+                if (pr == npairs - 1) {
+                    tc_commit(&b.acc_full[set]);
+                    tc_commit(&b.a_free);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// position-wide form (data gradient): per pair 7 x (B = dA_hi, B = dA_lo), N = 256
+template <int NST>
+__device__ __forceinline__ void qq_mma(PBars& b, const float* a_hi, const float* a_lo, const float* wring, int K, int npos,
+                                       uint32_t tmem_base, long long ntiles) {
+    constexpr uint32_t idesc = umma_idesc_bf16(TC_M, 2 * TC_M, 0, 0);
+    const uint32_t in_lbo = (uint32_t)npos * 16u;
+    const uint32_t bh_lo0 = desc_lo(smem_u32(a_hi), in_lbo), bl_lo0 = desc_lo(smem_u32(a_lo), in_lbo);
+    const uint32_t bh_lo6 = desc_lo(smem_u32(a_hi) + 6u * in_lbo, 16u), bl_lo6 = desc_lo(smem_u32(a_lo) + 6u * in_lbo, 16u);
+    const uint32_t hi32 = desc_hi(128u);
+    const uint32_t w_lo0 = desc_lo(smem_u32(wring), TC_WROWS * 16u);
+    const uint32_t ks_step_in = 2u * (uint32_t)npos;
+    constexpr uint32_t ks_step_w = 2u * TC_WROWS;
+    const int npairs = (K + 1) / 2;
+    uint32_t g = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t set = (uint32_t)(it & 1);
+        mbar_wait_backoff(&b.a_full, (uint32_t)(it & 1));
+        if (it >= 2) mbar_wait_backoff(&b.acc_free[set], (uint32_t)(((it >> 1) - 1) & 1));
+        for (int pr = 0; pr < npairs; ++pr, ++g) {
+            const uint32_t st = g % NST;
+            mbar_wait_backoff(&b.full[st], (g / NST) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t wb = w_lo0 + st * (PW_STAGE * 4u / 16u);
+                const uint32_t d = tmem_base + set * (2u * TC_M);
+                const uint32_t row = (uint32_t)(2 * pr);
+#pragma unroll
+                for (int ks = 0; ks < 7; ++ks) {
+                    uint64_t bh, bl;
+                    if (ks < 6) {
+                        const uint32_t off = row + (uint32_t)(ks >= 3 ? 1 : 0) + (uint32_t)(ks % 3) * ks_step_in;
+                        bh = desc_pack(bh_lo0 + off, hi32);
+                        bl = desc_pack(bl_lo0 + off, hi32);
+                    } else {
+                        bh = desc_pack(bh_lo6 + row, hi32);
+                        bl = desc_pack(bl_lo6 + row, hi32);
+                    }
+                    const uint64_t aw = desc_pack(wb + (uint32_t)ks * ks_step_w, hi32);
+                    umma_bf16(d, aw, bh, idesc, (pr | ks) ? 1u : 0u);
+                    umma_bf16(d, aw, bl, idesc, 1u);
+                }
+                tc_commit(&b.empty[st]);
+                if (pr == npairs - 1) {
+                    tc_commit(&b.acc_full[set]);
+                    tc_commit(&b.a_free);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t p_setup(PBars& b, uint32_t* tmem_slot, int a_free_count) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&b.full[i], 1); mbar_init(&b.empty[i], 1); }
@@ -256,22 +409,26 @@ __device__ __forceinline__ void q_mma(PBars& b, const float* a_hi, const float* 
     }
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(P_THREADS, 1) k_conv_dgrad_tcq(ConvDgradP a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ PBars bars;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int CCHU = PAIR ? 7 : TcP<true>::CCH;           // chunk slabs of the operand tile actually staged
     float* a_hi = smem;
-    float* a_lo = a_hi + (size_t)TcP<true>::CCH * a.npos * 4;
-    float* wring = a_lo + (size_t)TcP<true>::CCH * a.npos * 4;
+    float* a_lo = a_hi + (size_t)CCHU * a.npos * 4;
+    float* wring = a_lo + (size_t)CCHU * a.npos * 4;
     const long long qtot = (long long)a.p * a.Lin;
     const long long ntiles = (qtot + 2 * TC_M - 1) / (2 * TC_M);
     const uint32_t tmem = p_setup(bars, &tmem_slot, 1);
 
     if (warp == 8) {
-        p_producer<TC_STAGES, true>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
+        if (PAIR) pp_producer<TC_STAGES>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
+        else p_producer<TC_STAGES, true>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
     } else if (warp == 9) {
-        q_mma<TC_STAGES>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
+        if (PAIR) qq_mma<TC_STAGES>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
+        else q_mma<TC_STAGES>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
     } else {
         const int quarter = warp & 3, colhalf = warp >> 2;
         const int c = (quarter * 32 + lane) >> 1;                  // output channel of this TMEM lane (rows 2c, 2c+1)
@@ -320,6 +477,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_dgrad_tcq(ConvDgradP a) {
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// operand tile rows of the pair kernels: 256 positions + taps 0..K (an odd last tap is paired with a zero kernel at tap K)
+static int pair_npos(int K) { return (2 * TC_M + K + 7) & ~7; }
+
 int launch_conv_dgrad_tcp(nma_handle_s* h, int i, int p, cudaStream_t st) {
     const FlowDims& d = h->fd[i];
     ConvDgradP a;
@@ -331,14 +491,27 @@ int launch_conv_dgrad_tcp(nma_handle_s* h, int i, int p, cudaStream_t st) {
     a.need_dx = i > 0 ? 1 : 0;
     const long long ntiles = ((long long)p * d.Lin + 2 * TC_M - 1) / (2 * TC_M);
     const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
+    if (h->use_bf16 && h->dgrad_wide && h->tap_pairs) {
+        a.npos = pair_npos(h->cfg.K);
+        const int smem = 2 * 7 * a.npos * 16 + TC_STAGES * PW_STAGE * 4;
+        static int configured = 0;
+        if (configured < smem) {
+            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tcq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = smem;
+        }
+        k_conv_dgrad_tcq<true><<<grid, P_THREADS, smem, st>>>(a);
+        nma_count_launch(1);
+        NMA_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (h->use_bf16 && h->dgrad_wide) {
         const int smem = (int)(tc_conv_smem_floats(2, h->cfg.K, TcP<true>::CCH) * 4);
         static int configured = 0;
         if (configured < smem) {
-            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tcq, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad_tcq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = smem;
         }
-        k_conv_dgrad_tcq<<<grid, P_THREADS, smem, st>>>(a);
+        k_conv_dgrad_tcq<false><<<grid, P_THREADS, smem, st>>>(a);
         nma_count_launch(1);
         NMA_CHECK_CUDA(cudaGetLastError());
         return 0;
@@ -399,8 +572,9 @@ struct ConvFwdP {
 
 #define PF_E_F (TC_CCH * 2 * TC_M * 4)          // floats of E_hi (or E_lo): [14][256][4]
 
-template <bool BF>
+template <bool BF, bool PAIR>
 __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
+    static_assert(BF || !PAIR, "tap pairs exist in the bf16 split only");
     extern __shared__ __align__(128) float smem[];
     __shared__ PBars bars;
     __shared__ uint64_t wh_bar;
@@ -410,7 +584,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
     // operand region: the conv operand tile (hi | lo) during the mainloop, E_hi | E_lo | hidden kernel (3xTF32, 140 KB)
     // during the epilogue; the weight ring follows the larger of the two (a.ring_off floats)
     float* a_hi = smem;
-    float* a_lo = a_hi + (size_t)TcP<BF>::CCH * a.npos * 4;
+    float* a_lo = a_hi + (size_t)(PAIR ? 7 : TcP<BF>::CCH) * a.npos * 4;
     float* wring = smem + a.ring_off;
     // 3xTF32: the epilogue's E_hi | E_lo | hidden kernel alias the operand buffer (e_off = 0), so the next tile's operand
     // load waits for the epilogue.  bf16 split: the operand tile is 80 KB and the epilogue operands - bf16 as well,
@@ -435,9 +609,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
     const uint32_t tmem = p_setup(bars, &tmem_slot, BF ? 1 : 1 + P_EPI_WARPS);
 
     if (warp == 8) {
-        p_producer<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
+        if (PAIR) pp_producer<2>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);          // 2 x 28 KB: what fits next to E
+        else p_producer<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src, a.npos, ntiles);
     } else if (warp == 9) {
-        p_mma<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
+        if (PAIR) pp_mma<2>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
+        else p_mma<TC_STAGES, BF>(bars, a_hi, a_lo, wring, a.src.K, a.npos, tmem, ntiles);
     } else {
         const int acc = warp >> 2, quarter = warp & 3;
         const int col = acc * TC_M + quarter * 32 + lane;
@@ -652,6 +828,22 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
     const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
     // operand region = max(conv operand tile, epilogue view E_hi | E_lo | hidden kernel); the ring follows it
     const int epi_f = 2 * PF_E_F + TC_WSTAGE;
+    if (h->use_bf16 && h->tap_pairs) {
+        // [operand tile hi | lo, 7 chunks][E_hi | E_lo | hidden kernel, all bf16][ring: 2 pair stages]
+        a.npos = pair_npos(h->cfg.K);
+        a.e_off = 2 * 7 * a.npos * 4;
+        a.ring_off = a.e_off + 2 * (TcP<true>::CCH * 2 * TC_M * 4) + TcP<true>::WSTAGE;
+        const int smem = (a.ring_off + 2 * PW_STAGE) * 4;
+        static int configured = 0;
+        if (configured < smem) {
+            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tcp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = smem;
+        }
+        k_conv_fwd_tcp<true, true><<<grid, P_THREADS, smem, st>>>(a);
+        nma_count_launch(2);
+        NMA_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (h->use_bf16) {
         // [operand tile hi | lo][E_hi | E_lo | hidden kernel, all bf16][ring]
         a.e_off = 2 * TcP<true>::CCH * a.npos * 4;
@@ -659,10 +851,10 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
         const int smem = (a.ring_off + TC_STAGES * TcP<true>::WSTAGE) * 4;
         static int configured = 0;
         if (configured < smem) {
-            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tcp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tcp<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = smem;
         }
-        k_conv_fwd_tcp<true><<<grid, P_THREADS, smem, st>>>(a);
+        k_conv_fwd_tcp<true, false><<<grid, P_THREADS, smem, st>>>(a);
         nma_count_launch(2);
         NMA_CHECK_CUDA(cudaGetLastError());
         return 0;
@@ -673,10 +865,10 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
     const int smem = 2 * TC_CCH * a.npos * 16 + TC_STAGES * TC_WSTAGE * 4;
     static int configured = 0;
     if (configured < smem) {
-        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tcp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tcp<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    k_conv_fwd_tcp<false><<<grid, P_THREADS, smem, st>>>(a);
+    k_conv_fwd_tcp<false, false><<<grid, P_THREADS, smem, st>>>(a);
     nma_count_launch(2);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
