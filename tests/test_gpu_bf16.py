@@ -116,6 +116,9 @@ def test_both_data_gradient_forms_agree(monkeypatch):
         eng.set_series(arrays)
         outs.append({k: v.clone() for k, v in eng.elbo_fwd_bwd(*args).items()})
         torch.cuda.synchronize()
-    assert torch.equal(outs[0]["terms"], outs[1]["terms"])                     # the forward pass is the same code
+    # NMA_DGRAD_WIDE=0 also switches the tap-pair kernels off (they need the wide data gradient), so the two forward
+    # passes are different kernels as well: same values to the split's accuracy, not the same bits
+    assert _rel(outs[0]["terms"], outs[1]["terms"]) < 1e-5
+    assert _rel(outs[0]["lf"], outs[1]["lf"]) < 2e-5
     assert _rel(outs[0]["grad_params"], outs[1]["grad_params"]) < 2e-5
     assert _rel(outs[0]["grad_theta"], outs[1]["grad_theta"]) < 2e-5
