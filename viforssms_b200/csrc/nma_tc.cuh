@@ -21,6 +21,7 @@
 // 4e-6 .. 8e-6 with this split on all three conv GEMMs (bar 1e-4; 3xTF32: 4e-7).
 #pragma once
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "nma_conv_core.cuh"
 
 #define TC_CCH 14                 // reduction chunks of 4 channels: 56 >= 51 (fwd) / 50 (dgrad)
@@ -58,6 +59,14 @@ __device__ __forceinline__ void bf_split8(const float (&v)[8], uint4& hi, uint4&
     lo = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
 }
 __device__ __forceinline__ float bf_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
+
+// NMA_DIAG timing experiments (tools/time_stages.py) skip loads or MMAs and produce WRONG results on purpose: they are
+// honoured only when NMA_DIAG_I_KNOW_RESULTS_ARE_INVALID=1 is set as well, so a stray variable cannot corrupt a run.
+static inline int nma_diag_bits() {
+    const char* ok = getenv("NMA_DIAG_I_KNOW_RESULTS_ARE_INVALID");
+    const char* ed = getenv("NMA_DIAG");
+    return (ok && ok[0] == '1' && ed) ? atoi(ed) : 0;
+}
 
 // ---- mbarrier extras ----
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {

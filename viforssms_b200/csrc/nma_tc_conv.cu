@@ -924,8 +924,7 @@ static void wgrad_bf_geometry(ConvWgradBfArgs& a, long long rows, long long Lin,
     a.nq = nq;
     const char* ef = getenv("NMA_WB_FLUSH");
     a.flush = (ef && atoi(ef) > 0) ? atoi(ef) : WB_FLUSH;
-    const char* ed = getenv("NMA_DIAG");
-    a.diag = ed ? atoi(ed) : 0;
+    a.diag = nma_diag_bits();
 }
 
 int launch_conv_wgrad_bf(nma_handle_s* h, int i, int p, float* gp, cudaStream_t st) {

@@ -485,7 +485,7 @@ int launch_conv_dgrad_tcp(nma_handle_s* h, int i, int p, cudaStream_t st) {
     ConvDgradP a;
     a.src.a_hi = h->ws[i].dat_hi; a.src.a_lo = h->ws[i].dat_lo; a.src.Qalloc = h->ws[i].dat_Q;
     a.src.wt = h->ws[i].wtc_d; a.src.K = h->cfg.K;
-    { const char* ed = getenv("NMA_DIAG"); a.src.diag = (ed && (atoi(ed) & 4)) ? 1 : 0; }
+    a.src.diag = (nma_diag_bits() & 4) ? 1 : 0;
     a.df = h->ws[i].df; a.dx = h->ws[i].dx;
     a.Lin = d.Lin; a.LP = d.LP; a.XP = (d.L + 3) & ~3; a.p = p; a.npos = tc_conv_npos(2, h->cfg.K);
     a.need_dx = i > 0 ? 1 : 0;
@@ -814,7 +814,7 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
     ConvFwdP a;
     a.src.a_hi = h->ws[i].tin_hi; a.src.a_lo = h->ws[i].tin_lo; a.src.Qalloc = h->ws[i].tin_Q;
     a.src.wt = h->ws[i].wtc_f; a.src.K = h->cfg.K;
-    { const char* ed = getenv("NMA_DIAG"); a.src.diag = (ed && (atoi(ed) & 4)) ? 1 : 0; }
+    a.src.diag = (nma_diag_bits() & 4) ? 1 : 0;
     a.tb = h->ws[i].tb; a.whid = whid;
     a.hidb = params + h->po[i].hidb[0]; a.headw = params + h->po[i].headw; a.headb = params + h->po[i].headb;
     a.x_in = h->ws[i].x; a.x_out = h->ws[i + 1].x; a.h0 = h->ws[i].h[0]; a.h1 = h->ws[i].h[1]; a.s = h->ws[i].s;
