@@ -348,8 +348,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--rows", type=int, default=16384, help="rows (MC samples x subsequences) per GPU per step")
     ap.add_argument("--T", type=int, default=10 ** 8)
-    ap.add_argument("--cpu-rows", type=int, default=100)
-    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--cpu-rows", type=int, default=400, help="rows of the bounded CPU sample (throughput is flat in rows: +8 %% from 100 to 1000)")
+    ap.add_argument("--cpu-steps", type=int, default=50, help="steps of the cpu_baseline leg (about 10 s of CPU work on the 16-thread box)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--conv-split", default="bf16", choices=["tf32", "bf16"],
                     help="operand split of the conv GEMMs: 3xTF32 (kind::tf32) or 2-term bf16 (kind::f16, twice the rate)")
