@@ -216,8 +216,8 @@ def flow_forward(cfg, P: Dict[str, torch.Tensor], eps: torch.Tensor, theta: torc
     # init_dist.slp: sum over the last S slots of log N(eps; 0, 1)            (AR.py:33-34)
     logq = (-0.5 * eps[:, -S:] ** 2 - 0.5 * LOG2PI).sum(dim=1)
     for i in range(cfg.F):
-        if cfg.model == 3:
-            # lotka_volterra_partial_batch_fix_theta.py:343-344,71-76: EVERY flow reads the whole window
+        if cfg.model in (3, 4):
+            # lotka_volterra_partial_batch_fix_theta.py:343-344,71-76 (lotka_volterra_partial.py:68-76,279-281): EVERY flow reads the whole window
             # (ts_feats = self.time_feats, no i*K slice); 3 x dense(50) + dense(feat_dims = L_i - 1), then the
             # [window position, unit] matrix is TRANSPOSED: unit m becomes the conv position, window position w a
             # conv input channel
@@ -314,6 +314,9 @@ def elbo_terms(cfg, x_final: torch.Tensor, theta: torch.Tensor, time_feats: torc
     if cfg.model == 3:      # lotka_volterra_partial_batch_fix_theta.py:265-332,346-371
         sde_lp, obs_lp, _, lf = lv_terms(cfg, x_final, theta, time_feats, extra)
         return sde_lp, obs_lp, lf
+    if cfg.model == 4:      # lotka_volterra_partial.py:234-275,290-297
+        sde_lp, obs_lp, _, lf = lvr_terms(cfg, x_final, theta, time_feats, extra)
+        return sde_lp, obs_lp, lf
     raise ValueError("unknown model")
 
 
@@ -366,6 +369,61 @@ def lv_terms(cfg, x_final, theta, time_feats, extra):
     return sde_lp + x0_lp, obs_lp, extra_logq, lf
 
 
+def pad_series_lvr(obs, time_till, x0, dt, T, target_dims, F, K, fw) -> Dict[str, object]:
+    """lotka_volterra_partial.py:186-205 (flow_dims = 2)."""
+    D = 2
+    obs_flatten = np.reshape(obs, -1, 'F')
+    store = []
+    for i in range(0, fw * 5, 5):
+        store.append(np.concatenate((np.zeros(F * K + D - i), obs_flatten, np.zeros(i)), axis=0))
+    time_pad = np.concatenate((np.zeros(F * K + D), np.repeat(np.arange(dt, T + dt, dt), D)), axis=0)
+    time_till_pad = np.reshape(np.repeat(np.arange(np.round((F * K + D) * (dt / D), 1), 0., -dt), D), (D, -1), 'F')
+    return {
+        "obs_pad_store": store,
+        "time_pad": time_pad,
+        "time_till": np.reshape(np.concatenate((time_till_pad, time_till), 1), -1, 'F'),
+        "bin_feats": np.float32(np.concatenate((np.zeros(F * K + D), np.ones(target_dims * D)), axis=0)),
+        "mask_vals": np.concatenate((np.zeros((2, 1)), np.ones((D, target_dims))), axis=1),
+        "shift_vals": np.concatenate((np.expand_dims(x0, 1), np.zeros((D, target_dims))), axis=1),
+    }
+
+
+def lvr_terms(cfg, x_final, theta, time_feats, extra):
+    """Lotka-Volterra, learned theta (lotka_volterra_partial.py).  Returns (sde_log_prob, obs_log_prob, the log-det
+    term lf_log_prob receives on top of the flow's own logq, lf_sample [p,2,B+1]).
+
+    :290-297  lf_sample = Softplus(event_ndims=2).forward(flow output [p,2,B+1]) * mask + shift;
+              lf_log_prob += Softplus(event_ndims=2).inverse_log_det_jacobian(lf_sample[:, :, 1:])
+              = sum over the last two axes of -log(1 - exp(-y))            (one value per row)
+    :220-224  theta_eval = exp(theta sample), three rates
+    :235      observations Normal(loc=obs_eval, scale=1).log_prob(lf_sample[:, :, 1:]) * bin_feed
+    :237-262  Bivariate_Normal(mu = dt alpha(x_t), chol = sqrt(dt) sqrt_beta(x_t)).log_prob(x_{t+1} - x_t), all B steps
+    :39-52    log_prob = -1/2 log det - 1/2 d^T Sigma^-1 d - log 2 pi, det = prod(diag(chol))^2"""
+    B, dt, p = cfg.B, cfg.dt, x_final.shape[0]
+    neg = x_final.reshape(p, -1, 2).transpose(1, 2)                           # :286-287  [p,2,B+1]
+    lf = Fnn.softplus(neg) * extra["mask"] + extra["shift"]                   # :288-289
+    extra_logq = (-torch.log(-torch.expm1(-lf[:, :, 1:]))).reshape(p, -1).sum(dim=1)      # :291-293
+    th = [torch.exp(theta[:, k:k + 1]) for k in range(3)]
+    obs_eval = time_feats[:, -2 * B:, 0].reshape(p, -1, 2).transpose(1, 2)
+    obs_lp = (normal_logpdf(lf[:, :, 1:], obs_eval, 1.0) * extra["bin_feed"]).reshape(p, -1).sum(dim=1)
+    head, tail = lf[:, :, :-1], lf[:, :, 1:]
+    x1, x2 = head[:, 0, :], head[:, 1, :]
+    a1 = th[0] * x1 - th[1] * x1 * x2
+    a2 = th[1] * x1 * x2 - th[2] * x2
+    ca = torch.sqrt(th[0] * x1 + th[1] * x1 * x2)
+    cb = -th[1] * x1 * x2 / ca
+    cc = torch.sqrt(th[1] * x1 * x2 + th[2] * x2 - cb ** 2)
+    sq = math.sqrt(dt)
+    L11, L21, L22 = sq * ca, sq * cb, sq * cc
+    d1 = (tail[:, 0, :] - x1) - dt * a1
+    d2 = (tail[:, 1, :] - x2) - dt * a2
+    w1 = d1 / L11
+    w2 = (d2 - L21 * w1) / L22
+    log_det = 2.0 * (torch.log(L11) + torch.log(L22))
+    sde_lp = (-0.5 * log_det - 0.5 * (w1 ** 2 + w2 ** 2) - LOG2PI).sum(dim=1)
+    return sde_lp, obs_lp, extra_logq, lf
+
+
 def objective(cfg, obj: int, P, eps, theta, time_feats, extra=None, path_target: float = 0.0):
     """Scalar the library differentiates, plus the per-row terms [p,4] = (sde, obs, logq, base_lp).
 
@@ -374,8 +432,8 @@ def objective(cfg, obj: int, P, eps, theta, time_feats, extra=None, path_target:
     obj 2: sum (lf_sample - path_target)^2       [fitz_nag_NVP.py:288-289; SV_dense.py:251-252]
     """
     x_final, logq = flow_forward(cfg, P, eps, theta, time_feats)
-    if cfg.model == 3:
-        sde, obs, extra_logq, lf = lv_terms(cfg, x_final, theta, time_feats, extra)
+    if cfg.model in (3, 4):
+        sde, obs, extra_logq, lf = (lv_terms if cfg.model == 3 else lvr_terms)(cfg, x_final, theta, time_feats, extra)
         logq = logq + extra_logq                                              # lf_log_prob, LV fix-theta :369-370
     else:
         sde, obs, lf = elbo_terms(cfg, x_final, theta, time_feats, extra)

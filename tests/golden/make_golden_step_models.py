@@ -13,7 +13,7 @@ the model's tensors evaluate to.  Feed, base noise, the theta sample and the ini
 exactly as in make_golden_step.py; the feed comes from the oracle's gather, pinned bit-exactly to the scripts' own
 feed code by fhn_golden.npz / sv_golden.npz.
 
-Output: models_step_golden.npz (fhn_*, sv_*): inputs, per-row terms, path, gradient of -ELBO w.r.t. theta, and the
+Output: models_step_golden.npz (fhn_*, sv_*, lvr_* = lotka_volterra_partial.py): inputs, per-row terms, path, gradient of -ELBO w.r.t. theta, and the
 gradient w.r.t. every variable as per-variable norms + leading entries.
 """
 import hashlib
@@ -190,10 +190,73 @@ def sv(golden):
     print("sv: sde", golden["sv_sde"][:3], "global norm", float(flat.norm()))
 
 
+def lvr(golden):
+    """lotka_volterra_partial.py (learned theta) on the dat/LV_*.txt files the reference ships, at the script's own
+    kernel_len / batch_dims / depth / look-ahead (:466-476), 6 rows."""
+    p, K, B, F, fw, target_dims, dt, seed = 6, 20, 50, 3, 10, 500, 0.1, 23
+    T = 50.0
+    from viforssms_b200.config import lvr_config
+    d = os.path.join(REF, "dat")
+    obs = np.loadtxt(os.path.join(d, "LV_obs_partial.txt"), np.float32)
+    obs_bin = np.loadtxt(os.path.join(d, "LV_obs_binary.txt"), np.float32)
+    tt = np.loadtxt(os.path.join(d, "LV_time_till.txt"), np.float32)
+    x0 = np.array([100.0, 100.0])
+    cfg = lvr_config(p=p, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=target_dims, dt=dt, x0=x0)
+    layout, n = param_layout(cfg)
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    pads = O.pad_series_lvr(obs, tt, x0, dt, T, target_dims, F, K, fw)
+    idx = rs.choice(np.arange(0, target_dims, B), size=p, replace=False)
+    idx[0] = 0                                        # the row whose first state is pinned to x0
+    tf64, mask, shift, bin_feed = O.gather_feed_fhn(pads, obs_bin, idx, cfg.L0, B)     # same gather code (:354-386)
+    params = init_params(cfg, layout, n, g, None, T)
+    for i in range(F):          # observations reach 325 and time_till 10: keep the first feature layer's output O(1)
+        off, shape = layout[f"f{i}.feat0.w"]
+        params[off:off + shape[0] * shape[1]] *= 0.02
+    eps = torch.randn(p, cfg.L0, generator=g)
+    # theta sample around the script's prior means log(rate / 10) (:476)
+    theta = (torch.tensor([np.log(0.4428), np.log(0.0029), np.log(0.2957)]).float()[None, :]
+             + 0.05 * torch.randn(p, 3, generator=g)).float()
+    priors = [(np.log(4.428 / 10), 1e-4), (np.log(0.029 / 10), 1e-4), (np.log(2.957 / 10), 1e-4)]
+    network_dims = [50] * 5
+
+    ns = class_section("lotka_volterra_partial.py", p=p, no_flows=F, network_dims=network_dims, kernel_len=K)
+    st = tf_shim.STATE
+    st.__init__()
+    f32 = lambda a: np.asarray(a).astype(np.float32)
+    st.placeholders = [np.ones(1), f32(tf64), f32(mask), f32(shift), f32(bin_feed)]   # lotka_volterra_partial.py:180,207-217
+    st.samples = [eps.numpy()]
+    st.blob = params.double()
+    theta_dist = tf_shim.InjectedDistribution(theta.double().numpy(), np.zeros(p))
+    model = ns["VI_SSM"](obs, obs_bin, tt, x0, theta_dist, priors, dt, T, p, K, B, network_dims, target_dims, F, fw,
+                         learn_rate=1e-3, pre_train=False)
+    model.build_flow()
+    check_layout(st, layout, n)
+    scale = float(target_dims) / B
+    dev_obj = -(scale * (model.sde_loss - model.lf_log_prob + model.obs_loss)).sum()
+    g_theta = torch.autograd.grad(dev_obj, model.theta, retain_graph=True)[0]
+    gv = ns["AdamaxOptimizer"](learning_rate=1e-3, beta1=0.95).compute_gradients(-model.loss)
+    flat = torch.cat([gg.reshape(-1) for gg, _ in gv]).detach()
+    gv2 = ns["AdamaxOptimizer"](learning_rate=1e-3, beta1=0.9).compute_gradients((model.lf_sample - 75) ** 2)   # :299-300
+    flat2 = torch.cat([(gg if gg is not None else torch.zeros_like(v.value)).reshape(-1) for gg, v in gv2]).detach()
+    golden.update({
+        "lvr_hyper": np.array([p, K, B, F, fw, target_dims, seed]), "lvr_dt": np.array(dt), "lvr_idx": idx.astype(np.int64),
+        "lvr_obs": obs, "lvr_obs_bin": obs_bin, "lvr_time_till": tt,     # the three 2 x 500 input series (dat/LV_*.txt)
+        "lvr_eps": eps.numpy(), "lvr_theta": theta.numpy(), "lvr_params_sha_f32": np.array(sha(params.numpy())),
+        "lvr_sde": model.sde_loss.detach().numpy(), "lvr_obs_lp": model.obs_loss.detach().numpy(),
+        "lvr_logq": model.lf_log_prob.detach().numpy(), "lvr_lf_sample": model.lf_sample.detach().numpy(),
+        "lvr_elbo": model.loss.detach().numpy(), "lvr_grad_theta": g_theta.numpy(),
+    })
+    grads_summary(flat, layout, "lvr_", golden)
+    grads_summary(flat2, layout, "lvr_pre_", golden)
+    print("lvr: sde", golden["lvr_sde"][:3], "obs", golden["lvr_obs_lp"][:3], "global norm", float(flat.norm()))
+
+
 def main():
     golden = {}
     fhn(golden)
     sv(golden)
+    lvr(golden)
     path = os.path.join(HERE, "models_step_golden.npz")
     np.savez_compressed(path, **golden)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -175,6 +175,31 @@ class MultivariateNormalDiag:
         return self.n.log_prob(x).sum(dim=-1)
 
 
+class SoftplusBijector:
+    """tfb.Softplus(event_ndims): forward(x) = log(1 + exp(x)); inverse_log_det_jacobian(y) = -log(1 - exp(-y)) summed
+    over the last `event_ndims` axes of y (the 1.8 bijectors take event_ndims in the constructor and reduce their
+    log-determinants over that many trailing axes)."""
+
+    def __init__(self, event_ndims=0, **kw):
+        self.event_ndims = int(event_ndims)
+
+    def forward(self, x):
+        return torch.nn.functional.softplus(_t(x))
+
+    def inverse_log_det_jacobian(self, y):
+        v = -torch.log(-torch.expm1(-_t(y)))
+        return v.sum(dim=tuple(range(v.dim() - self.event_ndims, v.dim()))) if self.event_ndims else v
+
+
+class _Bijectors:
+    """tf.contrib.distributions.bijectors: Softplus is real, everything else (the theta posterior's chains, built in
+    the scripts' module-level part) is a mock."""
+    Softplus = SoftplusBijector
+
+    def __getattr__(self, name):
+        return mock.MagicMock(name="bijectors." + name)
+
+
 class InjectedDistribution:
     """Stands in for the theta posterior (tfd.TransformedDistribution of masked autoregressive flows, built in the
     scripts' main(), A11 of SURVEY section 8): hands out an injected sample and an injected log-density."""
@@ -308,7 +333,7 @@ def install():
     tf.layers = types.SimpleNamespace(dense=dense, conv1d=conv1d, batch_normalization=batch_normalization)
     tf.summary = mock.MagicMock(name="summary")
     tf.train = mock.MagicMock(name="train")
-    bij = mock.MagicMock(name="bijectors")
+    bij = _Bijectors()
     tf.contrib = types.SimpleNamespace(distributions=types.SimpleNamespace(
         Normal=Normal, MultivariateNormalDiag=MultivariateNormalDiag, bijectors=bij,
         TransformedDistribution=mock.MagicMock(name="TransformedDistribution")))

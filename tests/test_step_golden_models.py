@@ -12,7 +12,7 @@ import torch
 
 from oracle import nma_oracle as O
 from viforssms_b200 import feed
-from viforssms_b200.config import fhn_config, param_layout, sv_config
+from viforssms_b200.config import fhn_config, lvr_config, param_layout, sv_config
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -77,6 +77,30 @@ def sv_inputs(GM):
             {"mask": f32(mask), "shift": f32(shift), "dim_one": f32(dim_one)}, arrays)
 
 
+def lvr_inputs(GM):
+    """lotka_volterra_partial.py on the dat/LV_*.txt series the reference ships."""
+    p, K, B, F, fw, target_dims, seed = (int(v) for v in GM["lvr_hyper"])
+    dt = float(GM["lvr_dt"])
+    T = 50.0
+    obs, obs_bin, tt = GM["lvr_obs"], GM["lvr_obs_bin"], GM["lvr_time_till"]      # the input series ride in the fixture
+    x0 = np.array([100.0, 100.0])
+    cfg = lvr_config(p=p, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=target_dims, dt=dt, x0=x0)
+    layout, n = param_layout(cfg)
+    g = torch.Generator().manual_seed(seed)
+    params = _params(cfg, layout, n, g, None, T)
+    for i in range(F):
+        off, shape = layout[f"f{i}.feat0.w"]
+        params[off:off + shape[0] * shape[1]] *= 0.02
+    assert _sha(params.numpy()) == str(GM["lvr_params_sha_f32"])
+    idx = GM["lvr_idx"]
+    pads = O.pad_series_lvr(obs, tt, x0, dt, T, target_dims, F, K, fw)
+    tf64, mask, shift, bin_feed = O.gather_feed_fhn(pads, obs_bin, idx, cfg.L0, B)
+    f32 = lambda a: torch.from_numpy(np.asarray(a).astype(np.float32)).double()
+    arrays = feed.lvr_base_arrays(obs, obs_bin, tt, dt, T, target_dims, F, K, fw)
+    return (cfg, layout, n, params, torch.from_numpy(GM["lvr_eps"]), torch.from_numpy(GM["lvr_theta"]), idx, f32(tf64),
+            {"mask": f32(mask), "shift": f32(shift), "bin_feed": f32(bin_feed)}, arrays)
+
+
 def _close(got, want, rtol):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     return np.abs(got - want).max() <= rtol * max(1.0, np.abs(want).max())
@@ -135,3 +159,29 @@ def test_sv_oracle_matches_the_reference_classes(GM):
     pre = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, obj=2, extra=extra,
                            path_target=-7.0)
     check_grads(pre["grad_params"].numpy(), layout, GM, "sv_pre_", 1e-9, 1e-12)                 # :251-252
+
+
+def test_lvr_oracle_matches_the_reference_classes(GM):
+    """lotka_volterra_partial.py (learned theta): transposed wide feature layer, coupling flow, softplus path with
+    mask / shift, bivariate Euler-Maruyama density on the state differences with theta = exp(sample)."""
+    cfg, layout, n, params, eps, theta, idx, tf, extra, arrays = lvr_inputs(GM)
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, extra=extra)
+    t = ref["terms"].numpy()
+    assert _close(t[:, 0], GM["lvr_sde"], 1e-10)              # lotka_volterra_partial.py:237-262
+    assert _close(t[:, 1], GM["lvr_obs_lp"], 1e-10)           # :235
+    assert _close(t[:, 2], GM["lvr_logq"], 1e-10)             # :291-293
+    assert _close(ref["lf"].numpy(), GM["lvr_lf_sample"], 1e-10)
+    th = theta.double().numpy()
+    pri = [(np.log(4.428 / 10), 1e-4), (np.log(0.029 / 10), 1e-4), (np.log(2.957 / 10), 1e-4)]     # :476
+    prior = sum(-0.5 * ((th[:, k] - m) / s) ** 2 - 0.5 * np.log(2 * np.pi) - np.log(s) for k, (m, s) in enumerate(pri))
+    assert _close(cfg.scale * (t[:, 0] - t[:, 2] + t[:, 1]) + prior, GM["lvr_elbo"], 1e-10)       # :270-271
+    assert _close(ref["grad_theta"].numpy(), GM["lvr_grad_theta"], 1e-9)
+    check_grads(ref["grad_params"].numpy(), layout, GM, "lvr_", 1e-9, 1e-12)
+    pre = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, obj=2, extra=extra,
+                           path_target=75.0)
+    check_grads(pre["grad_params"].numpy(), layout, GM, "lvr_pre_", 1e-9, 1e-12)                 # :299-300
+    # the host side builds the same base arrays as the oracle's padding (and so as the script)
+    pads = O.pad_series_lvr(GM["lvr_obs"], GM["lvr_time_till"], np.array([100.0, 100.0]), cfg.dt, 50.0, 500, cfg.F, cfg.K, 10)
+    assert np.array_equal(arrays[1], pads["bin_feats"]) and np.array_equal(arrays[2], pads["time_pad"])
+    assert np.array_equal(arrays[3], pads["time_till"])
+    assert np.array_equal(arrays[0][:pads["obs_pad_store"][0].shape[0]], pads["obs_pad_store"][0])

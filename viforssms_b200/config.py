@@ -18,7 +18,9 @@ from typing import Dict, List, Tuple
 MODEL_AR = 0
 MODEL_FHN = 1
 MODEL_SV = 2
-MODEL_LV = 3      # Lotka-Volterra: feed (A0/A1) only so far; the flow and its ELBO are not built
+MODEL_LV = 3      # Lotka-Volterra, fixed theta (lotka_volterra_partial_batch_fix_theta.py)
+MODEL_LVR = 4     # Lotka-Volterra, learned theta (lotka_volterra_partial.py, the script whose data the reference ships)
+LV_MODELS = (MODEL_LV, MODEL_LVR)     # both use the transposed wide feature layer and the 1 + (L0 - 1)-channel conv
 
 MAX_CHAN = 32
 MAX_ARRAYS = 8
@@ -165,7 +167,7 @@ def param_layout(cfg: NMAConfig) -> Tuple[Dict[str, Tuple[int, Tuple[int, ...]]]
     for i in range(cfg.F):
         # LV (lotka_volterra_partial_batch_fix_theta.py:71-82): the 4th feature layer is as wide as the flow's conv
         # input (feat_dims = L_i - 1) and its TRANSPOSE feeds the conv, whose input channels are then 1 + (L0 - 1)
-        lv = cfg.model == MODEL_LV
+        lv = cfg.model in LV_MODELS
         for l in range(4):
             add(f"f{i}.feat{l}.w", (cfg.Cf_in if l == 0 else C, cfg.Lin(i) if (lv and l == 3) else C))
             add(f"f{i}.feat{l}.b", (cfg.Lin(i) if (lv and l == 3) else C,))
@@ -230,6 +232,23 @@ def sv_config(p=200, K=50, B=52, F=5, H=3, feat_window=5, target_dims=1508, dt=1
         scale=float(target_dims) / float(B), dt=dt, obs_std=1.0, x0=(x0, 0.0), n_arrays=4,
         chan_array=[0] * fw + [1, 2, 3], chan_offset=[5 * i for i in range(fw)] + [0, 0, 0],
         obs_array=0, bin_array=0, head_offset=F * K)
+
+
+def lvr_config(p=50, K=20, B=50, F=3, H=3, feat_window=10, target_dims=500, dt=0.1, x0=(100.0, 100.0)) -> NMAConfig:
+    """The Lotka-Volterra model of lotka_volterra_partial.py (learned theta; defaults = the script's :466-480, which runs
+    on the dat/LV_*.txt files the reference ships).  Same flow as `lv_config` (transposed wide 4th feature layer, conv
+    over 1 + (L0 - 1) channels, coupling / Permute / BN); p rows with their own window each, as in the FHN script.
+    ELBO (ibid. :234-275): path = softplus(flow output) * mask + shift, bivariate Euler-Maruyama density on the state
+    DIFFERENCES with theta = exp(theta sample) (3 rates), unit-variance Gaussian observations.
+
+    Base arrays (ibid. :186-205): as the FHN model except that bin_feats is 0 on the pad and 1 on the series and the
+    lead of time_till stops before 0; the time channel starts at dt as in FHN."""
+    fw = feat_window
+    return NMAConfig(
+        model=MODEL_LVR, p=p, K=K, B=B, D=2, F=F, H=H, bn=1, Cf=fw + 3, feat_aug=0, dtheta=3,
+        scale=float(target_dims) / float(B), dt=dt, obs_std=1.0, x0=(float(x0[0]), float(x0[1])), n_arrays=5,
+        chan_array=[0] * fw + [1, 2, 3], chan_offset=[5 * i for i in range(fw)] + [0, 0, 0],
+        obs_array=0, bin_array=4)
 
 
 def lv_config(p=1, K=20, B=151, F=3, H=3, feat_window=10, target_dims=151, dt=0.2, x0=(91.0, 99.0)) -> NMAConfig:

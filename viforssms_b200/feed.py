@@ -106,6 +106,21 @@ def sv_base_arrays(obs, dt: float, T: float, F: int, K: int, fw: int, exact_var:
     return [obs_pad, time_pad, var_pad, var_diff_pad]
 
 
+def lvr_base_arrays(obs, obs_bin, time_till, dt: float, T: float, target_dims: int, F: int, K: int,
+                    fw: int) -> List[np.ndarray]:
+    """Base arrays of the learned-theta Lotka-Volterra model in the order `config.lvr_config` expects
+    (lotka_volterra_partial.py:186-205).  obs, obs_bin, time_till: [2, target_dims]."""
+    D = 2
+    P2 = F * K + D
+    obs_flat = np.reshape(np.asarray(obs, dtype=np.float64), -1, 'F')
+    obs_pad = np.concatenate((np.zeros(P2), obs_flat, np.zeros(5 * max(fw - 1, 0))))
+    bin_feats = np.concatenate((np.zeros(P2), np.ones(target_dims * D)))
+    time_pad = np.concatenate((np.zeros(P2), np.repeat(np.arange(dt, T + dt, dt), D)))
+    lead = np.reshape(np.repeat(np.arange(np.round(P2 * (dt / D), 1), 0., -dt), D), (D, -1), 'F')
+    tt = np.reshape(np.concatenate((lead, np.asarray(time_till, dtype=np.float64)), 1), -1, 'F')
+    return [obs_pad, bin_feats, time_pad, tt, np.asarray(obs_bin, dtype=np.float64).reshape(-1)]
+
+
 def lv_base_arrays(obs, obs_bin, time_till, dt: float, T: float, target_dims: int, F: int, K: int, fw: int,
                    p_val: int = 1) -> List[np.ndarray]:
     """Base arrays of the Lotka-Volterra model in the order `config.lv_config` expects
