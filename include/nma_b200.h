@@ -32,7 +32,9 @@ extern "C" {
 #define NMA_MODEL_AR  0   /* AR.py:168-187 */
 #define NMA_MODEL_FHN 1   /* fitz_nag_NVP.py:232-266 */
 #define NMA_MODEL_SV  2   /* SV_dense.py:203-234 */
-#define NMA_MODEL_LV  3   /* lotka_volterra_partial_batch_fix_theta.py: nma_gather only; the step entry points return an error */
+#define NMA_MODEL_LV  3   /* lotka_volterra_partial_batch_fix_theta.py:265-371 (fixed theta) */
+#define NMA_MODEL_LVR 4   /* lotka_volterra_partial.py:234-297 (learned theta): same flow kernels as NMA_MODEL_LV, own ELBO
+                           * branch; NOT YET RUN ON HARDWARE - nma_create refuses it unless NMA_UNVERIFIED=1 is set */
 
 /* objectives (which scalar is differentiated) */
 #define NMA_OBJ_ELBO    0 /* -sum_rows scale*(sde - logq + obs)   AR.py:184-185,228-229 */

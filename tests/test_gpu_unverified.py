@@ -1,0 +1,52 @@
+"""GPU parity tests of code that was written after the round's GPU budget was spent and has NOT run on hardware yet.
+They are skipped unless NMA_UNVERIFIED=1 is set (the library refuses the model without it as well), so that a first
+failure cannot stop the verified suite; run them first thing with a GPU:
+
+    NMA_UNVERIFIED=1 python -m pytest tests/test_gpu_unverified.py -q -s
+
+  * NMA_MODEL_LVR: lotka_volterra_partial.py (learned theta) - the ELBO branch of k_elbo; its flow kernels are the
+    fixed-theta script's (verified).  Checked against the reference-classes fixture and the oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nma_oracle as O
+from test_step_golden_models import GM, check_grads, lvr_inputs  # noqa: F401
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("NMA_UNVERIFIED") != "1", reason="not yet run on hardware: set NMA_UNVERIFIED=1")]
+RTOL = 1e-4
+
+
+@pytest.mark.parametrize("objective,target,gprefix", [(0, 0.0, "lvr_"), (2, 75.0, "lvr_pre_")])
+def test_cuda_lvr_step_matches_the_reference_classes(GM, objective, target, gprefix):
+    from viforssms_b200.engine import NMAEngine
+    cfg, layout, n, params, eps, theta, idx, tf, extra, arrays = lvr_inputs(GM)
+    eng = NMAEngine(cfg)
+    eng.set_series(arrays)
+    got_tf, got_mask, got_shift = eng.gather(idx)
+    assert np.array_equal(got_tf.cpu().numpy(), tf.numpy().astype(np.float32))
+    assert np.array_equal(got_mask.cpu().numpy(), extra["mask"].numpy().astype(np.float32))
+    assert np.array_equal(got_shift.cpu().numpy(), extra["shift"].numpy().astype(np.float32))
+    dev = torch.device("cuda")
+    out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(np.asarray(idx)).to(dev),
+                           objective=objective, path_target=target)
+    torch.cuda.synchronize()
+    worst = check_grads(out["grad_params"].cpu().double().numpy(), layout, GM, gprefix, RTOL, 1e-6)
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, obj=objective, extra=extra,
+                           path_target=target)
+    gth = out["grad_theta"].cpu().double().numpy()
+    want = ref["grad_theta"].numpy()
+    assert np.linalg.norm(gth - want) <= RTOL * max(np.linalg.norm(want), 1e-6 * float(GM[gprefix + "global_norm"]))
+    if objective == 0:
+        t = out["terms"].cpu().double().numpy()
+        for k, key in ((0, "sde"), (1, "obs_lp"), (2, "logq")):
+            w = GM["lvr_" + key]
+            assert np.abs(t[:, k] - w).max() <= RTOL * max(1.0, np.abs(w).max()), key
+        lf = out["lf"].cpu().double().numpy().reshape(cfg.p, -1, 2).transpose(0, 2, 1)
+        assert np.linalg.norm(lf - GM["lvr_lf_sample"]) <= RTOL * np.linalg.norm(GM["lvr_lf_sample"])
+        assert np.linalg.norm(gth - GM["lvr_grad_theta"]) <= RTOL * np.linalg.norm(GM["lvr_grad_theta"])
+    print("CUDA vs reference classes (LV learned theta, objective %d): worst gradient slice error %.2e" % (objective, worst))

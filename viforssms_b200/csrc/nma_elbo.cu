@@ -2,7 +2,7 @@
 // entropy term) as one warp-per-row segmented reduction, fused with the gradient of the chosen
 // objective w.r.t. the final flow sample and theta.
 //   AR  : AR.py:168-187            FHN : fitz_nag_NVP.py:232-266            SV : SV_dense.py:203-246
-//   LV  : lotka_volterra_partial_batch_fix_theta.py:265-371
+//   LV  : lotka_volterra_partial_batch_fix_theta.py:265-371   LVR : lotka_volterra_partial.py:234-297
 #include "nma_common.cuh"
 
 #define LOG2PI_F 1.8378770664093453f
@@ -219,6 +219,83 @@ __global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
                 e2 += L11 * (t1 * u1) + L12 * (-t1 * u1) + L22 * (t1 * u1 + t2);
                 g1 += c_sde * e1;
                 g2 += c_sde * e2;
+            }
+            g1 += c_sq * 2.f * (u1 - a.path_target);
+            g2 += c_sq * 2.f * (u2 - a.path_target);
+            if (a.want_grad) {
+                dx[2 * j] = first ? 0.f : fmaf(g1, sigmoid_f(z1), h1);
+                dx[2 * j + 1] = first ? 0.f : fmaf(g2, sigmoid_f(z2), h2);
+            }
+            if (a.lf) { a.lf[(size_t)r * a.LF + 2 * j] = u1; a.lf[(size_t)r * a.LF + 2 * j + 1] = u2; }
+        }
+    } else if (a.model == NMA_MODEL_LVR) {
+        // Lotka-Volterra, learned theta (lotka_volterra_partial.py:234-297).  z[d][t] = x[2t+d] is the raw flow output,
+        // u[d][t] = softplus(z) * mask + shift the state (:288-289); rates = exp(theta) (:220-224).
+        //   terms[0] = sum_{t=0..B-1} log N2(u_{t+1} - u_t; dt alpha(u_t), dt S(u_t))             (:237-262, :39-52)
+        //   terms[1] = sum_{t=1..B} bin * log N(u_t; obs, 1)                                       (:235)
+        //   logq    += sum_{t=1..B} -log(1 - exp(-u_t)) = softplus(-z_t)                           (:291-293)
+        // HARDWARE STATUS: written against the oracle (which is pinned to the script's own classes,
+        // tests/test_step_golden_models.py) after the round's GPU budget was spent - not yet run on a B200.
+        const float t0 = expf(th[0]), t1 = expf(th[1]), t2 = expf(th[2]);
+        const float dt = a.dt;
+        const long long tlen = a.sv.len[a.bin_array] / 2;
+        const float cq = (a.objective == NMA_OBJ_ELBO) ? a.scale : 0.f;     // d objective / d logq
+        for (int j = lane; j <= B; j += 32) {
+            const bool first = (i0 + j) == 0;
+            const float z1 = x[2 * j], z2 = x[2 * j + 1];
+            const float u1 = first ? a.x0a : softplus_f(z1);
+            const float u2 = first ? a.x0b : softplus_f(z2);
+            float g1 = 0.f, g2 = 0.f;        // d objective / d u
+            float h1 = 0.f, h2 = 0.f;        // d objective / d z directly (the log-det of the softplus)
+            if (j >= 1) {
+                lq_extra += softplus_f(-z1) + softplus_f(-z2);
+                h1 += cq * (-sigmoid_f(-z1));
+                h2 += cq * (-sigmoid_f(-z2));
+                const long long slot = win0 + (a.L0 - 2 * B) + 2 * (j - 1);
+                const float y1 = series_chan(a.sv, 0, slot), y2 = series_chan(a.sv, 0, slot + 1);
+                const float w1 = series_raw(a.sv, a.bin_array, i0 + (j - 1));
+                const float w2 = series_raw(a.sv, a.bin_array, tlen + i0 + (j - 1));
+                const G1 o1 = gauss(u1, y1, 1.f), o2 = gauss(u2, y2, 1.f);
+                obs += o1.lp * w1 + o2.lp * w2;
+                g1 += c_obs * (-o1.dz) * w1;
+                g2 += c_obs * (-o2.dz) * w2;
+                // this state as the TARGET of the transition from t = j - 1 (whose state is x0 when pinned)
+                const bool pf = (i0 + j - 1) == 0;
+                const float p1 = pf ? a.x0a : softplus_f(x[2 * j - 2]), p2 = pf ? a.x0b : softplus_f(x[2 * j - 1]);
+                const float s11 = t0 * p1 + t1 * p1 * p2, s12 = -t1 * p1 * p2, s22 = t1 * p1 * p2 + t2 * p2;
+                const float Dd = s11 * s22 - s12 * s12;
+                const float d1 = (u1 - p1) - dt * (t0 * p1 - t1 * p1 * p2);
+                const float d2 = (u2 - p2) - dt * (t1 * p1 * p2 - t2 * p2);
+                g1 += c_sde * (-(s22 * d1 - s12 * d2) / (dt * Dd));
+                g2 += c_sde * (-(-s12 * d1 + s11 * d2) / (dt * Dd));
+            }
+            if (j < B) {     // this state as the SOURCE of the transition to t = j + 1: counted once here
+                const float n1 = softplus_f(x[2 * j + 2]), n2 = softplus_f(x[2 * j + 3]);     // j + 1 >= 1: never pinned
+                const float s11 = t0 * u1 + t1 * u1 * u2, s12 = -t1 * u1 * u2, s22 = t1 * u1 * u2 + t2 * u2;
+                const float Dd = s11 * s22 - s12 * s12;
+                const float d1 = (n1 - u1) - dt * (t0 * u1 - t1 * u1 * u2);
+                const float d2 = (n2 - u2) - dt * (t1 * u1 * u2 - t2 * u2);
+                const float Qf = s22 * d1 * d1 - 2.f * s12 * d1 * d2 + s11 * d2 * d2;
+                // log N2 = -log dt - 1/2 log D - Qf / (2 dt D) - log 2 pi   (det = prod(diag(chol))^2 = dt^2 D)
+                sde += -logf(dt) - 0.5f * logf(Dd) - 0.5f * Qf / (dt * Dd) - LOG2PI_F;
+                const float gm1 = (s22 * d1 - s12 * d2) / (dt * Dd), gm2 = (-s12 * d1 + s11 * d2) / (dt * Dd);   // Sigma^-1 delta
+                // through the difference and the mean: -d delta / d u = I + dt J_alpha
+                float e1 = gm1 * (1.f + dt * (t0 - t1 * u2)) + gm2 * (dt * t1 * u2);
+                float e2 = gm1 * (-dt * t1 * u1) + gm2 * (1.f + dt * (t1 * u1 - t2));
+                // through the covariance: dL/ds = -1/2 D_s / D - (Qf_s D - Qf D_s) / (2 dt D^2)
+                const float i2 = 1.f / (2.f * dt * Dd * Dd);
+                const float L11 = -0.5f * s22 / Dd - (d2 * d2 * Dd - Qf * s22) * i2;
+                const float L22 = -0.5f * s11 / Dd - (d1 * d1 * Dd - Qf * s11) * i2;
+                const float L12 = s12 / Dd - (-2.f * d1 * d2 * Dd + 2.f * Qf * s12) * i2;
+                e1 += L11 * (t0 + t1 * u2) + L12 * (-t1 * u2) + L22 * (t1 * u2);
+                e2 += L11 * (t1 * u1) + L12 * (-t1 * u1) + L22 * (t1 * u1 + t2);
+                g1 += c_sde * e1;
+                g2 += c_sde * e2;
+                // rates (chain through exp: d / d theta_k = rate_k d / d rate_k)
+                const float uu = u1 * u2;
+                gth[0] += t0 * (gm1 * dt * u1 + L11 * u1);
+                gth[1] += t1 * (dt * uu * (gm2 - gm1) + (L11 - L12 + L22) * uu);
+                gth[2] += t2 * (-gm2 * dt * u2 + L22 * u2);
             }
             g1 += c_sq * 2.f * (u1 - a.path_target);
             g2 += c_sq * 2.f * (u2 - a.path_target);

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import feed
-from .config import OBJ_ELBO, OBJ_PATH_SQ, NMAConfig, fhn_config, param_layout, sv_config
+from .config import OBJ_ELBO, OBJ_PATH_SQ, NMAConfig, fhn_config, lvr_config, param_layout, sv_config
 from .engine import NMAEngine
 from .theta_flow import ThetaFlow, prior_log_prob, prior_tensors
 from .trainer import glorot_blob
@@ -39,6 +39,7 @@ class _ModelVISSM:
     theta_star: Sequence[float] = ()
     theta_pos_index: Sequence[bool] = ()
     has_obs_term = True
+    finite_term = 0              # which per-row term the pre-training restart looks at (0 = sde, 2 = lf_log_prob)
 
     def _common(self, theta_dist: ThetaFlow, priors, p, kernel_len, batch_dims, network_dims, target_dims, no_flows,
                 feat_window, learn_rate, pre_train, device, seed, early_stopping):
@@ -120,7 +121,7 @@ class _ModelVISSM:
             m, v = self.slots["pre_theta"]
             tail = slice(self.n_nma, self.n_total)
             self.eng.adamax_step(self.blob[tail], self.grad2[tail], m[tail], v[tail], 1e-3, 0.9, clip=0.0)
-            return bool(torch.isfinite(out["terms"][:, 0]).all().item())
+            return bool(torch.isfinite(out["terms"][:, self.finite_term]).all().item())
         out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), self.idx_dev,
                                     objective=OBJ_ELBO, out=self.out)
         prior = prior_log_prob(theta, self.prior_t)
@@ -262,6 +263,46 @@ class FHN_VI_SSM(_ModelVISSM):
     def _pretrain_done(self, run, finite):
         self.pre_train_count = self.pre_train_count + 1 if finite else 0      # fitz_nag_NVP.py:378-381
         return self.pre_train_count == 500
+
+
+class LVR_VI_SSM(_ModelVISSM):
+    """lotka_volterra_partial.py:160-463 (class VI_SSM there): Lotka-Volterra with a learned theta posterior, on the
+    dat/LV_*.txt series the reference ships.  The flow kernels are those of the fixed-theta script; the ELBO branch
+    (NMA_MODEL_LVR) is checked on the CPU (tests/test_lvr_formulas.py) but has not run on hardware yet - the library refuses
+    the model unless NMA_UNVERIFIED=1 is set."""
+
+    grad_clip = 1e9                                                      # lotka_volterra_partial.py:335
+    pretrain_path_target = 75.0                                          # :299-300
+    theta_star = (math.log(0.5), math.log(0.0025), math.log(0.3))         # :302-303
+    theta_pos_index = (True, True, True)                                 # :306
+    has_obs_term = True
+    finite_term = 2                                                      # the script watches lf_log_prob (:390-396)
+
+    def __init__(self, obs, obs_bin, time_till, x0, theta_dist: ThetaFlow, priors, dt, T, p, kernel_len, batch_dims,
+                 network_dims, target_dims, no_flows, feat_window, learn_rate=1e-3, pre_train=True,
+                 device: Optional[torch.device] = None, seed: int = 1, early_stopping=1e99):
+        self._common(theta_dist, priors, p, kernel_len, batch_dims, network_dims, target_dims, no_flows, feat_window,
+                     learn_rate, pre_train, device, seed, early_stopping)
+        self.flow_dims = 2
+        self.dt, self.T = float(dt), float(T)
+        self.kernel_ext = self.kernel_len * self.no_flows + self.flow_dims * self.batch_dims + 2
+        self._series = (np.asarray(obs), np.asarray(obs_bin), np.asarray(time_till))
+        self.cfg = lvr_config(p=self.p, K=self.kernel_len, B=self.batch_dims, F=self.no_flows,
+                              H=len(self.network_dims) - 2, feat_window=self.feat_window,
+                              target_dims=self.target_dims, dt=self.dt, x0=(float(x0[0]), float(x0[1])))
+
+    def _base_arrays(self):
+        obs, obs_bin, tt = self._series
+        return feed.lvr_base_arrays(obs, obs_bin, tt, self.dt, self.T, self.target_dims, self.no_flows,
+                                    self.kernel_len, self.feat_window)
+
+    def _paths_from_lf(self, lf, idx):
+        # the library returns the state (softplus * mask + shift applied), interleaved as the flow lays it out
+        return lf.reshape(self.p, -1, 2).transpose(1, 2)
+
+    def _pretrain_done(self, run, finite):
+        self.pre_train_count = self.pre_train_count + 1 if finite else 0      # lotka_volterra_partial.py:392-398
+        return self.pre_train_count == 1000
 
 
 class SV_VI_SSM(_ModelVISSM):
