@@ -36,9 +36,12 @@ lotka_volterra_partial_batch_fix_theta.py under a stub `tensorflow`).  The torch
   * FHN and SV models: the same, from the class sections of fitz_nag_NVP.py and SV_dense.py exec'd verbatim
     (tests/golden/make_golden_step_models.py -> models_step_golden.npz; tests/test_step_golden_models.py): terms, path,
     ELBO, gradients of -ELBO and of the scripts' pre-training objective, 1e-10 / 1e-9.
-  * LV (fixed theta) model and the theta posterior (tf.contrib bijector chains): still "parity unpinned" - pinned only
-    by fp64 autograd + gradcheck of this restatement (tests/test_oracle.py); the shim does not cover
-    tfd.TransformedDistribution / tfb.Chain / tfb.Softplus(event_ndims=2) yet.
+  * Both Lotka-Volterra scripts likewise (lvr_* = lotka_volterra_partial.py, lvf_* = ..._batch_fix_theta.py); the
+    fixed-theta script under BOTH readings of how Softplus(event_ndims=2) reduces the log-determinant of a flattened
+    [states, 2] matrix - this restatement implements the per-state reading and equals the script's classes under it.
+  * Still "parity unpinned": the theta posterior (tf.contrib masked-autoregressive-flow chains; restated on the host in
+    viforssms_b200/theta_flow.py, executed from the reference nowhere) and which of the two event_ndims readings
+    TensorFlow 1.8 really computes.
 """
 from __future__ import annotations
 

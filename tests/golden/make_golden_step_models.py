@@ -252,11 +252,70 @@ def lvr(golden):
     print("lvr: sde", golden["lvr_sde"][:3], "obs", golden["lvr_obs_lp"][:3], "global norm", float(flat.norm()))
 
 
+def lv_fixed(golden):
+    """lotka_volterra_partial_batch_fix_theta.py (fixed theta) at p_val = 3 short series, under BOTH readings of how
+    Softplus(event_ndims=2) reduces the log-determinant of the flattened [states, 2] matrix (tf_shim.EVENT_REDUCTION)."""
+    from viforssms_b200.config import lv_config
+    p, K, B, F, fw, dt, seed = 3, 4, 6, 2, 2, 0.2, 24
+    N = p * B
+    T = (N - 1) * dt
+    cfg = lv_config(p=p, K=K, B=B, F=F, H=2, feat_window=fw, target_dims=B, dt=dt, x0=(11.0, 9.5))
+    layout, n = param_layout(cfg)
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    t = np.arange(N, dtype=np.float64)
+    obs = np.stack([12.0 + 4.0 * np.sin(0.3 * t) + 0.3 * rs.standard_normal(N),
+                    9.0 + 3.0 * np.cos(0.3 * t) + 0.3 * rs.standard_normal(N)])
+    obs_bin = (rs.uniform(size=(2, N)) < 0.7).astype(np.float64)
+    obs = np.where(obs_bin > 0, obs, np.log1p(np.exp(-2.0)) + 1.0)
+    tt = rs.uniform(0.0, 1.0, size=(2, N)).round(1)
+    x0 = np.array(cfg.x0)
+    x0_std = np.array([1.0, 1.0])
+    pads = O.pad_series_lv(obs, tt, x0, dt, T, N, 1, F, K, fw)
+    idx = np.arange(p, dtype=np.int64) * B
+    tf64, mask, shift, bin_feed = O.gather_feed_lv(pads, obs_bin, idx, cfg.L0, B)
+    params = init_params(cfg, layout, n, g, None, T)
+    for i in range(F):
+        off, _ = layout[f"f{i}.head.b"]
+        params[off] = 3.0
+    eps = torch.randn(p, cfg.L0, generator=g)
+    theta_vals = np.log1p(np.exp([-1.0, -6.0, -1.0, -2.0]))          # the script's constants (:688-691), softplus'd
+    network_dims = [50] * 4
+    f32 = lambda a: np.asarray(a).astype(np.float32)
+    golden.update({"lvf_hyper": np.array([p, K, B, F, fw, seed]), "lvf_dt": np.array(dt), "lvf_obs": obs,
+                   "lvf_obs_bin": obs_bin, "lvf_time_till": tt, "lvf_eps": eps.numpy(), "lvf_theta": theta_vals,
+                   "lvf_params_sha_f32": np.array(sha(params.numpy()))})
+    for reading in ("per_state", "literal"):
+        tf_shim.EVENT_REDUCTION = reading
+        ns = class_section("lotka_volterra_partial_batch_fix_theta.py", p_val=p, no_flows=F, network_dims=network_dims,
+                           kernel_len=K)
+        st = tf_shim.STATE
+        st.__init__()
+        st.placeholders = [np.ones(1), f32(tf64), f32(mask), f32(shift), f32(bin_feed)]      # :197,234-247
+        st.samples = [eps.numpy()]
+        st.blob = params.double()
+        # the script's `priors` ARE its theta values (:190); p_val series of target_dims = B steps each
+        model = ns["VI_SSM"](obs, obs_bin, tt, x0, x0_std, list(theta_vals), dt, T, p, K, B, network_dims, B, F, fw,
+                             learn_rate=1e-3, pre_train=False)
+        model.build_flow()
+        check_layout(st, layout, n)
+        gv = ns["AdamaxOptimizer"](learning_rate=1e-3, beta1=0.95).compute_gradients(-model.loss)
+        flat = torch.cat([gg.reshape(-1) for gg, _ in gv]).detach()
+        pre = "lvf_%s_" % reading
+        golden.update({pre + "sde": model.sde_loss.detach().numpy(), pre + "obs_lp": model.obs_loss.detach().numpy(),
+                       pre + "logq": model.lf_log_prob.detach().numpy(),
+                       pre + "lf_sample": model.lf_sample.detach().numpy(), pre + "elbo": model.loss.detach().numpy()})
+        grads_summary(flat, layout, pre, golden)
+        print("lv fixed theta (%s): sde" % reading, golden[pre + "sde"], "global norm", float(flat.norm()))
+    tf_shim.EVENT_REDUCTION = "literal"
+
+
 def main():
     golden = {}
     fhn(golden)
     sv(golden)
     lvr(golden)
+    lv_fixed(golden)
     path = os.path.join(HERE, "models_step_golden.npz")
     np.savez_compressed(path, **golden)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -175,6 +175,79 @@ class MultivariateNormalDiag:
         return self.n.log_prob(x).sum(dim=-1)
 
 
+# How a bijector reduces its log-determinant.  "literal": over the last `event_ndims` axes of whatever tensor it is
+# handed - the TF-1.8 behaviour as remembered (Bijector._event_dims_tensor).  "per_state": the same, except that the
+# leading (batch) axis is never reduced - the change of variables the LV script's comments describe.  The two differ only where a
+# script hands a bijector with event_ndims = 2 a rank-2 [states, 2] tensor (lotka_volterra_partial_batch_fix_theta.py:
+# 303-314: one scalar for all states, versus one value per state).  Which one TF 1.8 really computes cannot be settled
+# without running it; tests/golden/make_golden_step_models.py stores both.
+EVENT_REDUCTION = "literal"
+
+
+def _reduce_event(v, event_ndims):
+    if not event_ndims:
+        return v
+    first = v.dim() - event_ndims
+    if EVENT_REDUCTION == "per_state":
+        first = max(first, 1)
+    return v.sum(dim=tuple(range(first, v.dim())))
+
+
+class AffineBijector:
+    """tfb.Affine(shift, scale_diag) (event_ndims = 1) and tfb.AffineScalar(shift, scale) (event_ndims = 0):
+    forward(x) = scale * x + shift; inverse_log_det_jacobian = -sum log|scale| (a constant)."""
+
+    def __init__(self, shift=0.0, scale_diag=None, scale=None, **kw):
+        self.shift = _t(shift)
+        self.scale = _t(scale_diag if scale_diag is not None else (1.0 if scale is None else scale))
+        self.event_ndims = 1 if scale_diag is not None else 0
+
+    def forward(self, x):
+        return _t(x) * self.scale + self.shift
+
+    def inverse(self, y):
+        return (_t(y) - self.shift) / self.scale
+
+    def inverse_log_det_jacobian(self, y):
+        return -torch.log(torch.abs(self.scale)).sum()
+
+
+class ChainBijector:
+    """tfb.Chain([b_0, ..., b_n]): forward = b_0 o ... o b_n; inverse applies b_0^-1 first; the inverse log-determinant is
+    the sum of every member's own (each reduced by the member's own event_ndims), evaluated along the inverse pass."""
+
+    def __init__(self, bijectors, **kw):
+        self.bijectors = list(bijectors)
+
+    def forward(self, x):
+        for b in reversed(self.bijectors):
+            x = b.forward(x)
+        return x
+
+    def inverse(self, y):
+        for b in self.bijectors:
+            y = b.inverse(y)
+        return y
+
+    def inverse_log_det_jacobian(self, y):
+        total = 0.0
+        for b in self.bijectors:
+            total = total + b.inverse_log_det_jacobian(y)
+            y = b.inverse(y)
+        return total
+
+
+class TransformedDistribution:
+    """tfd.TransformedDistribution(distribution, bijector): log_prob(y) = distribution.log_prob(bijector.inverse(y)) +
+    bijector.inverse_log_det_jacobian(y)."""
+
+    def __init__(self, distribution, bijector, **kw):
+        self.distribution, self.bijector = distribution, bijector
+
+    def log_prob(self, y):
+        return self.distribution.log_prob(self.bijector.inverse(y)) + self.bijector.inverse_log_det_jacobian(y)
+
+
 class SoftplusBijector:
     """tfb.Softplus(event_ndims): forward(x) = log(1 + exp(x)); inverse_log_det_jacobian(y) = -log(1 - exp(-y)) summed
     over the last `event_ndims` axes of y (the 1.8 bijectors take event_ndims in the constructor and reduce their
@@ -186,15 +259,21 @@ class SoftplusBijector:
     def forward(self, x):
         return torch.nn.functional.softplus(_t(x))
 
+    def inverse(self, y):
+        y = _t(y)
+        return y + torch.log(-torch.expm1(-y))          # log(exp(y) - 1) without the overflow
+
     def inverse_log_det_jacobian(self, y):
-        v = -torch.log(-torch.expm1(-_t(y)))
-        return v.sum(dim=tuple(range(v.dim() - self.event_ndims, v.dim()))) if self.event_ndims else v
+        return _reduce_event(-torch.log(-torch.expm1(-_t(y))), self.event_ndims)
 
 
 class _Bijectors:
-    """tf.contrib.distributions.bijectors: Softplus is real, everything else (the theta posterior's chains, built in
-    the scripts' module-level part) is a mock."""
+    """tf.contrib.distributions.bijectors: Softplus, Affine, AffineScalar and Chain are real, everything else (the
+    theta posterior's masked autoregressive flows, built in the scripts' module-level part) is a mock."""
     Softplus = SoftplusBijector
+    Affine = AffineBijector
+    AffineScalar = AffineBijector
+    Chain = ChainBijector
 
     def __getattr__(self, name):
         return mock.MagicMock(name="bijectors." + name)
@@ -301,9 +380,14 @@ def install():
     tf.shape = lambda x, **k: [int(d) for d in _t(x).shape]
     tf.zeros = lambda shape, dtype=None, **k: torch.zeros([int(d) for d in shape], dtype=DT)
     tf.ones = lambda shape, dtype=None, **k: torch.ones([int(d) for d in shape], dtype=DT)
+    tf.reduce_min = lambda x, axis=None, **k: _t(x).min() if axis is None else _t(x).min(dim=axis).values
+    tf.reduce_max = lambda x, axis=None, **k: _t(x).max() if axis is None else _t(x).max(dim=axis).values
     tf.reduce_prod = lambda x, axis=None, **k: _t(x).prod() if axis is None else _t(x).prod(dim=axis)
     tf.matrix_inverse = lambda x, **k: torch.linalg.inv(_t(x))
     tf.matrix_diag_part = lambda x, **k: torch.diagonal(_t(x), dim1=-2, dim2=-1)
+    tf.eye = lambda n, **k: torch.eye(int(n), dtype=DT)
+    # a host array converted at float32 is ROUNDED to float32 (then carried in float64 like everything else)
+    tf.convert_to_tensor = lambda v, dtype=None, **k: _t(np.asarray(v, dtype=np.float32) if dtype == float32 and not isinstance(v, (torch.Tensor, Var)) else v)
     tf.set_random_seed = lambda *a, **k: None
     tf.InteractiveSession = lambda *a, **k: mock.MagicMock(name="session")
     tf.Session = tf.InteractiveSession
@@ -336,7 +420,7 @@ def install():
     bij = _Bijectors()
     tf.contrib = types.SimpleNamespace(distributions=types.SimpleNamespace(
         Normal=Normal, MultivariateNormalDiag=MultivariateNormalDiag, bijectors=bij,
-        TransformedDistribution=mock.MagicMock(name="TransformedDistribution")))
+        TransformedDistribution=TransformedDistribution))
     client = types.ModuleType("tensorflow.python.client")
     client.timeline = mock.MagicMock(name="timeline")
     sys.modules.setdefault("matplotlib", mock.MagicMock(name="matplotlib"))          # imported by the scripts, unused here

@@ -50,3 +50,25 @@ def test_cuda_lvr_step_matches_the_reference_classes(GM, objective, target, gpre
         assert np.linalg.norm(lf - GM["lvr_lf_sample"]) <= RTOL * np.linalg.norm(GM["lvr_lf_sample"])
         assert np.linalg.norm(gth - GM["lvr_grad_theta"]) <= RTOL * np.linalg.norm(GM["lvr_grad_theta"])
     print("CUDA vs reference classes (LV learned theta, objective %d): worst gradient slice error %.2e" % (objective, worst))
+
+
+def test_cuda_lv_fixed_theta_matches_the_reference_classes(GM):
+    """The (hardware-verified) fixed-theta LV path against the reference-classes fixture under the per-state reading;
+    parked here only because the test itself was written without a GPU at hand."""
+    from test_step_golden_models import lv_fixed_inputs
+    from viforssms_b200.engine import NMAEngine
+    cfg, layout, n, params, eps, theta, idx, tf, extra, arrays = lv_fixed_inputs(GM)
+    eng = NMAEngine(cfg)
+    eng.set_series(arrays)
+    dev = torch.device("cuda")
+    out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(np.asarray(idx)).to(dev))
+    torch.cuda.synchronize()
+    pre = "lvf_per_state_"
+    worst = check_grads(out["grad_params"].cpu().double().numpy(), layout, GM, pre, RTOL, 1e-6)
+    t = out["terms"].cpu().double().numpy()
+    for k, key in ((0, "sde"), (1, "obs_lp"), (2, "logq")):
+        w = GM[pre + key]
+        assert np.abs(t[:, k] - w).max() <= RTOL * max(1.0, np.abs(w).max()), key
+    lf = out["lf"].cpu().double().numpy().reshape(cfg.p, -1, 2).transpose(0, 2, 1)
+    assert np.linalg.norm(lf - GM[pre + "lf_sample"]) <= RTOL * np.linalg.norm(GM[pre + "lf_sample"])
+    print("CUDA vs reference classes (LV fixed theta, per-state reading): worst gradient slice error %.2e" % worst)

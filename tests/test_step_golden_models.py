@@ -12,7 +12,7 @@ import torch
 
 from oracle import nma_oracle as O
 from viforssms_b200 import feed
-from viforssms_b200.config import fhn_config, lvr_config, param_layout, sv_config
+from viforssms_b200.config import fhn_config, lv_config, lvr_config, param_layout, sv_config
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -185,3 +185,50 @@ def test_lvr_oracle_matches_the_reference_classes(GM):
     assert np.array_equal(arrays[1], pads["bin_feats"]) and np.array_equal(arrays[2], pads["time_pad"])
     assert np.array_equal(arrays[3], pads["time_till"])
     assert np.array_equal(arrays[0][:pads["obs_pad_store"][0].shape[0]], pads["obs_pad_store"][0])
+
+
+def lv_fixed_inputs(GM):
+    p, K, B, F, fw, seed = (int(v) for v in GM["lvf_hyper"])
+    dt = float(GM["lvf_dt"])
+    N = p * B
+    T = (N - 1) * dt
+    cfg = lv_config(p=p, K=K, B=B, F=F, H=2, feat_window=fw, target_dims=B, dt=dt, x0=(11.0, 9.5))
+    layout, n = param_layout(cfg)
+    g = torch.Generator().manual_seed(seed)
+    params = _params(cfg, layout, n, g, None, T)
+    for i in range(F):
+        off, _ = layout[f"f{i}.head.b"]
+        params[off] = 3.0
+    assert _sha(params.numpy()) == str(GM["lvf_params_sha_f32"])
+    obs, obs_bin, tt = GM["lvf_obs"], GM["lvf_obs_bin"], GM["lvf_time_till"]
+    pads = O.pad_series_lv(obs, tt, np.array(cfg.x0), dt, T, N, 1, F, K, fw)
+    idx = np.arange(p, dtype=np.int64) * B
+    tf64, mask, shift, bin_feed = O.gather_feed_lv(pads, obs_bin, idx, cfg.L0, B)
+    f32 = lambda a: torch.from_numpy(np.asarray(a).astype(np.float32)).double()
+    theta = torch.from_numpy(GM["lvf_theta"]).float().repeat(p, 1)
+    arrays = feed.lv_base_arrays(obs, obs_bin, tt, dt, T, N, F, K, fw, p_val=1)
+    return (cfg, layout, n, params, torch.from_numpy(GM["lvf_eps"]), theta, idx, f32(tf64),
+            {"mask": f32(mask), "shift": f32(shift), "bin_feed": f32(bin_feed)}, arrays)
+
+
+def test_lv_fixed_theta_oracle_matches_the_reference_classes_under_the_per_state_reading(GM):
+    """lotka_volterra_partial_batch_fix_theta.py: the script's classes run under both readings of how
+    Softplus(event_ndims=2) reduces the log-determinant of the flattened [states, 2] matrix (see
+    tests/golden/tf_shim.py, EVENT_REDUCTION).  The oracle - and the kernel - implement the per-state reading and agree
+    with the script under it in every term; under the literal reading ONLY the transition term differs, by the
+    log-determinants of the other states of the batch.  Which one TensorFlow 1.8 computes is the open question of
+    DESIGN.md section 0."""
+    cfg, layout, n, params, eps, theta, idx, tf, extra, _ = lv_fixed_inputs(GM)
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, extra=extra)
+    t = ref["terms"].numpy()
+    pre = "lvf_per_state_"
+    assert _close(t[:, 0], GM[pre + "sde"], 1e-9)
+    assert _close(t[:, 1], GM[pre + "obs_lp"], 1e-9)
+    assert _close(t[:, 2], GM[pre + "logq"], 1e-9)
+    assert _close(ref["lf"].numpy(), GM[pre + "lf_sample"], 1e-10)
+    assert _close(cfg.scale * (t[:, 0] - t[:, 2] + t[:, 1]), GM[pre + "elbo"], 1e-9)             # no prior term: :334-337
+    check_grads(ref["grad_params"].numpy(), layout, GM, pre, 1e-8, 1e-12)
+    lit = "lvf_literal_"
+    assert _close(t[:, 1], GM[lit + "obs_lp"], 1e-9) and _close(t[:, 2], GM[lit + "logq"], 1e-9)
+    assert _close(ref["lf"].numpy(), GM[lit + "lf_sample"], 1e-10)
+    assert not _close(t[:, 0], GM[lit + "sde"], 1e-3)
