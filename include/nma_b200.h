@@ -155,6 +155,21 @@ int nma_scan_ar1(const double* d_z, double* d_x, int64_t n, double x0, double a,
 int nma_time_till(const double* d_obs, int64_t n, int32_t impute, double* d_obs_fill, double* d_obs_binary,
                   double* d_time_till, void* stream);
 
+/* A11 on the device - the theta posterior of AR.py:376-391 (num_bijectors inverse masked-autoregressive-flow layers,
+ * masked_autoregressive_default_template(hidden_layers=[5,5,5]), fixed permutations in between), one thread per row.
+ * d_params: the flow's variables in creation order, per layer 4 x (kernel [in][out], bias); d_masks: the four block
+ * masks of one layer, concatenated (d*5 + 25 + 25 + 5*2d floats); d_perms [nb-1][d]; relu: 0 = elu template, 1 = relu.
+ *   fwd: z0 [p][d] ~ N(base_loc, base_scale) -> theta [p][d], log q(theta) [p]
+ *   bwd: dL/dtheta [p][d], dL/dlogq [p] (may be null) -> d_g_params (ACCUMULATED into), d_g_z0 [p][d] (may be null)
+ * NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent; arithmetic checked on the CPU,
+ * tests/test_theta_flow_formulas.py); nothing in the package calls them by default. */
+int nma_theta_flow_fwd(const float* d_params, const float* d_masks, const int32_t* d_perms, const float* d_z0,
+                       int32_t p, int32_t d, int32_t nb, int32_t relu, float base_loc, float base_scale,
+                       float* d_theta, float* d_logq, void* stream);
+int nma_theta_flow_bwd(const float* d_params, const float* d_masks, const int32_t* d_perms, const float* d_z0,
+                       int32_t p, int32_t d, int32_t nb, int32_t relu, const float* d_g_theta, const float* d_g_logq,
+                       float* d_g_params, float* d_g_z0, void* stream);
+
 /* A14 - rolling variances of the stochastic-volatility features (SV_dense.py:159-170):
  * d_var[i] = np.var(x[i : i+K]) for i in [0, n-K), on the float32 series, bit-exact with numpy's float32 np.var
  * (pairwise sums, two passes). */

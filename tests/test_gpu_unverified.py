@@ -72,3 +72,33 @@ def test_cuda_lv_fixed_theta_matches_the_reference_classes(GM):
     lf = out["lf"].cpu().double().numpy().reshape(cfg.p, -1, 2).transpose(0, 2, 1)
     assert np.linalg.norm(lf - GM[pre + "lf_sample"]) <= RTOL * np.linalg.norm(GM[pre + "lf_sample"])
     print("CUDA vs reference classes (LV fixed theta, per-state reading): worst gradient slice error %.2e" % worst)
+
+
+@pytest.mark.parametrize("d,nb,act", [(3, 5, "elu"), (5, 4, "elu"), (4, 4, "relu")])
+def test_device_theta_flow_matches_the_host_module(d, nb, act):
+    """nma_theta_flow_fwd / _bwd (two launches) against the host autograd module they are to replace."""
+    from viforssms_b200.engine import DeviceThetaFlow
+    from viforssms_b200.theta_flow import ThetaFlow
+    np.random.seed(7)
+    dev = torch.device("cuda")
+    flow = ThetaFlow(d, nb, base_loc=1.5, base_scale=0.5, activation=act)
+    g = torch.Generator().manual_seed(3)
+    flat = flow.init_values(g)
+    flat = (flat + 0.3 * torch.randn(flat.shape, generator=g) * (flat != 0)).to(dev).requires_grad_(True)
+    flow.bind(flat)
+    p = 1000
+    z0 = (1.5 + 0.5 * torch.randn(p, d, generator=g)).to(dev)
+    theta, lp = flow.sample_and_log_prob(z0)
+    g_theta = torch.randn(p, d, generator=g).to(dev)
+    g_logq = torch.randn(p, generator=g).to(dev)
+    ((theta * g_theta).sum() + (lp * g_logq).sum()).backward()
+    dflow = DeviceThetaFlow(flow, dev)
+    th2, lp2 = dflow.forward(flat.detach(), z0)
+    gp = torch.zeros_like(flat)
+    dflow.backward(flat.detach(), z0, g_theta, g_logq, gp)
+    torch.cuda.synchronize()
+    assert torch.allclose(th2, theta.detach(), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(lp2, lp.detach(), rtol=1e-5, atol=1e-4)
+    err = (gp - flat.grad).norm().item() / flat.grad.norm().item()
+    print("device theta flow (d=%d, nb=%d, %s): gradient rel err %.2e" % (d, nb, act, err))
+    assert err < 1e-4

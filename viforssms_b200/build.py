@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnma_b200.so")
-SOURCES = ["nma_api.cu", "nma_fwd.cu", "nma_tc_conv.cu", "nma_tc_conv2.cu", "nma_tc_feat.cu", "nma_elbo.cu", "nma_bwd.cu", "nma_adamax.cu", "nma_scan.cu", "nma_lv.cu"]
+SOURCES = ["nma_api.cu", "nma_fwd.cu", "nma_tc_conv.cu", "nma_tc_conv2.cu", "nma_tc_feat.cu", "nma_elbo.cu", "nma_bwd.cu", "nma_adamax.cu", "nma_scan.cu", "nma_lv.cu", "nma_theta_flow.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-DNMA_BUILD",

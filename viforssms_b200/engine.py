@@ -224,3 +224,36 @@ def rolling_var(x: torch.Tensor, K: int) -> torch.Tensor:
     out = torch.empty(x.numel() - K, dtype=torch.float32, device=x.device)
     _lib.check(lib.nma_rolling_var(_ptr(x), x.numel(), int(K), _ptr(out), _stream()), "nma_rolling_var")
     return out
+
+
+class DeviceThetaFlow:
+    """The theta posterior on the device (nma_theta_flow_fwd / _bwd; A11, AR.py:376-391): two launches instead of the
+    ~400 tiny ones of the host autograd module.  NOT YET RUN ON HARDWARE - see nma_b200.h; nothing uses it by default."""
+
+    def __init__(self, flow, device):
+        self.flow = flow
+        self.device = device
+        self._lib = _lib.load()
+        self.masks = torch.cat([torch.from_numpy(m).reshape(-1) for m in flow.masks_np]).float().to(device)
+        perms = np.stack(flow.perms).astype(np.int32) if flow.perms else np.zeros((0, flow.d), dtype=np.int32)
+        self.perms = torch.from_numpy(perms).to(device)
+        self.relu = 0 if flow.act is torch.nn.functional.elu else 1
+
+    def forward(self, params: torch.Tensor, z0: torch.Tensor):
+        f = self.flow
+        p = z0.shape[0]
+        theta = torch.empty(p, f.d, dtype=torch.float32, device=self.device)
+        logq = torch.empty(p, dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.nma_theta_flow_fwd(_ptr(params), _ptr(self.masks), _ptr(self.perms), _ptr(z0), p, f.d, f.nb,
+                                                self.relu, f.base_loc, f.base_scale, _ptr(theta), _ptr(logq), _stream()),
+                   "nma_theta_flow_fwd")
+        return theta, logq
+
+    def backward(self, params: torch.Tensor, z0: torch.Tensor, g_theta: torch.Tensor, g_logq: Optional[torch.Tensor],
+                 g_params: torch.Tensor) -> None:
+        """Accumulates d loss / d params into `g_params` (same length as `params`)."""
+        f = self.flow
+        p = z0.shape[0]
+        _lib.check(self._lib.nma_theta_flow_bwd(_ptr(params), _ptr(self.masks), _ptr(self.perms), _ptr(z0), p, f.d, f.nb,
+                                                self.relu, _ptr(g_theta), _ptr(g_logq) if g_logq is not None else None,
+                                                _ptr(g_params), None, _stream()), "nma_theta_flow_bwd")

@@ -18,7 +18,7 @@ EXPORTS = [
     "nma_last_error", "nma_version", "nma_create", "nma_destroy", "nma_param_count", "nma_param_layout",
     "nma_workspace_bytes", "nma_set_series", "nma_gather", "nma_elbo_fwd_bwd", "nma_forward_paths",
     "nma_adamax_step", "nma_scan_ar1", "nma_time_till", "nma_launch_stage", "nma_launch_count",
-    "nma_set_tensor_cores", "nma_get_tensor_cores", "nma_tc_conv_raw", "nma_tc_wgrad_raw", "nma_tc_wgrad_raw_bf", "nma_rolling_var",
+    "nma_set_tensor_cores", "nma_get_tensor_cores", "nma_tc_conv_raw", "nma_tc_wgrad_raw", "nma_tc_wgrad_raw_bf", "nma_rolling_var", "nma_theta_flow_fwd", "nma_theta_flow_bwd",
 ]
 
 _lib = None
@@ -82,6 +82,12 @@ def load() -> ctypes.CDLL:
     lib.nma_time_till.restype = c_int32
     lib.nma_rolling_var.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     lib.nma_rolling_var.restype = c_int32
+    lib.nma_theta_flow_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                       c_float, c_float, c_void_p, c_void_p, c_void_p]
+    lib.nma_theta_flow_fwd.restype = c_int32
+    lib.nma_theta_flow_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.nma_theta_flow_bwd.restype = c_int32
     _lib = lib
     return lib
 
