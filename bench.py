@@ -239,7 +239,7 @@ def run_native(args):
 
     stepper = ARStepper(T=args.T, rows=args.rows, K=K_LEN, B=B_DIMS, F=FLOWS, H=HID, fw=FW, theta=THETA_TRUE,
                         x0=10.0, obs_std=1.0, device=dev, rank=rank, world=world, seed=1,
-                        tensor_cores=7 if args.conv_split == "bf16" else 3)
+                        tensor_cores=7 if args.conv_split == "bf16" else 3, device_theta=args.device_theta)
     cfg = stepper.cfg
     fl = flops_per_row(cfg)
     units_step_rank = args.rows * B_DIMS
@@ -353,6 +353,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--conv-split", default="bf16", choices=["tf32", "bf16"],
                     help="operand split of the conv GEMMs: 3xTF32 (kind::tf32) or 2-term bf16 (kind::f16, twice the rate)")
+    ap.add_argument("--device-theta", action="store_true",
+                    help="theta posterior through nma_theta_flow_fwd/_bwd instead of the host autograd module "
+                         "(written without a GPU at hand: opt-in until tests/test_gpu_unverified.py has passed)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.warmup < 3:

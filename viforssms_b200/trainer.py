@@ -151,8 +151,10 @@ class ARStepper:
                  theta: Sequence[float] = (5.0, 0.5, 3.0), x0: float = 10.0, obs_std: float = 1.0,
                  device: Optional[torch.device] = None, rank: int = 0, world: int = 1, seed: int = 1,
                  lr: float = 1e-3, clip: float = 2.5e8, priors=((0.0, 10.0),) * 3, series=None, impute: int = 1,
-                 tensor_cores: Optional[int] = None):
+                 tensor_cores: Optional[int] = None, device_theta: bool = False):
         self.T, self.rows, self.rank, self.world = int(T), int(rows), rank, world
+        self.device_theta = bool(device_theta)     # theta posterior through nma_theta_flow_fwd / _bwd (not yet run on
+        #                                            hardware: opt-in; the default is the host autograd module)
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.lr, self.clip, self.priors = lr, clip, priors
         self.cfg = ar_config(p=rows, K=K, B=B, F=F, H=H, feat_window=fw, T=T, obs_std=obs_std, x0=x0)
@@ -189,6 +191,10 @@ class ARStepper:
         # eps / theta base noise come from torch's default CUDA generator (graph-capture safe)
         torch.cuda.manual_seed(seed * 1000 + rank)
         self.prior_t = prior_tensors(priors, self.device)
+        if self.device_theta:
+            from .engine import DeviceThetaFlow
+            self.dflow = DeviceThetaFlow(self.flow, self.device)
+            self._ones = torch.ones(rows, dtype=torch.float32, device=self.device)
         self.graph = None
         self._elbo_static = None
         self.launches_per_step = None
@@ -253,7 +259,31 @@ class ARStepper:
                 float(tt[0]))
 
     # ------------------------------------------------------------------
+    def _step_device_theta(self, idx_dev: torch.Tensor) -> torch.Tensor:
+        """The same iteration with the theta posterior on the device: -sum(ELBO) = device part (through theta) -
+        sum(log prior(theta)) + sum(log q(theta)), so d/dtheta = grad_theta + (theta - mean) / scale^2 and
+        d/dlogq = 1; nma_theta_flow_bwd turns the two into the gradient of the flow variables."""
+        cfg, rows = self.cfg, self.rows
+        z0 = self.flow.base_sample(rows, None, self.device)
+        flow_params = self.blob[self.n_nma:]
+        theta, logq_theta = self.dflow.forward(flow_params, z0)
+        eps = torch.randn(rows, cfg.L0, device=self.device)
+        out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta, idx_dev, out=self.out)
+        mean, scale = self.prior_t
+        g_theta = out["grad_theta"] + (theta - mean) / (scale * scale)
+        self.grad[self.n_nma:].zero_()
+        self.dflow.backward(flow_params, z0, g_theta.contiguous(), self._ones, self.grad[self.n_nma:])
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grad)
+        self.eng.adamax_step(self.blob, self.grad, self.m, self.v, self.lr, 0.95, clip=self.clip)
+        t = out["terms"]
+        tail = prior_log_prob(theta, self.prior_t) - logq_theta
+        return (float(cfg.scale) * (t[:, 0] - t[:, 2] + t[:, 1]) + tail).mean()
+
     def _step(self, idx_dev: torch.Tensor) -> torch.Tensor:
+        if self.device_theta:
+            return self._step_device_theta(idx_dev)
         cfg, rows = self.cfg, self.rows
         z0 = self.flow.base_sample(rows, None, self.device)
         theta, logq_theta = self.flow.sample_and_log_prob(z0)
