@@ -188,3 +188,35 @@ def test_sv_feed_arrays_and_rolling_variance():
             assert np.array_equal(arrays[0][i + cfg.head_offset:i + cfg.head_offset + B + 1], d1[r])
     want = np.array([np.var(obs[i:i + 50]) for i in range(len(obs) - 50)])
     assert np.allclose(feed.rolling_var(obs, 50), want, rtol=1e-10)
+
+
+def test_lvr_facade_constructor_and_base_arrays_on_the_host():
+    """LVR_VI_SSM (lotka_volterra_partial.py:162-217): the constructor's derived sizes and the base arrays it hands the
+    library, against the oracle's padding (which is the script's own, tests/test_step_golden_models.py)."""
+    import torch
+    from oracle import nma_oracle as O
+    from viforssms_b200.theta_flow import ThetaFlow
+    from viforssms_b200.vi_ssm_models import LVR_VI_SSM
+    rs = np.random.RandomState(2)
+    target_dims, dt, F, K, B, fw = 120, 0.1, 3, 6, 10, 4
+    T = target_dims * dt
+    obs = rs.uniform(1.0, 200.0, size=(2, target_dims))
+    obs_bin = (rs.uniform(size=(2, target_dims)) < 0.1).astype(np.float64)
+    tt = rs.uniform(0.1, 10.0, size=(2, target_dims)).round(1)
+    x0 = np.array([100.0, 90.0])
+    np.random.seed(1)
+    flow = ThetaFlow(3, 4, base_loc=0.0, base_scale=1.0, activation="elu")
+    m = LVR_VI_SSM(obs, obs_bin, tt, x0, flow, [(0.0, 1.0)] * 3, dt, T, 7, K, B, [50] * 5, target_dims, F, fw,
+                   device=torch.device("cpu"))
+    assert m.kernel_ext == K * F + 2 * B + 2 == m.cfg.L0
+    assert m.cfg.dtheta == 3 and m.cfg.D == 2 and m.cfg.H == 3 and m.cfg.x0 == (100.0, 90.0)
+    assert m.cfg.scale == target_dims / B
+    arrays = m._base_arrays()
+    pads = O.pad_series_lvr(obs, tt, x0, dt, T, target_dims, F, K, fw)
+    assert np.array_equal(arrays[1], pads["bin_feats"])
+    assert np.array_equal(arrays[2], pads["time_pad"])
+    assert np.array_equal(arrays[3], pads["time_till"])
+    for i, shifted in enumerate(pads["obs_pad_store"]):          # the look-ahead channels are ONE array read at offsets 5 i
+        n = shifted.shape[0]
+        assert np.array_equal(arrays[0][5 * i:5 * i + n], shifted)
+    assert np.array_equal(arrays[4].reshape(2, -1), obs_bin)
