@@ -21,4 +21,7 @@ timeout 150 python bench.py --no-cpu --device-theta > gpurun_out/first_bench_dev
 # the reference's own shape (p = 50 rows), where the theta flow's ~400 launches matter most
 timeout 150 python bench.py --no-cpu --rows 50 --steps 200 > gpurun_out/first_bench_p50.json 2> gpurun_out/first_bench_p50.err
 timeout 150 python bench.py --no-cpu --rows 50 --steps 200 --device-theta > gpurun_out/first_bench_p50_device_theta.json 2> gpurun_out/first_bench_p50_device_theta.err
+# 4. the drop-in script with and without the captured iteration (p = 50: launch-bound)
+( time NMA_MAX_STEPS=600 timeout 200 python main.py hyperparameters.txt ) > gpurun_out/first_main_eager.log 2>&1
+( time NMA_FACADE_GRAPH=1 NMA_MAX_STEPS=600 timeout 200 python main.py hyperparameters.txt ) > gpurun_out/first_main_graph.log 2>&1
 tail -3 gpurun_out/first_unverified.log gpurun_out/first_odd_pairs.log gpurun_out/first_suite.log

@@ -85,12 +85,40 @@ class VI_SSM:
 
     # ------------------------------------------------------------------
     def _iteration(self, batch_select: np.ndarray, pre_train: bool) -> None:
+        """One sess.run.  With NMA_FACADE_GRAPH=1 the body is captured once per optimiser into a CUDA graph and
+        replayed (at p = 50 the iteration is ~460 tiny launches, mostly the theta posterior: launch-bound); the
+        capture path was written without a GPU at hand and is therefore opt-in."""
+        self.idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(batch_select, dtype=np.int64)))
+        if os.environ.get("NMA_FACADE_GRAPH") != "1":
+            self._body(pre_train, self.gen)
+            return
+        if not hasattr(self, "_graphs"):
+            self._graphs, self._warm = {}, {True: 0, False: 0}
+            torch.cuda.manual_seed(self.seed)              # captured randn draws come from the default CUDA generator
+        g = self._graphs.get(pre_train)
+        if g is None:
+            if self._warm[pre_train] < 3:                  # eager warm-up on a side stream, as capture requires
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._body(pre_train, None)
+                torch.cuda.current_stream().wait_stream(side)
+                self._warm[pre_train] += 1
+                return
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body(pre_train, None)
+            self._graphs[pre_train] = g
+            return
+        g.replay()
+
+    def _body(self, pre_train: bool, gen) -> None:
         """The body of one sess.run: sample theta and eps, ELBO + gradients, clip, Adamax."""
         cfg = self.cfg
-        self.idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(batch_select, dtype=np.int64)))
-        z0 = self.theta_dist.base_sample(self.p, self.gen, self.device)
+        z0 = self.theta_dist.base_sample(self.p, gen, self.device)
         theta, logq_theta = self.theta_dist.sample_and_log_prob(z0)
-        eps = torch.randn(self.p, cfg.L0, device=self.device, generator=self.gen)
+        eps = torch.randn(self.p, cfg.L0, device=self.device, generator=gen)
         obj = OBJ_NEG_OBS if pre_train else OBJ_ELBO
         out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), self.idx_dev,
                                     objective=obj, out=self.out)
