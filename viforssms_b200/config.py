@@ -253,9 +253,8 @@ def lvr_config(p=50, K=20, B=50, F=3, H=3, feat_window=10, target_dims=500, dt=0
 
 def lv_config(p=1, K=20, B=151, F=3, H=3, feat_window=10, target_dims=151, dt=0.2, x0=(91.0, 99.0)) -> NMAConfig:
     """The Lotka-Volterra model of lotka_volterra_partial_batch_fix_theta.py (p_val = 1: one subsequence that is the
-    whole series).  Only the feed is built for this model: `NMAEngine.gather` reproduces time_feats / mask / shift
-    bit-exactly; the flow (transposed feature MLP, 364-channel conv) and the bivariate ELBO are the next widening
-    step, and `elbo_fwd_bwd` fails loudly for MODEL_LV.
+    whole series): feed, flow (transposed wide 4th feature layer, conv over 1 + (L0 - 1) channels, coupling / Permute /
+    BN) and the bivariate ELBO with its softplus bijector chains.
 
     Base arrays (ibid. :203-222): as the FHN model, except that bin_feats is 0 on the pad and 1 on the series, the
     time channel starts at 0, and the lead of time_till stops before 0.  Channel order :497-498."""
