@@ -108,15 +108,6 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         if (i < cfg->F && d.N < 1) { delete h; nma_set_error("nma_create: window too short"); return -1; }
     }
     h->is_lv = (cfg->model == NMA_MODEL_LV || cfg->model == NMA_MODEL_LVR) ? 1 : 0;
-    if (cfg->model == NMA_MODEL_LVR) {
-        const char* envu = getenv("NMA_UNVERIFIED");
-        if (!(envu && envu[0] == '1')) {
-            delete h;
-            nma_set_error("nma_create: NMA_MODEL_LVR (lotka_volterra_partial.py) has an oracle-checked design but its ELBO "
-                          "kernel branch has not been run on hardware yet; set NMA_UNVERIFIED=1 to use it");
-            return -3;
-        }
-    }
     h->LW = h->L0 - 1;
     h->LWP = (h->LW + 3) & ~3;
     h->conv_cin = h->is_lv ? 1 + h->LW : NMA_C1;
