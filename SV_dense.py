@@ -21,15 +21,26 @@ from viforssms_b200.vi_ssm_models import SV_VI_SSM as VI_SSM
 NP_DTYPE = np.float32
 np.random.seed(1)                      # SV_dense.py:18
 
-__all__ = ["VI_SSM", "main", "generate", "ThetaFlow", "NP_DTYPE"]
+__all__ = ["VI_SSM", "main", "generate", "simulate", "ThetaFlow", "NP_DTYPE"]
 
 THETA_STAR = (0.001, -.6, np.log(0.08), np.log(0.5))      # SV_dense.py:254
 
 
-def generate(n=1809, dt=1.0, x0=-8.5, s0=100.0, seed=1, path="dat/SV.dat"):
+def simulate(n=1809, dt=1.0, x0=-8.5, s0=100.0, seed=1, device=None):
     """Euler-Maruyama of the two-component SDE of SV_dense.py:211-223: price S with drift theta0*S and diffusion
-    S*exp(V/2), log-volatility V with drift theta1 - exp(theta2) V and diffusion exp(theta3)."""
+    S*exp(V/2), log-volatility V with drift theta1 - exp(theta2) V and diffusion exp(theta3).  Both recursions are
+    affine in their state (V: constant coefficient; S: multiplicative), so with `device` given they run as the library's
+    affine-map prefix scans (nma_scan_affine, the A12 kernel) instead of the Python loop."""
     rs = np.random.RandomState(seed)
+    if device is not None:
+        import torch
+        from viforssms_b200.engine import scan_affine
+        th = THETA_STAR
+        z = torch.from_numpy(rs.standard_normal((2, n))).to(device)
+        ones = torch.ones(n - 1, dtype=torch.float64, device=device)
+        v = scan_affine(ones * (1.0 - dt * np.exp(th[2])), dt * th[1] + np.sqrt(dt) * np.exp(th[3]) * z[1, :n - 1], x0)
+        mult = 1.0 + dt * th[0] + np.sqrt(dt) * torch.exp(0.5 * v[:n - 1]) * z[0, :n - 1]
+        return scan_affine(mult.contiguous(), torch.zeros_like(mult), s0).cpu().numpy()
     th = THETA_STAR
     s, v = np.empty(n), np.empty(n)
     s[0], v[0] = s0, x0
@@ -37,6 +48,12 @@ def generate(n=1809, dt=1.0, x0=-8.5, s0=100.0, seed=1, path="dat/SV.dat"):
     for t in range(n - 1):
         s[t + 1] = s[t] + dt * th[0] * s[t] + np.sqrt(dt) * s[t] * np.exp(0.5 * v[t]) * z[0, t]
         v[t + 1] = v[t] + dt * (th[1] - np.exp(th[2]) * v[t]) + np.sqrt(dt) * np.exp(th[3]) * z[1, t]
+    return s
+
+
+def generate(n=1809, dt=1.0, x0=-8.5, s0=100.0, seed=1, path="dat/SV.dat", device=None):
+    """Writes dat/SV.dat (SV_dense.py:406), which the reference repository does not ship."""
+    s = simulate(n, dt, x0, s0, seed, device)
     os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
     np.savetxt(path, s)
     return s

@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Headline benchmark: latent steps x MC samples per second of the fused NMA ELBO + gradient + Adamax
-step on a synthetic AR(1) series (BASELINE.json configs[4]: T = 10^8, kernel_len = 50, time-sharded).
+"""Benchmark of the fused NMA ELBO + gradient + Adamax step: latent steps x MC samples per second.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--rows P] [--T n]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                  [--config ar_1e8|ar_default|lv_fix_theta|fhn|sv] [--scaling weak|strong] [--rows P] [--T n]
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
+Headline (default): BASELINE.json configs[4] - synthetic AR(1) series, T = 10^8, kernel_len = 50, time-sharded over the
+GPUs.  The other configs are the reference scripts' own shapes on synthetic series of the scripts'
+own SDEs.  One JSON line on stdout (rank 0); DESIGN.md "Measurement" says what each key means.
 """
 import argparse
 import json
@@ -28,10 +30,18 @@ THETA_TRUE = (5.0, 0.5, 3.0)
 
 
 def flops_per_row(cfg):
-    """Algorithmic forward MACs per row; fwd+bwd FLOP = 6 x MAC."""
+    """Algorithmic forward MACs per row; fwd+bwd FLOP = 6 x MAC.  For the Lotka-Volterra models the
+    feature MLP runs over the whole window and ends in a layer as wide as the flow's conv input (conv over 1 + L0-1
+    channels)."""
     C = cfg.C
-    feat = sum(cfg.Lin(i) * (cfg.Cf_in * C + 3 * C * C) for i in range(cfg.F))
-    conv = sum(cfg.N(i) * cfg.K * (C + 1) * C for i in range(cfg.F))
+    lv = cfg.model in (3, 4)
+    if lv:
+        LW = cfg.L0 - 1
+        feat = sum(LW * (cfg.Cf_in * C + 2 * C * C + C * cfg.Lin(i)) for i in range(cfg.F))
+        conv = sum(cfg.N(i) * cfg.K * (LW + 1) * C for i in range(cfg.F))
+    else:
+        feat = sum(cfg.Lin(i) * (cfg.Cf_in * C + 3 * C * C) for i in range(cfg.F))
+        conv = sum(cfg.N(i) * cfg.K * (C + 1) * C for i in range(cfg.F))
     pw = sum(cfg.N(i) * cfg.H * C * C for i in range(cfg.F))
     head = sum((cfg.N(i) // (2 if cfg.D == 2 else 1)) * 2 * C for i in range(cfg.F))
     mac = feat + conv + pw + head
@@ -94,37 +104,441 @@ def measured_peaks():
             return d
         except Exception:
             pass
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0,
+            "source": "fallback"}
+
+
+def native_libs_loaded():
+    """This repository's shared objects mapped into this process (read from /proc/self/maps)."""
+    out = set()
+    try:
+        for line in open("/proc/self/maps"):
+            path = line.rstrip("\n").split(" ")[-1]
+            if path.endswith(".so") and os.path.realpath(path).startswith(os.path.realpath(ROOT)):
+                out.add(os.path.relpath(os.path.realpath(path), os.path.realpath(ROOT)))
+    except Exception:
+        pass
+    return sorted(out)
+
+
+def ncu_traffic(mode, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, per ROW, from this round's
+    `ncu --set full` capture of this very program (profiles/traffic.json, written by tools/summarize_ncu.py from the
+    .ncu-rep; rows of the capture recorded there).  None when no capture of this build is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        e = d[mode][kernel]
+        return float(e["dram_bytes"]) / float(e["rows"]), e.get("source")
+    except Exception:
+        return None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------
+class AR1e8:
+    """BASELINE.json configs[4]: AR(1), T = 10^8, generated on the device (A12/A13 scans), time-sharded."""
+    name = "ar_1e8"
+
+    def __init__(self, args, dev, rank, world):
+        from viforssms_b200.trainer import ARStepper
+        self.args, self.world = args, world
+        rows = args.rows if args.rows else 16384
+        if args.scaling == "strong":
+            rows = max(rows // world, 1)
+        self.rows = rows
+        self.tc = 7 if args.conv_split == "bf16" else 3
+        self.st = ARStepper(T=args.T, rows=rows, K=K_LEN, B=B_DIMS, F=FLOWS, H=HID, fw=FW, theta=THETA_TRUE, x0=10.0,
+                            obs_std=1.0, device=dev, rank=rank, world=world, seed=1, tensor_cores=self.tc,
+                            device_theta=not args.host_theta)
+        self.cfg = self.st.cfg
+        self.units_per_step_rank = rows * B_DIMS
+        self.h2d_bytes, self.d2h_bytes = self.st.h2d_bytes, self.st.d2h_bytes
+
+    def describe(self):
+        a = self.args
+        return {"workload": "AR(1) synthetic T=%d, kernel_len=50, batch_dims=50, no_flows=3, network_dims=50,50,50, "
+                            "feat_window=10 (BASELINE.json configs[4])" % a.T,
+                "rows_per_gpu_per_step": self.rows, "units_per_row": B_DIMS,
+                "l2": "per-step working set (saved activations and tensor-core operands, ~1.1 MB per row: %.1f GB at these "
+                      "rows) far exceeds the 126 MB L2; no flush needed" % (self.rows * 1.075e6 / 1e9),
+                "parallelism": "time-sharded series, rows sharded %d-way, gradient all-reduce issued by the library "
+                               "(NCCL, per flow, side stream)" % self.world,
+                "launch": "eager" if a.no_graph else "one CUDA graph per step",
+                "step": "one nma_train_step call: in-library Philox noise, theta posterior, ELBO + gradients, all-reduce, "
+                        "clip + Adamax, logged means" if not a.host_theta else "host-composed (autograd theta posterior)",
+                "conv_operands": self.operands()}
+
+    def operands(self):
+        return {7: "2-term bf16 split (3 products, kind::f16), fp32 accumulate",
+                3: "3xTF32 split (kind::tf32), fp32 accumulate"}[self.tc]
+
+    def dtype(self):
+        return "bf16x2-split/f32acc" if self.tc == 7 else "tf32x3-split/f32acc"
+
+    def prepare(self):
+        from viforssms_b200 import lib as _lib
+        L = _lib.load()
+        if not self.args.no_graph:
+            self.st.capture()
+        else:
+            n0 = L.nma_launch_count()
+            self.st.step_resident()
+            self.st.launches_per_step = int(L.nma_launch_count() - n0)
+
+    @property
+    def launches_per_step(self):
+        return self.st.launches_per_step
+
+    def step_resident(self):
+        self.st.step_resident()
+
+    def step_e2e(self):
+        return self.st.step_e2e()
+
+    def switch_operands(self, tc):
+        """Re-run in the other operand split of the conv GEMMs (the graph is re-captured)."""
+        st = self.st
+        if st.graph is not None:
+            torch.cuda.synchronize()
+            st.graph.reset()
+            st.graph = None
+        st.eng.set_tensor_cores(tc)
+        self.tc = tc
+        self.prepare()
+
+    STAGE_NAMES = {0: "conv_fwd", 1: "conv_dgrad", 2: "conv_wgrad", 3: "epi_bwd", 5: "feat_bwd"}
+
+    def roofline(self, peaks, ms_step):
+        """Times every kernel family of the step alone (CUDA events on the launching stream, re-launched on the
+        workspace the last step left) and reports the dominant one against the tensor-pipe roofline: the conv is a dense
+        contraction (K*(C+1) = 2550 deep, 50 wide), SURVEY section 8d.  achieved = ALGORITHMIC flops of that launch
+        (2 * rows * N_i * K * 51 * 50) / its duration; peak = the measured bf16 figure for kind::f16 MMAs (bf16 split),
+        half of it for kind::tf32."""
+        st, cfg = self.st, self.cfg
+        stages, best = {}, None
+        for i in range(cfg.F):
+            for sid, name in self.STAGE_NAMES.items():
+                ms = st.time_stage(sid, i)
+                stages["%s[%d]" % (name, i)] = round(ms, 4)
+                if sid in (0, 1, 2):
+                    flop = 2.0 * st.rows * cfg.N(i) * cfg.K * (cfg.C + 1) * cfg.C
+                    if best is None or ms > best[0]:
+                        best = (ms, "%s[%d]" % (name, i), flop)
+        stages["feat_fwd[all]"] = round(st.time_stage(4, 0), 4)
+        ms, name, flop = best
+        bf = bool(st.eng.bf16_split)
+        peak = (1.0 if bf else 0.5) * float(peaks["bf16_tflops"])
+        achieved = flop / (ms * 1e-3) / 1e12
+        conv_ms = sum(v for k, v in stages.items() if k.startswith("conv_"))
+        per_row, src = ncu_traffic("bf16" if bf else "tf32", name)
+        roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": per_row * st.rows if per_row is not None else None,
+                "traffic_note": ("dram bytes of this launch: %s, per row x rows" % src) if per_row is not None else
+                                "no ncu capture of this build committed (profiles/traffic.json)",
+                "peak_source": ("bf16_tflops (%s) of MEASURED_PEAKS.json: the kernel issues kind::f16 MMAs, 3 per algorithmic MAC"
+                                if bf else "0.5 x bf16_tflops (%s) of MEASURED_PEAKS.json = TF32 dense") % peaks.get("source"),
+                "ms_per_launch": ms, "flop_per_launch": flop,
+                "conv_share_of_step": conv_ms / ms_step if ms_step > 0 else None}
+        return roof, stages
+
+    def cpu_inputs(self, rows):
+        from oracle import nma_oracle as O
+        from viforssms_b200.config import ar_config, param_layout
+        cfg = ar_config(p=rows, K=K_LEN, B=B_DIMS, F=FLOWS, H=HID, feat_window=FW, T=10 ** 8)
+        layout, n = param_layout(cfg)
+        g = torch.Generator().manual_seed(1)
+        params = O.glorot_init(layout, n, g)
+        tf = torch.randn(rows, cfg.L0, cfg.Cf, generator=g)
+        tf[:, :, -1] = 1.0
+        return cfg, layout, n, params, tf, None, torch.tensor([4.0, 0.5, 1.0]), 2.5e8
+
+    def cpu_rows(self):
+        return self.args.cpu_rows or 400
+
+    def close(self):
+        self.st.close()
+
+
+class FacadeWorkload:
+    """configs[0..3]: the reference scripts' own shapes, driven through the drop-in VI_SSM classes (the call a user of
+    the script makes: `_iteration(batch_select)` = one sess.run).  `step_resident` replays the iteration with the
+    subsequence starts already on the device; `step_e2e` draws them with the script's own np.random.choice call, copies
+    them in and reads the ELBO back."""
+
+    def __init__(self, args, dev, rank, world):
+        self.args, self.dev = args, dev
+        if world != 1:
+            raise SystemExit("--config %s is a single-GPU workload (the script's own shape); use ar_1e8 for --gpus > 1" % self.name)
+        np.random.seed(1)
+        self.m = self.build(dev)
+        self.m.build_flow()
+        self.cfg = self.m.cfg
+        self.rows = self.cfg.p
+        self.units_per_step_rank = self.cfg.p * self.cfg.B
+        self.h2d_bytes, self.d2h_bytes = self.cfg.p * 8, 32
+        self.launches_per_step = None
+
+    def dtype(self):
+        tc = int(self.m.eng._lib.nma_get_tensor_cores(self.m.eng._h))
+        return "bf16x2-split/f32acc" if tc & 4 else ("tf32x3-split/f32acc" if tc & 1 else "f32")
+
+    def describe(self):
+        c = self.cfg
+        return {"workload": self.title, "rows_per_gpu_per_step": c.p, "units_per_row": c.B,
+                "shape": {"p": c.p, "kernel_len": c.K, "batch_dims": c.B, "flow_dims": c.D, "no_flows": c.F,
+                          "hidden_1x1": c.H, "feature_channels": c.Cf, "dtheta": c.dtheta},
+                "l2": "working set of %.1f MB fits the 126 MB L2; a 256 MB buffer is written between timed steps"
+                      % (self.m.eng.workspace_bytes / 1e6),
+                "parallelism": "single GPU",
+                "launch": "eager" if os.environ.get("NMA_FACADE_GRAPH") == "0" else "one CUDA graph per step",
+                "compute": self.dtype()}
+
+    def _draw(self):
+        return self.m._draw()
+
+    def _run(self):
+        self.m._main_iteration()
+
+    def prepare(self):
+        from viforssms_b200 import lib as _lib
+        L = _lib.load()
+        self.flush = torch.empty(64 << 20, dtype=torch.float32, device=self.dev)
+        self.m.pre_train = False
+        self.m.idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(self._draw(), dtype=np.int64)))
+        n0 = L.nma_launch_count()
+        self._run()                      # eager
+        self.launches_per_step = int(L.nma_launch_count() - n0)
+        self._run()                      # capture + replay
+        self._run()
+        torch.cuda.synchronize()
+
+    def step_resident(self):
+        self.flush.zero_()               # 256 MB > L2: the next step starts cold
+        self._run()
+
+    def step_e2e(self):
+        self.flush.zero_()
+        idx = np.ascontiguousarray(self._draw(), dtype=np.int64)
+        self.m.idx_dev.copy_(torch.from_numpy(idx))
+        self._run()
+        return float(self.m.scalars_dev[0].item())
+
+    def roofline(self, peaks, ms_step):
+        """Whole-step figure: these shapes (p = 1..200 rows) do not fill the machine, the step is latency-bound; achieved
+        = algorithmic FLOP of the step / step time against the peak of the pipe its conv runs on."""
+        fl = flops_per_row(self.cfg)
+        achieved = fl["flop_step"] * self.cfg.p / (ms_step * 1e-3) / 1e12
+        dt = self.dtype()
+        if dt == "f32":
+            clock = float(peaks.get("sm_max_mhz") or 1965.0)
+            peak, src = 148 * 128 * 2 * clock * 1e6 / 1e12, "theoretical FP32 FMA (148 SMs x 128 lanes x 2 x %.0f MHz): the D=2 models run the FP32 SIMT conv; MEASURED_PEAKS.json has no FP32 figure" % clock
+        elif dt.startswith("bf16"):
+            peak, src = float(peaks["bf16_tflops"]), "bf16_tflops (%s) of MEASURED_PEAKS.json" % peaks.get("source")
+        else:
+            peak, src = 0.5 * float(peaks["bf16_tflops"]), "0.5 x bf16_tflops (%s) of MEASURED_PEAKS.json = TF32 dense" % peaks.get("source")
+        # the step without the L2 flush in between (what the flush costs is not the kernels' time)
+        st = torch.cuda.current_stream()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(20):
+            self._run()
+        e1.record(st)
+        torch.cuda.synchronize()
+        warm_ms = e0.elapsed_time(e1) / 20
+        roof = {"bound": "tensor" if dt != "f32" else "fp32-fma", "kernel": "whole step (%d kernels, one CUDA graph)" % self.launches_per_step,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": src, "ms_per_launch": ms_step, "flop_per_launch": fl["flop_step"] * self.cfg.p,
+                "ms_per_step_warm_l2": warm_ms,
+                "note": "latency-bound shape: %d rows x %d kernels per step" % (self.cfg.p, self.launches_per_step)}
+        return roof, {"step_cold_l2": round(ms_step, 4), "step_warm_l2": round(warm_ms, 4)}
+
+    def cpu_rows(self):
+        return self.args.cpu_rows or self.cfg.p
+
+    def cpu_inputs(self, rows):
+        """Inputs of the oracle step at this workload's shape: the windows the device gathers (so the CPU arm sees the same
+        series), `rows` of them."""
+        from oracle import nma_oracle as O
+        from viforssms_b200.config import param_layout
+        import copy
+        cfg = copy.copy(self.cfg)
+        cfg.p = rows
+        layout, n = param_layout(cfg)
+        idx = np.resize(np.ascontiguousarray(self._draw(), dtype=np.int64), rows)
+        tf, mask, shift = self.m.eng.gather(torch.from_numpy(idx).to(self.dev)) if rows <= self.cfg.p else (None, None, None)
+        if tf is None:
+            raise SystemExit("--cpu-rows must not exceed the script's p for --config %s" % self.name)
+        extra = self.cpu_extra(idx, tf.cpu(), mask.cpu(), shift.cpu())
+        params = self.m.blob[:self.m.n_nma].cpu().clone()
+        return cfg, layout, n, params, tf.cpu(), extra, self.theta_center(), float(self.m.grad_clip)
+
+    def close(self):
+        m = self.m
+        torch.cuda.synchronize()
+        for g in ([getattr(m, "_graph", None)] + list(getattr(m, "_graphs", {}).values())):
+            if g is not None:
+                g.reset()
+        m.eng.close()
+
+
+class ARDefault(FacadeWorkload):
+    name = "ar_default"
+    title = ("AR(1) default: python main.py hyperparameters.txt - dat/AR_obs_partial.txt (T=5000), p=50, kernel_len=50, "
+             "batch_dims=50, 3 flows (BASELINE.json configs[0])")
+
+    def build(self, dev):
+        import AR as ar_mod
+        d = os.path.join(ROOT, "dat")
+        obs = np.loadtxt(os.path.join(d, "AR_obs_partial.txt"), np.float32)
+        obs_bin = np.loadtxt(os.path.join(d, "AR_obs_binary.txt"), np.float32)
+        tt = np.loadtxt(os.path.join(d, "AR_time_till.txt"), np.float32)
+        self.series = (obs, obs_bin, tt)
+        flow = ar_mod.ThetaFlow(3, 5, base_loc=1.5, base_scale=0.5, activation="elu")
+        return ar_mod.VI_SSM(obs, 1.0, 10.0, flow, [(0., 10.0)] * 3, 5000, 50, 50, 50, [50] * 3, 3, 10, obs_bin, tt,
+                             pre_train=False, device=dev)
+
+    def _draw(self):
+        return self.m._draw(False)
+
+    def _run(self):
+        self.m._run(False)
+
+    def cpu_extra(self, idx, tf, mask, shift):
+        return None
+
+    def theta_center(self):
+        return torch.tensor([4.0, 0.5, 1.0])
+
+
+class FHN(FacadeWorkload):
+    name = "fhn"
+    title = ("FitzHugh-Nagumo SDE, RealNVP coupling flow (fitz_nag_NVP.py:452-465): synthetic Euler-Maruyama series of 10^5 "
+             "steps at theta*, p=50, kernel_len=20, batch_dims=50, 3 flows, 3 hidden 1x1 + BN (BASELINE.json configs[2])")
+
+    def build(self, dev):
+        import fitz_nag_NVP as mod
+        N, dt = 100000, 0.1
+        obs, obs_bin, tt = mod.simulate(N, dt=dt)
+        self.series = (obs, obs_bin, tt)
+        flow = mod.ThetaFlow(5, 4, base_loc=0., base_scale=1., activation="elu")
+        return mod.VI_SSM(obs, obs_bin, tt, np.array([2., 3.]), flow, [(0., 10.)] * 5, dt, N * dt, 50, 20, 50, [50] * 5, N,
+                          3, 10, learn_rate=1e-4, pre_train=False, device=dev)
+
+    def cpu_extra(self, idx, tf, mask, shift):
+        obs_bin = self.series[1]
+        B = self.cfg.B
+        bf = np.stack([obs_bin[:, i:i + B] for i in idx])
+        return {"bin_feed": torch.from_numpy(bf.astype(np.float32))}
+
+    def theta_center(self):
+        return torch.tensor([0.69, 1.0, 1.5, -0.69, -1.2])
+
+
+class SV(FacadeWorkload):
+    name = "sv"
+    title = ("Stochastic volatility dense model (SV_dense.py:405-416): synthetic 1809-price series, p=200, kernel_len=50, "
+             "batch_dims=52, 5 flows, 3 hidden 1x1 + BN (BASELINE.json configs[3])")
+
+    def build(self, dev):
+        import SV_dense as mod
+        obs = mod.simulate(1809).astype(np.float32)[300:]
+        T = obs.shape[0] - 1
+        n = (T // 52) * 52                      # batch_dims must tile the series (the script's own 1508 = 29 x 52)
+        obs = obs[:n + 1]
+        self.series = (obs,)
+        flow = mod.ThetaFlow(4, 5, base_loc=0., base_scale=1., activation="relu")
+        return mod.VI_SSM(obs, -8.5, flow, [(0., 10.0)] * 4, 1.0, float(n), 200, 50, 52, [50] * 5, n, 5, 5,
+                          learn_rate=1e-4, pre_train=False, device=dev)
+
+    def cpu_extra(self, idx, tf, mask, shift):
+        obs = self.series[0]
+        B = self.cfg.B
+        dim_one = np.stack([obs[i:i + B + 1] for i in idx])
+        return {"mask": mask[:, 0], "shift": shift[:, 0], "dim_one": torch.from_numpy(dim_one.astype(np.float32))}
+
+    def theta_center(self):
+        return torch.tensor([0.001, -0.6, -2.5, -0.7])
+
+
+class LVFix(FacadeWorkload):
+    name = "lv_fix_theta"
+    title = ("Lotka-Volterra partial-observation SDE, fixed theta (lotka_volterra_partial_batch_fix_theta.py:616-631): one "
+             "synthetic 151-step series, p_val=1, kernel_len=20, batch_dims=151, 3 flows (BASELINE.json configs[1])")
+
+    def build(self, dev):
+        import lotka_volterra_partial_batch_fix_theta as mod
+        obs = mod.simulate(1).astype(np.float32)
+        self.series = (obs, np.ones_like(obs), np.zeros_like(obs))
+        priors = mod.softplus_np_(np.array([-1.0, -6.0, -1.0, -2.0]))
+        return mod.VI_SSM(obs, self.series[1], self.series[2], np.array([91., 99.], np.float32),
+                          np.array([1., 1.], np.float32), priors, 0.2, 30, 1, 20, 151, [50] * 5, 151, 3, 10,
+                          learn_rate=1e-3, pre_train=False, device=dev)
+
+    def prepare(self):
+        super().prepare()
+        self.h2d_bytes = 8
+
+    def cpu_extra(self, idx, tf, mask, shift):
+        obs_bin = self.series[1]
+        B = self.cfg.B
+        bf = np.stack([obs_bin[:, i:i + B] for i in idx])
+        return {"mask": mask, "shift": shift, "bin_feed": torch.from_numpy(bf.astype(np.float32))}
+
+    def theta_center(self):
+        return torch.tensor(np.log1p(np.exp([-1.0, -6.0, -1.0, -2.0])), dtype=torch.float32)
+
+
+WORKLOADS = {c.name: c for c in (AR1e8, ARDefault, LVFix, FHN, SV)}
 
 
 # ----------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference step on host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_step_time(rows, steps, warmup, threads):
-    """Times the oracle (torch-CPU fp32 restatement of AR.py's train step incl. Adamax) on `rows` rows."""
+def cpu_step_time(wl, rows, steps, warmup, threads):
+    """Times the oracle (torch-CPU fp32 restatement of the script's train step incl. clip + Adamax) on `rows` rows of
+    the workload's shape."""
     from oracle import nma_oracle as O
-    from viforssms_b200.config import ar_config, param_layout
     torch.set_num_threads(threads)
-    cfg = ar_config(p=rows, K=K_LEN, B=B_DIMS, F=FLOWS, H=HID, feat_window=FW, T=10 ** 8)
-    layout, n = param_layout(cfg)
+    cfg, layout, n, params, tf, extra, theta_c, clip = wl.cpu_inputs(rows)
     g = torch.Generator().manual_seed(1)
-    params = O.glorot_init(layout, n, g)
+    params = params.float()
     m = torch.zeros(n); v = torch.zeros(n)
-    tf = torch.randn(rows, cfg.L0, cfg.Cf, generator=g)
-    tf[:, :, -1] = 1.0
+    tf = tf.float()
+    if extra is not None:
+        extra = {k: t.float() for k, t in extra.items()}
     times = []
     for it in range(warmup + steps):
         eps = torch.randn(rows, cfg.L0, generator=g)
-        theta = torch.tensor(THETA_TRUE).log().abs().repeat(rows, 1) * 0 + torch.tensor([4.0, 0.5, 1.0]) \
-            + 0.1 * torch.randn(rows, 3, generator=g)
+        theta = theta_c.float().repeat(rows, 1) + 0.05 * torch.randn(rows, cfg.dtheta, generator=g)
         t0 = time.perf_counter()
-        r = O.step_reference(cfg, layout, params, eps, theta, tf)
+        r = O.step_reference(cfg, layout, params, eps, theta, tf, extra=extra)
         gn = float(r["grad_params"].norm())
-        params, m, v = O.adamax_step(params, r["grad_params"], m, v, 1e-3, 0.95, clip=(2.5e8, gn))
+        params, m, v = O.adamax_step(params, r["grad_params"], m, v, 1e-3, 0.95, clip=(clip, gn))
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     return float(np.median(times)), float(np.sum(times)), cfg
+
+
+class _CpuOnlyAR:
+    """The AR T=10^8 workload's CPU arm needs no device."""
+    name = "ar_1e8"
+    cpu_inputs = AR1e8.cpu_inputs
+
+    def __init__(self, args):
+        self.args = args
+
+    def cpu_rows(self):
+        return self.args.cpu_rows or 400
+
+    def describe(self):
+        a = self.args
+        rows = a.rows if a.rows else 16384
+        return {"workload": "AR(1) synthetic T=%d, kernel_len=50, batch_dims=50, no_flows=3, network_dims=50,50,50, "
+                            "feat_window=10 (BASELINE.json configs[4])" % a.T,
+                "rows_per_gpu_per_step": rows if a.scaling == "weak" else max(rows // a.gpus, 1), "units_per_row": B_DIMS}
 
 
 def run_reference(args):
@@ -132,94 +546,54 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = args.cpu_rows
-    med, total, cfg = cpu_step_time(rows, args.steps, args.warmup, threads)
-    units = rows * B_DIMS
+    if args.config == "ar_1e8":
+        wl = _CpuOnlyAR(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("the reference arm of --config %s reads the workload's windows through the device gather" % args.config)
+        torch.cuda.set_device(0)
+        wl = WORKLOADS[args.config](args, torch.device("cuda", 0), 0, 1)
+    rows = wl.cpu_rows()
+    med, total, cfg = cpu_step_time(wl, rows, args.steps, args.warmup, threads)
+    units = rows * cfg.B
     value = units / med
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),      # the native arm's config, key for key; the bounded sample is described below
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": wl.describe(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d rows x %d steps of the same AR(1) K=50 B=50 3-flow step (torch-CPU fp32 oracle, "
-                                   "the reference's TensorFlow 1.8 cannot be installed)" % (rows, args.steps)},
+                         "sample": "%d rows x %d steps of the same step (torch-CPU fp32 oracle port of the reference's graph; "
+                                   "its TensorFlow 1.8 cannot be installed here)" % (rows, args.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(args, rows_note=None):
-    c = {"workload": "AR(1) synthetic T=%d, kernel_len=50, batch_dims=50, no_flows=3, network_dims=50,50,50, "
-                     "feat_window=10 (BASELINE.json configs[4])" % args.T,
-         "rows_per_gpu_per_step": args.rows, "units_per_row": B_DIMS,
-         "l2": "per-step working set (saved activations and tensor-core operands, ~1.1 MB per row: %.1f GB at these rows) far "
-               "exceeds the 126 MB L2; no flush needed" % (args.rows * 1.075e6 / 1e9),
-         "parallelism": "time-sharded series, rows sharded %d-way, NCCL gradient all-reduce" % args.gpus,
-         "launch": "eager" if args.no_graph else "one CUDA graph per step",
-         "conv_operands": {"bf16": "2-term bf16 split (3 products, kind::f16), fp32 accumulate",
-                           "tf32": "3xTF32 split (kind::tf32), fp32 accumulate"}[args.conv_split]}
-    if rows_note:
-        c["note"] = rows_note
-    return c
-
-
-
-STAGE_NAMES = {0: "conv_fwd", 1: "conv_dgrad", 2: "conv_wgrad", 3: "epi_bwd", 5: "feat_bwd"}
-# dram__bytes_read.sum + dram__bytes_write.sum per ROW of the flow-0 launch of each tcgen05 conv kernel, from the
-# ncu --set full capture in profiles/r01_final.md (2048 rows: 301.2 / 239.0 / 1346.5 MB); scaled by rows below
-NCU_DRAM_BYTES_PER_ROW = {"conv_fwd[0]": 301.2e6 / 2048, "conv_dgrad[0]": 239.0e6 / 2048, "conv_wgrad[0]": 1346.5e6 / 2048}
-# the same for the bf16-split kernels (profiles/r01_bf16.md: 119.6+90.5 / 105.7+43.6 / 552.7+14.4 MB at 2048 rows)
-NCU_DRAM_BYTES_PER_ROW_BF16 = {"conv_fwd[0]": 210.1e6 / 2048, "conv_dgrad[0]": 149.3e6 / 2048, "conv_wgrad[0]": 567.1e6 / 2048}
-
-
-def roofline_report(stepper, peaks, ms_step):
-    """Times every kernel family of the step alone (CUDA events on the launching stream, re-launched on
-    the workspace the last step left) and reports the dominant one against the tensor-pipe roofline.
-
-    The conv is a dense contraction (K*(C+1) = 2550 deep, 50 wide): the governing roofline is the tensor
-    pipe, not HBM.  achieved = ALGORITHMIC flops of that launch (2 * rows * N_i * K * 51 * 50,
-    DESIGN.md) / its duration.  peak = TF32 dense, taken as 1/2 of the MEASURED bf16 burst figure in
-    MEASURED_PEAKS.json (the file has no TF32 number; tcgen05 kind::tf32 runs at half the kind::f16 rate)."""
-    cfg = stepper.cfg
-    stages = {}
-    best = None
-    for i in range(cfg.F):
-        for st, name in STAGE_NAMES.items():
-            ms = stepper.time_stage(st, i)
-            stages["%s[%d]" % (name, i)] = round(ms, 4)
-            if st in (0, 1, 2):
-                flop = 2.0 * stepper.rows * cfg.N(i) * cfg.K * (cfg.C + 1) * cfg.C
-                if best is None or ms > best[0]:
-                    best = (ms, "%s[%d]" % (name, i), flop)
-    stages["feat_fwd[all]"] = round(stepper.time_stage(4, 0), 4)
-    ms, name, flop = best
-    bf = bool(stepper.eng.bf16_split)
-    # kind::f16 (the bf16 split) runs at the measured bf16 figure, kind::tf32 at half of it
-    tf32_peak = (1.0 if bf else 0.5) * float(peaks["bf16_tflops"])
-    achieved = flop / (ms * 1e-3) / 1e12
-    conv_ms = sum(v for k, v in stages.items() if k.startswith("conv_"))
-    roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": achieved / tf32_peak,
-            "traffic": ((NCU_DRAM_BYTES_PER_ROW_BF16 if bf else NCU_DRAM_BYTES_PER_ROW)[name] * stepper.rows
-                        if (name in NCU_DRAM_BYTES_PER_ROW and stepper.eng.tensor_cores and cfg.K == 50) else None),
-            "traffic_note": "dram bytes of this launch: ncu --set full at 2048 rows (profiles/%s) scaled by rows"
-                            % ("r01_bf16.md" if bf else "r01_final.md"),
-            "peak_source": ("bf16_tflops (%s) of MEASURED_PEAKS.json: the kernel issues kind::f16 MMAs, 3 per algorithmic MAC"
-                            if bf else "0.5 x bf16_tflops (%s) of MEASURED_PEAKS.json = TF32 dense") % peaks.get("source", "measured"),
-            "ms_per_launch": ms, "flop_per_launch": flop,
-            "conv_share_of_step": conv_ms / ms_step if ms_step > 0 else None}
-    return roof, stages
-
 # ----------------------------------------------------------------------------------------------
 # native arm
 # ----------------------------------------------------------------------------------------------
+def timed(wl, steps, fn, barrier, world, dev, host_clock=False):
+    st = torch.cuda.current_stream()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(st)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    e1.record(st)
+    barrier()
+    host = (time.perf_counter() - t0) * 1e3
+    ms = torch.tensor([max(e0.elapsed_time(e1), host) if host_clock else e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
 def run_native(args):
     import torch.distributed as dist
-    from viforssms_b200.config import ar_config, param_layout
-    from viforssms_b200.trainer import ARStepper
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -227,7 +601,7 @@ def run_native(args):
         raise SystemExit("bench.py --impl native needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # NCCL announces itself on stdout when its communicator is created ("NCCL version ..."); stdout must carry exactly one
+    # NCCL announces itself on stdout when a communicator is created ("NCCL version ..."); stdout must carry exactly one
     # JSON line, so file descriptor 1 points at stderr until the communicators exist (restored before the timed region)
     saved_stdout = None
     if world > 1:
@@ -237,14 +611,9 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
 
-    stepper = ARStepper(T=args.T, rows=args.rows, K=K_LEN, B=B_DIMS, F=FLOWS, H=HID, fw=FW, theta=THETA_TRUE,
-                        x0=10.0, obs_std=1.0, device=dev, rank=rank, world=world, seed=1,
-                        tensor_cores=7 if args.conv_split == "bf16" else 3, device_theta=args.device_theta)
-    cfg = stepper.cfg
+    wl = WORKLOADS[args.config](args, dev, rank, world)
+    cfg = wl.cfg
     fl = flops_per_row(cfg)
-    units_step_rank = args.rows * B_DIMS
-    from viforssms_b200 import lib as _lib
-    L = _lib.load()
 
     def barrier():
         if world > 1:
@@ -252,14 +621,9 @@ def run_native(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg ----------------
-    if not args.no_graph:
-        stepper.capture()          # the iteration as one CUDA graph (3 eager warm-up steps inside)
-    else:
-        n0 = L.nma_launch_count()
-        stepper.step_resident()
-        stepper.launches_per_step = int(L.nma_launch_count() - n0)
+    wl.prepare()
     for _ in range(args.warmup):
-        stepper.step_resident()
+        wl.step_resident()
     barrier()
     if saved_stdout is not None:
         sys.stdout.flush()
@@ -268,98 +632,94 @@ def run_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    st = torch.cuda.current_stream()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    for _ in range(args.steps):
-        stepper.step_resident()
-    e1.record(st)
-    barrier()
-    launches = stepper.launches_per_step * args.steps     # kernels of this library per step (counted on an eager step) x steps
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = timed(wl, args.steps, wl.step_resident, barrier, world, dev)
     clocks = sampler.stop() if rank == 0 else None
+    launches = wl.launches_per_step * args.steps     # kernels of this library per step (counted on an eager step) x steps
 
     # ---------------- end-to-end leg (host buffers, H2D + D2H inside the timed region) ----------------
     for _ in range(2):
-        stepper.step_e2e()
-    barrier()
-    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
-    f0.record(st)
-    t_host0 = time.perf_counter()
-    for _ in range(args.steps):
-        stepper.step_e2e()
-    f1.record(st)
-    barrier()
-    t_host = time.perf_counter() - t_host0
-    ms2 = torch.tensor([max(f0.elapsed_time(f1), t_host * 1e3)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_ms_total = float(ms2.item())
+        wl.step_e2e()
+    e2e_ms_total = timed(wl, args.steps, wl.step_e2e, barrier, world, dev, host_clock=True)
 
-    # ---------------- dominant kernel, timed alone (rank 0) ----------------
-    roof = None
-    cpu_base = None
-    stages = None
+    # ---------------- dominant kernel, timed alone; the other operand split; CPU baseline (rank 0) ----------------
+    roof = stages = cpu_base = None
+    alt = {}
     if rank == 0:
         peaks = measured_peaks()
-        roof, stages = roofline_report(stepper, peaks, ms_total / args.steps)
-        if world == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
-            med, total, _ = cpu_step_time(args.cpu_rows, args.cpu_steps, 2, threads)
-            cpu_base = {"value": args.cpu_rows * B_DIMS / med, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "%d rows x %d steps (%.1f s) of the same step on the torch-CPU fp32 oracle; the "
-                                  "reference's TensorFlow 1.8 cannot be installed here" % (args.cpu_rows, args.cpu_steps, total)}
+        roof, stages = wl.roofline(peaks, ms_total / args.steps)
+    if args.config == "ar_1e8" and not args.no_alt:
+        other = 3 if wl.tc == 7 else 7
+        main_tc = wl.tc
+        wl.switch_operands(other)
+        for _ in range(3):
+            wl.step_resident()
+        ms_alt = timed(wl, args.steps, wl.step_resident, barrier, world, dev)
+        alt[wl.dtype()] = {"value": wl.units_per_step_rank * world * args.steps / (ms_alt * 1e-3), "unit": UNIT,
+                           "ms_per_step": ms_alt / args.steps, "conv_operands": wl.operands()}
+        wl.switch_operands(main_tc)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rows = wl.cpu_rows()
+        med, total, ccfg = cpu_step_time(wl, rows, args.cpu_steps, 2, threads)
+        cpu_base = {"value": rows * ccfg.B / med, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": "%d rows x %d steps (%.1f s) of the same step on the torch-CPU fp32 oracle; the reference's "
+                              "TensorFlow 1.8 cannot be installed here" % (rows, args.cpu_steps, total)}
 
     if rank == 0:
-        units_total = units_step_rank * world * args.steps
-        value = units_total / (ms_total * 1e-3)
-        wc = workload_config(args)
+        units_total = wl.units_per_step_rank * world * args.steps
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": wc, "workspace_bytes": int(stepper.eng.workspace_bytes),
+            "metric": METRIC, "value": units_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": wl.dtype(), "data": "synthetic", "config": wl.describe(),
+            "workspace_bytes": int((wl.st if hasattr(wl, "st") else wl.m).eng.workspace_bytes),
             "clocks": clocks,
-            "e2e": {"value": units_total / (e2e_ms_total * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": stepper.h2d_bytes, "d2h_bytes_per_step": stepper.d2h_bytes,
-                    "ms_per_step": e2e_ms_total / args.steps},
-            "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu_base, "stage_ms": stages,
-            "flop_per_unit": fl["flop_step"] / B_DIMS,
-            "achieved_tflops_step": fl["flop_step"] * args.rows * world * args.steps / (ms_total * 1e-3) / 1e12,
+            "e2e": {"value": units_total / (e2e_ms_total * 1e-3), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
+                    "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": e2e_ms_total / args.steps},
+            "gpu_launches": launches, "gpu_launches_per_step": wl.launches_per_step,
+            "roofline": roof, "cpu_baseline": cpu_base, "stage_ms": stages, "other_operand_split": alt or None,
+            "flop_per_unit": fl["flop_step"] / cfg.B,
+            "achieved_tflops_step": fl["flop_step"] * wl.rows * world * args.steps / (ms_total * 1e-3) / 1e12,
+            "native_so_loaded": native_libs_loaded(),
         }
         print(json.dumps(line), flush=True)
-    # Leave without tearing NCCL down: the CUDA graph holds captured NCCL kernels, and destroying the communicator
-    # while such a graph is alive blocks forever (seen on 8 GPUs: the line was printed, the job never exited).
-    stepper.close()
-    torch.cuda.synchronize()
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)
+    # orderly teardown: graph -> library communicator -> handle (wl.close), then torch's process group, then a normal
+    # interpreter exit (atexit hooks run)
+    wl.close()
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--rows", type=int, default=16384, help="rows (MC samples x subsequences) per GPU per step")
+    ap.add_argument("--config", default="ar_1e8", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rows per GPU; strong: --rows in total, split over the GPUs")
+    ap.add_argument("--rows", type=int, default=None, help="ar_1e8: rows (MC samples x subsequences) per step (default 16384)")
     ap.add_argument("--T", type=int, default=10 ** 8)
-    ap.add_argument("--cpu-rows", type=int, default=400, help="rows of the bounded CPU sample (throughput is flat in rows: +8 %% from 100 to 1000)")
-    ap.add_argument("--cpu-steps", type=int, default=50, help="steps of the cpu_baseline leg (about 10 s of CPU work on the 16-thread box)")
+    ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the bounded CPU sample (ar_1e8: 400; throughput is flat in rows)")
+    ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the cpu_baseline leg (about 10 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the leg in the other operand split of the conv GEMMs")
     ap.add_argument("--conv-split", default="bf16", choices=["tf32", "bf16"],
-                    help="operand split of the conv GEMMs: 3xTF32 (kind::tf32) or 2-term bf16 (kind::f16, twice the rate)")
-    ap.add_argument("--device-theta", action="store_true",
-                    help="theta posterior through nma_theta_flow_fwd/_bwd instead of the host autograd module "
-                         "(written without a GPU at hand: opt-in until tests/test_gpu_unverified.py has passed)")
+                    help="operand split of the conv GEMMs: 2-term bf16 on kind::f16 (library default for AR-type models) or 3xTF32")
+    ap.add_argument("--host-theta", action="store_true",
+                    help="comparison path: theta posterior as a host autograd module, torch.randn noise (~400 ATen launches per step)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    small = args.config != "ar_1e8"
+    if args.steps is None:
+        args.steps = 200 if small else 10
+    if args.cpu_steps is None:
+        args.cpu_steps = {"ar_1e8": 50, "ar_default": 100, "fhn": 100, "sv": 20, "lv_fix_theta": 100}[args.config]
+    if args.no_graph and small:
+        os.environ["NMA_FACADE_GRAPH"] = "0"
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -22,13 +22,14 @@ from viforssms_b200.vi_ssm_models import FHN_VI_SSM as VI_SSM
 NP_DTYPE = np.float32
 np.random.seed(1)                      # fitz_nag_NVP.py:21
 
-__all__ = ["VI_SSM", "main", "generate", "ThetaFlow", "NP_DTYPE"]
+__all__ = ["VI_SSM", "main", "generate", "simulate", "ThetaFlow", "NP_DTYPE"]
 
 THETA_STAR = (np.log(2.), 1., 1.5, np.log(.5), np.log(.3))      # fitz_nag_NVP.py:292
 
 
-def generate(target_dims=1000000, dt=0.1, x0=(2., 3.), obs_every=10, obs_std=0.1, seed=1, dat_dir="dat"):
-    """Euler-Maruyama of dX = alpha dt + sqrt(beta) dW with the drift / diffusion of fitz_nag_NVP.py:243-255."""
+def simulate(target_dims=1000000, dt=0.1, x0=(2., 3.), obs_every=10, obs_std=0.1, seed=1):
+    """Euler-Maruyama of dX = alpha dt + sqrt(beta) dW with the drift / diffusion of fitz_nag_NVP.py:243-255; returns
+    (obs, obs_bin, time_till), each [2, target_dims], in the layout the script reads."""
     rs = np.random.RandomState(seed)
     th = THETA_STAR
     x = np.empty((2, target_dims + 1))
@@ -46,6 +47,12 @@ def generate(target_dims=1000000, dt=0.1, x0=(2., 3.), obs_every=10, obs_std=0.1
     nxt = np.minimum(((np.arange(target_dims) // obs_every) + 1) * obs_every - 1, target_dims - 1)
     obs = noisy[:, nxt]                                   # every step carries the NEXT observation (look-ahead fill)
     time_till = np.tile((nxt - np.arange(target_dims)) * dt, (2, 1))
+    return obs, obs_bin, time_till
+
+
+def generate(target_dims=1000000, dt=0.1, x0=(2., 3.), obs_every=10, obs_std=0.1, seed=1, dat_dir="dat"):
+    """Writes the three files fitz_nag_NVP.py:452-454 loads (the reference repository does not ship them)."""
+    obs, obs_bin, time_till = simulate(target_dims, dt, x0, obs_every, obs_std, seed)
     os.makedirs(dat_dir, exist_ok=True)
     np.savetxt(os.path.join(dat_dir, "fitz_nag_obs_partial.txt"), obs)
     np.savetxt(os.path.join(dat_dir, "fitz_nag_obs_binary.txt"), obs_bin)

@@ -33,8 +33,7 @@ extern "C" {
 #define NMA_MODEL_FHN 1   /* fitz_nag_NVP.py:232-266 */
 #define NMA_MODEL_SV  2   /* SV_dense.py:203-234 */
 #define NMA_MODEL_LV  3   /* lotka_volterra_partial_batch_fix_theta.py:265-371 (fixed theta) */
-#define NMA_MODEL_LVR 4   /* lotka_volterra_partial.py:234-297 (learned theta): same flow kernels as NMA_MODEL_LV, own ELBO
-                           * branch; NOT YET RUN ON HARDWARE - nma_create refuses it unless NMA_UNVERIFIED=1 is set */
+#define NMA_MODEL_LVR 4   /* lotka_volterra_partial.py:234-297 (learned theta): same flow kernels as NMA_MODEL_LV, own ELBO branch */
 
 /* objectives (which scalar is differentiated) */
 #define NMA_OBJ_ELBO    0 /* -sum_rows scale*(sde - logq + obs)   AR.py:184-185,228-229 */
@@ -98,6 +97,10 @@ int nma_gather(nma_handle h, const int64_t* d_idx, int32_t p, float* d_time_feat
  *   d_grad_params [n_params]  d objective / d params   (overwritten)
  *   d_grad_theta  [p,dtheta]  d objective / d theta    (overwritten)
  *   d_flags       [p]    bit0 = non-finite ELBO term in that row (fitz_nag_NVP.py:378-381 needs it)
+ * d_eps == NULL: the library draws the base noise itself, as the reference does in-graph (AR.py:31-35): Philox4x32-10 +
+ * Box-Muller keyed by (seed, device-resident draw counter) - nma_set_seed; nma_philox_normal(stream_id 0) reproduces it.
+ * On a handle with a communicator (nma_comm_create / nma_comm_init) the call also issues the all-reduce of every flow's
+ * gradient section on the library's side stream; nma_comm_wait(h, stream) orders `stream` behind them.
  */
 int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
                      const int64_t* d_idx, int32_t p, int32_t objective, float path_target,
@@ -107,6 +110,58 @@ int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float* d_eps, co
 /* forward only — save_paths (AR.py:323-362; fitz_nag_NVP.py:409-448) */
 int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
                       const int64_t* d_idx, int32_t p, float* d_terms, float* d_lf, void* stream);
+
+/* ---- the whole iteration: what ONE sess.run([self.train_step, self.merged], feed_dict) executes (AR.py:300-301) ----
+ * noise (in-graph in the reference, AR.py:31-35,117-118) -> theta ~ q(theta), log q(theta) (AR.py:376-391) -> flow, ELBO
+ * terms, gradients (AR.py:44-110,168-187,228-229) incl. log prior(theta) - log q(theta) (AR.py:178-185) and the backward
+ * pass through the theta posterior -> gradient all-reduce over the time shards (if a communicator is set) ->
+ * tf.global_norm + clip_by_global_norm + Adamax over EVERY variable (AR.py:230-234; optimisers/adamax.py:42-58) -> the
+ * logged scalars (AR.py:207-224).  No host round trip, no library kernel in between; CUDA-graph capturable.
+ *   d_blob / d_grad / d_m / d_v : [nma_param_count(h) + nma_theta_flow_param_count(dtheta, nb)]  NMA variables followed by
+ *                                 the theta posterior's (creation order: per layer 4 x (kernel [in][out], bias))
+ *   d_scalars [8] : mean ELBO, scale*mean sde, mean log q(theta), scale*mean obs, scale*mean log q(path), global norm,
+ *                   rows with a non-finite term, draw counter after the step
+ *   d_theta_out   : [p][dtheta] the theta sample (may be NULL);  d_lf_out : [p][L_F] the final flow sample (may be NULL)
+ * nma_set_theta_flow with nb = 0 declares "no posterior": theta is the constant prior_mean in every row
+ * (lotka_volterra_partial_batch_fix_theta.py:190), the blob holds the NMA variables only.                              */
+typedef struct nma_step_opts {
+    int32_t objective;      /* NMA_OBJ_* */
+    float   path_target;
+    int32_t prior_on;       /* 1: + log prior(theta) - log q(theta) in the objective (AR.py:184-185); 0: pre-training heads */
+    int32_t obs_in_elbo;    /* 1: the observation term is part of the ELBO (0 for SV_dense.py:238-241) */
+    int32_t tf_mask_grad;   /* 1: TensorFlow's masked_dense semantics - masked kernel entries of the theta posterior get a
+                             *    gradient (it counts in tf.global_norm) and are reset by the kernel constraint after the update */
+    float   lr, beta1, beta2, eps, clip;   /* clip <= 0: no clipping (the pre-train optimisers, AR.py:201-202) */
+} nma_step_opts;
+/* theta posterior of AR.py:376-391 (see nma_theta_flow_fwd below for the layouts) and the diagonal Gaussian prior of
+ * AR.py:178-182 (host arrays of dtheta floats).  Device pointers are borrowed until nma_destroy. */
+int nma_set_theta_flow(nma_handle h, const float* d_masks, const int32_t* d_perms, int32_t nb, int32_t relu,
+                       float base_loc, float base_scale, const float* prior_mean, const float* prior_scale);
+int64_t nma_theta_flow_param_count(int32_t dtheta, int32_t nb);
+int nma_train_step(nma_handle h, float* d_blob, float* d_grad, float* d_m, float* d_v, const int64_t* d_idx, int32_t p,
+                   const nma_step_opts* opts, float* d_scalars, float* d_theta_out, float* d_lf_out, void* stream);
+/* seed and draw counter of the in-library noise (the counter lives on the device and advances once per call that draws) */
+int nma_set_seed(nma_handle h, uint64_t seed, uint64_t counter);
+int nma_get_counter(nma_handle h, uint64_t* counter_out);
+/* the normals a call draws for (seed, counter): stream_id 0 = eps [p*L0] (loc 0, scale 1), 1 = the theta posterior's base
+ * sample [p*dtheta] (loc, scale of the base distribution) */
+int nma_philox_normal(float* d_out, int64_t n, uint64_t seed, uint64_t counter, uint32_t stream_id, float loc, float scale,
+                      void* stream);
+/* borrowed views of what the last nma_train_step left in the workspace (any pointer argument may be NULL) */
+int nma_step_buffers(nma_handle h, float** d_eps, float** d_z0, float** d_theta, float** d_logq_theta, float** d_terms,
+                     float** d_row_elbo);
+
+/* ---- multi-GPU: the step's one collective, issued by the library on its own side stream ----
+ * nma_comm_unique_id + nma_comm_create build an NCCL communicator owned by the handle (every rank calls create with the id
+ * rank 0 made); nma_comm_init adopts an ncclComm_t the caller owns.  libnccl.so.2 is resolved at run time.  Destroy every
+ * CUDA graph that captured a step before nma_comm_destroy / nma_destroy. */
+int nma_comm_unique_id(char* out128);
+int nma_comm_create(nma_handle h, const char* id128, int32_t rank, int32_t world);
+int nma_comm_init(nma_handle h, void* nccl_comm);
+int nma_comm_destroy(nma_handle h);
+int nma_comm_world(nma_handle h);
+int nma_comm_wait(nma_handle h, void* stream);
+int nma_comm_allreduce(nma_handle h, float* d_buf, int64_t count, void* stream);
 
 /* The K-tap conv (AR.py:61-62) and its data gradient run on the tcgen05 tensor cores (3xTF32 split, fp32
  * accumulate) whenever the configuration allows it (flow_dims = 1, kernel_len <= 190); the FP32 SIMT kernels
@@ -147,8 +202,15 @@ int nma_adamax_step(float* d_params, const float* d_grads, float* d_m, float* d_
                     float lr, float beta1, float beta2, float eps, float clip,
                     float* d_norm_out, float* d_scratch, void* stream);
 
-/* A12 — AR(1) series simulation (AR_dat_gen.py:11-15) as an affine-map prefix scan.
- * x[0] = x0; x[i] = a*x[i-1] + b + c*z[i-1]  (i = 1..n);  d_z: n standard normals. d_x: n+1. */
+/* A12 — AR(1) series simulation (AR_dat_gen.py:11-15) as an affine-map prefix scan: single pass, decoupled look-back,
+ * warp-shuffle tile scan (16 B of HBM traffic per element).
+ * x[0] = x0; x[i] = a*x[i-1] + b + c*z[i-1]  (i = 1..n);  d_z: n standard normals. d_x: n+1.
+ * d_scratch: nma_scan_scratch_bytes(n) bytes, 16-byte aligned (cleared by the call).
+ * nma_scan_affine: the same scan over per-element maps, x[i] = A[i-1]*x[i-1] + D[i-1] (the Euler-Maruyama recursions of
+ * the stochastic-volatility generator, SV_dense.py:211-223, are of this form). */
+int64_t nma_scan_scratch_bytes(int64_t n);
+int nma_scan_affine(const double* d_A, const double* d_D, double* d_x, int64_t n, double x0, void* d_scratch,
+                    int64_t scratch_bytes, void* stream);
 int nma_scan_ar1(const double* d_z, double* d_x, int64_t n, double x0, double a, double b, double c,
                  void* d_scratch, int64_t scratch_bytes, void* stream);
 /* A13 — hold-fill + time-till-next-observation (AR_dat_gen.py:17-31) for every-`impute`-th sampling. */
@@ -161,14 +223,19 @@ int nma_time_till(const double* d_obs, int64_t n, int32_t impute, double* d_obs_
  * masks of one layer, concatenated (d*5 + 25 + 25 + 5*2d floats); d_perms [nb-1][d]; relu: 0 = elu template, 1 = relu.
  *   fwd: z0 [p][d] ~ N(base_loc, base_scale) -> theta [p][d], log q(theta) [p]
  *   bwd: dL/dtheta [p][d], dL/dlogq [p] (may be null) -> d_g_params (ACCUMULATED into), d_g_z0 [p][d] (may be null)
- * NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent; arithmetic checked on the CPU,
- * tests/test_theta_flow_formulas.py); nothing in the package calls them by default. */
+ * Checked against the host autograd module on the B200 (tests/test_gpu_lvr_theta.py) and, formula by formula, on the CPU
+ * (tests/test_theta_flow_formulas.py).  _bwd_ex: constant d/dlogq when d_g_logq is NULL; mask_grad = 1 gives TensorFlow's
+ * masked_dense gradient (non-zero at masked kernel entries), nma_theta_flow_constrain re-applies the masks after an update. */
 int nma_theta_flow_fwd(const float* d_params, const float* d_masks, const int32_t* d_perms, const float* d_z0,
                        int32_t p, int32_t d, int32_t nb, int32_t relu, float base_loc, float base_scale,
                        float* d_theta, float* d_logq, void* stream);
 int nma_theta_flow_bwd(const float* d_params, const float* d_masks, const int32_t* d_perms, const float* d_z0,
                        int32_t p, int32_t d, int32_t nb, int32_t relu, const float* d_g_theta, const float* d_g_logq,
                        float* d_g_params, float* d_g_z0, void* stream);
+int nma_theta_flow_bwd_ex(const float* d_params, const float* d_masks, const int32_t* d_perms, const float* d_z0,
+                          int32_t p, int32_t d, int32_t nb, int32_t relu, const float* d_g_theta, const float* d_g_logq,
+                          float g_logq_const, int32_t mask_grad, float* d_g_params, float* d_g_z0, void* stream);
+int nma_theta_flow_constrain(float* d_flow_params, const float* d_masks, int32_t d, int32_t nb, void* stream);
 
 /* A14 - rolling variances of the stochastic-volatility features (SV_dense.py:159-170):
  * d_var[i] = np.var(x[i : i+K]) for i in [0, n-K), on the float32 series, bit-exact with numpy's float32 np.var

@@ -21,7 +21,7 @@ from viforssms_b200.vi_ssm_models import LV_VI_SSM as VI_SSM
 NP_DTYPE = np.float32
 np.random.seed(1)
 
-__all__ = ["VI_SSM", "main", "generate", "NP_DTYPE"]
+__all__ = ["VI_SSM", "main", "generate", "simulate", "NP_DTYPE"]
 DAT = 'dat/our_files/fix_theta'
 
 
@@ -29,7 +29,9 @@ def softplus_np_(x):
     return np.log(1 + np.exp(x))
 
 
-def generate(n_series=4, T=30, dt=0.2, seed=1, dat_dir=DAT):
+def simulate(n_series=4, T=30, dt=0.2, seed=1):
+    """Euler-Maruyama of the script's SDE (:274-290), observations 1 + softplus(N(x, (theta3 x)^2) - 1); returns the
+    [2, n_series * 151] observation matrix of the dense layout."""
     rs = np.random.RandomState(seed)
     th = softplus_np_(np.array([-1.0, -6.0, -1.0, -2.0]))
     n = int(np.int32(T / dt)) + 1
@@ -45,6 +47,11 @@ def generate(n_series=4, T=30, dt=0.2, seed=1, dat_dir=DAT):
             cc = np.sqrt(th[1] * x[0] * x[1] + th[2] * x[1] - cb ** 2)
             z = rs.standard_normal(2)
             x = np.maximum(x + dt * a + np.sqrt(dt) * np.array([ca * z[0], cb * z[0] + cc * z[1]]), 1.5)
+    return obs
+
+
+def generate(n_series=4, T=30, dt=0.2, seed=1, dat_dir=DAT):
+    obs = simulate(n_series, T, dt, seed)
     os.makedirs(dat_dir, exist_ok=True)
     np.savetxt(os.path.join(dat_dir, 'LV_obs_partial_dense_test.txt'), obs)
     np.savetxt(os.path.join(dat_dir, 'LV_obs_binary_dense_test.txt'), np.ones_like(obs))

@@ -1,11 +1,6 @@
-"""GPU parity tests of code that was written after the round's GPU budget was spent and has NOT run on hardware yet.
-They are skipped unless NMA_UNVERIFIED=1 is set (the library refuses the model without it as well), so that a first
-failure cannot stop the verified suite; run them first thing with a GPU:
-
-    NMA_UNVERIFIED=1 python -m pytest tests/test_gpu_unverified.py -q -s
-
-  * NMA_MODEL_LVR: lotka_volterra_partial.py (learned theta) - the ELBO branch of k_elbo; its flow kernels are the
-    fixed-theta script's (verified).  Checked against the reference-classes fixture and the oracle.
+"""GPU parity tests of the learned-theta Lotka-Volterra model (lotka_volterra_partial.py, NMA_MODEL_LVR), the fixed-theta
+one against the reference-classes fixture, and the theta posterior on the device (nma_theta_flow_fwd / _bwd) against the
+host autograd module.  (First run on a B200 at the start of round 2: all green, profiles/r02_first_gpu_run.log.)
 """
 import os
 
@@ -16,8 +11,7 @@ import torch
 from oracle import nma_oracle as O
 from test_step_golden_models import GM, check_grads, lvr_inputs  # noqa: F401
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NMA_UNVERIFIED") != "1", reason="not yet run on hardware: set NMA_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 RTOL = 1e-4
 
 
@@ -104,21 +98,32 @@ def test_device_theta_flow_matches_the_host_module(d, nb, act):
     assert err < 1e-4
 
 
-def test_ar_stepper_with_device_theta_matches_the_host_theta_path():
-    """One training iteration with the theta posterior on the device against the same iteration with the host autograd
-    module: same seeds, same draws, so the gradient blobs and the updated parameters must agree."""
+@pytest.mark.parametrize("mask_grad", [False, True])
+def test_ar_stepper_train_step_matches_the_host_theta_path(mask_grad):
+    """One training iteration as ONE nma_train_step call (in-library noise, device theta posterior, clip + Adamax)
+    against the same iteration composed on the host (autograd theta posterior, nma_elbo_fwd_bwd, nma_adamax_step) with
+    the noise the library drew injected: gradient blobs and updated variables must agree, under both gradient semantics
+    of the masked kernels."""
     from viforssms_b200.trainer import ARStepper
     dev = torch.device("cuda", 0)
-    res = []
-    for device_theta in (False, True):
-        st = ARStepper(T=20000, rows=64, device=dev, seed=5, device_theta=device_theta)
-        st._step(st.idx_dev)
-        torch.cuda.synchronize()
-        res.append((st.grad.clone(), st.blob.clone()))
-        st.close()
-    g0, g1 = res[0][0], res[1][0]
+    a = ARStepper(T=20000, rows=64, device=dev, seed=5, device_theta=True, tf_mask_grad=mask_grad)
+    a._step(a.idx_dev)
+    torch.cuda.synchronize()
+    buf = a.eng.step_buffers(a.rows)
+    assert a.eng.draw_counter() == 1
+    b = ARStepper(T=20000, rows=64, device=dev, seed=5, device_theta=False, tf_mask_grad=mask_grad)
+    assert torch.equal(a.idx_dev, b.idx_dev)
+    elbo_b = b._step_host_theta(b.idx_dev, z0=buf["z0"], eps=buf["eps"])
+    torch.cuda.synchronize()
+    g0, g1 = b.grad, a.grad
     err = (g1 - g0).norm().item() / g0.norm().item()
     tail = (g1[-580:] - g0[-580:]).norm().item() / g0[-580:].norm().item()
-    print("device theta in the stepper: gradient rel err %.2e (flow variables alone %.2e)" % (err, tail))
+    print("nma_train_step vs host composition (mask_grad=%s): gradient rel err %.2e (flow variables alone %.2e)"
+          % (mask_grad, err, tail))
     assert err < 1e-5 and tail < 1e-4
-    assert torch.allclose(res[0][1], res[1][1], rtol=0, atol=1e-5)
+    masked = (a.flow.mask_flat() == 0).to(dev)
+    assert (g1[-580:][masked].abs().max().item() > 0) == mask_grad
+    assert torch.allclose(a.blob, b.blob, rtol=0, atol=1e-5)
+    assert torch.all(a.blob[-580:][masked] == 0)                   # the kernel constraint
+    assert abs(a.scalars[0].item() - elbo_b.item()) <= 1e-4 * abs(elbo_b.item())
+    a.close(); b.close()

@@ -1,7 +1,8 @@
 """The device theta-posterior kernels (viforssms_b200/csrc/nma_theta_flow.cu: k_theta_flow_fwd / k_theta_flow_bwd),
-transliterated to float64 numpy statement by statement, against the host autograd module they are to replace
-(viforssms_b200/theta_flow.py).  The kernels were written after the round's GPU budget was spent; this is their CPU
-pre-flight check (parameter layout, masks, permutation direction, clip-with-gradient, every hand-derived gradient)."""
+transliterated to float64 numpy statement by statement, against the host autograd module (viforssms_b200/theta_flow.py):
+parameter layout, masks, permutation direction, clip-with-gradient, every hand-derived gradient - under both gradient
+semantics of the masked kernels (mask multiplied in the forward pass / TensorFlow's masked_dense, where masked entries
+receive a gradient that the kernel constraint wipes after the update)."""
 import numpy as np
 import pytest
 import torch
@@ -50,7 +51,7 @@ def kernel_fwd(params, masks, perms, z0, d, nb, relu, loc, scale):
     return z, lp
 
 
-def kernel_bwd(params, masks, perms, z0, d, nb, relu, g_theta, g_logq):
+def kernel_bwd(params, masks, perms, z0, d, nb, relu, g_theta, g_logq, mask_grad=False):
     sizes, LP = _layout(d)
     G = np.zeros_like(params)
     zin, z = [], z0.copy()
@@ -90,16 +91,17 @@ def kernel_bwd(params, masks, perms, z0, d, nb, relu, g_theta, g_logq):
             W = P[wo:wo + a * b].reshape(a, b)
             go = g if i == 3 else g * _dact(hs[i + 1], relu)
             G[k * LP + bo:k * LP + bo + b] += go
-            G[k * LP + wo:k * LP + wo + a * b] += (np.outer(hs[i], go) * masks[i]).reshape(-1)
+            G[k * LP + wo:k * LP + wo + a * b] += (np.outer(hs[i], go) * (1.0 if mask_grad else masks[i])).reshape(-1)
             g = (W * masks[i]) @ go
         gz = gz + g
     return G, gz
 
 
+@pytest.mark.parametrize("mask_grad", [False, True])
 @pytest.mark.parametrize("d,nb,act", [(3, 5, "elu"), (5, 4, "elu"), (4, 4, "relu")])
-def test_theta_flow_kernel_formulas_against_the_host_module(d, nb, act):
+def test_theta_flow_kernel_formulas_against_the_host_module(d, nb, act, mask_grad):
     np.random.seed(7)
-    flow = ThetaFlow(d, nb, base_loc=1.5, base_scale=0.5, activation=act)
+    flow = ThetaFlow(d, nb, base_loc=1.5, base_scale=0.5, activation=act, tf_mask_grad=mask_grad)
     g = torch.Generator().manual_seed(3)
     flat = flow.init_values(g).double()
     flat = flat + 0.3 * torch.randn(flat.shape, generator=g, dtype=torch.float64) * (flat != 0)   # keep masked entries zero
@@ -132,9 +134,15 @@ def test_theta_flow_kernel_formulas_against_the_host_module(d, nb, act):
         assert np.allclose(th, theta[r].detach().numpy(), rtol=1e-12, atol=1e-12)
         assert abs(l - lp[r].item()) <= 1e-12 * max(1.0, abs(lp[r].item()))
         Gr, gz = kernel_bwd(params, masks, perms, z0[r].detach().numpy(), d, nb, act == "relu",
-                            g_theta[r].numpy(), g_logq[r].item())
+                            g_theta[r].numpy(), g_logq[r].item(), mask_grad)
         G += Gr
         # z0 enters log q through the base density as well; the kernel returns only the flow part
         base = -(z0[r].detach().numpy() - 1.5) / 0.25 * g_logq[r].item()
         assert np.allclose(gz + base, gz0[r].numpy(), rtol=1e-9, atol=1e-10)
     assert np.allclose(G, gflat.numpy(), rtol=1e-9, atol=1e-10 * np.abs(gflat.numpy()).max())
+    masked = (flow.mask_flat().numpy() == 0)
+    assert masked.any() and (np.abs(G[masked]).max() > 0) == mask_grad      # the semantics differ exactly there
+    # the kernel constraint: re-masking leaves the (already masked) variables untouched
+    before = flat.detach().clone()
+    flow.constrain()
+    assert torch.equal(flat.detach(), before)

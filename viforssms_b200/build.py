@@ -9,7 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnma_b200.so")
-SOURCES = ["nma_api.cu", "nma_fwd.cu", "nma_tc_conv.cu", "nma_tc_conv2.cu", "nma_tc_feat.cu", "nma_elbo.cu", "nma_bwd.cu", "nma_adamax.cu", "nma_scan.cu", "nma_lv.cu", "nma_theta_flow.cu"]
+SOURCES = ["nma_api.cu", "nma_fwd.cu", "nma_tc_conv.cu", "nma_tc_conv2.cu", "nma_tc_feat.cu", "nma_elbo.cu", "nma_bwd.cu", "nma_adamax.cu", "nma_scan.cu", "nma_lv.cu", "nma_theta_flow.cu",
+           "nma_step.cu", "nma_comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-DNMA_BUILD",
@@ -50,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with ThreadPoolExecutor(max_workers=min(6, len(jobs))) as ex:
             logs = list(ex.map(run, jobs))
     if jobs or force or _stale(LIB, objs):
-        run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"])
     with open(os.path.join(objdir, "ptxas.log"), "a" if not force else "w") as f:
         for lg in logs:
             f.write(lg)

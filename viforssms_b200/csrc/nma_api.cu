@@ -176,6 +176,11 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
             off[i].wtc_feat = reserve((int64_t)10 * TC_CCH * 128 * 4);
         }
     }
+    // whole-iteration entry point (nma_step.cu)
+    struct { int64_t eps, z0, theta, logq, gth, terms, relbo, flags, norm, counter; } so;
+    so.eps = reserve(p * h->L0); so.z0 = reserve(p * 8); so.theta = reserve(p * 8); so.logq = reserve(p);
+    so.gth = reserve(p * 8); so.terms = reserve(p * 4); so.relbo = reserve(p); so.flags = reserve(p);
+    so.norm = reserve(1024 + 64); so.counter = reserve(4);
     h->arena_bytes = total;
     cudaError_t e = cudaMalloc(&h->arena, (size_t)total);
     if (e != cudaSuccess) {
@@ -208,6 +213,12 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
             w.wtc_feat = (float*)(base + off[i].wtc_feat);
         }
     }
+    h->step.eps = (float*)(base + so.eps); h->step.z0 = (float*)(base + so.z0); h->step.theta = (float*)(base + so.theta);
+    h->step.logq_theta = (float*)(base + so.logq); h->step.g_theta = (float*)(base + so.gth);
+    h->step.terms = (float*)(base + so.terms); h->step.row_elbo = (float*)(base + so.relbo);
+    h->step.flags = (uint32_t*)(base + so.flags); h->step.norm = (float*)(base + so.norm);
+    h->step.counter = (unsigned long long*)(base + so.counter);
+    h->step.seed = 1;
     {
         const char* envb = getenv("NMA_TC_BF16");
         h->bf16_ok = bf16_path_ok(h);
@@ -219,6 +230,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
 
 extern "C" int nma_destroy(nma_handle h) {
     if (!h) return 0;
+    comm_release(h);
     if (h->arena) cudaFree(h->arena);
     delete h;
     return 0;
@@ -329,15 +341,19 @@ static int forward_all(nma_handle_s* h, const float* params, const float* eps, c
     return 0;
 }
 
-extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
-                                const int64_t* d_idx, int32_t p, int32_t objective, float path_target, float* d_terms,
-                                float* d_lf, float* d_grad_params, float* d_grad_theta, uint32_t* d_flags,
-                                void* stream) {
-    if (check_step_args(h, p, d_params, d_eps, d_theta, d_idx)) return -1;
-    if (check_model_built(h)) return -3;
-    if (!d_terms || !d_grad_params || !d_grad_theta) { nma_set_error("null output pointer"); return -1; }
-    if (objective < 0 || objective > 2) { nma_set_error("unknown objective %d", objective); return -1; }
-    cudaStream_t st = (cudaStream_t)stream;
+// section of the flat gradient that belongs to flow i (TF creation order: everything of flow i is contiguous)
+static void flow_section(const nma_handle_s* h, int i, int64_t* off, int64_t* count) {
+    *off = h->po[i].featw[0];
+    *count = (i + 1 < h->cfg.F ? h->po[i + 1].featw[0] : h->n_params) - *off;
+}
+
+// forward + ELBO + backward on the handle's workspace.  With a communicator (nma_comm.cu) and per_flow_collective, the
+// all-reduce of flow i's gradient section is issued on the side stream as soon as that flow's backward kernels are
+// queued, so it runs under the backward pass of the earlier flows.
+int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d_eps, const float* d_theta,
+                          const int64_t* d_idx, int p, int objective, float path_target, float* d_terms, float* d_lf,
+                          float* d_grad_params, float* d_grad_theta, uint32_t* d_flags, bool per_flow_collective,
+                          cudaStream_t st) {
     int rc;
     NMA_CHECK_CUDA(cudaMemsetAsync(d_grad_params, 0, (size_t)h->n_params * 4, st));
     if ((rc = forward_all(h, d_params, d_eps, d_theta, d_idx, p, true, st))) return rc;
@@ -351,16 +367,45 @@ extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float
             if ((rc = launch_lv_conv_wgrad(h, i, p, d_grad_params, st))) return rc;
             if ((rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
             if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
-            continue;
+        } else {
+            if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, st) : launch_conv_dgrad(h, i, p, st)))) return rc;
+            if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, st)
+                       : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, st)
+                                   : launch_conv_wgrad(h, i, p, d_grad_params, st))))
+                return rc;
+            if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
         }
-        if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, st) : launch_conv_dgrad(h, i, p, st)))) return rc;
-        if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, st)
-                   : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, st)
-                               : launch_conv_wgrad(h, i, p, d_grad_params, st))))
-            return rc;
-        if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
+        // theta-bias MLP of this flow (AR.py:63-68): its gradient completes the flow's section of the blob
+        if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, i, st))) return rc;
+        if (per_flow_collective && h->comm.comm) {
+            int64_t off, count;
+            flow_section(h, i, &off, &count);
+            if ((rc = comm_allreduce_after(h, d_grad_params + off, count, i, st))) return rc;
+        }
     }
-    if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, st))) return rc;
+    return 0;
+}
+
+extern "C" int nma_elbo_fwd_bwd(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
+                                const int64_t* d_idx, int32_t p, int32_t objective, float path_target, float* d_terms,
+                                float* d_lf, float* d_grad_params, float* d_grad_theta, uint32_t* d_flags,
+                                void* stream) {
+    if (check_step_args(h, p, d_params, d_params, d_theta, d_idx)) return -1;
+    if (check_model_built(h)) return -3;
+    if (!d_terms || !d_grad_params || !d_grad_theta) { nma_set_error("null output pointer"); return -1; }
+    if (objective < 0 || objective > 2) { nma_set_error("unknown objective %d", objective); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const bool draw = (d_eps == nullptr);      // eps == NULL: the library draws the base noise (Philox4x32-10, nma_step.cu)
+    if (draw) {
+        if ((rc = launch_philox_normal(h->step.eps, (int64_t)p * h->L0, h->step.seed, h->step.counter, 0, 0u, 0.f, 1.f, st)))
+            return rc;
+        d_eps = h->step.eps;
+    }
+    if ((rc = step_forward_backward(h, d_params, d_eps, d_theta, d_idx, p, objective, path_target, d_terms, d_lf,
+                                    d_grad_params, d_grad_theta, d_flags, true, st)))
+        return rc;
+    if (draw && (rc = launch_counter_bump(h, st))) return rc;
     return 0;
 }
 
@@ -390,11 +435,20 @@ extern "C" int64_t nma_launch_count(void) { return g_launches; }
 
 extern "C" int nma_forward_paths(nma_handle h, const float* d_params, const float* d_eps, const float* d_theta,
                                  const int64_t* d_idx, int32_t p, float* d_terms, float* d_lf, void* stream) {
-    if (check_step_args(h, p, d_params, d_eps, d_theta, d_idx)) return -1;
+    if (check_step_args(h, p, d_params, d_params, d_theta, d_idx)) return -1;
     if (check_model_built(h)) return -3;
     if (!d_terms) { nma_set_error("null output pointer"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    const bool draw = (d_eps == nullptr);
+    if (draw) {
+        if ((rc = launch_philox_normal(h->step.eps, (int64_t)p * h->L0, h->step.seed, h->step.counter, 0, 0u, 0.f, 1.f, st)))
+            return rc;
+        d_eps = h->step.eps;
+    }
     if ((rc = forward_all(h, d_params, d_eps, d_theta, d_idx, p, false, st))) return rc;
-    return launch_elbo(h, d_theta, d_eps, d_idx, p, NMA_OBJ_ELBO, 0.f, d_terms, d_lf, nullptr, nullptr, false, st);
+    if ((rc = launch_elbo(h, d_theta, d_eps, d_idx, p, NMA_OBJ_ELBO, 0.f, d_terms, d_lf, nullptr, nullptr, false, st)))
+        return rc;
+    if (draw && (rc = launch_counter_bump(h, st))) return rc;
+    return 0;
 }

@@ -778,11 +778,11 @@ struct ThetaBwdArgs {
     float* gb[NMA_MAX_FLOWS][3];
     const float* theta;
     float* grad_theta;                  // [p][dth], accumulated with atomics (already holds the ELBO part)
-    int p, dth, rows_per_cta;
+    int p, dth, rows_per_cta, flow0;
 };
 
 __global__ void __launch_bounds__(BWD_THREADS) k_theta_bwd(ThetaBwdArgs a) {
-    const int i = blockIdx.y, tid = threadIdx.x;
+    const int i = a.flow0 + blockIdx.y, tid = threadIdx.x;
     __shared__ float W2[NMA_C * NMA_C], W3[NMA_C * NMA_C], W1[8 * NMA_C];
     __shared__ float d3[NMA_C], d2[NMA_C], d1[NMA_C], t1[NMA_C], t2[NMA_C], th[8];
     for (int t = tid; t < NMA_C * NMA_C; t += blockDim.x) { W2[t] = a.w[i][1][t]; W3[t] = a.w[i][2][t]; }
@@ -848,8 +848,9 @@ __global__ void __launch_bounds__(BWD_THREADS) k_theta_bwd(ThetaBwdArgs a) {
 }
 
 int launch_theta_bwd(nma_handle_s* h, const float* params, const float* theta, int p, float* gp, float* grad_theta,
-                     cudaStream_t st) {
+                     int flow, cudaStream_t st) {
     ThetaBwdArgs a;
+    a.flow0 = flow < 0 ? 0 : flow;
     for (int i = 0; i < h->cfg.F; ++i) {
         for (int l = 0; l < 3; ++l) {
             a.w[i][l] = params + h->po[i].thw[l];
@@ -864,7 +865,7 @@ int launch_theta_bwd(nma_handle_s* h, const float* params, const float* theta, i
     if (ctas > p) ctas = p;
     a.rows_per_cta = (p + ctas - 1) / ctas;
     ctas = (p + a.rows_per_cta - 1) / a.rows_per_cta;
-    k_theta_bwd<<<dim3(ctas, h->cfg.F), BWD_THREADS, 0, st>>>(a);
+    k_theta_bwd<<<dim3(ctas, flow < 0 ? h->cfg.F : 1), BWD_THREADS, 0, st>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;

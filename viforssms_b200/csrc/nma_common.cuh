@@ -55,6 +55,39 @@ struct FlowWs {
     long long tin_Q, dat_Q;
 };
 
+// nma_train_step (nma_step.cu): the theta posterior registered with nma_set_theta_flow and the per-row buffers of the
+// part of sess.run(train_step) that surrounds nma_elbo_fwd_bwd (AR.py:117-118,178-185,226-234)
+struct StepWs {
+    float* eps;              // [p][L0]      base noise drawn in the library (eps == NULL)
+    float* z0;               // [p][8]       base sample of the theta posterior
+    float* theta;            // [p][dtheta]
+    float* logq_theta;       // [p]
+    float* g_theta;          // [p][dtheta]  d objective / d theta (ELBO part + prior part)
+    float* terms;            // [p][4]
+    float* row_elbo;         // [p]
+    uint32_t* flags;         // [p]
+    float* norm;             // [1] global norm, [1..1024] partial sums of k_sumsq
+    unsigned long long* counter;   // [2]  device-resident draw counter (Philox offset), bumped by the last kernel of a call
+    unsigned long long seed;
+    // theta posterior (borrowed device pointers)
+    const float* tf_masks;
+    const int32_t* tf_perms;
+    int tf_nb, tf_relu, tf_set;
+    float tf_base_loc, tf_base_scale;
+    float prior_mean[8], prior_scale[8];
+};
+
+// NCCL communicator used for the gradient all-reduce (nma_comm.cu); the library resolves libnccl.so.2 at run time
+struct CommState {
+    void* comm;              // ncclComm_t
+    int owned;               // created by nma_comm_create (destroyed by nma_comm_destroy / nma_destroy)
+    int world, rank;
+    cudaStream_t side;       // the collective's stream
+    cudaEvent_t ev_ready[NMA_MAX_FLOWS + 2];   // a gradient section is complete on the compute stream
+    cudaEvent_t ev_done;     // all collectives of the step have been issued and finished on `side`
+    int pending;             // collectives issued since the last join
+};
+
 struct nma_handle_s {
     nma_config cfg;
     int L0, S, Cf_in, feat_off, KP;
@@ -85,6 +118,10 @@ struct nma_handle_s {
     // conv has 1 + LW input channels.  For the other models conv_cin = 51 and feat_out[i] = 50.
     int is_lv, conv_cin, LW, LWP;
     int feat_out[NMA_MAX_FLOWS];
+    // ---- whole-iteration entry point (nma_step.cu: nma_train_step) ----
+    StepWs step;
+    // ---- gradient all-reduce inside the library (nma_comm.cu) ----
+    CommState comm;
 };
 
 // device-side copy of what kernels need about the series and the channel table
@@ -141,7 +178,20 @@ int launch_conv_dgrad(nma_handle_s* h, int flow, int p, cudaStream_t st);
 int launch_conv_wgrad(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
 int launch_feat_bwd(nma_handle_s* h, int flow, const float* params, int p, float* grad_params, cudaStream_t st);
 int launch_theta_bwd(nma_handle_s* h, const float* params, const float* theta, int p, float* grad_params,
-                     float* grad_theta, cudaStream_t st);
+                     float* grad_theta, int flow, cudaStream_t st);   // flow < 0: every flow in one launch
+// nma_comm.cu: all-reduce(sum) of grad[off, off+count) on the side stream once `st` has reached this point; no-op without
+// a communicator.  comm_join makes `st` wait for everything issued so far.
+int comm_allreduce_after(nma_handle_s* h, float* d_buf, int64_t count, int slot, cudaStream_t st);
+int comm_join(nma_handle_s* h, cudaStream_t st);
+void comm_release(nma_handle_s* h);
+// nma_step.cu
+int launch_philox_normal(float* d_out, int64_t n, unsigned long long seed, const unsigned long long* d_counter,
+                         unsigned long long counter_host, uint32_t stream_id, float loc, float scale, cudaStream_t st);
+int launch_counter_bump(nma_handle_s* h, cudaStream_t st);
+int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d_eps, const float* d_theta,
+                          const int64_t* d_idx, int p, int objective, float path_target, float* d_terms, float* d_lf,
+                          float* d_grad_params, float* d_grad_theta, uint32_t* d_flags, bool per_flow_collective,
+                          cudaStream_t st);
 // Lotka-Volterra instances (nma_lv.cu)
 int launch_lv_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
                        cudaStream_t st);

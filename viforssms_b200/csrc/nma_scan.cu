@@ -1,12 +1,25 @@
 // A12/A13: data-side scans for 10^8-step synthetic series (AR_dat_gen.py:11-31), float64 like the reference.
-//   nma_scan_ar1  : x[i] = a x[i-1] + b + c z[i-1] as a prefix scan over affine maps (compose-then-apply)
-//   nma_time_till : hold-fill, observation indicator and count-down to the next observation
-// Both are HBM-bound streaming kernels.
+//   nma_scan_ar1    : x[i] = a x[i-1] + b + c z[i-1] as a prefix scan over affine maps
+//   nma_scan_affine : x[i] = A[i-1] x[i-1] + D[i-1] (per-element maps: the stochastic-volatility generator, SV_dense.py:211-223)
+//   nma_time_till   : hold-fill, observation indicator and count-down to the next observation
+// All HBM-bound streaming kernels.
+//
+// The scan is SINGLE-PASS with decoupled look-back (Merrill & Garland 2016): every tile of 4096 elements is read once
+// and written once - 16 B per element for the AR(1) form (8 B noise in, 8 B state out), which is the algorithmic
+// minimum - instead of the reduce / carry / apply passes (24 B per element and a serial carry over 24 k tile aggregates)
+// this file used to have.  Tiles take their index from an atomic ticket (so a tile's predecessors are always resident
+// or finished), scan themselves with warp shuffles (thread composite -> warp inclusive scan -> 8 warp aggregates), publish
+// their aggregate, and warp 0 walks back over up to 32 predecessor descriptors at a time until it meets one that already
+// carries an inclusive prefix.  An affine map is 16 bytes, so a descriptor is (flag, A, D) with the payload written
+// before the flag and fenced (release) / read after it (acquire).  Composition is associative but not commutative:
+// every reduction below keeps the older map on the inside.
 #include "nma_common.cuh"
 
 #define SC_THREADS 256
 #define SC_ITEMS 16
 #define SC_CHUNK (SC_THREADS * SC_ITEMS)
+#define SC_PADDED (SC_CHUNK + SC_CHUNK / 16)
+#define SC_PAD(i) ((i) + ((i) >> 4))            // one pad slot per 16 doubles: a thread's 16 items at stride 17 (no bank conflicts)
 
 struct Aff { double A, D; };   // x -> A x + D
 __device__ __forceinline__ Aff compose(const Aff& first, const Aff& second) {   // apply `first`, then `second`
@@ -15,92 +28,197 @@ __device__ __forceinline__ Aff compose(const Aff& first, const Aff& second) {   
     r.D = fma(second.A, first.D, second.D);
     return r;
 }
-
-// block-wide inclusive scan of per-thread composites (Hillis-Steele over shared memory)
-__device__ __forceinline__ Aff block_scan(Aff v, Aff* sh) {
-    const int t = threadIdx.x;
-    sh[t] = v;
-    __syncthreads();
-    for (int o = 1; o < SC_THREADS; o <<= 1) {
-        Aff prev = sh[t];
-        if (t >= o) prev = compose(sh[t - o], sh[t]);
-        __syncthreads();
-        sh[t] = prev;
-        __syncthreads();
-    }
-    return sh[t];
+__device__ __forceinline__ Aff aff_shfl_up(const Aff& v, int o) {
+    Aff r; r.A = __shfl_up_sync(0xffffffffu, v.A, o); r.D = __shfl_up_sync(0xffffffffu, v.D, o); return r;
+}
+__device__ __forceinline__ Aff aff_shfl_down(const Aff& v, int o) {
+    Aff r; r.A = __shfl_down_sync(0xffffffffu, v.A, o); r.D = __shfl_down_sync(0xffffffffu, v.D, o); return r;
 }
 
-__device__ __forceinline__ Aff thread_composite(const double* __restrict__ z, int64_t n, int64_t base, double a, double b,
-                                                double c) {
-    Aff acc; acc.A = 1.0; acc.D = 0.0;
+// tile descriptor: flag 0 = not ready, 1 = aggregate of this tile alone, 2 = inclusive prefix of everything up to it
+struct TileDesc { int flag; int pad; Aff agg; Aff incl; };
+struct ScanScratch { unsigned int ticket; unsigned int pad[3]; };     // followed by TileDesc[ntiles]
+
+struct ScanArgs {
+    const double* z;        // AR(1) form: noise; affine form: D
+    const double* Aarr;     // affine form: per-element multiplier (null: the constant a)
+    double* x;              // [n + 1]
+    long long n;
+    double x0, a, b, c;
+    ScanScratch* scratch;
+};
+
+template <bool GENERIC>
+__global__ void __launch_bounds__(SC_THREADS) k_scan_lookback(ScanArgs g) {
+    extern __shared__ double sc_smem[];                 // [SC_PADDED] D (then the outputs); generic form: + [SC_PADDED] A
+    double* sD = sc_smem;
+    double* sA = sc_smem + SC_PADDED;
+    __shared__ Aff s_warp[SC_THREADS / 32];
+    __shared__ Aff s_tile_excl;
+    __shared__ unsigned int s_tile;
+    TileDesc* desc = reinterpret_cast<TileDesc*>(g.scratch + 1);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(&g.scratch->ticket, 1u);
+    __syncthreads();
+    const long long tile = s_tile;
+    const long long base = tile * SC_CHUNK;
+    // ---- coalesced load of the tile (element i of the tile -> padded slot) ----
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; ++k) {
-        const int64_t i = base + k;
-        if (i < n) { Aff e; e.A = a; e.D = fma(c, z[i], b); acc = compose(acc, e); }
+        const int i = k * SC_THREADS + t;
+        const long long gi = base + i;
+        double d = 0.0, a = 1.0;                       // identity map beyond the end
+        if (gi < g.n) {
+            if (GENERIC) { d = __ldg(g.z + gi); a = __ldg(g.Aarr + gi); }
+            else { d = fma(g.c, __ldg(g.z + gi), g.b); a = g.a; }
+        }
+        sD[SC_PAD(i)] = d;
+        if (GENERIC) sA[SC_PAD(i)] = a;
     }
-    return acc;
-}
-
-__global__ void __launch_bounds__(SC_THREADS) k_scan_reduce(const double* __restrict__ z, int64_t n, double a, double b,
-                                                            double c, Aff* __restrict__ agg) {
-    __shared__ Aff sh[SC_THREADS];
-    const int64_t base = (int64_t)blockIdx.x * SC_CHUNK + (int64_t)threadIdx.x * SC_ITEMS;
-    Aff v = thread_composite(z, n, base, a, b, c);
-    v = block_scan(v, sh);
-    if (threadIdx.x == SC_THREADS - 1) agg[blockIdx.x] = v;
-}
-
-// sequential carry over the (n / 4096) block aggregates: start value of every block
-__global__ void k_scan_carry(Aff* __restrict__ agg, int64_t nblocks, double x0) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    double x = x0;
-    for (int64_t b = 0; b < nblocks; ++b) {
-        const Aff g = agg[b];
-        agg[b].D = x;                 // reuse the slot: D <- value entering block b
-        x = fma(g.A, x, g.D);
-    }
-}
-
-__global__ void __launch_bounds__(SC_THREADS) k_scan_apply(const double* __restrict__ z, double* __restrict__ x, int64_t n,
-                                                           double x0, double a, double b, double c,
-                                                           const Aff* __restrict__ agg) {
-    __shared__ Aff sh[SC_THREADS];
-    const int64_t base = (int64_t)blockIdx.x * SC_CHUNK + (int64_t)threadIdx.x * SC_ITEMS;
-    Aff v = thread_composite(z, n, base, a, b, c);
-    Aff inc = block_scan(v, sh);
-    // exclusive prefix of this thread = inclusive of the previous thread
     __syncthreads();
-    sh[threadIdx.x] = inc;
-    __syncthreads();
-    double xin = agg[blockIdx.x].D;
-    if (threadIdx.x > 0) { const Aff pre = sh[threadIdx.x - 1]; xin = fma(pre.A, xin, pre.D); }
-    if (blockIdx.x == 0 && threadIdx.x == 0) x[0] = x0;
+    // ---- thread composite over its 16 consecutive elements ----
+    double eD[SC_ITEMS], eA[SC_ITEMS];
+    Aff mine; mine.A = 1.0; mine.D = 0.0;
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; ++k) {
-        const int64_t i = base + k;
-        if (i < n) { xin = fma(a, xin, fma(c, z[i], b)); x[i + 1] = xin; }
+        const int i = t * SC_ITEMS + k;
+        eD[k] = sD[SC_PAD(i)];
+        eA[k] = GENERIC ? sA[SC_PAD(i)] : ((base + i < g.n) ? g.a : 1.0);
+        mine.D = fma(eA[k], mine.D, eD[k]);
+        mine.A = eA[k] * mine.A;
     }
+    // ---- warp inclusive scan (shuffles), warp aggregates, scan of the 8 aggregates ----
+    Aff inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Aff prev = aff_shfl_up(inc, o);
+        if (lane >= o) inc = compose(prev, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    Aff warp_excl; warp_excl.A = 1.0; warp_excl.D = 0.0;
+    Aff tile_agg; tile_agg.A = 1.0; tile_agg.D = 0.0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; ++w) {
+        if (w == warp) warp_excl = tile_agg;
+        tile_agg = compose(tile_agg, s_warp[w]);
+    }
+    // exclusive prefix of this thread within the tile
+    Aff up = aff_shfl_up(inc, 1);
+    if (lane == 0) { up.A = 1.0; up.D = 0.0; }
+    const Aff thr_excl = compose(warp_excl, up);
+    // ---- publish the aggregate, look back (warp 0) ----
+    if (warp == 0) {
+        TileDesc* me = desc + tile;
+        if (tile == 0) {
+            if (lane == 0) {
+                me->incl = tile_agg;
+                __threadfence();
+                *reinterpret_cast<volatile int*>(&me->flag) = 2;
+                s_tile_excl.A = 1.0; s_tile_excl.D = 0.0;
+            }
+        } else {
+            if (lane == 0) {
+                me->agg = tile_agg;
+                __threadfence();
+                *reinterpret_cast<volatile int*>(&me->flag) = 1;
+            }
+            Aff excl; excl.A = 1.0; excl.D = 0.0;       // composite of the predecessors gathered so far (newer side)
+            long long look = tile - 1;                  // newest tile of the current window
+            while (true) {
+                const long long j = look - lane;        // lane l looks at the l-th predecessor of the window
+                int flag = 2;
+                Aff v; v.A = 1.0; v.D = 0.0;
+                if (j >= 0) {
+                    const volatile int* fp = reinterpret_cast<const volatile int*>(&desc[j].flag);
+                    do { flag = *fp; } while (flag == 0);
+                    __threadfence();
+                    const volatile double* src = reinterpret_cast<const volatile double*>(flag == 2 ? &desc[j].incl : &desc[j].agg);
+                    v.A = src[0]; v.D = src[1];
+                }
+                // first lane (newest-to-oldest) that carries an inclusive prefix (lanes past tile 0 count as inclusive identity)
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2);
+                const int cut = incl_mask ? (__ffs(incl_mask) - 1) : 31;      // lanes 0..cut take part
+                if (lane > cut) { v.A = 1.0; v.D = 0.0; }
+                // ordered reduction: lane l <- compose(older lanes ..., lane l); older = higher lane
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const Aff older = aff_shfl_down(v, o);
+                    if (lane + o < 32) v = compose(older, v);
+                }
+                const Aff window = {__shfl_sync(0xffffffffu, v.A, 0), __shfl_sync(0xffffffffu, v.D, 0)};
+                excl = compose(window, excl);
+                if (incl_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                me->incl = compose(excl, tile_agg);
+                __threadfence();
+                *reinterpret_cast<volatile int*>(&me->flag) = 2;
+                s_tile_excl = excl;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- apply: value entering this thread's first element, then the recursion itself ----
+    const Aff pre = compose(s_tile_excl, thr_excl);
+    double xin = fma(pre.A, g.x0, pre.D);
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        xin = fma(eA[k], xin, eD[k]);
+        sD[SC_PAD(t * SC_ITEMS + k)] = xin;
+    }
+    __syncthreads();
+    if (tile == 0 && t == 0) g.x[0] = g.x0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const int i = k * SC_THREADS + t;
+        const long long gi = base + i;
+        if (gi < g.n) g.x[gi + 1] = sD[SC_PAD(i)];
+    }
+}
+
+static int64_t scan_scratch_bytes(int64_t n) {
+    const int64_t ntiles = (n + SC_CHUNK - 1) / SC_CHUNK;
+    return (int64_t)sizeof(ScanScratch) + ntiles * (int64_t)sizeof(TileDesc);
+}
+extern "C" int64_t nma_scan_scratch_bytes(int64_t n) { return n < 1 ? 0 : scan_scratch_bytes(n); }
+
+static int scan_launch(const double* d_z, const double* d_A, double* d_x, int64_t n, double x0, double a, double b, double c,
+                       void* d_scratch, int64_t scratch_bytes, cudaStream_t st) {
+    const int64_t need = scan_scratch_bytes(n);
+    if (scratch_bytes < need) { nma_set_error("nma_scan: scratch needs %lld bytes (nma_scan_scratch_bytes)", (long long)need); return -1; }
+    if (((uintptr_t)d_scratch & 15) != 0) { nma_set_error("nma_scan: scratch must be 16-byte aligned"); return -1; }
+    const int64_t ntiles = (n + SC_CHUNK - 1) / SC_CHUNK;
+    NMA_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, (size_t)need, st));      // ticket and every flag back to 0
+    ScanArgs g;
+    g.z = d_z; g.Aarr = d_A; g.x = d_x; g.n = n; g.x0 = x0; g.a = a; g.b = b; g.c = c; g.scratch = (ScanScratch*)d_scratch;
+    const size_t smem1 = (size_t)SC_PADDED * sizeof(double);
+    if (d_A) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            NMA_CHECK_CUDA(cudaFuncSetAttribute(k_scan_lookback<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem1)));
+            attr_set = true;
+        }
+        k_scan_lookback<true><<<(unsigned)ntiles, SC_THREADS, 2 * smem1, st>>>(g);
+    } else {
+        k_scan_lookback<false><<<(unsigned)ntiles, SC_THREADS, smem1, st>>>(g);
+    }
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int nma_scan_ar1(const double* d_z, double* d_x, int64_t n, double x0, double a, double b, double c,
                             void* d_scratch, int64_t scratch_bytes, void* stream) {
     if (!d_z || !d_x || n < 1 || !d_scratch) { nma_set_error("nma_scan_ar1: bad argument"); return -1; }
-    const int64_t nblocks = (n + SC_CHUNK - 1) / SC_CHUNK;
-    if (scratch_bytes < nblocks * (int64_t)sizeof(Aff)) {
-        nma_set_error("nma_scan_ar1: scratch needs %lld bytes", (long long)(nblocks * sizeof(Aff)));
-        return -1;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    Aff* agg = (Aff*)d_scratch;
-    k_scan_reduce<<<(unsigned)nblocks, SC_THREADS, 0, st>>>(d_z, n, a, b, c, agg);
-    nma_count_launch(1);
-    k_scan_carry<<<1, 32, 0, st>>>(agg, nblocks, x0);
-    nma_count_launch(1);
-    k_scan_apply<<<(unsigned)nblocks, SC_THREADS, 0, st>>>(d_z, d_x, n, x0, a, b, c, agg);
-    nma_count_launch(1);
-    NMA_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    return scan_launch(d_z, nullptr, d_x, n, x0, a, b, c, d_scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int nma_scan_affine(const double* d_A, const double* d_D, double* d_x, int64_t n, double x0, void* d_scratch,
+                               int64_t scratch_bytes, void* stream) {
+    if (!d_A || !d_D || !d_x || n < 1 || !d_scratch) { nma_set_error("nma_scan_affine: bad argument"); return -1; }
+    return scan_launch(d_D, d_A, d_x, n, x0, 1.0, 0.0, 1.0, d_scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 // AR_dat_gen.py:17-31.  obs has n+1 entries; kept items are obs[impute], obs[2*impute], ...

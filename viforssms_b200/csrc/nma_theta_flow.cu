@@ -6,10 +6,14 @@
 // The host-side autograd module (viforssms_b200/theta_flow.py) costs ~400 tiny launches per step, which is most of
 // a p = 50 step; these two launches replace them.
 //
-// HARDWARE STATUS: written after the round's GPU budget was spent.  The arithmetic below is replayed statement by
-// statement in float64 against autograd of theta_flow.py (tests/test_theta_flow_formulas.py); the kernels themselves
-// have not run on a B200 yet, nothing calls them by default, and their GPU test (tests/test_gpu_unverified.py) is
-// skipped unless NMA_UNVERIFIED=1.
+// The arithmetic below is replayed statement by statement in float64 against autograd of theta_flow.py
+// (tests/test_theta_flow_formulas.py); on the B200 the kernels agree with the host module to 2.6e-7 on the parameter
+// gradients (tests/test_gpu_lvr_theta.py).  nma_train_step (nma_step.cu) is their caller.
+//
+// mask_grad: TensorFlow's masked_dense keeps masked kernel entries at zero through the initialiser and a
+// kernel_constraint applied after every update, but does not multiply the mask in the forward pass, so the gradient it
+// hands to tf.global_norm (AR.py:230) is NOT zero at masked entries.  mask_grad = 1 reproduces that (the caller re-applies
+// the mask after the update, nma_theta_flow_constrain); mask_grad = 0 gives the gradient of the masked forward pass.
 //
 // Per layer k, with the masked MLP  out = W3.(act(W2.(act(W1.(act(W0.z + b0)) + b1)) + b2)) + b3  (W_i = kernel * mask,
 // sizes d -> 5 -> 5 -> 5 -> 2d):  shift_j = out[2j], ls_j = clip(out[2j+1], -5, 3) (value clipped, gradient passed
@@ -35,6 +39,8 @@ struct ThetaFlowArgs {
     float* g_z0;               // [p][d]   (bwd; may be null)
     int p, d, nb, relu;
     float base_loc, base_scale;
+    float g_logq_const;        // (bwd) used when g_logq is null
+    int mask_grad;             // (bwd) 1: TensorFlow's masked_dense gradient (masked entries receive h * g as well)
 };
 
 __device__ __forceinline__ float tf_act(float a, int relu) { return relu ? fmaxf(a, 0.f) : elu_f(a); }
@@ -108,6 +114,7 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd(ThetaFlowArgs a) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = r < a.p;            // every lane walks the whole kernel: the parameter gradients are warp sums
+    const bool mg = a.mask_grad != 0;
     const int d = a.d, LP = tf_layer_params(d);
     float zin[TF_NBMAX][TF_DMAX];          // input of every layer (recomputed forward)
     float z[TF_DMAX], zn[TF_DMAX], h1[TF_H], h2[TF_H], h3[TF_H], out[2 * TF_DMAX];
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd(ThetaFlowArgs a) {
         }
         for (int j = 0; j < d; ++j) z[j] = (k < a.nb - 1) ? zn[a.perms[k * d + j]] : zn[j];
     }
-    const float glp = (valid && a.g_logq) ? a.g_logq[r] : 0.f;
+    const float glp = valid ? (a.g_logq ? a.g_logq[r] : a.g_logq_const) : 0.f;
     float gz[TF_DMAX], gzn[TF_DMAX];       // gradient w.r.t. the layer's (permuted) output, then w.r.t. its input
     for (int j = 0; j < d; ++j) gz[j] = valid ? a.g_theta[(size_t)r * d + j] : 0.f;
     for (int k = a.nb - 1; k >= 0; --k) {
@@ -166,8 +173,8 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd(ThetaFlowArgs a) {
 #pragma unroll
             for (int i = 0; i < TF_H; ++i) {
                 const float m = __ldg(M3 + i * 2 * d + o);
-                const float sw = warp_sum(h3[i] * go) * m;
-                if (lane == 0 && m != 0.f) atomicAdd(G3 + i * 2 * d + o, sw);
+                const float sw = warp_sum(h3[i] * go) * (mg ? 1.f : m);
+                if (lane == 0 && (mg || m != 0.f)) atomicAdd(G3 + i * 2 * d + o, sw);
                 g3[i] = fmaf(go, __ldg(W3 + i * 2 * d + o) * m, g3[i]);
             }
         }
@@ -182,8 +189,8 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd(ThetaFlowArgs a) {
 #pragma unroll
             for (int i = 0; i < TF_H; ++i) {
                 const float m = __ldg(M2 + i * TF_H + o);
-                const float sw = warp_sum(h2[i] * go) * m;
-                if (lane == 0 && m != 0.f) atomicAdd(G2 + i * TF_H + o, sw);
+                const float sw = warp_sum(h2[i] * go) * (mg ? 1.f : m);
+                if (lane == 0 && (mg || m != 0.f)) atomicAdd(G2 + i * TF_H + o, sw);
                 g2[i] = fmaf(go, __ldg(W2 + i * TF_H + o) * m, g2[i]);
             }
         }
@@ -198,8 +205,8 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd(ThetaFlowArgs a) {
 #pragma unroll
             for (int i = 0; i < TF_H; ++i) {
                 const float m = __ldg(M1 + i * TF_H + o);
-                const float sw = warp_sum(h1[i] * go) * m;
-                if (lane == 0 && m != 0.f) atomicAdd(G1 + i * TF_H + o, sw);
+                const float sw = warp_sum(h1[i] * go) * (mg ? 1.f : m);
+                if (lane == 0 && (mg || m != 0.f)) atomicAdd(G1 + i * TF_H + o, sw);
                 g1[i] = fmaf(go, __ldg(W1 + i * TF_H + o) * m, g1[i]);
             }
         }
@@ -211,8 +218,8 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd(ThetaFlowArgs a) {
             if (lane == 0) atomicAdd(G0 + d * TF_H + o, sb);
             for (int i = 0; i < d; ++i) {
                 const float m = __ldg(M0 + i * TF_H + o);
-                const float sw = warp_sum(z[i] * go) * m;
-                if (lane == 0 && m != 0.f) atomicAdd(G0 + i * TF_H + o, sw);
+                const float sw = warp_sum(z[i] * go) * (mg ? 1.f : m);
+                if (lane == 0 && (mg || m != 0.f)) atomicAdd(G0 + i * TF_H + o, sw);
                 gz[i] = fmaf(go, __ldg(W0 + i * TF_H + o) * m, gz[i]);
             }
         }
@@ -243,17 +250,25 @@ extern "C" int nma_theta_flow_fwd(const float* d_params, const float* d_masks, c
     return 0;
 }
 
-extern "C" int nma_theta_flow_bwd(const float* d_params, const float* d_masks, const int32_t* d_perms, const float* d_z0,
-                                  int32_t p, int32_t d, int32_t nb, int32_t relu, const float* d_g_theta,
-                                  const float* d_g_logq, float* d_g_params, float* d_g_z0, void* stream) {
+extern "C" int nma_theta_flow_bwd_ex(const float* d_params, const float* d_masks, const int32_t* d_perms, const float* d_z0,
+                                     int32_t p, int32_t d, int32_t nb, int32_t relu, const float* d_g_theta,
+                                     const float* d_g_logq, float g_logq_const, int32_t mask_grad, float* d_g_params,
+                                     float* d_g_z0, void* stream) {
     if (tf_check(p, d, nb, d_params, d_masks, d_z0)) return -1;
     if (!d_g_theta || !d_g_params || (nb > 1 && !d_perms)) { nma_set_error("nma_theta_flow_bwd: null pointer"); return -1; }
     ThetaFlowArgs a = {};
     a.params = d_params; a.masks = d_masks; a.perms = d_perms; a.z0 = d_z0;
     a.g_theta = d_g_theta; a.g_logq = d_g_logq; a.g_params = d_g_params; a.g_z0 = d_g_z0;
-    a.p = p; a.d = d; a.nb = nb; a.relu = relu;
+    a.p = p; a.d = d; a.nb = nb; a.relu = relu; a.g_logq_const = g_logq_const; a.mask_grad = mask_grad;
     k_theta_flow_bwd<<<(p + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int nma_theta_flow_bwd(const float* d_params, const float* d_masks, const int32_t* d_perms, const float* d_z0,
+                                  int32_t p, int32_t d, int32_t nb, int32_t relu, const float* d_g_theta,
+                                  const float* d_g_logq, float* d_g_params, float* d_g_z0, void* stream) {
+    return nma_theta_flow_bwd_ex(d_params, d_masks, d_perms, d_z0, p, d, nb, relu, d_g_theta, d_g_logq, 0.f, 0, d_g_params,
+                                 d_g_z0, stream);
 }

@@ -24,6 +24,13 @@ def _stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _DevView:
+    """A borrowed fp32 device buffer of the library, seen through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
 class NMAEngine:
     def __init__(self, cfg: NMAConfig, device: Optional[torch.device] = None, tensor_cores: Optional[bool] = None):
         if not torch.cuda.is_available():
@@ -134,12 +141,13 @@ class NMAEngine:
             "flags": torch.empty(p, dtype=torch.int32, device=d),
         }
 
-    def elbo_fwd_bwd(self, params: torch.Tensor, eps: torch.Tensor, theta: torch.Tensor, idx: torch.Tensor,
+    def elbo_fwd_bwd(self, params: torch.Tensor, eps: Optional[torch.Tensor], theta: torch.Tensor, idx: torch.Tensor,
                      objective: int = 0, path_target: float = 0.0, out: Optional[Dict[str, torch.Tensor]] = None):
+        """eps=None: the library draws the base noise (Philox, `set_seed`)."""
         p = idx.numel()
-        assert params.is_cuda and eps.is_cuda and theta.is_cuda and idx.is_cuda
+        assert params.is_cuda and theta.is_cuda and idx.is_cuda
         assert params.dtype == torch.float32 and params.numel() == self.n_params and params.is_contiguous()
-        assert eps.shape == (p, self.cfg.L0) and eps.is_contiguous() and eps.dtype == torch.float32
+        assert eps is None or (eps.is_cuda and eps.shape == (p, self.cfg.L0) and eps.is_contiguous() and eps.dtype == torch.float32)
         assert theta.shape == (p, self.cfg.dtheta) and theta.is_contiguous() and theta.dtype == torch.float32
         assert idx.dtype == torch.int64
         if out is None:
@@ -157,6 +165,99 @@ class NMAEngine:
         _lib.check(self._lib.nma_forward_paths(self._h, _ptr(params), _ptr(eps), _ptr(theta), _ptr(idx), p,
                                                _ptr(terms), _ptr(lf), _stream()), "nma_forward_paths")
         return terms, lf
+
+    # ------------------------------------------------------------------
+    # the whole iteration (nma_train_step): one sess.run([train_step, merged]) of the reference
+    # ------------------------------------------------------------------
+    def set_theta_flow(self, flow, priors) -> None:
+        """Registers the theta posterior (viforssms_b200.theta_flow.ThetaFlow: masks, permutations, base distribution)
+        and the diagonal Gaussian prior [(mean, scale), ...] of AR.py:178-182 with the handle."""
+        masks = torch.cat([torch.from_numpy(m).reshape(-1) for m in flow.masks_np]).float().to(self.device)
+        perms = np.stack(flow.perms).astype(np.int32) if flow.perms else np.zeros((0, flow.d), dtype=np.int32)
+        self._tf_masks, self._tf_perms = masks, torch.from_numpy(perms).to(self.device)      # borrowed by the handle
+        self._tf_flow = flow
+        relu = 0 if flow.act is torch.nn.functional.elu else 1
+        d = self.cfg.dtheta
+        assert flow.d == d and len(priors) == d
+        pm = (ctypes.c_float * d)(*[float(m) for m, _ in priors])
+        ps = (ctypes.c_float * d)(*[float(s) for _, s in priors])
+        _lib.check(self._lib.nma_set_theta_flow(self._h, _ptr(self._tf_masks), _ptr(self._tf_perms) if flow.nb > 1 else None,
+                                                flow.nb, relu, flow.base_loc, flow.base_scale, pm, ps),
+                   "nma_set_theta_flow")
+        assert int(self._lib.nma_theta_flow_param_count(d, flow.nb)) == flow.n_params
+
+    def set_fixed_theta(self, theta) -> None:
+        """No theta posterior: theta is the constant `theta` in every row (the fixed-theta Lotka-Volterra script)."""
+        d = self.cfg.dtheta
+        assert len(theta) == d
+        self._tf_flow = None
+        pm = (ctypes.c_float * d)(*[float(t) for t in theta])
+        ps = (ctypes.c_float * d)(*([1.0] * d))
+        _lib.check(self._lib.nma_set_theta_flow(self._h, None, None, 0, 0, 0.0, 1.0, pm, ps), "nma_set_theta_flow")
+
+    def set_seed(self, seed: int, counter: int = 0) -> None:
+        _lib.check(self._lib.nma_set_seed(self._h, int(seed), int(counter)), "nma_set_seed")
+
+    def draw_counter(self) -> int:
+        out = ctypes.c_uint64(0)
+        _lib.check(self._lib.nma_get_counter(self._h, ctypes.byref(out)), "nma_get_counter")
+        return int(out.value)
+
+    def train_step(self, blob, grad, m, v, idx, scalars, *, objective=0, path_target=0.0, prior_on=True, obs_in_elbo=True,
+                   tf_mask_grad=True, lr=1e-3, beta1=0.95, beta2=0.999, eps=1e-8, clip=0.0, theta_out=None,
+                   lf_out=None) -> None:
+        """nma_train_step on flat fp32 tensors (NMA variables ++ theta-posterior variables); everything stays on the
+        device, `scalars` [8] receives the logged means (see nma_b200.h)."""
+        n = self.n_params + (self._tf_flow.n_params if self._tf_flow is not None else 0)
+        for t in (blob, grad, m, v):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+        assert idx.is_cuda and idx.dtype == torch.int64 and scalars.numel() >= 8 and scalars.dtype == torch.float32
+        o = _lib.StepOpts(int(objective), float(path_target), int(bool(prior_on)), int(bool(obs_in_elbo)),
+                          int(bool(tf_mask_grad)), float(lr), float(beta1), float(beta2), float(eps), float(clip))
+        _lib.check(self._lib.nma_train_step(self._h, _ptr(blob), _ptr(grad), _ptr(m), _ptr(v), _ptr(idx), idx.numel(),
+                                            ctypes.byref(o), _ptr(scalars), _ptr(theta_out), _ptr(lf_out), _stream()),
+                   "nma_train_step")
+
+    def step_buffers(self, p: int) -> Dict[str, torch.Tensor]:
+        """Copies of what the last train_step left in the workspace: eps, z0, theta, logq_theta, terms, row_elbo."""
+        ptrs = [c_void_p() for _ in range(6)]
+        _lib.check(self._lib.nma_step_buffers(self._h, *[ctypes.byref(q) for q in ptrs]), "nma_step_buffers")
+        cfg = self.cfg
+        shapes = {"eps": (p, cfg.L0), "z0": (p, cfg.dtheta), "theta": (p, cfg.dtheta), "logq_theta": (p,), "terms": (p, 4),
+                  "row_elbo": (p,)}
+        out = {}
+        for (name, shape), q in zip(shapes.items(), ptrs):
+            out[name] = torch.as_tensor(_DevView(q.value, shape), device=self.device).clone()
+        return out
+
+    # ------------------------------------------------------------------
+    # multi-GPU: the library's own NCCL communicator for the gradient all-reduce
+    # ------------------------------------------------------------------
+    def comm_create(self, rank: int, world: int, group=None) -> None:
+        """Collective over `group` (any torch.distributed backend): rank 0 makes the NCCL id, everyone joins."""
+        import torch.distributed as dist
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(self._lib.nma_comm_unique_id(buf), "nma_comm_unique_id")
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        backend = dist.get_backend(group)
+        if backend == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.nma_comm_create(self._h, raw, int(rank), int(world)), "nma_comm_create")
+
+    def comm_destroy(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.nma_comm_destroy(self._h)
+
+    def comm_wait(self) -> None:
+        _lib.check(self._lib.nma_comm_wait(self._h, _stream()), "nma_comm_wait")
+
+    def comm_allreduce(self, t: torch.Tensor) -> None:
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        _lib.check(self._lib.nma_comm_allreduce(self._h, _ptr(t), t.numel(), _stream()), "nma_comm_allreduce")
 
     def adamax_step(self, params, grads, m, v, lr, beta1, beta2=0.999, eps=1e-8, clip=0.0) -> torch.Tensor:
         """In-place clip + Adamax on flat fp32 tensors; returns the 1-element global-norm tensor (device)."""
@@ -196,10 +297,23 @@ def scan_ar1(z: torch.Tensor, x0: float, a: float, b: float, c: float) -> torch.
     assert z.is_cuda and z.dtype == torch.float64 and z.is_contiguous()
     n = z.numel()
     x = torch.empty(n + 1, dtype=torch.float64, device=z.device)
-    nblocks = (n + 4095) // 4096
-    scratch = torch.empty(nblocks * 2, dtype=torch.float64, device=z.device)
+    scratch = torch.empty((int(lib.nma_scan_scratch_bytes(n)) + 7) // 8, dtype=torch.float64, device=z.device)
     _lib.check(lib.nma_scan_ar1(_ptr(z), _ptr(x), n, x0, a, b, c, _ptr(scratch), scratch.numel() * 8, _stream()),
                "nma_scan_ar1")
+    return x
+
+
+def scan_affine(A: torch.Tensor, D: torch.Tensor, x0: float) -> torch.Tensor:
+    """x[0]=x0, x[i] = A[i-1]*x[i-1] + D[i-1] on device (float64): the per-element form of the A12 scan."""
+    lib = _lib.load()
+    assert A.is_cuda and D.is_cuda and A.dtype == torch.float64 and D.dtype == torch.float64
+    A, D = A.contiguous(), D.contiguous()
+    n = A.numel()
+    assert D.numel() == n
+    x = torch.empty(n + 1, dtype=torch.float64, device=A.device)
+    scratch = torch.empty((int(lib.nma_scan_scratch_bytes(n)) + 7) // 8, dtype=torch.float64, device=A.device)
+    _lib.check(lib.nma_scan_affine(_ptr(A), _ptr(D), _ptr(x), n, float(x0), _ptr(scratch), scratch.numel() * 8, _stream()),
+               "nma_scan_affine")
     return x
 
 
@@ -226,9 +340,19 @@ def rolling_var(x: torch.Tensor, K: int) -> torch.Tensor:
     return out
 
 
+def philox_normal(n: int, seed: int, counter: int, stream_id: int, loc: float = 0.0, scale: float = 1.0,
+                  device=None) -> torch.Tensor:
+    """The normals the library draws for (seed, counter): stream 0 = eps, 1 = the theta posterior's base sample."""
+    lib = _lib.load()
+    out = torch.empty(n, dtype=torch.float32, device=device if device is not None else "cuda")
+    _lib.check(lib.nma_philox_normal(_ptr(out), n, int(seed), int(counter), int(stream_id), float(loc), float(scale),
+                                     _stream()), "nma_philox_normal")
+    return out
+
+
 class DeviceThetaFlow:
     """The theta posterior on the device (nma_theta_flow_fwd / _bwd; A11, AR.py:376-391): two launches instead of the
-    ~400 tiny ones of the host autograd module.  NOT YET RUN ON HARDWARE - see nma_b200.h; nothing uses it by default."""
+    ~400 tiny ones of the host autograd module (which remains the test reference, tests/test_gpu_lvr_theta.py)."""
 
     def __init__(self, flow, device):
         self.flow = flow

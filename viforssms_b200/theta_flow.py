@@ -41,7 +41,12 @@ class ThetaFlow:
     HIDDEN = (5, 5, 5)
 
     def __init__(self, dtheta: int, num_bijectors: int, base_loc: float, base_scale: float, activation: str = "elu",
-                 permutations: Optional[Sequence[Sequence[int]]] = None):
+                 permutations: Optional[Sequence[Sequence[int]]] = None, tf_mask_grad: bool = True):
+        # TensorFlow's masked_dense does not multiply the mask in the forward pass: masked kernel entries are zero through
+        # the initialiser and a kernel_constraint re-applied after every update, so they DO receive a gradient (which
+        # counts in tf.global_norm, AR.py:230) that the constraint then wipes.  tf_mask_grad=True reproduces that (call
+        # `constrain()` after each update); False multiplies the mask in the forward pass (zero gradient there).
+        self.tf_mask_grad = bool(tf_mask_grad)
         self.d = dtheta
         self.nb = num_bijectors
         self.base_loc = float(base_loc)
@@ -77,6 +82,21 @@ class ThetaFlow:
         self.masks = [torch.from_numpy(m).to(flat.device) for m in self.masks_np]
         self._perm_t = [torch.from_numpy(pm).to(flat.device) for pm in self.perms]
 
+    def mask_flat(self) -> torch.Tensor:
+        """Per-variable multiplier of the kernel constraint: the block masks on kernels, 1 on biases."""
+        one = []
+        for (a, b), m in zip(self.shapes, self.masks_np):
+            one.append(torch.from_numpy(m).reshape(-1))
+            one.append(torch.ones(b))
+        return torch.cat(one * self.nb)
+
+    def constrain(self) -> None:
+        """kernel_constraint=lambda x: mask * x of masked_dense, applied after an update of the bound variables."""
+        if getattr(self, "_mask_flat", None) is None or self._mask_flat.device != self.flat.device:
+            self._mask_flat = self.mask_flat().to(self.flat.device)
+        with torch.no_grad():
+            self.flat.mul_(self._mask_flat)
+
     def _unpack(self):
         layers = []
         off = 0
@@ -92,7 +112,7 @@ class ThetaFlow:
     def _shift_log_scale(self, layer, z):
         h = z
         for i, (w, b) in enumerate(layer):
-            h = h @ (w * self.masks[i]) + b
+            h = h @ (w if self.tf_mask_grad else w * self.masks[i]) + b
             if i < len(layer) - 1:
                 h = self.act(h)
         h = h.reshape(z.shape[0], self.d, 2)

@@ -151,10 +151,14 @@ class ARStepper:
                  theta: Sequence[float] = (5.0, 0.5, 3.0), x0: float = 10.0, obs_std: float = 1.0,
                  device: Optional[torch.device] = None, rank: int = 0, world: int = 1, seed: int = 1,
                  lr: float = 1e-3, clip: float = 2.5e8, priors=((0.0, 10.0),) * 3, series=None, impute: int = 1,
-                 tensor_cores: Optional[int] = None, device_theta: bool = False):
+                 tensor_cores: Optional[int] = None, device_theta: bool = True, tf_mask_grad: bool = True,
+                 unscaled_time_weights: bool = False):
         self.T, self.rows, self.rank, self.world = int(T), int(rows), rank, world
-        self.device_theta = bool(device_theta)     # theta posterior through nma_theta_flow_fwd / _bwd (not yet run on
-        #                                            hardware: opt-in; the default is the host autograd module)
+        # device_theta=True (default): the whole iteration is ONE nma_train_step call - in-library Philox noise, theta
+        # posterior, ELBO + gradients, per-flow NCCL all-reduce, clip + Adamax, logged scalars; no ATen kernel in the step.
+        # False: the host autograd theta posterior + torch.randn (the comparison path of the tests).
+        self.device_theta = bool(device_theta)
+        self.tf_mask_grad = bool(tf_mask_grad)
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.lr, self.clip, self.priors = lr, clip, priors
         self.cfg = ar_config(p=rows, K=K, B=B, F=F, H=H, feat_window=fw, T=T, obs_std=obs_std, x0=x0)
@@ -173,11 +177,14 @@ class ARStepper:
         nma = glorot_blob(cfg, g)
         # the raw time-index channel reaches T (AR.py:139-140): keep first-layer activations O(1) at init
         layout, n_nma = param_layout(cfg)
+        # (unscaled_time_weights=True keeps plain Glorot values there, which is what the reference's initialiser gives)
         for i in range(F):
+            if unscaled_time_weights:
+                break
             off, shape = layout[f"f{i}.feat0.w"]
             nma[off:off + shape[0] * shape[1]].reshape(shape)[fw + 1, :] *= 10.0 / max(self.T, 1)
         perms = [np.random.RandomState(seed + 17 + k).permutation(3) for k in range(4)]
-        self.flow = ThetaFlow(3, 5, 1.5, 0.5, "elu", perms)            # AR.py:378-390
+        self.flow = ThetaFlow(3, 5, 1.5, 0.5, "elu", perms, tf_mask_grad=tf_mask_grad)            # AR.py:378-390
         tf_init = self.flow.init_values(g)
         self.n_nma, self.n_total = n_nma, n_nma + self.flow.n_params
         self.blob = torch.cat([nma, tf_init]).to(self.device)
@@ -191,10 +198,13 @@ class ARStepper:
         # eps / theta base noise come from torch's default CUDA generator (graph-capture safe)
         torch.cuda.manual_seed(seed * 1000 + rank)
         self.prior_t = prior_tensors(priors, self.device)
-        if self.device_theta:
-            from .engine import DeviceThetaFlow
-            self.dflow = DeviceThetaFlow(self.flow, self.device)
-            self._ones = torch.ones(rows, dtype=torch.float32, device=self.device)
+        self.eng.set_theta_flow(self.flow, list(priors))
+        self.eng.set_seed(seed * 1000 + rank, 0)
+        self.scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
+        if world > 1:
+            # the library's own NCCL communicator: the gradient all-reduce is issued inside nma_train_step /
+            # nma_elbo_fwd_bwd, per flow, on the library's side stream
+            self.eng.comm_create(rank, world)
         self.graph = None
         self._elbo_static = None
         self.launches_per_step = None
@@ -259,35 +269,24 @@ class ARStepper:
                 float(tt[0]))
 
     # ------------------------------------------------------------------
-    def _step_device_theta(self, idx_dev: torch.Tensor) -> torch.Tensor:
-        """The same iteration with the theta posterior on the device: -sum(ELBO) = device part (through theta) -
-        sum(log prior(theta)) + sum(log q(theta)), so d/dtheta = grad_theta + (theta - mean) / scale^2 and
-        d/dlogq = 1; nma_theta_flow_bwd turns the two into the gradient of the flow variables."""
-        cfg, rows = self.cfg, self.rows
-        z0 = self.flow.base_sample(rows, None, self.device)
-        flow_params = self.blob[self.n_nma:]
-        theta, logq_theta = self.dflow.forward(flow_params, z0)
-        eps = torch.randn(rows, cfg.L0, device=self.device)
-        out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta, idx_dev, out=self.out)
-        mean, scale = self.prior_t
-        g_theta = out["grad_theta"] + (theta - mean) / (scale * scale)
-        self.grad[self.n_nma:].zero_()
-        self.dflow.backward(flow_params, z0, g_theta.contiguous(), self._ones, self.grad[self.n_nma:])
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grad)
-        self.eng.adamax_step(self.blob, self.grad, self.m, self.v, self.lr, 0.95, clip=self.clip)
-        t = out["terms"]
-        tail = prior_log_prob(theta, self.prior_t) - logq_theta
-        return (float(cfg.scale) * (t[:, 0] - t[:, 2] + t[:, 1]) + tail).mean()
-
     def _step(self, idx_dev: torch.Tensor) -> torch.Tensor:
-        if self.device_theta:
-            return self._step_device_theta(idx_dev)
+        """One iteration = one nma_train_step call (AR.py:300-301); returns the mean ELBO (a view of `scalars`)."""
+        if not self.device_theta:
+            return self._step_host_theta(idx_dev)
+        self.eng.train_step(self.blob, self.grad, self.m, self.v, idx_dev, self.scalars, objective=0, prior_on=True,
+                            tf_mask_grad=self.tf_mask_grad, lr=self.lr, beta1=0.95, clip=self.clip)
+        return self.scalars[0]
+
+    def _step_host_theta(self, idx_dev: torch.Tensor, z0: Optional[torch.Tensor] = None,
+                         eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The same iteration with the theta posterior as a host autograd module and torch.randn noise (or the injected
+        `z0` / `eps`): the comparison path of the tests (tests/test_gpu_lvr_theta.py); ~400 small ATen launches."""
         cfg, rows = self.cfg, self.rows
-        z0 = self.flow.base_sample(rows, None, self.device)
+        if z0 is None:
+            z0 = self.flow.base_sample(rows, None, self.device)
         theta, logq_theta = self.flow.sample_and_log_prob(z0)
-        eps = torch.randn(rows, cfg.L0, device=self.device)
+        if eps is None:
+            eps = torch.randn(rows, cfg.L0, device=self.device)
         out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), idx_dev, out=self.out)
         # host-side remainder of -sum(ELBO): the theta path (AR.py:178-185)
         tail = prior_log_prob(theta, self.prior_t) - logq_theta
@@ -296,9 +295,11 @@ class ARStepper:
         host_loss.backward()
         self.grad[self.n_nma:].copy_(self.theta_leaf.grad)
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grad)
+            self.eng.comm_wait()                                   # the flow sections were all-reduced by the library
+            self.eng.comm_allreduce(self.grad[self.n_nma:])
         self.eng.adamax_step(self.blob, self.grad, self.m, self.v, self.lr, 0.95, clip=self.clip)
+        if self.tf_mask_grad:
+            self.flow.constrain()
         t = out["terms"]
         elbo = (float(cfg.scale) * (t[:, 0] - t[:, 2] + t[:, 1]) + tail.detach()).mean()
         return elbo
@@ -318,7 +319,8 @@ class ARStepper:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: the index feeder's thread may pin host memory while this thread captures
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._elbo_static = self._step(self.idx_dev)
         self.graph = g
 
@@ -360,7 +362,14 @@ class ARStepper:
         return e0.elapsed_time(e1) / reps
 
     def close(self):
+        """Teardown in the order NCCL needs: stop feeding, drain the device, destroy the captured graph (it holds the
+        library's NCCL kernels when world > 1), then the communicator, then the handle."""
         self.feeder.close()
-        self.graph = None            # drop the captured graph (it references NCCL kernels when world > 1)
+        torch.cuda.synchronize(self.device)
+        if self.graph is not None:
+            self.graph.reset()
+        self.graph = None
         self._elbo_static = None
+        torch.cuda.synchronize(self.device)
+        self.eng.comm_destroy()
         self.eng.close()

@@ -25,6 +25,24 @@ from .theta_flow import ThetaFlow, prior_log_prob, prior_tensors
 from .trainer import glorot_blob
 
 
+def restore_theta_perms(model, ck) -> None:
+    """The theta posterior's fixed permutations are drawn from numpy's global stream when the model is built
+    (AR.py:384-385): a checkpoint is only meaningful with the permutations it was trained with, so re-bind them."""
+    perms = ck.get("perms")
+    if perms is None:
+        return
+    flow = model.theta_dist
+    new = [np.asarray(pm, dtype=np.int64) for pm in perms]
+    if len(new) != len(flow.perms) or any(len(a) != flow.d for a in new):
+        raise ValueError("checkpoint was written by a theta posterior of a different shape")
+    if any(not np.array_equal(a, b) for a, b in zip(new, flow.perms)):
+        flow.perms = new
+        if flow.flat is not None:
+            flow.bind(flow.flat)
+        if model.eng is not None:
+            model.eng.set_theta_flow(flow, model.priors)
+
+
 class VI_SSM:
     def __init__(self, obs, obs_std, x0, theta_dist: ThetaFlow, priors: Sequence[Tuple[float, float]], T, p,
                  kernel_len, batch_dims, network_dims, no_flows, feat_window, obs_bin, time_till, pre_train=False,
@@ -80,42 +98,76 @@ class VI_SSM:
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(self.seed)
         self.idx_dev = torch.empty(self.p, dtype=torch.int64, device=self.device)
-        self.scalars = {}
+        self._scalars_host = {}
         self.prior_t = prior_tensors(self.priors, self.device)
+        # the whole iteration is one nma_train_step call (in-library noise, theta posterior, ELBO + gradients, clip +
+        # Adamax, logged means); NMA_HOST_THETA=1 keeps the host autograd theta posterior (comparison path)
+        self.eng.set_theta_flow(self.theta_dist, self.priors)
+        self.eng.set_seed(self.seed, 0)
+        self.scalars_dev = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._theta_last = torch.zeros(self.p, cfg.dtheta, dtype=torch.float32, device=self.device)
+        self._host_theta = os.environ.get("NMA_HOST_THETA") == "1"
+        self._use_graph = os.environ.get("NMA_FACADE_GRAPH", "1") != "0" and not self._host_theta
+        self._graphs, self._seen = {}, set()
 
     # ------------------------------------------------------------------
     def _iteration(self, batch_select: np.ndarray, pre_train: bool) -> None:
-        """One sess.run.  With NMA_FACADE_GRAPH=1 the body is captured once per optimiser into a CUDA graph and
-        replayed (at p = 50 the iteration is ~460 tiny launches, mostly the theta posterior: launch-bound); the
-        capture path was written without a GPU at hand and is therefore opt-in."""
-        self.idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(batch_select, dtype=np.int64)))
-        if os.environ.get("NMA_FACADE_GRAPH") != "1":
-            self._body(pre_train, self.gen)
+        """One sess.run.  The body is a fixed sequence of stream-ordered C-ABI calls, so after one eager iteration per
+        optimiser it is captured into a CUDA graph and replayed: at p = 50 the iteration is launch-bound otherwise.
+        Every call trains (the capturing call replays the graph it has just recorded)."""
+        self.idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(batch_select, dtype=np.int64)), non_blocking=True)
+        self._run(pre_train)
+
+    def _run(self, pre_train: bool) -> None:
+        """The iteration on the subsequence starts already in `idx_dev`."""
+        if not self._use_graph:
+            self._body(pre_train)
             return
-        if not hasattr(self, "_graphs"):
-            self._graphs, self._warm = {}, {True: 0, False: 0}
-            torch.cuda.manual_seed(self.seed)              # captured randn draws come from the default CUDA generator
         g = self._graphs.get(pre_train)
         if g is None:
-            if self._warm[pre_train] < 3:                  # eager warm-up on a side stream, as capture requires
-                side = torch.cuda.Stream(device=self.device)
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    self._body(pre_train, None)
-                torch.cuda.current_stream().wait_stream(side)
-                self._warm[pre_train] += 1
+            if pre_train not in self._seen:           # first call of this optimiser: eager
+                self._seen.add(pre_train)
+                self._body(pre_train)
                 return
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._body(pre_train, None)
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._body(pre_train)
             self._graphs[pre_train] = g
-            return
         g.replay()
 
-    def _body(self, pre_train: bool, gen) -> None:
-        """The body of one sess.run: sample theta and eps, ELBO + gradients, clip, Adamax."""
+    def _body(self, pre_train: bool) -> None:
+        """The body of one sess.run: sample theta and eps, ELBO + gradients, clip, Adamax, summaries."""
+        if self._host_theta:
+            return self._body_host_theta(pre_train)
+        if pre_train:       # AdamaxOptimizer(1e-3, beta1=0.9).minimize(-obs_loss): no clipping (AR.py:201-202)
+            m, v = self.slots["pre"]
+            self.eng.train_step(self.blob, self.grad, m, v, self.idx_dev, self.scalars_dev, objective=OBJ_NEG_OBS,
+                                prior_on=False, lr=1e-3, beta1=0.9, clip=0.0, theta_out=self._theta_last)
+        else:               # clip_by_global_norm + AdamaxOptimizer(lr, beta1=0.95) (AR.py:226-234)
+            m, v = self.slots["main"]
+            self.eng.train_step(self.blob, self.grad, m, v, self.idx_dev, self.scalars_dev, objective=OBJ_ELBO,
+                                prior_on=True, lr=self.learn_rate, beta1=0.95, clip=self.grad_clip,
+                                theta_out=self._theta_last)
+
+    TAGS = ("loss/ELBO", "loss/SDE_log_prob", "loss/theta_log_prob", "loss/obs_log_prob", "loss/path_log_prob",
+            "optimize/global_norm")
+
+    @property
+    def scalars(self) -> dict:
+        return self.read_scalars()
+
+    def read_scalars(self) -> dict:
+        """The summaries of the last iteration (AR.py:207-224) - ONE device-to-host copy."""
+        if self._host_theta:
+            return {k: float(v) for k, v in self._scalars_host.items()}
+        vals = self.scalars_dev.cpu().tolist()
+        return dict(zip(self.TAGS, vals[:6]))
+
+    def _body_host_theta(self, pre_train: bool) -> None:
+        """The same iteration with the host autograd theta posterior and torch.randn noise (comparison path)."""
         cfg = self.cfg
+        gen = self.gen
         z0 = self.theta_dist.base_sample(self.p, gen, self.device)
         theta, logq_theta = self.theta_dist.sample_and_log_prob(z0)
         eps = torch.randn(self.p, cfg.L0, device=self.device, generator=gen)
@@ -129,21 +181,23 @@ class VI_SSM:
         self.theta_leaf.grad = None
         host_loss.backward()
         self.grad[self.n_nma:].copy_(self.theta_leaf.grad)
-        if pre_train:       # AdamaxOptimizer(1e-3, beta1=0.9).minimize(-obs_loss): no clipping (AR.py:201-202)
+        if pre_train:
             m, v = self.slots["pre"]
             self.eng.adamax_step(self.blob, self.grad, m, v, 1e-3, 0.9, clip=0.0)
-        else:               # clip_by_global_norm + AdamaxOptimizer(lr, beta1=0.95) (AR.py:226-234)
+        else:
             m, v = self.slots["main"]
             norm = self.eng.adamax_step(self.blob, self.grad, m, v, self.learn_rate, 0.95, clip=self.grad_clip)
             t = out["terms"]
             scale = float(cfg.scale)
             elbo = scale * (t[:, 0] - t[:, 2] + t[:, 1]) + prior.detach() - logq_theta.detach()
-            self.scalars = {
+            self._scalars_host = {
                 "loss/ELBO": elbo.mean(), "loss/SDE_log_prob": scale * t[:, 0].mean(),
                 "loss/theta_log_prob": logq_theta.detach().mean(), "loss/obs_log_prob": scale * t[:, 1].mean(),
                 "loss/path_log_prob": scale * t[:, 2].mean(), "optimize/global_norm": norm.clone()[0],
             }
             self._theta_last = theta.detach()
+        if self.theta_dist.tf_mask_grad:
+            self.theta_dist.constrain()
 
     def _draw(self, replace_bool: bool) -> np.ndarray:
         sample_index = np.arange(0, self.T, self.batch_dims)
@@ -180,7 +234,7 @@ class VI_SSM:
             else:
                 self._iteration(batch_select, pre_train=False)
                 if writer is not None and run % log_every == 0:
-                    for tag, val in self.scalars.items():
+                    for tag, val in self.read_scalars().items():
                         writer.add_scalar(tag, float(val), run)
                     th = self._theta_last
                     for i, pos in enumerate(theta_pos_index):
@@ -207,6 +261,7 @@ class VI_SSM:
         for k, (m, v) in ck["slots"].items():
             self.slots[k][0].copy_(m.to(self.device))
             self.slots[k][1].copy_(v.to(self.device))
+        restore_theta_perms(self, ck)
         print("Model restored")
 
     # ------------------------------------------------------------------

@@ -60,7 +60,7 @@ class _ModelVISSM:
         self.seed = seed
         self.early_stopping = early_stopping
         self.eng: Optional[NMAEngine] = None
-        self.scalars = {}
+        self._scalars_host = {}
         self.pre_train_count = 0
 
     # supplied by the subclass -------------------------------------------------
@@ -94,6 +94,15 @@ class _ModelVISSM:
         self.idx_dev = torch.empty(self.p, dtype=torch.int64, device=self.device)
         self.prior_t = prior_tensors(self.priors, self.device)
         self.theta_star_t = torch.tensor(list(self.theta_star), dtype=torch.float32, device=self.device)
+        # main iterations are one nma_train_step call, captured into a CUDA graph after the first eager one
+        # (NMA_HOST_THETA=1 keeps the host autograd theta posterior; NMA_FACADE_GRAPH=0 launches eagerly)
+        self.eng.set_theta_flow(self.theta_dist, self.priors)
+        self.eng.set_seed(self.seed, 0)
+        self.scalars_dev = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._theta_last = torch.zeros(self.p, cfg.dtheta, dtype=torch.float32, device=self.device)
+        self._host_theta = os.environ.get("NMA_HOST_THETA") == "1"
+        self._use_graph = os.environ.get("NMA_FACADE_GRAPH", "1") != "0"
+        self._graph, self._main_seen = None, False
 
     # ------------------------------------------------------------------
     def _iteration(self, batch_select: np.ndarray, pre_train: bool) -> bool:
@@ -121,7 +130,12 @@ class _ModelVISSM:
             m, v = self.slots["pre_theta"]
             tail = slice(self.n_nma, self.n_total)
             self.eng.adamax_step(self.blob[tail], self.grad2[tail], m[tail], v[tail], 1e-3, 0.9, clip=0.0)
+            if self.theta_dist.tf_mask_grad:
+                self.theta_dist.constrain()
             return bool(torch.isfinite(out["terms"][:, self.finite_term]).all().item())
+        if not self._host_theta:
+            self._main_iteration()
+            return True
         out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), self.idx_dev,
                                     objective=OBJ_ELBO, out=self.out)
         prior = prior_log_prob(theta, self.prior_t)
@@ -135,13 +149,50 @@ class _ModelVISSM:
         scale = float(cfg.scale)
         obs = t[:, 1] if self.has_obs_term else torch.zeros_like(t[:, 1])
         elbo = scale * (t[:, 0] - t[:, 2] + obs) + prior.detach() - logq_theta.detach()
-        self.scalars = {"loss/ELBO": elbo.mean(), "loss/SDE_log_prob": scale * t[:, 0].mean(),
+        self._scalars_host = {"loss/ELBO": elbo.mean(), "loss/SDE_log_prob": scale * t[:, 0].mean(),
                         "loss/theta_log_prob": logq_theta.detach().mean(),
                         "loss/path_log_prob": scale * t[:, 2].mean(), "optimize/global_norm": norm.clone()[0]}
         if self.has_obs_term:
-            self.scalars["loss/obs_log_prob"] = scale * t[:, 1].mean()
+            self._scalars_host["loss/obs_log_prob"] = scale * t[:, 1].mean()
         self._theta_last = theta.detach()
+        if self.theta_dist.tf_mask_grad:
+            self.theta_dist.constrain()
         return True
+
+    def _main_body(self) -> None:
+        m, v = self.slots["main"]
+        self.eng.train_step(self.blob, self.grad, m, v, self.idx_dev, self.scalars_dev, objective=OBJ_ELBO, prior_on=True,
+                            obs_in_elbo=self.has_obs_term, lr=self.learn_rate, beta1=0.95, clip=self.grad_clip,
+                            theta_out=self._theta_last)
+
+    def _main_iteration(self) -> None:
+        """One ELBO iteration: a single nma_train_step call, replayed from a CUDA graph after the first eager one."""
+        if not self._use_graph:
+            return self._main_body()
+        if self._graph is None:
+            if not self._main_seen:
+                self._main_seen = True
+                return self._main_body()
+            torch.cuda.synchronize(self.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+                self._main_body()
+        self._graph.replay()
+
+    @property
+    def scalars(self) -> dict:
+        return self.read_scalars()
+
+    def read_scalars(self) -> dict:
+        """The summaries of the last iteration - ONE device-to-host copy."""
+        if self._host_theta:
+            return {k: float(v) for k, v in self._scalars_host.items()}
+        vals = self.scalars_dev.cpu().tolist()
+        out = {"loss/ELBO": vals[0], "loss/SDE_log_prob": vals[1], "loss/theta_log_prob": vals[2],
+               "loss/path_log_prob": vals[4], "optimize/global_norm": vals[5]}
+        if self.has_obs_term:
+            out["loss/obs_log_prob"] = vals[3]
+        return out
 
     def _draw(self) -> np.ndarray:
         replace_bool = bool(self.batch_dims * self.p >= self.target_dims)
@@ -176,7 +227,7 @@ class _ModelVISSM:
             else:
                 self._iteration(batch_select, pre_train=False)
                 if writer is not None and run % log_every == 0:
-                    for tag, val in self.scalars.items():
+                    for tag, val in self.read_scalars().items():
                         writer.add_scalar(tag, float(val), run)
                     th = self._theta_last
                     for i, pos in enumerate(self.theta_pos_index):
@@ -203,6 +254,8 @@ class _ModelVISSM:
         for k, (m, v) in ck["slots"].items():
             self.slots[k][0].copy_(m.to(self.device))
             self.slots[k][1].copy_(v.to(self.device))
+        from .vi_ssm import restore_theta_perms
+        restore_theta_perms(self, ck)
         print("Model restored")
 
     def sample_paths(self, temp_index: int) -> torch.Tensor:
@@ -406,7 +459,6 @@ class LV_VI_SSM:
                              target_dims=self.target_dims, dt=self.dt, x0=np.asarray(x0_mean, dtype=np.float64))
         self.cfg.obs_std = float(x0_std[0])          # this model's only use of the field: the scale of p(x0)
         self.eng: Optional[NMAEngine] = None
-        self.scalars = {}
 
     def build_flow(self) -> None:
         cfg = self.cfg
@@ -426,30 +478,53 @@ class LV_VI_SSM:
         self.gen.manual_seed(self.seed)
         self.idx_dev = torch.empty(self.p_val, dtype=torch.int64, device=self.device)
         self.theta = torch.tensor(self.priors, dtype=torch.float32, device=self.device).repeat(self.p_val, 1).contiguous()
+        # ELBO iterations: one nma_train_step call (in-library noise, constant theta), replayed from a CUDA graph
+        self.eng.set_fixed_theta([float(v) for v in self.priors])
+        self.eng.set_seed(self.seed, 0)
+        self.scalars_dev = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._lf_dev = torch.zeros(self.p_val, cfg.L(cfg.F), dtype=torch.float32, device=self.device)
+        self._use_graph = os.environ.get("NMA_FACADE_GRAPH", "1") != "0"
+        self._graph, self._main_seen = None, False
 
     def _iteration(self, batch_select: np.ndarray, pre_train: bool) -> bool:
         cfg = self.cfg
         self.idx_dev.copy_(torch.from_numpy(np.ascontiguousarray(batch_select, dtype=np.int64)))
-        eps = torch.randn(self.p_val, cfg.L0, device=self.device, generator=self.gen)
         if pre_train:
+            eps = torch.randn(self.p_val, cfg.L0, device=self.device, generator=self.gen)
             out = self.eng.elbo_fwd_bwd(self.blob, eps, self.theta, self.idx_dev, objective=OBJ_PATH_SQ,
                                         path_target=self.pretrain_path_target, out=self.out)
             m, v = self.slots["pre_path"]
             self.eng.adamax_step(self.blob, self.grad, m, v, 1e-3, 0.9, clip=0.0)
             self.lf_sample = out["lf"].reshape(self.p_val, -1, 2).transpose(1, 2)
             return bool(torch.isfinite(out["terms"][:, 2]).all().item())      # `test = lf_log_prob`, :507-510
-        out = self.eng.elbo_fwd_bwd(self.blob, eps, self.theta, self.idx_dev, objective=OBJ_ELBO, out=self.out)
-        m, v = self.slots["main"]
-        norm = self.eng.adamax_step(self.blob, self.grad, m, v, self.learn_rate, 0.95, clip=self.grad_clip)
-        t = out["terms"]
-        scale = float(cfg.scale)
-        elbo = scale * (t[:, 0] - t[:, 2] + t[:, 1])
-        self.scalars = {"loss/NELBO": -elbo.mean(), "loss/ELBO": elbo.mean(),
-                        "loss/SDE_log_prob p(x)": scale * t[:, 0].mean(),
-                        "loss/obs_log_prob p(y|x)": scale * t[:, 1].mean(),
-                        "loss/path_log_prob q(x)": scale * t[:, 2].mean(), "optimize/global_norm": norm.clone()[0]}
-        self.lf_sample = out["lf"].reshape(self.p_val, -1, 2).transpose(1, 2)
+        self._main_iteration()
+        self.lf_sample = self._lf_dev.reshape(self.p_val, -1, 2).transpose(1, 2)
         return True
+
+    def _main_body(self) -> None:
+        m, v = self.slots["main"]
+        self.eng.train_step(self.blob, self.grad, m, v, self.idx_dev, self.scalars_dev, objective=OBJ_ELBO, prior_on=False,
+                            lr=self.learn_rate, beta1=0.95, clip=self.grad_clip, lf_out=self._lf_dev)
+
+    def _main_iteration(self) -> None:
+        if not self._use_graph:
+            return self._main_body()
+        if self._graph is None:
+            if not self._main_seen:
+                self._main_seen = True
+                return self._main_body()
+            torch.cuda.synchronize(self.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+                self._main_body()
+        self._graph.replay()
+
+    @property
+    def scalars(self) -> dict:
+        """The script's summaries (:436-448) of the last ELBO iteration - one device-to-host copy."""
+        v = self.scalars_dev.cpu().tolist()
+        return {"loss/NELBO": -v[0], "loss/ELBO": v[0], "loss/SDE_log_prob p(x)": v[1], "loss/obs_log_prob p(y|x)": v[3],
+                "loss/path_log_prob q(x)": v[4], "optimize/global_norm": v[5]}
 
     def _draw(self) -> np.ndarray:
         return feed.sample_indices_lv(self.target_dims, self.batch_dims, self.p_val)
