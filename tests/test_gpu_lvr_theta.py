@@ -68,14 +68,15 @@ def test_cuda_lv_fixed_theta_matches_the_reference_classes(GM):
     print("CUDA vs reference classes (LV fixed theta, per-state reading): worst gradient slice error %.2e" % worst)
 
 
+@pytest.mark.parametrize("mask_grad", [False, True])
 @pytest.mark.parametrize("d,nb,act", [(3, 5, "elu"), (5, 4, "elu"), (4, 4, "relu")])
-def test_device_theta_flow_matches_the_host_module(d, nb, act):
+def test_device_theta_flow_matches_the_host_module(d, nb, act, mask_grad):
     """nma_theta_flow_fwd / _bwd (two launches) against the host autograd module they are to replace."""
     from viforssms_b200.engine import DeviceThetaFlow
     from viforssms_b200.theta_flow import ThetaFlow
     np.random.seed(7)
     dev = torch.device("cuda")
-    flow = ThetaFlow(d, nb, base_loc=1.5, base_scale=0.5, activation=act)
+    flow = ThetaFlow(d, nb, base_loc=1.5, base_scale=0.5, activation=act, tf_mask_grad=mask_grad)
     g = torch.Generator().manual_seed(3)
     flat = flow.init_values(g)
     flat = (flat + 0.3 * torch.randn(flat.shape, generator=g) * (flat != 0)).to(dev).requires_grad_(True)

@@ -222,7 +222,8 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     {
         const char* envb = getenv("NMA_TC_BF16");
         h->bf16_ok = bf16_path_ok(h);
-        h->use_bf16 = (h->bf16_ok && envb && envb[0] == '1') ? 1 : 0;
+        // default where the kernels cover the model (AR-type): the 2-term bf16 split; NMA_TC_BF16=0 selects 3xTF32
+        h->use_bf16 = (h->bf16_ok && !(envb && envb[0] == '0')) ? 1 : 0;
     }
     *out = h;
     return 0;

@@ -378,6 +378,7 @@ class DeviceThetaFlow:
         """Accumulates d loss / d params into `g_params` (same length as `params`)."""
         f = self.flow
         p = z0.shape[0]
-        _lib.check(self._lib.nma_theta_flow_bwd(_ptr(params), _ptr(self.masks), _ptr(self.perms), _ptr(z0), p, f.d, f.nb,
-                                                self.relu, _ptr(g_theta), _ptr(g_logq) if g_logq is not None else None,
-                                                _ptr(g_params), None, _stream()), "nma_theta_flow_bwd")
+        _lib.check(self._lib.nma_theta_flow_bwd_ex(_ptr(params), _ptr(self.masks), _ptr(self.perms), _ptr(z0), p, f.d, f.nb,
+                                                   self.relu, _ptr(g_theta), _ptr(g_logq) if g_logq is not None else None,
+                                                   0.0, int(f.tf_mask_grad), _ptr(g_params), None, _stream()),
+                   "nma_theta_flow_bwd_ex")

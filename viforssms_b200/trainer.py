@@ -201,7 +201,8 @@ class ARStepper:
         self.eng.set_theta_flow(self.flow, list(priors))
         self.eng.set_seed(seed * 1000 + rank, 0)
         self.scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
-        if world > 1:
+        import torch.distributed as dist
+        if world > 1 and dist.is_available() and dist.is_initialized():
             # the library's own NCCL communicator: the gradient all-reduce is issued inside nma_train_step /
             # nma_elbo_fwd_bwd, per flow, on the library's side stream
             self.eng.comm_create(rank, world)
