@@ -908,6 +908,367 @@ __global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArg
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------
+// The same weight gradient with dA as a TMEM-RESIDENT A operand ("TS" form of tcgen05.mma) - the default.
+//
+// Why: an M = 128 MMA with both operands in shared memory is paced by operand fetch (~88 B/clk per SM: 8 KB for the
+// 64 cycles of math of a 128 x 128 x 16 instruction, profiles/r01_bf16.md), which held k_conv_wgrad_bf at ~26 % of its
+// own MMA floor.  dA is the operand every tap of a CTA shares, so it is written ONCE per stage into tensor memory -
+// transposed to the K-major form the A-from-TMEM path requires, lane = channel (64 hi rows over 64 lo rows), column =
+// two consecutive positions - and every MMA then fetches only its 2 KB B operand from shared memory:
+//     D[tap][(hl, f), c] += dA_t[(hl, f), q] * in[q + tap][c]          M = 128, N = 64, K = 16 positions
+// B is the `in` slab of ONE tap (hi part, then lo part: two instructions into the same accumulator), MN-major straight
+// from the conv operand layout as before; no second shifted copy of the slabs, 30 KB instead of 53 KB per stage.  All
+// four products of the split are accumulated (hi.hi + hi.lo in the hi lanes, lo.hi + lo.lo in the lo lanes; the
+// epilogue adds the two lanes of a channel through the atomics).
+// CTA = (group of <= 4 taps, range of stages); warps 0-7 transpose dA into TMEM AND drain the accumulators (they run
+// WS_LAG stages ahead of the drain), warp 8 TMA, warp 9 MMA.  Accumulators are drained tap by tap (own barrier per
+// tap), so the drain of tap t overlaps the MMAs of the other taps.
+// ---------------------------------------------------------------------------
+#define WS_KT 64
+#define WS_TAPS 4
+#define WS_APOS (WS_KT + 8)                 // `in` positions per stage: tap offsets 0..3, padded to a multiple of 8
+#define WS_STAGES 6
+#define WS_LAG 3
+#define WS_FLUSH 8                          // stages per drain: 8 x 4 k-steps x 2 instructions = 64-MMA chains
+#define WS_IN_UNITS (8 * WS_APOS)           // 16-byte units of in_hi (or in_lo): 8 chunk slabs
+#define WS_DA_SLAB (WS_KT + 1)              // +1 unit: the transposing 2-byte reads of a warp hit 16 distinct banks
+#define WS_DA_UNITS (16 * WS_DA_SLAB)
+#define WS_STAGE_UNITS (2 * WS_IN_UNITS + WS_DA_UNITS)
+#define WS_NCOPY 28
+#define WS_DCOLS (WS_TAPS * TC_N)           // accumulator columns; the A buffers follow
+#define WS_MMA_WARPS 2                      // issuing warps (taps split between them): one warp's instruction stream is
+                                            // the limit otherwise (tools/micro/mma_rate.cu: the pipe itself takes an N = 64
+                                            // A-from-TMEM instruction every 32 cycles)
+#define WS_THREADS (32 * (10 + WS_MMA_WARPS))   // warps 0-7 transpose + drain, 8 and 11 TMA, 9-10 MMA
+
+struct ConvWgradTsArgs {
+    const uint4* in_hi; const uint4* in_lo; long long in_Q;
+    const uint4* da_hi; const uint4* da_lo; long long da_Q;
+    float* gW;
+    int K, ngroups, nstages_total, nq, spr, flush;
+    long long Lin, Nv;
+    int diag;      // NMA_DIAG timing experiments (results invalid): 1 no TMA copies, 2 no transposition, 4 no MMAs, 8 no TMEM drain loads
+};
+
+// Barrier helpers on precomputed 32-bit shared addresses.  Taking `&bar[i]` of a static __shared__ array inside a loop makes
+// the compiler rebuild the address from SR_CgaCtaId every time (S2UR + ULEA, ~100 cycles of latency each): with ~6 barrier
+// operations per stage and warp that alone paced k_conv_wgrad_ts at ~760 cycles per stage with every other piece of work
+// switched off (profiles/r02_wgrad_ts.md).  The addresses are formed once per kernel and hidden from rematerialisation.
+__device__ __forceinline__ uint32_t smem_addr_once(const void* p) {
+    uint32_t a = smem_u32(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// mbarrier wait without the clock reads of mbar_wait_backoff (hot per-stage waits); the watchdog is a poll counter:
+// a lost arrival must fail loudly, not hang the device
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    // every lane polls: one polling lane + __syncwarp was measured 1.9x SLOWER on the whole kernel (round 2; round 1 saw
+    // the same on the forward kernel).  The suspend-time hint lets a waiting warp sleep in the barrier unit.
+    uint32_t done = 0, polls = 0;
+    while (!done) {
+        if (++polls > (1u << 27)) __trap();
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs a) {
+    extern __shared__ __align__(128) uint4 smem_u[];
+    __shared__ uint64_t full[WS_STAGES], empty[WS_STAGES], a_ready[WS_STAGES], acc_full[WS_TAPS], acc_free[WS_TAPS];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y;
+    const int base = a.K / a.ngroups, rem = a.K % a.ngroups;
+    const int nt = base + (g < rem ? 1 : 0);                    // taps of this CTA
+    const int k0 = g * base + (g < rem ? g : rem);              // first tap
+    const int s_begin = (int)((long long)a.nstages_total * blockIdx.x / a.nq);
+    const int s_end = (int)((long long)a.nstages_total * (blockIdx.x + 1) / a.nq);
+    const int nst = s_end - s_begin;
+
+    // slabs of chunk 7 (channel slots 56..63) are never loaded: zero everything once
+    for (int t = tid; t < WS_STAGES * WS_STAGE_UNITS; t += blockDim.x) smem_u[t] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        for (int i = 0; i < WS_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], WS_MMA_WARPS); mbar_init(&a_ready[i], 4); }
+        for (int i = 0; i < WS_TAPS; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t full_a = smem_addr_once(full), empty_a = smem_addr_once(empty), aready_a = smem_addr_once(a_ready);
+    const uint32_t accfull_a = smem_addr_once(acc_full), accfree_a = smem_addr_once(acc_free);
+    const uint32_t sbase = smem_addr_once(smem_u);
+
+    if (warp == 8 || warp == 11) {
+        // ===== TMA producers: two warps, each takes every other stage (a warp's chain of barrier wait, address arithmetic and
+        // 28 copy instructions per stage is ~400 cycles long: one warp alone could not keep up with the 850-cycle stages) =====
+        const int pw = warp == 8 ? 0 : 1;
+        long long row = (s_begin + pw) / a.spr;
+        int blk = (int)((s_begin + pw) - row * a.spr), st = pw;
+        uint32_t ph = 0;
+        for (int si = pw; si < nst; si += 2) {
+            if (si >= WS_STAGES) mbar_wait_spin(empty_a + 8u * st, ph ^ 1u);
+            const uint32_t sb = sbase + (uint32_t)st * (WS_STAGE_UNITS * 16u), fb = full_a + 8u * st;
+            const long long q0 = row * a.Lin + (long long)blk * WS_KT;
+            const long long left = a.Nv - (long long)blk * WS_KT;     // the last stage of a row copies only what its k-steps read
+            const uint32_t npos_b = left >= WS_KT ? (uint32_t)WS_KT : (uint32_t)((left + 15) / 16) * 16u;
+            const uint32_t npos_a = npos_b + 8u;
+            if (a.diag & 1) {
+                if (elect_one()) mbar_expect_tx_a(fb, 0u);
+            } else if (elect_one()) {
+                mbar_expect_tx_a(fb, 14u * npos_a * 16u + 14u * npos_b * 16u);
+                const uint4* ih = a.in_hi + q0 + k0;
+                const uint4* il = a.in_lo + q0 + k0;
+                const uint4* dh = a.da_hi + q0 + (a.K - 1);
+                const uint4* dl = a.da_lo + q0 + (a.K - 1);
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    bulk_g2s_a(sb + (2 * WS_IN_UNITS + c * WS_DA_SLAB) * 16u, dh + (size_t)c * a.da_Q, npos_b * 16u, fb);
+                    bulk_g2s_a(sb + (2 * WS_IN_UNITS + (8 + c) * WS_DA_SLAB) * 16u, dl + (size_t)c * a.da_Q, npos_b * 16u, fb);
+                }
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    bulk_g2s_a(sb + (c * WS_APOS) * 16u, ih + (size_t)c * a.in_Q, npos_a * 16u, fb);
+                    bulk_g2s_a(sb + (WS_IN_UNITS + c * WS_APOS) * 16u, il + (size_t)c * a.in_Q, npos_a * 16u, fb);
+                }
+            }
+            __syncwarp();
+            blk += 2;
+            while (blk >= a.spr) { blk -= a.spr; ++row; }
+            st += 2;
+            if (st >= WS_STAGES) { st -= WS_STAGES; ph ^= 1u; }
+        }
+    } else if (warp == 9 || warp == 10) {
+        // ===== MMA issuers: warp 9 + w owns taps w, w + WS_MMA_WARPS, ... =====
+        // A warp's own instruction stream must stay far below the ~41 cycles an instruction
+        // occupies the tensor pipe: taps and k-steps are unrolled with compile-time descriptor offsets (a rolled loop
+        // with runtime offsets cost ~7 uniform-datapath instructions per MMA and paced the kernel at ~2900 cycles per
+        // stage, profiles/r02_wgrad_ts.md), and the stage's position inside its row is tracked incrementally.
+        constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N, 0, 1);        // A from TMEM (K-major), B MN-major
+        const uint32_t b_hi32 = desc_hi(WS_APOS * 16u);                        // stride offset: next channel chunk
+        int blk = (int)((long long)s_begin % a.spr);
+        const int nks_last = (int)((a.Nv - (long long)(a.spr - 1) * WS_KT + 15) / 16);
+        int st = 0, in_chunk = 0, ci = 0;
+        uint32_t ph = 0;                                                     // parity of full / a_ready for this ring pass
+        const int mw = warp - 9;
+        for (int si = 0; si < nst; ++si) {
+            const bool chunk_first = in_chunk == 0;
+            const bool chunk_last = (in_chunk == a.flush - 1) || (si == nst - 1);
+            mbar_wait_spin(full_a + 8u * st, ph);
+            mbar_wait_spin(aready_a + 8u * st, ph);
+            tc_fence_after();
+            const int nks = (blk == a.spr - 1) ? nks_last : WS_KT / 16;
+            if (chunk_first && ci > 0) {            // the previous chunk's sums have been drained from these tiles
+#pragma unroll
+                for (int t = 0; t < WS_TAPS; ++t)
+                    if (t < nt && (t % WS_MMA_WARPS) == mw) mbar_wait_spin(accfree_a + 8u * t, (uint32_t)((ci - 1) & 1));
+                tc_fence_after();
+            }
+            if (elect_one()) {
+                const uint32_t ub_hi = sbase + (uint32_t)(st * WS_STAGE_UNITS) * 16u;
+                const uint32_t bh0 = desc_lo(ub_hi, 128u);                    // leading offset: next 8 positions
+                const uint32_t bl0 = bh0 + WS_IN_UNITS;                       // lo slabs follow the hi slabs (16-byte units)
+                const uint32_t ta = tmem + (uint32_t)(WS_DCOLS + st * (WS_KT / 2));
+                // k-step-major, taps innermost: consecutive instructions accumulate into DIFFERENT tiles (an instruction
+                // that accumulates into the tile of its predecessor waits for it: ~80 cycles, whatever the shape)
+#pragma unroll
+                for (int ks = 0; ks < WS_KT / 16; ++ks) {
+                    if (ks < nks && !(a.diag & 4)) {
+#pragma unroll
+                        for (int t = 0; t < WS_TAPS; ++t)
+                            if (t < nt && (t % WS_MMA_WARPS) == mw)
+                                umma_bf16_ts(tmem + (uint32_t)(t * TC_N), ta + (uint32_t)(8 * ks),
+                                             desc_pack(bh0 + (uint32_t)(t + 16 * ks), b_hi32), idesc, (chunk_first && ks == 0) ? 0u : 1u);
+#pragma unroll
+                        for (int t = 0; t < WS_TAPS; ++t)
+                            if (t < nt && (t % WS_MMA_WARPS) == mw)
+                                umma_bf16_ts(tmem + (uint32_t)(t * TC_N), ta + (uint32_t)(8 * ks),
+                                             desc_pack(bl0 + (uint32_t)(t + 16 * ks), b_hi32), idesc, 1u);
+                    }
+                }
+                if (chunk_last) {
+#pragma unroll
+                    for (int t = 0; t < WS_TAPS; ++t)
+                        if (t < nt && (t % WS_MMA_WARPS) == mw) tc_commit_a(accfull_a + 8u * t);
+                }
+                tc_commit_a(empty_a + 8u * st);
+            }
+            __syncwarp();
+            if (++blk == a.spr) blk = 0;
+            if (++st == WS_STAGES) { st = 0; ph ^= 1u; }
+            if (chunk_last) { in_chunk = 0; ++ci; } else ++in_chunk;
+        }
+    } else {
+        // ===== warps 0-7: dA -> TMEM (transposed), WS_LAG stages ahead of the accumulator drain =====
+        // (ring slot, parity and the position inside the drain chunk are tracked incrementally: these warps' own
+        // instruction stream - ~150 instructions per stage with runtime modulos - paced the kernel before)
+        const int quarter = warp & 3, half = warp >> 2;
+        const int m = quarter * 32 + lane, part = m >> 6, f = m & 63;
+        float acc[WS_TAPS][32];
+#pragma unroll
+        for (int t = 0; t < WS_TAPS; ++t)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[t][i] = 0.f;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+        // group `half` (4 warps = all 128 lanes) transposes the stages of its parity, all 64 positions of them
+        const uint16_t* src0 = reinterpret_cast<const uint16_t*>(smem_u + 2 * WS_IN_UNITS + (part * 8 + (f >> 3)) * WS_DA_SLAB) + (f & 7);
+        int st = half, in_chunk = 0, ci = 0;
+        uint32_t ph = 0;
+        for (int si = 0; si < nst + WS_LAG; ++si) {
+            if (si < nst && (si & 1) == half) {
+                // the A buffer of this stage slot was read by the MMAs of stage si - WS_STAGES
+                if (si >= WS_STAGES) mbar_wait_spin(empty_a + 8u * st, ph ^ 1u);
+                mbar_wait_spin(full_a + 8u * st, ph);
+                tc_fence_after();
+                if (!(a.diag & 2)) {
+                    const uint16_t* src = src0 + (size_t)st * (WS_STAGE_UNITS * 8);
+                    uint32_t r[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        r[j] = (uint32_t)src[(2 * j) * 8] | ((uint32_t)src[(2 * j + 1) * 8] << 16);
+                    tmem_st32(lane_addr + (uint32_t)(WS_DCOLS + st * (WS_KT / 2)), r);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(aready_a + 8u * st);
+                st += 2;
+                if (st >= WS_STAGES) { st -= WS_STAGES; ph ^= 1u; }
+            }
+            if (si >= WS_LAG) {
+                const bool last = (in_chunk == a.flush - 1) || (si - WS_LAG == nst - 1);
+                if (last) {
+#pragma unroll
+                    for (int t = 0; t < WS_TAPS; ++t) {
+                        if (t < nt) {
+                            mbar_wait_spin(accfull_a + 8u * t, (uint32_t)(ci & 1));
+                            tc_fence_after();
+                            if (!(a.diag & 8)) {
+                                float v[32];
+                                tmem_ld32(lane_addr + (uint32_t)(t * TC_N + half * 32), v);
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) acc[t][i] += v[i];
+                            }
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_a(accfree_a + 8u * t);
+                        }
+                    }
+                    in_chunk = 0; ++ci;
+                } else {
+                    ++in_chunk;
+                }
+            }
+        }
+        // TMEM lane = (part, f): both parts of a channel add into the same weight gradient entry
+#pragma unroll
+        for (int t = 0; t < WS_TAPS; ++t) {
+            const int tap = k0 + t;
+            if (t < nt && tap < a.K && f < NMA_C) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int c = half * 32 + i;
+                    if (c < NMA_C1) atomicAdd(a.gW + ((size_t)tap * NMA_C1 + c) * NMA_C + f, acc[t][i]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static void wgrad_ts_geometry(ConvWgradTsArgs& a, long long rows, long long Lin, long long Nv, int sm_count) {
+    a.ngroups = (a.K + WS_TAPS - 1) / WS_TAPS;
+    // the last k-step of a row reads up to 15 positions past Nv: they must fall into the zero gap of K-1 slots
+    if (rows > 1 && ((16 - Nv % 16) % 16) > a.K - 1) { Nv = Lin = rows * Lin; rows = 1; }
+    a.Lin = Lin; a.Nv = Nv;
+    a.spr = (int)((Nv + WS_KT - 1) / WS_KT);
+    a.nstages_total = (int)(rows * a.spr);
+    int nq = (3 * sm_count) / a.ngroups;
+    if (nq < 1) nq = 1;
+    if (nq > a.nstages_total) nq = a.nstages_total;
+    a.nq = nq;
+    a.flush = WS_FLUSH;
+    a.diag = nma_diag_bits();
+    if (a.diag) { const char* ef = getenv("NMA_WS_FLUSH"); if (ef && atoi(ef) > 0) a.flush = atoi(ef); }
+}
+
+static bool wgrad_use_ts() {
+    const char* e = getenv("NMA_WGRAD_TS");
+    return !(e && e[0] == '0');
+}
+
+static int launch_wgrad_ts(ConvWgradTsArgs& a, cudaStream_t st) {
+    const int smem = WS_STAGES * WS_STAGE_UNITS * 16;
+    static int configured = 0;
+    if (configured < smem) {
+        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_wgrad_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    k_conv_wgrad_ts<<<dim3(a.nq, a.ngroups), WS_THREADS, smem, st>>>(a);
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // rows of Lin flattened positions each, the first Nv of which carry dA (rows = 1, Lin = Nv = Q: plain flattened walk)
 static void wgrad_bf_geometry(ConvWgradBfArgs& a, long long rows, long long Lin, long long Nv, int sm_count) {
     a.npairs = (a.K + 1) / 2;
@@ -934,6 +1295,13 @@ int launch_conv_wgrad_bf(nma_handle_s* h, int i, int p, float* gp, cudaStream_t 
     a.da_hi = (const uint4*)h->ws[i].dat_hi; a.da_lo = (const uint4*)h->ws[i].dat_lo; a.da_Q = h->ws[i].dat_Q;
     a.gW = gp + h->po[i].convw;
     a.K = h->cfg.K;
+    if (wgrad_use_ts()) {
+        ConvWgradTsArgs t;
+        t.in_hi = a.in_hi; t.in_lo = a.in_lo; t.in_Q = a.in_Q; t.da_hi = a.da_hi; t.da_lo = a.da_lo; t.da_Q = a.da_Q;
+        t.gW = a.gW; t.K = a.K;
+        wgrad_ts_geometry(t, p, d.Lin, d.N, h->sm_count);
+        return launch_wgrad_ts(t, st);
+    }
     wgrad_bf_geometry(a, p, d.Lin, d.N, h->sm_count);
     const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
     static int configured = 0;
@@ -964,10 +1332,18 @@ extern "C" int nma_tc_wgrad_raw_bf(const float* d_in, const float* d_da, float* 
     ConvWgradBfArgs a;
     a.in_hi = ih; a.in_lo = il; a.in_Q = Qalloc; a.da_hi = dh; a.da_lo = dl; a.da_Q = Qalloc;
     a.gW = d_gw; a.K = K;
-    wgrad_bf_geometry(a, 1, Q, Q, 4);
-    const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
-    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) k_conv_wgrad_bf<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
+    cudaError_t e = cudaSuccess;
+    if (wgrad_use_ts()) {
+        ConvWgradTsArgs t;
+        t.in_hi = ih; t.in_lo = il; t.in_Q = Qalloc; t.da_hi = dh; t.da_lo = dl; t.da_Q = Qalloc; t.gW = d_gw; t.K = K;
+        wgrad_ts_geometry(t, 1, Q, Q, 4);
+        if (launch_wgrad_ts(t, st)) e = cudaErrorUnknown;
+    } else {
+        wgrad_bf_geometry(a, 1, Q, Q, 4);
+        const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
+        e = cudaFuncSetAttribute(k_conv_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) k_conv_wgrad_bf<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
+    }
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(st);
     cudaFree(ih); cudaFree(il); cudaFree(dh); cudaFree(dl);
