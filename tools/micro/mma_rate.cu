@@ -143,6 +143,53 @@ __global__ void __launch_bounds__(128, 1) k_commit_tput(int iters, int nmma, int
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// nw warps issue concurrently, each into its own accumulator tiles (N = 64, A from TMEM): cycles per instruction overall
+__global__ void __launch_bounds__(192, 1) k_multi_issue(int iters, int nw, long long* out) {
+    extern __shared__ __align__(128) uint4 sm[];
+    __shared__ uint64_t fin;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < 8192; t += blockDim.x) sm[t] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { mbar_init(&fin, nw); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+    const uint64_t bd = desc_pack(desc_lo(smem_u32(sm) + 65536u, 128u), desc_hi(1152u));
+    const long long t0 = clock64();
+    if (warp >= 1 && warp <= nw) {
+        if (elect_one()) {
+            for (int i = 0; i < iters; ++i) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mma_ts(tmem + (uint32_t)((warp - 1) * 64), tmem + 480u, bd, idesc, 1u);
+            }
+            tc_commit(&fin);
+        }
+        __syncwarp();
+    }
+    if (warp == 1) {
+        mbar_wait_backoff(&fin, 0);
+        if (elect_one() && blockIdx.x == 0) out[0] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+void run_multi(int nw, long long* d_out) {
+    const int iters = 1000;
+    cudaFuncSetAttribute(k_multi_issue, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_multi_issue<<<148, 192, 200 * 1024>>>(iters, nw, d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, d_out, 8, cudaMemcpyDeviceToHost);
+    printf("%d warps issuing concurrently (N=64 TS, own tiles): %7.1f cycles per instruction overall %s\n", nw, (double)c / (iters * 8.0 * nw),
+           e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 void run_tput(int nmma, int ncommit, long long* d_out) {
     const int iters = 1000;
     cudaFuncSetAttribute(k_commit_tput, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -208,5 +255,8 @@ int main() {
     run_tput(32, 4, d_out);
     run_tput(0, 1, d_out);
     run_tput(8, 1, d_out);
+    run_multi(1, d_out);
+    run_multi(2, d_out);
+    run_multi(4, d_out);
     return 0;
 }

@@ -72,5 +72,29 @@ def full(path):
         print("| `%s` | " % short(r[kn]) + " | ".join(vals) + " |")
 
 
+def traffic(path, mode, label, rows, index="0"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of launch number `index` in the capture -> profiles/traffic.json,
+    which bench.py reads for roofline.traffic (per row x rows):
+        python tools/summarize_ncu.py traffic gpurun_out/x.ncu-rep bf16 'conv_wgrad[0]' 2048 [launch index]"""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rws = list(csv.reader(io.StringIO(out)))
+    hdr, units = rws[0], rws[1]
+    r = rws[2 + int(index)]
+    def val(name):
+        i = hdr.index(name)
+        v = float(r[i].replace(",", ""))
+        return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+    total = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = os.path.join(root, "profiles", "traffic.json")
+    d = json.load(open(dst)) if os.path.exists(dst) else {}
+    d.setdefault(mode, {})[label] = {"dram_bytes": total, "rows": int(rows), "kernel": short(r[hdr.index("Kernel Name")]),
+                                     "source": "ncu --set full, %s (launch %s: %s rows)" % (os.path.basename(path), index, rows)}
+    json.dump(d, open(dst, "w"), indent=1)
+    print(label, mode, "%.1f MB at %s rows = %.1f KB per row" % (total / 1e6, rows, total / float(rows) / 1e3))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -120,17 +120,13 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     {
         const char* env = getenv("NMA_TC");
         h->use_tc = h->tc_ok && !(env && env[0] == '0');
-        const char* envp = getenv("NMA_TC_PERSIST");
-        h->use_tc_persist = !(envp && envp[0] == '0');
+        h->use_tc_persist = 1;
         const char* envf = getenv("NMA_TC_FEAT");
         h->use_tc_feat = h->use_tc && !(envf && envf[0] == '0');
         h->use_bf16 = 0;            // decided below, once the kernels that understand the format are known to run
-        const char* envw = getenv("NMA_DGRAD_WIDE");
-        h->dgrad_wide = (envw && envw[0] == '0') ? 0 : 1;
-        const char* envp2 = getenv("NMA_TAP_PAIRS");
-        // default for even kernel_len (every reference script); the zero-kernel pairing of an odd last tap is written but
-        // has not been run on hardware yet, so odd kernel_len keeps the tap-by-tap kernels unless NMA_TAP_PAIRS=1 insists
-        h->tap_pairs = (h->dgrad_wide && !(envp2 && envp2[0] == '0') && ((cfg->K % 2 == 0) || (envp2 && envp2[0] == '1'))) ? 1 : 0;
+        h->dgrad_wide = 1;
+        // taps in pairs for even kernel_len (every reference script); odd kernel_len keeps the tap-by-tap kernels
+        h->tap_pairs = (cfg->K % 2 == 0) ? 1 : 0;
     }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
@@ -240,9 +236,7 @@ extern "C" int nma_destroy(nma_handle h) {
 // The bf16-split conv operands are produced by k_feat_fwd_tc / k_conv_fwd_tcp / k_epi_bwd_tc only: the format is
 // available exactly when those kernels are the ones that run (AR-type model, one hidden layer, no batch-norm).
 static int bf16_path_ok(const nma_handle_s* h) {
-    const char* enve = getenv("NMA_TC_EPI");
-    return h->use_tc && h->use_tc_feat && conv_fwd_tcp_supported(h) && epi_bwd_tc_supported(h) &&
-           !(enve && enve[0] == '0');
+    return h->use_tc && h->use_tc_feat && conv_fwd_tcp_supported(h) && epi_bwd_tc_supported(h);
 }
 
 // bit 0: conv on tcgen05; bit 1: feature MLP and head backward on tcgen05 as well; bit 2: the conv GEMMs in the

@@ -312,10 +312,7 @@ static int persistent_grid(const nma_handle_s* h, int p, int per_sm) {
 }
 
 int launch_epi_bwd(nma_handle_s* h, int i, const float* params, int p, int objective, float* gp, cudaStream_t st) {
-    {
-        const char* env = getenv("NMA_TC_EPI");
-        if (epi_bwd_tc_supported(h) && !(env && env[0] == '0')) return launch_epi_bwd_tc(h, i, params, p, objective, gp, st);
-    }
+    if (epi_bwd_tc_supported(h)) return launch_epi_bwd_tc(h, i, params, p, objective, gp, st);
     const FlowDims& d = h->fd[i];
     EpiBwdArgs a;
     for (int l = 0; l < NMA_MAXH; ++l) {

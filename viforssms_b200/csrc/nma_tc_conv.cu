@@ -1057,7 +1057,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
     const uint32_t accfull_a = smem_addr_once(acc_full), accfree_a = smem_addr_once(acc_free);
     const uint32_t sbase = smem_addr_once(smem_u);
 
-    if (warp == 8 || warp == 11) {
+    if (warp == 8 || warp == 9 + WS_MMA_WARPS) {
         // ===== TMA producers: two warps, each takes every other stage (a warp's chain of barrier wait, address arithmetic and
         // 28 copy instructions per stage is ~400 cycles long: one warp alone could not keep up with the 850-cycle stages) =====
         const int pw = warp == 8 ? 0 : 1;
@@ -1096,7 +1096,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
             st += 2;
             if (st >= WS_STAGES) { st -= WS_STAGES; ph ^= 1u; }
         }
-    } else if (warp == 9 || warp == 10) {
+    } else if (warp >= 9 && warp < 9 + WS_MMA_WARPS) {
         // ===== MMA issuers: warp 9 + w owns taps w, w + WS_MMA_WARPS, ... =====
         // A warp's own instruction stream must stay far below the ~41 cycles an instruction
         // occupies the tensor pipe: taps and k-steps are unrolled with compile-time descriptor offsets (a rolled loop

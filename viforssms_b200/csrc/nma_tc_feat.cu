@@ -1001,10 +1001,7 @@ int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int ob
     a.Lin = d.Lin; a.p = p;
     a.cq = (objective == NMA_OBJ_ELBO) ? (float)h->cfg.scale : 0.f;
     a.bf = h->use_bf16;
-    {
-        const char* env = getenv("NMA_DTB_FUSED");           // 0: per-row sums by k_dtb_from_dat from the operand instead
-        a.dtb = (env && env[0] == '0') ? nullptr : h->ws[i].dtb;
-    }
+    a.dtb = h->ws[i].dtb;                                    // per-row sums of dA taken from registers in this kernel
     if (a.dtb) NMA_CHECK_CUDA(cudaMemsetAsync(a.dtb, 0, (size_t)p * NMA_C * 4, st));
     const long long ntiles = ((long long)p * d.N + FT_M - 1) / FT_M;
     const int grid = (int)(ntiles < h->sm_count ? ntiles : h->sm_count);
