@@ -727,195 +727,18 @@ extern "C" int nma_tc_wgrad_raw(const float* d_in, const float* d_da, float* d_g
 }
 
 // ---------------------------------------------------------------------------
-// weight gradient in the bf16 split:  dW[k][c][f] = sum_q inp_flat[q + k][c] * dA_flat[q][f]   on kind::f16
+// weight gradient in the bf16 split:  dW[k][c][f] = sum_q inp_flat[q + k][c] * dA_flat[q][f]   on kind::f16,
+// with dA as a TMEM-RESIDENT A operand (the "TS" form of tcgen05.mma).
 //
 // 16-bit operands may be MN-major, and the conv operand layout [channel/8][position][8 x bf16] IS the no-swizzle
 // MN-major canonical layout of a (channels x positions) matrix with the positions as the reduction: 8 consecutive
 // positions of one channel chunk are one 128-byte core matrix, the next 8 positions follow at +128 B (leading byte
-// offset), the next channel chunk at the slab stride (stride byte offset).  So both operands are fed to the tensor
-// core exactly as the forward pass and the head backward wrote them: no transposes, no unit building - the TMA engine
-// copies slabs, one thread issues MMAs.  Tap t is, again, a +16t-byte start address.
-//   A (M = 128): rows 0-63 = the 64 channel slots at tap t, rows 64-127 = the same at tap t+1: the slabs are staged
-//                twice, the second copy read from one position further on, so that all 16 chunk slabs of a tap pair
-//                lie at one stride.  hi and lo parts are separate tiles.
-//   B (N = 128): 64 hi | 64 lo channel slots of dA: the dat_hi slabs followed by the dat_lo slabs.
-//   D[pair]:     128 TMEM columns: A_hi x [B_hi | B_lo] -> main | correction, A_lo x B_hi (N = 64) -> correction.
-// K = 16 positions per MMA; a stage is 64 positions; the accumulators are drained TMEM -> registers every 8 stages
-// (32-MMA chains: the tensor core accumulates with truncation) and summed in round-to-nearest fp32.
-// CTA = (group of <= 4 tap pairs, range of stages); warps 0-7 drain, warp 8 TMA (all lanes issue), warp 9 MMA.
-// ---------------------------------------------------------------------------
-#define WB_KT 64
-#define WB_APOS (WB_KT + 8)                 // tap offsets 0..6 inside a group of 4 pairs
-#define WB_STAGES 4
-#define WB_FLUSH 8
-#define WB_A_UNITS (16 * WB_APOS)           // 16-byte units of A_hi (or A_lo): 16 chunk slabs
-#define WB_B_UNITS (16 * WB_KT)
-#define WB_STAGE_UNITS (2 * WB_A_UNITS + WB_B_UNITS)
-#define WB_NCOPY 42                         // bulk copies per stage: 2 x 2 x 7 A slabs + 2 x 7 B slabs (chunk 7 is all zero)
-
-struct ConvWgradBfArgs {
-    const uint4* in_hi; const uint4* in_lo; long long in_Q;      // [8][in_Q] 16-byte units
-    const uint4* da_hi; const uint4* da_lo; long long da_Q;      // dA(q) at unit q + K - 1
-    float* gW;                                                   // [K][51][50]
-    int K, npairs, ngroups, nstages_total, nq;
-    // stages walk the VALID dA positions only: row r contributes positions [r*Lin, r*Lin + Nv) in spr stages of 64 (the
-    // last one of a row with fewer k-steps); the K-1 slots between rows hold dA = 0 and would be wasted reduction steps
-    // (24 % / 33 % / 49 % of the flattened positions of the three flows of the AR configuration)
-    long long Lin, Nv;
-    int spr;
-    int flush;                                                   // stages per accumulator drain (WB_FLUSH)
-    int diag;                                                    // NMA_DIAG timing experiments (results invalid): 1 no A loads, 2 no B loads, 8 / 16 see the MMA loop
-};
-
-__global__ void __launch_bounds__(WGT_THREADS, 1) k_conv_wgrad_bf(ConvWgradBfArgs a) {
-    extern __shared__ __align__(128) uint4 smem_u[];
-    __shared__ uint64_t full[WB_STAGES], empty[WB_STAGES], acc_full, acc_free;
-    __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.y;
-    const int base = a.npairs / a.ngroups, rem = a.npairs % a.ngroups;
-    const int np = base + (g < rem ? 1 : 0);                    // tap pairs of this CTA
-    const int k0 = 2 * (g * base + (g < rem ? g : rem));        // first tap
-    const int s_begin = (int)((long long)a.nstages_total * blockIdx.x / a.nq);
-    const int s_end = (int)((long long)a.nstages_total * (blockIdx.x + 1) / a.nq);
-    const int nst = s_end - s_begin;
-    const int nchunks = (nst + a.flush - 1) / a.flush;
-
-    // slabs of chunk 7 (channel slots 56..63) are never loaded: zero everything once
-    for (int t = tid; t < WB_STAGES * WB_STAGE_UNITS; t += blockDim.x) smem_u[t] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) {
-        for (int i = 0; i < WB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(&acc_full, 1); mbar_init(&acc_free, 8);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(&tmem_slot, 512);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-
-    if (warp == 8) {
-        // ===== TMA producer: every lane issues its share of the stage's 42 slab copies =====
-        for (int si = 0; si < nst; ++si) {
-            const int st = si % WB_STAGES;
-            if (si >= WB_STAGES) mbar_wait_backoff(&empty[st], (uint32_t)(((si / WB_STAGES) - 1) & 1));
-            uint4* sb = smem_u + (size_t)st * WB_STAGE_UNITS;
-            const long long gs = s_begin + si, row = gs / a.spr;
-            const long long q0 = row * a.Lin + (gs - row * a.spr) * WB_KT;
-            // the last stage of a row has fewer k-steps: copy only the positions they read
-            const long long left = a.Nv - (gs - row * a.spr) * WB_KT;
-            const uint32_t npos_b = left >= WB_KT ? (uint32_t)WB_KT : (uint32_t)((left + 15) / 16) * 16u;
-            const uint32_t npos_a = npos_b + 8u;
-            if (lane == 0)
-                mbar_expect_tx(&full[st], ((a.diag & 1) ? 0u : 28u * npos_a * 16u) + ((a.diag & 2) ? 0u : 14u * npos_b * 16u));
-            __syncwarp();
-            for (int idx = lane; idx < WB_NCOPY; idx += 32) {
-                if ((idx < 28 && (a.diag & 1)) || (idx >= 28 && (a.diag & 2))) continue;
-                if (idx < 28) {
-                    const int hl = idx / 14, r2 = idx - hl * 14, copy = r2 / 7, c = r2 - copy * 7;
-                    const uint4* src = (hl ? a.in_lo : a.in_hi) + (size_t)c * a.in_Q + q0 + k0 + copy;
-                    bulk_g2s(sb + hl * WB_A_UNITS + (copy * 8 + c) * WB_APOS, src, npos_a * 16u, &full[st]);
-                } else {
-                    const int j = idx - 28, hl = j / 7, c = j - hl * 7;
-                    const uint4* src = (hl ? a.da_lo : a.da_hi) + (size_t)c * a.da_Q + q0 + (a.K - 1);
-                    bulk_g2s(sb + 2 * WB_A_UNITS + (hl * 8 + c) * WB_KT, src, npos_b * 16u, &full[st]);
-                }
-            }
-            __syncwarp();
-        }
-    } else if (warp == 9) {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc_n64 = umma_idesc_bf16(TC_M, TC_N, 1, 1);
-        constexpr uint32_t idesc_n128 = umma_idesc_bf16(TC_M, 2 * TC_N, 1, 1);
-        const uint32_t sbase = smem_u32(smem_u);
-        const uint32_t a_hi32 = desc_hi(WB_APOS * 16u), b_hi32 = desc_hi(WB_KT * 16u);    // stride offset: next channel chunk
-        for (int si = 0; si < nst; ++si) {
-            const int st = si % WB_STAGES;
-            const int ci = si / a.flush;
-            const bool chunk_first = (si % a.flush) == 0;
-            const bool chunk_last = ((si % a.flush) == a.flush - 1) || (si == nst - 1);
-            if (chunk_first && ci > 0) mbar_wait_backoff(&acc_free, (uint32_t)((ci - 1) & 1));
-            mbar_wait_backoff(&full[st], (uint32_t)((si / WB_STAGES) & 1));
-            tc_fence_after();
-            const long long gs = s_begin + si;
-            const long long left = a.Nv - (gs % a.spr) * WB_KT;                  // valid positions from this stage's start
-            const int nks = left >= WB_KT ? WB_KT / 16 : (int)((left + 15) / 16);
-            if (elect_one()) {
-                const uint32_t ua_hi = sbase + (uint32_t)(st * WB_STAGE_UNITS) * 16u;
-                const uint32_t ua_lo = ua_hi + WB_A_UNITS * 16u;
-                const uint32_t ub = ua_lo + WB_A_UNITS * 16u;
-                const uint32_t ah0 = desc_lo(ua_hi, 128u), al0 = desc_lo(ua_lo, 128u), b0 = desc_lo(ub, 128u);   // leading offset: next 8 positions
-                for (int pr = 0; pr < np; ++pr) {
-                    const uint32_t d = tmem + (uint32_t)(pr * 2 * TC_N);
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint32_t aoff = (uint32_t)(2 * pr + 16 * ks);          // 16-byte units = positions
-                        const uint64_t ah = desc_pack(ah0 + aoff, a_hi32), al = desc_pack(al0 + aoff, a_hi32);
-                        const uint64_t bw = desc_pack(b0 + (uint32_t)(16 * ks), b_hi32);
-                        umma_bf16(d, ah, bw, idesc_n128, (chunk_first && ks == 0) ? 0u : 1u);
-                        if (a.diag & 16) continue;                                        // timing experiment: no correction MMA
-                        if (a.diag & 8) umma_bf16(d, al, bw, idesc_n128, 1u);             // timing experiment: N = 128 instead of 64
-                        else umma_bf16(d + TC_N, al, bw, idesc_n64, 1u);
-                    }
-                }
-                tc_commit(&empty[st]);
-                if (chunk_last) tc_commit(&acc_full);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===== drain warps =====
-        const int quarter = warp & 3, colhalf = warp >> 2;
-        float acc[WGT_MAXPAIRS][32];
-#pragma unroll
-        for (int pr = 0; pr < WGT_MAXPAIRS; ++pr)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[pr][i] = 0.f;
-        for (int ci = 0; ci < nchunks; ++ci) {
-            mbar_wait_backoff(&acc_full, (uint32_t)(ci & 1));
-            tc_fence_after();
-#pragma unroll
-            for (int pr = 0; pr < WGT_MAXPAIRS; ++pr) {
-                if (pr < np) {
-                    float v[32], c2[32];
-                    const uint32_t ta = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pr * 2 * TC_N + colhalf * 32);
-                    tmem_ld32(ta, v);
-                    tmem_ld32(ta + TC_N, c2);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[pr][i] += v[i] + c2[i];
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_free);
-        }
-        // TMEM lane = M row = j*64 + channel slot
-        const int M = quarter * 32 + lane, j = M >> 6, c = M & 63;
-#pragma unroll
-        for (int pr = 0; pr < WGT_MAXPAIRS; ++pr) {
-            const int tap = k0 + 2 * pr + j;
-            if (pr < np && tap < a.K && c < NMA_C1) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int f = colhalf * 32 + i;
-                    if (f < NMA_C) atomicAdd(a.gW + ((size_t)tap * NMA_C1 + c) * NMA_C + f, acc[pr][i]);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------
-// The same weight gradient with dA as a TMEM-RESIDENT A operand ("TS" form of tcgen05.mma) - the default.
-//
-// Why: an M = 128 MMA with both operands in shared memory is paced by operand fetch (~88 B/clk per SM: 8 KB for the
-// 64 cycles of math of a 128 x 128 x 16 instruction, profiles/r01_bf16.md), which held k_conv_wgrad_bf at ~26 % of its
-// own MMA floor.  dA is the operand every tap of a CTA shares, so it is written ONCE per stage into tensor memory -
-// transposed to the K-major form the A-from-TMEM path requires, lane = channel (64 hi rows over 64 lo rows), column =
-// two consecutive positions - and every MMA then fetches only its 2 KB B operand from shared memory:
+// offset), the next channel chunk at the slab stride (stride byte offset).  So the `in` operand is fed to the tensor
+// core exactly as the forward pass wrote it - the TMA engine copies slabs - and tap t is a +16t-byte start address.
+// dA is the operand every tap of a CTA shares, so it is written ONCE per stage into tensor memory - transposed to the
+// K-major form the A-from-TMEM path requires, lane = channel (64 hi rows over 64 lo rows), column = two consecutive
+// positions - and every MMA then fetches only its 2 KB B operand from shared memory and runs at the pipe's own rate
+// (32 cycles for M = 128, N = 64, K = 16; 48 with A in shared memory: tools/micro/mma_rate.cu):
 //     D[tap][(hl, f), c] += dA_t[(hl, f), q] * in[q + tap][c]          M = 128, N = 64, K = 16 positions
 // B is the `in` slab of ONE tap (hi part, then lo part: two instructions into the same accumulator), MN-major straight
 // from the conv operand layout as before; no second shifted copy of the slabs, 30 KB instead of 53 KB per stage.  All
@@ -1248,12 +1071,6 @@ static void wgrad_ts_geometry(ConvWgradTsArgs& a, long long rows, long long Lin,
     a.nq = nq;
     a.flush = WS_FLUSH;
     a.diag = nma_diag_bits();
-    if (a.diag) { const char* ef = getenv("NMA_WS_FLUSH"); if (ef && atoi(ef) > 0) a.flush = atoi(ef); }
-}
-
-static bool wgrad_use_ts() {
-    const char* e = getenv("NMA_WGRAD_TS");
-    return !(e && e[0] == '0');
 }
 
 static int launch_wgrad_ts(ConvWgradTsArgs& a, cudaStream_t st) {
@@ -1269,50 +1086,15 @@ static int launch_wgrad_ts(ConvWgradTsArgs& a, cudaStream_t st) {
     return 0;
 }
 
-// rows of Lin flattened positions each, the first Nv of which carry dA (rows = 1, Lin = Nv = Q: plain flattened walk)
-static void wgrad_bf_geometry(ConvWgradBfArgs& a, long long rows, long long Lin, long long Nv, int sm_count) {
-    a.npairs = (a.K + 1) / 2;
-    a.ngroups = (a.npairs + WGT_MAXPAIRS - 1) / WGT_MAXPAIRS;
-    // the last k-step of a row reads up to 15 positions past Nv: they must fall into the zero gap of K-1 slots
-    if (rows > 1 && ((16 - Nv % 16) % 16) > a.K - 1) { Nv = Lin = rows * Lin; rows = 1; }
-    a.Lin = Lin; a.Nv = Nv;
-    a.spr = (int)((Nv + WB_KT - 1) / WB_KT);
-    a.nstages_total = (int)(rows * a.spr);
-    const char* ew = getenv("NMA_WB_WAVES");
-    int nq = (((ew && atoi(ew) > 0) ? atoi(ew) : 3) * sm_count) / a.ngroups;
-    if (nq < 1) nq = 1;
-    if (nq > a.nstages_total) nq = a.nstages_total;
-    a.nq = nq;
-    const char* ef = getenv("NMA_WB_FLUSH");
-    a.flush = (ef && atoi(ef) > 0) ? atoi(ef) : WB_FLUSH;
-    a.diag = nma_diag_bits();
-}
-
 int launch_conv_wgrad_bf(nma_handle_s* h, int i, int p, float* gp, cudaStream_t st) {
     const FlowDims& d = h->fd[i];
-    ConvWgradBfArgs a;
-    a.in_hi = (const uint4*)h->ws[i].tin_hi; a.in_lo = (const uint4*)h->ws[i].tin_lo; a.in_Q = h->ws[i].tin_Q;
-    a.da_hi = (const uint4*)h->ws[i].dat_hi; a.da_lo = (const uint4*)h->ws[i].dat_lo; a.da_Q = h->ws[i].dat_Q;
-    a.gW = gp + h->po[i].convw;
-    a.K = h->cfg.K;
-    if (wgrad_use_ts()) {
-        ConvWgradTsArgs t;
-        t.in_hi = a.in_hi; t.in_lo = a.in_lo; t.in_Q = a.in_Q; t.da_hi = a.da_hi; t.da_lo = a.da_lo; t.da_Q = a.da_Q;
-        t.gW = a.gW; t.K = a.K;
-        wgrad_ts_geometry(t, p, d.Lin, d.N, h->sm_count);
-        return launch_wgrad_ts(t, st);
-    }
-    wgrad_bf_geometry(a, p, d.Lin, d.N, h->sm_count);
-    const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
-    static int configured = 0;
-    if (configured < smem) {
-        NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
-    k_conv_wgrad_bf<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
-    nma_count_launch(1);
-    NMA_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    ConvWgradTsArgs t;
+    t.in_hi = (const uint4*)h->ws[i].tin_hi; t.in_lo = (const uint4*)h->ws[i].tin_lo; t.in_Q = h->ws[i].tin_Q;
+    t.da_hi = (const uint4*)h->ws[i].dat_hi; t.da_lo = (const uint4*)h->ws[i].dat_lo; t.da_Q = h->ws[i].dat_Q;
+    t.gW = gp + h->po[i].convw;
+    t.K = h->cfg.K;
+    wgrad_ts_geometry(t, p, d.Lin, d.N, h->sm_count);
+    return launch_wgrad_ts(t, st);
 }
 
 // test hook: the bare bf16-split weight gradient, same contract as nma_tc_wgrad_raw
@@ -1329,21 +1111,11 @@ extern "C" int nma_tc_wgrad_raw_bf(const float* d_in, const float* d_da, float* 
     k_tc_split_in_bf<<<296, 256, 0, st>>>(d_in, Q, Qalloc, ih, il);
     // dA(q) lives at unit q + K - 1; only q <= Q-K contribute
     k_tc_split_in_bf<<<296, 256, 0, st>>>(d_da, Q - K + 1, Qalloc, dh + (K - 1), dl + (K - 1));
-    ConvWgradBfArgs a;
-    a.in_hi = ih; a.in_lo = il; a.in_Q = Qalloc; a.da_hi = dh; a.da_lo = dl; a.da_Q = Qalloc;
-    a.gW = d_gw; a.K = K;
     cudaError_t e = cudaSuccess;
-    if (wgrad_use_ts()) {
-        ConvWgradTsArgs t;
-        t.in_hi = ih; t.in_lo = il; t.in_Q = Qalloc; t.da_hi = dh; t.da_lo = dl; t.da_Q = Qalloc; t.gW = d_gw; t.K = K;
-        wgrad_ts_geometry(t, 1, Q, Q, 4);
-        if (launch_wgrad_ts(t, st)) e = cudaErrorUnknown;
-    } else {
-        wgrad_bf_geometry(a, 1, Q, Q, 4);
-        const int smem = WB_STAGES * WB_STAGE_UNITS * 16;
-        e = cudaFuncSetAttribute(k_conv_wgrad_bf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) k_conv_wgrad_bf<<<dim3(a.nq, a.ngroups), WGT_THREADS, smem, st>>>(a);
-    }
+    ConvWgradTsArgs t;
+    t.in_hi = ih; t.in_lo = il; t.in_Q = Qalloc; t.da_hi = dh; t.da_lo = dl; t.da_Q = Qalloc; t.gW = d_gw; t.K = K;
+    wgrad_ts_geometry(t, 1, Q, Q, 4);
+    if (launch_wgrad_ts(t, st)) e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaError_t e2 = cudaStreamSynchronize(st);
     cudaFree(ih); cudaFree(il); cudaFree(dh); cudaFree(dl);
