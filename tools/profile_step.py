@@ -1,5 +1,5 @@
 """A few plain (eager, one launch per kernel) training steps at a fixed size; the LAST step is bracketed by
-cudaProfilerStart/Stop so `ncu --profile-from-start off` sees exactly one step (tools/gpu_profile.sh)."""
+cudaProfilerStart/Stop so `ncu --profile-from-start off` sees exactly one step (tools/r02_evidence.sh)."""
 import argparse
 import os
 import sys

@@ -60,7 +60,7 @@ __device__ __forceinline__ void bf_split8(const float (&v)[8], uint4& hi, uint4&
 }
 __device__ __forceinline__ float bf_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
 
-// NMA_DIAG timing experiments (tools/time_stages.py) skip loads or MMAs and produce WRONG results on purpose: they are
+// NMA_DIAG timing experiments (tools/r02_diag.sh) skip loads or MMAs and produce WRONG results on purpose: they are
 // honoured only when NMA_DIAG_I_KNOW_RESULTS_ARE_INVALID=1 is set as well, so a stray variable cannot corrupt a run.
 static inline int nma_diag_bits() {
     const char* ok = getenv("NMA_DIAG_I_KNOW_RESULTS_ARE_INVALID");
