@@ -220,3 +220,26 @@ def test_lvr_facade_constructor_and_base_arrays_on_the_host():
         n = shifted.shape[0]
         assert np.array_equal(arrays[0][5 * i:5 * i + n], shifted)
     assert np.array_equal(arrays[4].reshape(2, -1), obs_bin)
+
+
+def test_series_generators_write_the_layouts_the_scripts_read(tmp_path):
+    """The reference ships no FHN / SV / fixed-theta LV series; the root scripts' generators
+    produce them in the layouts the scripts load (fitz_nag_NVP.py:452-454, SV_dense.py:406,
+    lotka_volterra_partial_batch_fix_theta.py:655-668)."""
+    import numpy as np
+    import fitz_nag_NVP as fhn
+    import SV_dense as sv
+    import lotka_volterra_partial_batch_fix_theta as lv
+    obs, obs_bin, tt = fhn.generate(400, dat_dir=str(tmp_path))
+    for name, want in (("fitz_nag_obs_partial.txt", obs), ("fitz_nag_obs_binary.txt", obs_bin), ("fitz_nag_time_till.txt", tt)):
+        got = np.loadtxt(tmp_path / name)
+        assert got.shape == (2, 400) and np.allclose(got, want)
+    assert obs_bin[:, 9::10].all() and obs_bin.sum() == 2 * 40              # both components observed every 10th step
+    assert np.allclose(tt[0, :10], 0.1 * np.arange(9, -1, -1))               # countdown to the next observation, in time units
+    assert np.array_equal(obs[:, 0], obs[:, 9])                              # look-ahead fill: a step carries the NEXT observation
+    assert np.isfinite(obs).all() and np.abs(obs).max() < 10.0
+    s = sv.generate(500, path=str(tmp_path / "SV.dat"))
+    assert np.allclose(np.loadtxt(tmp_path / "SV.dat"), s) and s.shape == (500,) and (s > 0).all()
+    o = lv.generate(2, dat_dir=str(tmp_path))
+    assert o.shape == (2, 2 * 151) and (o > 1.0).all()                       # observations are 1 + softplus(. - 1)
+    assert np.loadtxt(tmp_path / "LV_obs_binary_dense_test.txt").all()
