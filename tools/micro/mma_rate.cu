@@ -190,6 +190,70 @@ void run_multi(int nw, long long* d_out) {
            e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+// the issue stream of the conv kernels: per instruction a fresh descriptor pair whose low words live in VECTOR registers
+// (derived from a value the compiler cannot prove warp-uniform), as in p_mma / pp_mma of nma_tc_conv2.cu.
+// mode 0: SS N=128 + SS N=64 alternating (forward kernel's pair of instructions); mode 1: the same with uniform descriptors
+__global__ void __launch_bounds__(128, 1) k_issue_stream(int iters, int mode, const int* __restrict__ zero, long long* out) {
+    extern __shared__ __align__(128) uint4 sm[];
+    __shared__ uint64_t fin;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < 8192; t += blockDim.x) sm[t] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { mbar_init(&fin, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    constexpr uint32_t id128 = umma_idesc_bf16(128, 128, 0, 0), id64 = umma_idesc_bf16(128, 64, 0, 0);
+    if (warp == 1) {
+        // per-thread (vector) base: zero[] is 0 at run time, unknown at compile time
+        const uint32_t vbase = smem_u32(sm) + (uint32_t)zero[threadIdx.x & 31];
+        const uint32_t ubase = smem_u32(sm);
+        const uint32_t hi32 = desc_hi(128u);
+        const long long t0 = clock64();
+        if (elect_one()) {
+            for (int i = 0; i < iters; ++i) {
+                const uint32_t row = (uint32_t)(2 * (i % 25));
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+#pragma unroll
+                    for (int ks = 0; ks < 7; ++ks) {
+                        const uint32_t base = mode == 0 ? vbase : ubase;
+                        const uint32_t alo = desc_lo(base, 4096u) + row + (uint32_t)(a * 128) + (uint32_t)(ks % 3) * 512u;
+                        const uint32_t blo = desc_lo(base + 65536u, 2048u) + (uint32_t)ks * 256u;
+                        umma_bf16(tmem + (uint32_t)(a * 128), desc_pack(alo, hi32), desc_pack(blo, hi32), id128, 1u);
+                        umma_bf16(tmem + (uint32_t)(a * 128 + 64), desc_pack(alo + 8192u, hi32), desc_pack(blo, hi32), id64, 1u);
+                    }
+                }
+            }
+            tc_commit(&fin);
+        }
+        __syncwarp();
+        mbar_wait_backoff(&fin, 0);
+        if (elect_one() && blockIdx.x == 0) out[0] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+void run_stream(int mode, long long* d_out) {
+    const int iters = 500;
+    int* zero;
+    cudaMalloc(&zero, 128);
+    cudaMemset(zero, 0, 128);
+    cudaFuncSetAttribute(k_issue_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_issue_stream<<<148, 128, 200 * 1024>>>(iters, mode, zero, d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, d_out, 8, cudaMemcpyDeviceToHost);
+    printf("forward-kernel issue stream (14 x [SS N=128, SS N=64] per stage, math 112 cycles per pair), descriptors from %s registers: %7.1f cycles per pair %s\n",
+           mode == 0 ? "VECTOR" : "uniform", (double)c / (iters * 14.0), e == cudaSuccess ? "" : cudaGetErrorString(e));
+    cudaFree(zero);
+}
+
 void run_tput(int nmma, int ncommit, long long* d_out) {
     const int iters = 1000;
     cudaFuncSetAttribute(k_commit_tput, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -258,5 +322,7 @@ int main() {
     run_multi(1, d_out);
     run_multi(2, d_out);
     run_multi(4, d_out);
+    run_stream(0, d_out);
+    run_stream(1, d_out);
     return 0;
 }
