@@ -34,6 +34,8 @@ extern "C" {
 #define NMA_MODEL_SV  2   /* SV_dense.py:203-234 */
 #define NMA_MODEL_LV  3   /* lotka_volterra_partial_batch_fix_theta.py:265-371 (fixed theta) */
 #define NMA_MODEL_LVR 4   /* lotka_volterra_partial.py:234-297 (learned theta): same flow kernels as NMA_MODEL_LV, own ELBO branch */
+#define NMA_MODEL_LVB 5   /* lotka_volterra_partial_batch.py:300-371 (learned softplus-theta, p_val windows): NMA_MODEL_LV's
+                           * flow, observation and x0 terms, the plain bivariate transition density, d/dtheta of all of it */
 
 /* objectives (which scalar is differentiated) */
 #define NMA_OBJ_ELBO    0 /* -sum_rows scale*(sde - logq + obs)   AR.py:184-185,228-229 */
@@ -63,6 +65,9 @@ typedef struct nma_config {
     float   dt;
     float   obs_std;
     float   x0[2];
+    int32_t n_pinned;   /* leading states of the series pinned to x0 by mask / shift: 1 (0 reads as 1); p_val for the
+                         * Lotka-Volterra batch scripts (lotka_volterra_partial_batch.py:237-240) */
+    int32_t reserved;
 } nma_config;
 
 typedef struct nma_handle_s* nma_handle;
@@ -136,7 +141,10 @@ typedef struct nma_step_opts {
 /* theta posterior of AR.py:376-391 (see nma_theta_flow_fwd below for the layouts) and the diagonal Gaussian prior of
  * AR.py:178-182 (host arrays of dtheta floats).  Device pointers are borrowed until nma_destroy. */
 int nma_set_theta_flow(nma_handle h, const float* d_masks, const int32_t* d_perms, int32_t nb, int32_t relu,
-                       float base_loc, float base_scale, const float* prior_mean, const float* prior_scale);
+                       float base_loc, float base_scale, const float* prior_mean, const float* prior_scale,
+                       int32_t softplus_out);
+/* softplus_out = 1: the chain ends in tfb.Softplus (lotka_volterra_partial_batch.py:741) - theta = softplus(flow output),
+ * log q carries its Jacobian - and the prior is the Softplus-transformed diagonal Gaussian of ibid. :358-365. */
 int64_t nma_theta_flow_param_count(int32_t dtheta, int32_t nb);
 int nma_train_step(nma_handle h, float* d_blob, float* d_grad, float* d_m, float* d_v, const int64_t* d_idx, int32_t p,
                    const nma_step_opts* opts, float* d_scalars, float* d_theta_out, float* d_lf_out, void* stream);

@@ -219,7 +219,7 @@ def flow_forward(cfg, P: Dict[str, torch.Tensor], eps: torch.Tensor, theta: torc
     # init_dist.slp: sum over the last S slots of log N(eps; 0, 1)            (AR.py:33-34)
     logq = (-0.5 * eps[:, -S:] ** 2 - 0.5 * LOG2PI).sum(dim=1)
     for i in range(cfg.F):
-        if cfg.model in (3, 4):
+        if cfg.model in (3, 4, 5):
             # lotka_volterra_partial_batch_fix_theta.py:343-344,71-76 (lotka_volterra_partial.py:68-76,279-281): EVERY flow reads the whole window
             # (ts_feats = self.time_feats, no i*K slice); 3 x dense(50) + dense(feat_dims = L_i - 1), then the
             # [window position, unit] matrix is TRANSPOSED: unit m becomes the conv position, window position w a
@@ -323,8 +323,9 @@ def elbo_terms(cfg, x_final: torch.Tensor, theta: torch.Tensor, time_feats: torc
     raise ValueError("unknown model")
 
 
-def lv_terms(cfg, x_final, theta, time_feats, extra):
-    """Lotka-Volterra (fixed theta).  Returns (sde_log_prob incl. the x0 term, obs_log_prob, the log-det term that
+def lv_terms(cfg, x_final, theta, time_feats, extra, chain_on_transition=True):
+    """Lotka-Volterra (fixed theta; with chain_on_transition=False the learned-theta batch script
+    lotka_volterra_partial_batch.py:300-343, whose transition density is the plain bivariate normal of the state).  Returns (sde_log_prob incl. the x0 term, obs_log_prob, the log-det term that
     lf_log_prob receives on top of the flow's own logq, lf_sample [p,2,B+1]).
 
     Bijector conventions (SURVEY Appendix D): Chain composes right to left; Softplus.ildj(y) = -log(1 - exp(-y));
@@ -356,20 +357,31 @@ def lv_terms(cfg, x_final, theta, time_feats, extra):
     cc = torch.sqrt(th[1] * x1 * x2 + th[2] * x2 - cb ** 2)
     sq = math.sqrt(dt)
     L11, L21, L22 = sq * ca, sq * cb, sq * cc                                 # chol = sqrt(dt) [[a,0],[b,c]]
-    d1 = inv(nxt[:, 0, :]) - (x1 + dt * a1)
-    d2 = inv(nxt[:, 1, :]) - (x2 + dt * a2)
+    tgt = inv(nxt) if chain_on_transition else nxt
+    d1 = tgt[:, 0, :] - (x1 + dt * a1)
+    d2 = tgt[:, 1, :] - (x2 + dt * a2)
     # Bivariate_Normal.normal_log_prob (:54-58): det = prod(diag(chol))^2, cov_inv = inverse(chol chol^T), both from the
     # un-jittered chol (the +1e-6 copy is stored but never used)
     w1 = d1 / L11
     w2 = (d2 - L21 * w1) / L22
     log_det = 2.0 * (torch.log(L11) + torch.log(L22))
     n_lp = -0.5 * log_det - 0.5 * (w1 ** 2 + w2 ** 2) - LOG2PI
-    sde_lp = (n_lp + ildj(nxt[:, 0, :]) + ildj(nxt[:, 1, :])).sum(dim=1)
+    sde_lp = ((n_lp + ildj(nxt[:, 0, :]) + ildj(nxt[:, 1, :])) if chain_on_transition else n_lp).sum(dim=1)
     # p(x0) (:316-326): transformed diagonal Gaussian on the first retained state lf[:, :, 1]
     x0s = lf[:, :, 1]
     mean = torch.as_tensor(cfg.x0, dtype=x_final.dtype)
     x0_lp = (normal_logpdf(inv(x0s), mean, cfg.obs_std) + ildj(x0s)).sum(dim=1)   # x0_std rides in cfg.obs_std
     return sde_lp + x0_lp, obs_lp, extra_logq, lf
+
+
+def lvb_theta_prior(theta, priors):
+    """lotka_volterra_partial_batch.py:358-365: TransformedDistribution(MultivariateNormalDiag(mean, scale),
+    Softplus(event_ndims=2)).log_prob(theta) = log N(softplus^-1(theta); mean, scale) - sum log(1 - exp(-theta)), the
+    log-det summed over the components of a row."""
+    mean = torch.as_tensor([m for m, _ in priors], dtype=theta.dtype)
+    sd = torch.as_tensor([s for _, s in priors], dtype=theta.dtype)
+    u = theta + torch.log(-torch.expm1(-theta))
+    return (normal_logpdf(u, mean, sd) - torch.log(-torch.expm1(-theta))).sum(dim=1)
 
 
 def pad_series_lvr(obs, time_till, x0, dt, T, target_dims, F, K, fw) -> Dict[str, object]:
@@ -435,8 +447,11 @@ def objective(cfg, obj: int, P, eps, theta, time_feats, extra=None, path_target:
     obj 2: sum (lf_sample - path_target)^2       [fitz_nag_NVP.py:288-289; SV_dense.py:251-252]
     """
     x_final, logq = flow_forward(cfg, P, eps, theta, time_feats)
-    if cfg.model in (3, 4):
-        sde, obs, extra_logq, lf = (lv_terms if cfg.model == 3 else lvr_terms)(cfg, x_final, theta, time_feats, extra)
+    if cfg.model in (3, 4, 5):
+        if cfg.model == 5:          # lotka_volterra_partial_batch.py: learned theta, no chain on the transition density
+            sde, obs, extra_logq, lf = lv_terms(cfg, x_final, theta, time_feats, extra, chain_on_transition=False)
+        else:
+            sde, obs, extra_logq, lf = (lv_terms if cfg.model == 3 else lvr_terms)(cfg, x_final, theta, time_feats, extra)
         logq = logq + extra_logq                                              # lf_log_prob, LV fix-theta :369-370
     else:
         sde, obs, lf = elbo_terms(cfg, x_final, theta, time_feats, extra)

@@ -310,12 +310,82 @@ def lv_fixed(golden):
     tf_shim.EVENT_REDUCTION = "literal"
 
 
+def lv_batch(golden):
+    """lotka_volterra_partial_batch.py - the fixed-theta script's flow with a LEARNED theta (softplus-transformed posterior
+    and prior, :198-200,358-365), the plain bivariate transition density (no bijector chain, :339-343) and p_val = 3 windows
+    per iteration whose first p_val states are pinned (mask_vals, :237-240) - at short series."""
+    from viforssms_b200.config import lv_config
+    p, K, B, F, fw, dt, seed = 3, 4, 6, 2, 2, 0.2, 31
+    N = p * B
+    T = (B - 1) * dt                     # the script's T is the length of ONE series: target_dims = T / dt + 1 = B (:681-683)
+    cfg = lv_config(p=p, K=K, B=B, F=F, H=2, feat_window=fw, target_dims=B, dt=dt, x0=(11.0, 9.5))
+    layout, n = param_layout(cfg)
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    t = np.arange(N, dtype=np.float64)
+    obs = np.stack([12.0 + 4.0 * np.sin(0.3 * t) + 0.3 * rs.standard_normal(N),
+                    9.0 + 3.0 * np.cos(0.3 * t) + 0.3 * rs.standard_normal(N)])
+    obs_bin = (rs.uniform(size=(2, N)) < 0.7).astype(np.float64)
+    obs = np.where(obs_bin > 0, obs, np.log1p(np.exp(-2.0)) + 1.0)
+    tt = rs.uniform(0.0, 1.0, size=(2, N)).round(1)
+    x0 = np.array(cfg.x0)
+    x0_std = np.array([1.0, 1.0])
+    pads = O.pad_series_lv(obs, tt, x0, dt, T, B, p, F, K, fw)
+    idx = np.arange(p, dtype=np.int64) * B
+    tf64, mask, shift, bin_feed = O.gather_feed_lv(pads, obs_bin, idx, cfg.L0, B)
+    params = init_params(cfg, layout, n, g, None, T)
+    for i in range(F):
+        off, _ = layout[f"f{i}.head.b"]
+        params[off] = 3.0
+    eps = torch.randn(p, cfg.L0, generator=g)
+    theta = torch.tensor(np.log1p(np.exp([-1.0, -6.0, -1.0, -2.0]))).repeat(p, 1) * (1.0 + 0.1 * torch.randn(p, 4, generator=g).double())
+    theta_lp = torch.randn(p, generator=g).double()
+    priors = [(-1.0, np.sqrt(0.1)), (-6.0, np.sqrt(0.1)), (-1.0, np.sqrt(0.1)), (-2.0, np.sqrt(0.1))]     # :689-690
+    network_dims = [50] * 4
+    f32 = lambda a: np.asarray(a).astype(np.float32)
+    tf_shim.EVENT_REDUCTION = "per_state"
+    ns = class_section("lotka_volterra_partial_batch.py", p_val=p, no_flows=F, network_dims=network_dims, kernel_len=K)
+    st = tf_shim.STATE
+    st.__init__()
+    st.placeholders = [np.ones(1), f32(tf64), f32(mask), f32(shift), f32(bin_feed)]
+    st.samples = [eps.numpy()]
+    st.blob = params.double()
+    theta_dist = tf_shim.InjectedDistribution(theta.numpy(), theta_lp.numpy())
+    model = ns["VI_SSM"](obs, obs_bin, tt, x0, x0_std, theta_dist, priors, dt, T, p, K, B, network_dims, B, F, fw,
+                         learn_rate=1e-3, pre_train=False)
+    model.build_flow()
+    check_layout(st, layout, n)
+    golden["lvb_mask_vals"] = np.asarray(model.mask_vals)
+    golden["lvb_shift_vals"] = np.asarray(model.shift_vals)
+    scale = float(B) / B
+    loss, sde, obs_lp, prior_lp = model._ELBO()
+    dev_obj = -(scale * (sde - model.lf_log_prob + obs_lp)).sum()
+    g_theta = torch.autograd.grad(dev_obj, model.theta, retain_graph=True)[0]
+    gv = ns["AdamaxOptimizer"](learning_rate=1e-3, beta1=0.95).compute_gradients(-loss)
+    flat = torch.cat([gg.reshape(-1) for gg, _ in gv]).detach()
+    golden.update({"lvb_hyper": np.array([p, K, B, F, fw, seed]), "lvb_dt": np.array(dt), "lvb_obs": obs, "lvb_obs_bin": obs_bin,
+                   "lvb_time_till": tt, "lvb_eps": eps.numpy(), "lvb_theta": theta.numpy(), "lvb_theta_lp": theta_lp.numpy(),
+                   "lvb_params_sha_f32": np.array(sha(params.numpy())), "lvb_sde": sde.detach().numpy(),
+                   "lvb_obs_lp": obs_lp.detach().numpy(), "lvb_logq": model.lf_log_prob.detach().numpy(),
+                   "lvb_prior": prior_lp.detach().numpy(), "lvb_lf_sample": model.lf_sample.detach().numpy(),
+                   "lvb_elbo": loss.detach().numpy(), "lvb_grad_theta": g_theta.numpy()})
+    grads_summary(flat, layout, "lvb_", golden)
+    print("lv batch: sde", golden["lvb_sde"], "obs", golden["lvb_obs_lp"], "prior", golden["lvb_prior"], "global norm", float(flat.norm()))
+    tf_shim.EVENT_REDUCTION = "literal"
+
+
 def main():
     golden = {}
+    if "--only-lvb" in sys.argv:
+        golden = dict(np.load(os.path.join(HERE, "models_step_golden.npz")))
+        lv_batch(golden)
+        np.savez_compressed(os.path.join(HERE, "models_step_golden.npz"), **golden)
+        return
     fhn(golden)
     sv(golden)
     lvr(golden)
     lv_fixed(golden)
+    lv_batch(golden)
     path = os.path.join(HERE, "models_step_golden.npz")
     np.savez_compressed(path, **golden)
     print("wrote", path, os.path.getsize(path), "bytes")

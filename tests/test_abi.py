@@ -26,9 +26,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_matches_header_size():
-    """sizeof(struct nma_config): 16 int32 + 2*32 int32 + double + 4 floats, natural alignment."""
+    """sizeof(struct nma_config): 16 int32 + 2*32 int32 + double + 4 floats + 2 int32, natural alignment."""
     from viforssms_b200.config import CConfig
-    assert ctypes.sizeof(CConfig) == 16 * 4 + 2 * 32 * 4 + 8 + 4 * 4
+    assert ctypes.sizeof(CConfig) == 16 * 4 + 2 * 32 * 4 + 8 + 4 * 4 + 2 * 4
 
 
 def test_no_gpu_means_loud_failure():

@@ -232,3 +232,48 @@ def test_lv_fixed_theta_oracle_matches_the_reference_classes_under_the_per_state
     assert _close(t[:, 1], GM[lit + "obs_lp"], 1e-9) and _close(t[:, 2], GM[lit + "logq"], 1e-9)
     assert _close(ref["lf"].numpy(), GM[lit + "lf_sample"], 1e-10)
     assert not _close(t[:, 0], GM[lit + "sde"], 1e-3)
+
+
+def lvb_inputs(GM):
+    """Inputs of the lotka_volterra_partial_batch.py fixture (p_val = 3 windows tiling three concatenated 6-step series)."""
+    from viforssms_b200.config import lvb_config
+    p, K, B, F, fw, seed = (int(v) for v in GM["lvb_hyper"])
+    dt = float(GM["lvb_dt"])
+    N, T = p * B, (B - 1) * dt
+    cfg = lvb_config(p=p, K=K, B=B, F=F, H=2, feat_window=fw, target_dims=B, dt=dt, x0=(11.0, 9.5))
+    layout, n = param_layout(cfg)
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    obs, obs_bin, tt = GM["lvb_obs"], GM["lvb_obs_bin"], GM["lvb_time_till"]
+    pads = O.pad_series_lv(obs, tt, np.array(cfg.x0), dt, T, B, p, F, K, fw)
+    idx = np.arange(p, dtype=np.int64) * B
+    tf64, mask, shift, bin_feed = O.gather_feed_lv(pads, obs_bin, idx, cfg.L0, B)
+    params = _params(cfg, layout, n, g, None, T)
+    for i in range(F):
+        off, _ = layout[f"f{i}.head.b"]
+        params[off] = 3.0
+    assert _sha(params.numpy()) == str(GM["lvb_params_sha_f32"])
+    f32 = lambda a: torch.from_numpy(np.asarray(a).astype(np.float32)).double()
+    extra = {"mask": f32(mask), "shift": f32(shift), "bin_feed": f32(bin_feed)}
+    arrays = feed.lv_base_arrays(obs, obs_bin, tt, dt, T, B, F, K, fw, p_val=p)
+    eps = torch.from_numpy(GM["lvb_eps"])
+    theta = torch.from_numpy(GM["lvb_theta"])
+    return cfg, layout, n, params, eps, theta, idx, f32(tf64), extra, arrays
+
+
+def test_lv_batch_oracle_matches_the_reference_classes(GM):
+    """lotka_volterra_partial_batch.py: learned softplus-theta, plain bivariate transition density, p_val = 3 windows whose
+    first p_val states are pinned - the oracle against the script's own classes run over the TF stand-in."""
+    cfg, layout, n, params, eps, theta, idx, tf, extra, arrays = lvb_inputs(GM)
+    assert np.array_equal(extra["mask"][0, :, :4].numpy(), [[0, 0, 0, 1]] * 2) and extra["mask"][1:].min() == 1   # :237-240
+    ref = O.step_reference(cfg, layout, params.double(), eps.double(), theta.double(), tf, extra=extra)
+    t = ref["terms"].numpy()
+    assert _close(t[:, 0], GM["lvb_sde"], 1e-10) and _close(t[:, 1], GM["lvb_obs_lp"], 1e-10) and _close(t[:, 2], GM["lvb_logq"], 1e-10)
+    assert _close(ref["lf"].numpy(), GM["lvb_lf_sample"], 1e-10)
+    check_grads(ref["grad_params"].numpy(), layout, GM, "lvb_", 1e-9, 1e-12)
+    assert _close(ref["grad_theta"].numpy(), GM["lvb_grad_theta"], 1e-9)
+    priors = [(-1.0, np.sqrt(0.1)), (-6.0, np.sqrt(0.1)), (-1.0, np.sqrt(0.1)), (-2.0, np.sqrt(0.1))]
+    prior = O.lvb_theta_prior(theta.double(), priors).numpy()
+    assert _close(prior, GM["lvb_prior"], 1e-10)
+    elbo = cfg.scale * (t[:, 0] - t[:, 2] + t[:, 1]) + prior - GM["lvb_theta_lp"]
+    assert _close(elbo, GM["lvb_elbo"], 1e-10)

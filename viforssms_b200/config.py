@@ -20,7 +20,8 @@ MODEL_FHN = 1
 MODEL_SV = 2
 MODEL_LV = 3      # Lotka-Volterra, fixed theta (lotka_volterra_partial_batch_fix_theta.py)
 MODEL_LVR = 4     # Lotka-Volterra, learned theta (lotka_volterra_partial.py, the script whose data the reference ships)
-LV_MODELS = (MODEL_LV, MODEL_LVR)     # both use the transposed wide feature layer and the 1 + (L0 - 1)-channel conv
+MODEL_LVB = 5     # Lotka-Volterra, learned softplus-theta, p_val windows per iteration (lotka_volterra_partial_batch.py)
+LV_MODELS = (MODEL_LV, MODEL_LVR, MODEL_LVB)     # all use the transposed wide feature layer and the 1 + (L0 - 1)-channel conv
 
 MAX_CHAN = 32
 MAX_ARRAYS = 8
@@ -57,6 +58,8 @@ class CConfig(ctypes.Structure):
         ("dt", ctypes.c_float),
         ("obs_std", ctypes.c_float),
         ("x0", ctypes.c_float * 2),
+        ("n_pinned", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -86,6 +89,7 @@ class NMAConfig:
     obs_array: int = 0        # base array holding the evaluated observations
     bin_array: int = 3        # base array holding the observation indicator (AR: padded obs_bin)
     head_offset: int = 0
+    n_pinned: int = 1         # leading states of the series that mask / shift pin to x0 (p_val in the LV batch scripts)
 
     # ---- derived ----
     @property
@@ -143,6 +147,7 @@ class NMAConfig:
         c.obs_std = float(self.obs_std)
         c.x0[0] = float(self.x0[0])
         c.x0[1] = float(self.x0[1])
+        c.n_pinned = int(self.n_pinned)
         return c
 
 
@@ -249,6 +254,16 @@ def lvr_config(p=50, K=20, B=50, F=3, H=3, feat_window=10, target_dims=500, dt=0
         scale=float(target_dims) / float(B), dt=dt, obs_std=1.0, x0=(float(x0[0]), float(x0[1])), n_arrays=5,
         chan_array=[0] * fw + [1, 2, 3], chan_offset=[5 * i for i in range(fw)] + [0, 0, 0],
         obs_array=0, bin_array=4)
+
+
+def lvb_config(p=3, K=20, B=151, F=3, H=3, feat_window=10, target_dims=151, dt=0.2, x0=(91.0, 99.0)) -> NMAConfig:
+    """lotka_volterra_partial_batch.py (:677-764): the flow, feed and observation model of `lv_config` with a LEARNED theta
+    (4 softplus-scale parameters sampled per row, :198-200), the plain bivariate transition density (:339-343) and p = p_val
+    windows per iteration tiling p_val concatenated series, the first p_val states of which are pinned (:237-240)."""
+    cfg = lv_config(p=p, K=K, B=B, F=F, H=H, feat_window=feat_window, target_dims=target_dims, dt=dt, x0=x0)
+    cfg.model = MODEL_LVB
+    cfg.n_pinned = p
+    return cfg
 
 
 def lv_config(p=1, K=20, B=151, F=3, H=3, feat_window=10, target_dims=151, dt=0.2, x0=(91.0, 99.0)) -> NMAConfig:

@@ -107,7 +107,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         d.NP = (d.N + 3) & ~3;
         if (i < cfg->F && d.N < 1) { delete h; nma_set_error("nma_create: window too short"); return -1; }
     }
-    h->is_lv = (cfg->model == NMA_MODEL_LV || cfg->model == NMA_MODEL_LVR) ? 1 : 0;
+    h->is_lv = (cfg->model == NMA_MODEL_LV || cfg->model == NMA_MODEL_LVR || cfg->model == NMA_MODEL_LVB) ? 1 : 0;
     h->LW = h->L0 - 1;
     h->LWP = (h->LW + 3) & ~3;
     h->conv_cin = h->is_lv ? 1 + h->LW : NMA_C1;
@@ -173,8 +173,8 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         }
     }
     // whole-iteration entry point (nma_step.cu)
-    struct { int64_t eps, z0, theta, logq, gth, terms, relbo, flags, norm, counter; } so;
-    so.eps = reserve(p * h->L0); so.z0 = reserve(p * 8); so.theta = reserve(p * 8); so.logq = reserve(p);
+    struct { int64_t eps, z0, theta, u, logq, gth, terms, relbo, flags, norm, counter; } so;
+    so.eps = reserve(p * h->L0); so.z0 = reserve(p * 8); so.theta = reserve(p * 8); so.u = reserve(p * 8); so.logq = reserve(p);
     so.gth = reserve(p * 8); so.terms = reserve(p * 4); so.relbo = reserve(p); so.flags = reserve(p);
     so.norm = reserve(1024 + 64); so.counter = reserve(4);
     h->arena_bytes = total;
@@ -210,6 +210,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
         }
     }
     h->step.eps = (float*)(base + so.eps); h->step.z0 = (float*)(base + so.z0); h->step.theta = (float*)(base + so.theta);
+    h->step.u = (float*)(base + so.u);
     h->step.logq_theta = (float*)(base + so.logq); h->step.g_theta = (float*)(base + so.gth);
     h->step.terms = (float*)(base + so.terms); h->step.row_elbo = (float*)(base + so.relbo);
     h->step.flags = (uint32_t*)(base + so.flags); h->step.norm = (float*)(base + so.norm);
@@ -310,7 +311,7 @@ static int check_step_args(nma_handle h, int p, const void* a, const void* b, co
     return 0;
 }
 static int check_model_built(nma_handle h) {
-    if (h->cfg.model < NMA_MODEL_AR || h->cfg.model > NMA_MODEL_LVR) {
+    if (h->cfg.model < NMA_MODEL_AR || h->cfg.model > NMA_MODEL_LVB) {
         nma_set_error("unknown model %d", h->cfg.model);
         return -3;
     }

@@ -61,6 +61,7 @@ struct StepWs {
     float* eps;              // [p][L0]      base noise drawn in the library (eps == NULL)
     float* z0;               // [p][8]       base sample of the theta posterior
     float* theta;            // [p][dtheta]
+    float* u;                // [p][8]       pre-softplus sample (posteriors that end in a Softplus bijector)
     float* logq_theta;       // [p]
     float* g_theta;          // [p][dtheta]  d objective / d theta (ELBO part + prior part)
     float* terms;            // [p][4]
@@ -72,7 +73,7 @@ struct StepWs {
     // theta posterior (borrowed device pointers)
     const float* tf_masks;
     const int32_t* tf_perms;
-    int tf_nb, tf_relu, tf_set;
+    int tf_nb, tf_relu, tf_set, tf_softplus;
     float tf_base_loc, tf_base_scale;
     float prior_mean[8], prior_scale[8];
 };

@@ -20,7 +20,7 @@ struct ElboArgs {
     float* lf;              // [p][LF]   (may be null)
     float* grad_theta;      // [p][dth]  (may be null)
     uint32_t* flags;        // [p]       (may be null)
-    int p, model, F, B, D, S, L0, LF, XPF, dth, Cf, obs_array, bin_array, head_offset;
+    int p, model, F, B, D, S, L0, LF, XPF, dth, Cf, obs_array, bin_array, head_offset, n_pinned;
     int objective, want_grad;
     float scale, dt, obs_std, path_target, x0a, x0b;
 };
@@ -141,30 +141,42 @@ __global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
             if (a.want_grad) { dx[2 * j] = g1; dx[2 * j + 1] = g2; }
             if (a.lf) { a.lf[(size_t)r * a.LF + 2 * j] = x1; a.lf[(size_t)r * a.LF + 2 * j + 1] = x2; }
         }
-    } else if (a.model == NMA_MODEL_LV) {
-        // Lotka-Volterra, fixed theta (lotka_volterra_partial_batch_fix_theta.py:265-371).  z[d][t] = x[2t+d] is the raw
-        // flow output, lf[d][t] = (softplus(z) + 1) * mask + shift the state (:355-358,367).  For t >= 1 (mask = 1)
-        // the inverse of the transition / x0 bijector chain at the state is simply z + 1 and every chain's
-        // inverse-log-det at the state is softplus(-z) per component.
-        //   terms[0] = sum_{t=1..B-1} log N2(z_{t+1} + 1; lf_t + dt alpha(lf_t), dt S(lf_t)) + ildj(lf_{t+1})  +  log p(x0 = lf_1)
+    } else if (a.model == NMA_MODEL_LV || a.model == NMA_MODEL_LVB) {
+        // Lotka-Volterra with the softplus-transformed path: fixed theta (lotka_volterra_partial_batch_fix_theta.py:265-371)
+        // and learned theta (lotka_volterra_partial_batch.py:300-371).  z[d][t] = x[2t+d] is the raw flow output,
+        // lf[d][t] = (softplus(z) + 1) * mask + shift the state (:355-358,367): the first n_pinned states of the concatenated
+        // series are pinned to x0 (mask_vals = zeros((2, p_val)) ++ ones, :216-219 / :237-240).  For an unpinned state the
+        // inverse of the x0 / transition bijector chain at the state is z + 1 and every chain's inverse-log-det is
+        // softplus(-z) per component; for a pinned one both are constants of x0.
+        //   fixed theta:   terms[0] = sum_t log N2(chain^-1(lf_{t+1}); lf_t + dt alpha(lf_t), dt S(lf_t)) + ildj(lf_{t+1})  +  log p(x0 = lf_1)
+        //   learned theta: terms[0] = sum_t log N2(lf_{t+1}; lf_t + dt alpha(lf_t), dt S(lf_t))  +  log p(x0 = lf_1)   (:339-343: no chain)
+        //                  and d terms / d theta for all four rates
         //   terms[1] = sum_{t=1..B} bin * [log N(u_t; lf_t, theta3 lf_t) + ildj_obs],  u = 1 + softplus^-1(obs - 1)
-        //   logq    += sum_{t=1..B} softplus(-z_t)   (collected in `base`-independent `lq_extra`)
+        //   logq    += sum_{t=1..B} ildj(lf_t)   (collected in `lq_extra`)
+        const bool chain = a.model == NMA_MODEL_LV;
+        const bool lvb = !chain;
+        const int npin = a.n_pinned;
         const float t0 = th[0], t1 = th[1], t2 = th[2], t3 = th[3];
         const float dt = a.dt;
         const long long tlen = a.sv.len[a.bin_array] / 2;
         const float cq = (a.objective == NMA_OBJ_ELBO) ? a.scale : 0.f;     // d objective / d logq
+        const float jx0a = -logf(-expm1f(-(a.x0a - 1.f))), jx0b = -logf(-expm1f(-(a.x0b - 1.f)));   // ildj at a pinned state
         for (int j = lane; j <= B; j += 32) {
-            const bool first = (i0 + j) == 0;
+            const bool pin = (i0 + j) < npin;
             const float z1 = x[2 * j], z2 = x[2 * j + 1];
-            const float u1 = first ? a.x0a : softplus_f(z1) + 1.f;
-            const float u2 = first ? a.x0b : softplus_f(z2) + 1.f;
+            const float u1 = pin ? a.x0a : softplus_f(z1) + 1.f;
+            const float u2 = pin ? a.x0b : softplus_f(z2) + 1.f;
             float g1 = 0.f, g2 = 0.f;        // d objective / d lf (chain to z below)
             float h1 = 0.f, h2 = 0.f;        // d objective / d z directly (the z + 1 arguments and the log-dets)
             if (j >= 1) {
                 // entropy correction and observation
-                lq_extra += softplus_f(-z1) + softplus_f(-z2);
-                h1 += cq * (-sigmoid_f(-z1));
-                h2 += cq * (-sigmoid_f(-z2));
+                if (!pin) {
+                    lq_extra += softplus_f(-z1) + softplus_f(-z2);
+                    h1 += cq * (-sigmoid_f(-z1));
+                    h2 += cq * (-sigmoid_f(-z2));
+                } else {
+                    lq_extra += jx0a + jx0b;
+                }
                 const long long slot = win0 + (a.L0 - 2 * B) + 2 * (j - 1);
                 const float y1 = series_chan(a.sv, 0, slot), y2 = series_chan(a.sv, 0, slot + 1);
                 const float w1 = series_raw(a.sv, a.bin_array, i0 + (j - 1));
@@ -179,33 +191,55 @@ __global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
                 // d/d loc with scale = theta3 * loc:  q * v / (theta3 loc^2) - 1 / loc
                 g1 += c_obs * w1 * (q1 * v1 / (s1 * u1) - 1.f / u1);
                 g2 += c_obs * w2 * (q2 * v2 / (s2 * u2) - 1.f / u2);
+                // d/d theta3: (q^2 - 1) / theta3 per observed component
+                if (lvb) gth[3] += c_obs * (w1 * (q1 * q1 - 1.f) + w2 * (q2 * q2 - 1.f)) / t3;
             }
-            if (j == 1) {   // p(x0) on the first retained state: N(z + 1; x0_mean, x0_std) + softplus(-z)
-                const G1 p1 = gauss(z1 + 1.f, a.x0a, a.obs_std), p2 = gauss(z2 + 1.f, a.x0b, a.obs_std);
-                sde += p1.lp + p2.lp + softplus_f(-z1) + softplus_f(-z2);
-                h1 += c_sde * (-p1.dz - sigmoid_f(-z1));
-                h2 += c_sde * (-p2.dz - sigmoid_f(-z2));
+            if (j == 1) {   // p(x0) on the first retained state: N(chain^-1(lf_1); x0_mean, x0_std) + ildj(lf_1)
+                if (!pin) {
+                    const G1 p1 = gauss(z1 + 1.f, a.x0a, a.obs_std), p2 = gauss(z2 + 1.f, a.x0b, a.obs_std);
+                    sde += p1.lp + p2.lp + softplus_f(-z1) + softplus_f(-z2);
+                    h1 += c_sde * (-p1.dz - sigmoid_f(-z1));
+                    h2 += c_sde * (-p2.dz - sigmoid_f(-z2));
+                } else {
+                    const G1 p1 = gauss(a.x0a - jx0a, a.x0a, a.obs_std), p2 = gauss(a.x0b - jx0b, a.x0b, a.obs_std);
+                    sde += p1.lp + p2.lp + jx0a + jx0b;
+                }
             }
             if (j >= 2) {   // this state as the TARGET of the transition from t = j - 1
-                const float pz1 = x[2 * j - 2], pz2 = x[2 * j - 1];
-                const float p1 = softplus_f(pz1) + 1.f, p2 = softplus_f(pz2) + 1.f;     // j - 1 >= 1: never the pinned state
+                const bool ppin = (i0 + j - 1) < npin;
+                const float p1 = ppin ? a.x0a : softplus_f(x[2 * j - 2]) + 1.f;
+                const float p2 = ppin ? a.x0b : softplus_f(x[2 * j - 1]) + 1.f;
                 const float s11 = t0 * p1 + t1 * p1 * p2, s12 = -t1 * p1 * p2, s22 = t1 * p1 * p2 + t2 * p2;
                 const float Dd = s11 * s22 - s12 * s12;
-                const float d1 = (z1 + 1.f) - (p1 + dt * (t0 * p1 - t1 * p1 * p2));
-                const float d2 = (z2 + 1.f) - (p2 + dt * (t1 * p1 * p2 - t2 * p2));
+                const float tv1 = chain ? (pin ? a.x0a - jx0a : z1 + 1.f) : u1;
+                const float tv2 = chain ? (pin ? a.x0b - jx0b : z2 + 1.f) : u2;
+                const float d1 = tv1 - (p1 + dt * (t0 * p1 - t1 * p1 * p2));
+                const float d2 = tv2 - (p2 + dt * (t1 * p1 * p2 - t2 * p2));
                 const float gm1 = (s22 * d1 - s12 * d2) / (dt * Dd), gm2 = (-s12 * d1 + s11 * d2) / (dt * Dd);   // Sigma^-1 delta
-                h1 += c_sde * (-gm1 - sigmoid_f(-z1));
-                h2 += c_sde * (-gm2 - sigmoid_f(-z2));
+                if (chain) {
+                    if (!pin) {
+                        h1 += c_sde * (-gm1 - sigmoid_f(-z1));
+                        h2 += c_sde * (-gm2 - sigmoid_f(-z2));
+                    }
+                } else {        // the density is evaluated at the state itself
+                    g1 += c_sde * (-gm1);
+                    g2 += c_sde * (-gm2);
+                }
             }
             if (j >= 1 && j < B) {   // this state as the SOURCE of the transition to t = j + 1
+                const bool npn = (i0 + j + 1) < npin;
                 const float nz1 = x[2 * j + 2], nz2 = x[2 * j + 3];
+                const float n1 = npn ? a.x0a : softplus_f(nz1) + 1.f, n2 = npn ? a.x0b : softplus_f(nz2) + 1.f;
+                const float tv1 = chain ? (npn ? a.x0a - jx0a : nz1 + 1.f) : n1;
+                const float tv2 = chain ? (npn ? a.x0b - jx0b : nz2 + 1.f) : n2;
                 const float s11 = t0 * u1 + t1 * u1 * u2, s12 = -t1 * u1 * u2, s22 = t1 * u1 * u2 + t2 * u2;
                 const float Dd = s11 * s22 - s12 * s12;
-                const float d1 = (nz1 + 1.f) - (u1 + dt * (t0 * u1 - t1 * u1 * u2));
-                const float d2 = (nz2 + 1.f) - (u2 + dt * (t1 * u1 * u2 - t2 * u2));
+                const float d1 = tv1 - (u1 + dt * (t0 * u1 - t1 * u1 * u2));
+                const float d2 = tv2 - (u2 + dt * (t1 * u1 * u2 - t2 * u2));
                 const float Qf = s22 * d1 * d1 - 2.f * s12 * d1 * d2 + s11 * d2 * d2;
                 // log N2 = -log dt - 1/2 log D - Qf / (2 dt D) - log 2 pi   (det = (dt a c)^2 = dt^2 D, :50-58)
-                sde += -logf(dt) - 0.5f * logf(Dd) - 0.5f * Qf / (dt * Dd) - LOG2PI_F + softplus_f(-nz1) + softplus_f(-nz2);
+                sde += -logf(dt) - 0.5f * logf(Dd) - 0.5f * Qf / (dt * Dd) - LOG2PI_F;
+                if (chain) sde += npn ? (jx0a + jx0b) : (softplus_f(-nz1) + softplus_f(-nz2));
                 const float gm1 = (s22 * d1 - s12 * d2) / (dt * Dd), gm2 = (-s12 * d1 + s11 * d2) / (dt * Dd);
                 // through the mean: d mu / d u = I + dt J_alpha
                 float e1 = gm1 * (1.f + dt * (t0 - t1 * u2)) + gm2 * (dt * t1 * u2);
@@ -219,12 +253,18 @@ __global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
                 e2 += L11 * (t1 * u1) + L12 * (-t1 * u1) + L22 * (t1 * u1 + t2);
                 g1 += c_sde * e1;
                 g2 += c_sde * e2;
+                if (lvb) {   // d log N2 / d theta: mu = u + dt alpha(u, theta), Sigma = dt S(u, theta), S linear in theta
+                    const float uu = u1 * u2;
+                    gth[0] += gm1 * dt * u1 + L11 * u1;
+                    gth[1] += dt * uu * (gm2 - gm1) + uu * (L11 - L12 + L22);
+                    gth[2] += -gm2 * dt * u2 + L22 * u2;
+                }
             }
             g1 += c_sq * 2.f * (u1 - a.path_target);
             g2 += c_sq * 2.f * (u2 - a.path_target);
             if (a.want_grad) {
-                dx[2 * j] = first ? 0.f : fmaf(g1, sigmoid_f(z1), h1);
-                dx[2 * j + 1] = first ? 0.f : fmaf(g2, sigmoid_f(z2), h2);
+                dx[2 * j] = pin ? 0.f : fmaf(g1, sigmoid_f(z1), h1);
+                dx[2 * j + 1] = pin ? 0.f : fmaf(g2, sigmoid_f(z2), h2);
             }
             if (a.lf) { a.lf[(size_t)r * a.LF + 2 * j] = u1; a.lf[(size_t)r * a.LF + 2 * j + 1] = u2; }
         }
@@ -367,7 +407,9 @@ __global__ void __launch_bounds__(128) k_elbo(ElboArgs a) {
         a.terms[(size_t)r * 4 + 3] = base;
         if (a.flags) a.flags[r] = (isfinite(sde) && isfinite(obs) && isfinite(logq)) ? 0u : 1u;
         if (a.grad_theta && a.want_grad)
-            for (int k = 0; k < a.dth; ++k) a.grad_theta[(size_t)r * a.dth + k] = c_sde * gth[k];
+            // (the learned-theta LV model's observation part d/dtheta3 is already weighted with c_obs)
+            for (int k = 0; k < a.dth; ++k)
+                a.grad_theta[(size_t)r * a.dth + k] = (a.model == NMA_MODEL_LVB && k == 3) ? gth[k] : c_sde * gth[k];
     }
 }
 
@@ -383,6 +425,7 @@ int launch_elbo(nma_handle_s* h, const float* theta, const float* eps, const int
     a.p = p; a.model = h->cfg.model; a.F = F; a.B = h->cfg.B; a.D = h->cfg.D; a.S = h->S; a.L0 = h->L0;
     a.LF = h->fd[F].L; a.XPF = (h->fd[F].L + 3) & ~3; a.dth = h->cfg.dtheta; a.Cf = h->cfg.Cf;
     a.obs_array = h->cfg.obs_array; a.bin_array = h->cfg.bin_array; a.head_offset = h->cfg.head_offset;
+    a.n_pinned = h->cfg.n_pinned > 0 ? h->cfg.n_pinned : 1;
     a.objective = objective; a.want_grad = want_grad ? 1 : 0;
     a.scale = (float)h->cfg.scale; a.dt = h->cfg.dt; a.obs_std = h->cfg.obs_std; a.path_target = path_target;
     a.x0a = h->cfg.x0[0]; a.x0b = h->cfg.x0[1];

@@ -8,7 +8,7 @@
 // ---------------------------------------------------------------------------
 // nma_gather: materialise the feed the reference builds on the host every iteration
 // ---------------------------------------------------------------------------
-__global__ void k_gather(SeriesView sv, const int64_t* __restrict__ idx, int p, int L0, int B, float x0a, float x0b,
+__global__ void k_gather(SeriesView sv, const int64_t* __restrict__ idx, int p, int L0, int B, float x0a, float x0b, int npin,
                          float* __restrict__ tf, float* __restrict__ mask, float* __restrict__ shift) {
     const int r = blockIdx.x;
     const long long win0 = (long long)sv.D * idx[r];
@@ -17,11 +17,12 @@ __global__ void k_gather(SeriesView sv, const int64_t* __restrict__ idx, int p, 
         const int slot = t / sv.Cf, c = t - slot * sv.Cf;
         tf[(size_t)r * n + t] = series_val(sv, c, win0 + slot);
     }
-    // mask_vals = [0,1,1,...], shift_vals = [x0,0,0,...] sliced at idx (AR.py:145-148,285-288)
+    // mask_vals = [0,1,1,...], shift_vals = [x0,0,0,...] sliced at idx (AR.py:145-148,285-288); the Lotka-Volterra batch
+    // scripts pin the first p_val states (lotka_volterra_partial_batch.py:237-240)
     const int nm = sv.D * (B + 1);
     for (int t = threadIdx.x; t < nm; t += blockDim.x) {
         const int d = t / (B + 1), j = t - d * (B + 1);
-        const bool first = (idx[r] + j) == 0;
+        const bool first = (idx[r] + j) < npin;
         if (mask) mask[(size_t)r * nm + t] = first ? 0.f : 1.f;
         if (shift) shift[(size_t)r * nm + t] = first ? (d == 0 ? x0a : x0b) : 0.f;
     }
@@ -29,7 +30,8 @@ __global__ void k_gather(SeriesView sv, const int64_t* __restrict__ idx, int p, 
 
 int launch_gather(nma_handle_s* h, const int64_t* idx, int p, float* tf, float* mask, float* shift, cudaStream_t st) {
     SeriesView sv = nma_series_view(h);
-    k_gather<<<p, 256, 0, st>>>(sv, idx, p, h->L0, h->cfg.B, h->cfg.x0[0], h->cfg.x0[1], tf, mask, shift);
+    k_gather<<<p, 256, 0, st>>>(sv, idx, p, h->L0, h->cfg.B, h->cfg.x0[0], h->cfg.x0[1], h->cfg.n_pinned > 0 ? h->cfg.n_pinned : 1,
+                                tf, mask, shift);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -107,7 +107,8 @@ extern "C" int nma_get_counter(nma_handle h, uint64_t* out) {
 // theta posterior registration
 // ---------------------------------------------------------------------------
 extern "C" int nma_set_theta_flow(nma_handle h, const float* d_masks, const int32_t* d_perms, int32_t nb, int32_t relu,
-                                  float base_loc, float base_scale, const float* prior_mean, const float* prior_scale) {
+                                  float base_loc, float base_scale, const float* prior_mean, const float* prior_scale,
+                                  int32_t softplus_out) {
     if (!h) { nma_set_error("null handle"); return -1; }
     // nb == 0: no posterior - theta is the constant prior_mean in every row (lotka_volterra_partial_batch_fix_theta.py:190)
     if (nb < 0 || nb > 8 || (nb > 0 && !d_masks) || (nb > 1 && !d_perms) || !prior_mean || !prior_scale || h->cfg.dtheta > 8) {
@@ -116,6 +117,7 @@ extern "C" int nma_set_theta_flow(nma_handle h, const float* d_masks, const int3
     }
     h->step.tf_masks = d_masks; h->step.tf_perms = d_perms; h->step.tf_nb = nb; h->step.tf_relu = relu;
     h->step.tf_base_loc = base_loc; h->step.tf_base_scale = base_scale;
+    h->step.tf_softplus = (softplus_out && nb > 0) ? 1 : 0;
     for (int k = 0; k < h->cfg.dtheta; ++k) {
         h->step.prior_mean[k] = prior_mean[k];
         h->step.prior_scale[k] = prior_scale[k];
@@ -138,6 +140,7 @@ struct TailArgs {
     const float* grad_theta;   // [p][d]   d(-sum_rows scale * (sde - logq + obs)) / d theta  (or the pre-train objective's)
     float* g_theta;            // [p][d]
     float* row_elbo;           // [p]
+    const float* u;            // [p][d] pre-softplus sample when the posterior ends in a Softplus bijector (else null)
     int p, d, prior_on;
     float scale, obs_weight;
     float mean[8], sd[8];
@@ -148,12 +151,23 @@ __global__ void __launch_bounds__(128) k_step_tail(TailArgs a) {
     if (r >= a.p) return;
     float prior = 0.f;
     for (int k = 0; k < a.d; ++k) {
-        const float th = a.theta[(size_t)r * a.d + k];
-        const float z = (th - a.mean[k]) / a.sd[k];
-        // MultivariateNormalDiag(prior_mean, prior_scale).log_prob(theta)  (AR.py:178-182)
-        prior += -0.5f * z * z - 0.5f * 1.8378770664093453f - logf(a.sd[k]);
-        // objective = -sum_rows (... + prior - log q(theta)): d/dtheta gains +z/sd
-        a.g_theta[(size_t)r * a.d + k] = a.grad_theta[(size_t)r * a.d + k] + (a.prior_on ? z / a.sd[k] : 0.f);
+        if (a.u) {
+            // theta = softplus(u); prior = TransformedDistribution(MultivariateNormalDiag, Softplus) (lotka_volterra_partial_batch.py
+            // :358-365): log N(u; mean, sd) - log sigmoid(u).  The posterior carries the same Jacobian, so in prior - log q(theta)
+            // it cancels: the flow receives d/du = d/dtheta * sigmoid(u) + (u - mean) / sd^2 and d/dlog q_u = 1.
+            const float u = a.u[(size_t)r * a.d + k];
+            const float sg = sigmoid_f(u);
+            const float z = (u - a.mean[k]) / a.sd[k];
+            prior += -0.5f * z * z - 0.5f * 1.8378770664093453f - logf(a.sd[k]) - logf(sg);
+            a.g_theta[(size_t)r * a.d + k] = a.grad_theta[(size_t)r * a.d + k] * sg + (a.prior_on ? z / a.sd[k] : 0.f);
+        } else {
+            const float th = a.theta[(size_t)r * a.d + k];
+            const float z = (th - a.mean[k]) / a.sd[k];
+            // MultivariateNormalDiag(prior_mean, prior_scale).log_prob(theta)  (AR.py:178-182)
+            prior += -0.5f * z * z - 0.5f * 1.8378770664093453f - logf(a.sd[k]);
+            // objective = -sum_rows (... + prior - log q(theta)): d/dtheta gains +z/sd
+            a.g_theta[(size_t)r * a.d + k] = a.grad_theta[(size_t)r * a.d + k] + (a.prior_on ? z / a.sd[k] : 0.f);
+        }
     }
     const float* t = a.terms + (size_t)r * 4;
     a.row_elbo[r] = a.scale * (t[0] - t[2] + a.obs_weight * t[1]) + (a.prior_on ? prior - a.logq_theta[r] : 0.f);   // AR.py:184
@@ -226,6 +240,20 @@ extern "C" int nma_theta_flow_constrain(float* d_flow_params, const float* d_mas
 // ---------------------------------------------------------------------------
 // the iteration
 // ---------------------------------------------------------------------------
+// Softplus bijector at the end of the posterior chain (lotka_volterra_partial_batch.py:741): theta = softplus(u),
+// log q(theta) = log q_u(u) - sum log sigmoid(u)
+__global__ void k_theta_softplus(const float* __restrict__ u, float* __restrict__ theta, float* __restrict__ logq, int p, int d) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p) return;
+    float lj = 0.f;
+    for (int k = 0; k < d; ++k) {
+        const float v = u[(size_t)r * d + k];
+        theta[(size_t)r * d + k] = softplus_f(v);
+        lj += logf(sigmoid_f(v));
+    }
+    logq[r] -= lj;
+}
+
 struct FixedTheta { float* theta; float* logq; int p, d; float v[8]; };
 __global__ void k_fixed_theta(FixedTheta a) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,8 +284,12 @@ extern "C" int nma_train_step(nma_handle h, float* d_blob, float* d_grad, float*
     if (nb > 0) {
         if ((rc = launch_philox_normal(w.z0, (int64_t)p * d, w.seed, w.counter, 0, 1u, w.tf_base_loc, w.tf_base_scale, st))) return rc;
         if ((rc = nma_theta_flow_fwd(flow_params, w.tf_masks, w.tf_perms, w.z0, p, d, nb, w.tf_relu, w.tf_base_loc,
-                                     w.tf_base_scale, w.theta, w.logq_theta, stream)))
+                                     w.tf_base_scale, w.tf_softplus ? w.u : w.theta, w.logq_theta, stream)))
             return rc;
+        if (w.tf_softplus) {
+            k_theta_softplus<<<(p + 127) / 128, 128, 0, st>>>(w.u, w.theta, w.logq_theta, p, d);
+            nma_count_launch(1);
+        }
         NMA_CHECK_CUDA(cudaMemsetAsync(flow_grad, 0, (size_t)n_flow * 4, st));
     } else {
         FixedTheta f;
@@ -274,6 +306,7 @@ extern "C" int nma_train_step(nma_handle h, float* d_blob, float* d_grad, float*
     {
         TailArgs a;
         a.theta = w.theta; a.logq_theta = w.logq_theta; a.terms = w.terms; a.grad_theta = w.g_theta; a.g_theta = w.g_theta;
+        a.u = (w.tf_softplus && nb > 0) ? w.u : nullptr;
         a.row_elbo = w.row_elbo; a.p = p; a.d = d; a.prior_on = (o->prior_on && nb > 0) ? 1 : 0; a.scale = (float)h->cfg.scale;
         a.obs_weight = o->obs_in_elbo ? 1.f : 0.f;
         for (int k = 0; k < 8; ++k) { a.mean[k] = w.prior_mean[k]; a.sd[k] = k < d ? w.prior_scale[k] : 1.f; }

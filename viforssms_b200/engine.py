@@ -182,8 +182,8 @@ class NMAEngine:
         pm = (ctypes.c_float * d)(*[float(m) for m, _ in priors])
         ps = (ctypes.c_float * d)(*[float(s) for _, s in priors])
         _lib.check(self._lib.nma_set_theta_flow(self._h, _ptr(self._tf_masks), _ptr(self._tf_perms) if flow.nb > 1 else None,
-                                                flow.nb, relu, flow.base_loc, flow.base_scale, pm, ps),
-                   "nma_set_theta_flow")
+                                                flow.nb, relu, flow.base_loc, flow.base_scale, pm, ps,
+                                                int(getattr(flow, "softplus_out", False))), "nma_set_theta_flow")
         assert int(self._lib.nma_theta_flow_param_count(d, flow.nb)) == flow.n_params
 
     def set_fixed_theta(self, theta) -> None:
@@ -193,7 +193,7 @@ class NMAEngine:
         self._tf_flow = None
         pm = (ctypes.c_float * d)(*[float(t) for t in theta])
         ps = (ctypes.c_float * d)(*([1.0] * d))
-        _lib.check(self._lib.nma_set_theta_flow(self._h, None, None, 0, 0, 0.0, 1.0, pm, ps), "nma_set_theta_flow")
+        _lib.check(self._lib.nma_set_theta_flow(self._h, None, None, 0, 0, 0.0, 1.0, pm, ps, 0), "nma_set_theta_flow")
 
     def set_seed(self, seed: int, counter: int = 0) -> None:
         _lib.check(self._lib.nma_set_seed(self._h, int(seed), int(counter)), "nma_set_seed")

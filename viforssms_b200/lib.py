@@ -109,7 +109,7 @@ def load() -> ctypes.CDLL:
     lib.nma_theta_flow_constrain.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.nma_theta_flow_constrain.restype = c_int32
     lib.nma_set_theta_flow.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_float,
-                                       POINTER(c_float), POINTER(c_float)]
+                                       POINTER(c_float), POINTER(c_float), c_int32]
     lib.nma_set_theta_flow.restype = c_int32
     lib.nma_theta_flow_param_count.argtypes = [c_int32, c_int32]
     lib.nma_theta_flow_param_count.restype = c_int64

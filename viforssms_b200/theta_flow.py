@@ -41,12 +41,16 @@ class ThetaFlow:
     HIDDEN = (5, 5, 5)
 
     def __init__(self, dtheta: int, num_bijectors: int, base_loc: float, base_scale: float, activation: str = "elu",
-                 permutations: Optional[Sequence[Sequence[int]]] = None, tf_mask_grad: bool = True):
+                 permutations: Optional[Sequence[Sequence[int]]] = None, tf_mask_grad: bool = True,
+                 softplus_out: bool = False):
         # TensorFlow's masked_dense does not multiply the mask in the forward pass: masked kernel entries are zero through
         # the initialiser and a kernel_constraint re-applied after every update, so they DO receive a gradient (which
         # counts in tf.global_norm, AR.py:230) that the constraint then wipes.  tf_mask_grad=True reproduces that (call
         # `constrain()` after each update); False multiplies the mask in the forward pass (zero gradient there).
         self.tf_mask_grad = bool(tf_mask_grad)
+        # the chain ends in tfb.Softplus(event_ndims=2) (lotka_volterra_partial_batch.py:741): theta = softplus(u) > 0 and
+        # log q(theta) = log q_u(u) - sum log sigmoid(u)
+        self.softplus_out = bool(softplus_out)
         self.d = dtheta
         self.nb = num_bijectors
         self.base_loc = float(base_loc)
@@ -132,6 +136,9 @@ class ThetaFlow:
             lp = lp + log_scale.sum(dim=1)
             if k < self.nb - 1:
                 z = z[:, self._perm_t[k]]
+        if self.softplus_out:
+            lp = lp - torch.nn.functional.logsigmoid(z).sum(dim=1)
+            z = torch.nn.functional.softplus(z)
         return z, lp
 
     def base_sample(self, p: int, gen: Optional[torch.Generator], device) -> torch.Tensor:

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import feed
-from .config import OBJ_ELBO, OBJ_PATH_SQ, NMAConfig, fhn_config, lvr_config, param_layout, sv_config
+from .config import OBJ_ELBO, OBJ_PATH_SQ, NMAConfig, fhn_config, lvb_config, lvr_config, param_layout, sv_config
 from .engine import NMAEngine
 from .theta_flow import ThetaFlow, prior_log_prob, prior_tensors
 from .trainer import glorot_blob
@@ -40,6 +40,7 @@ class _ModelVISSM:
     theta_pos_index: Sequence[bool] = ()
     has_obs_term = True
     finite_term = 0              # which per-row term the pre-training restart looks at (0 = sde, 2 = lf_log_prob)
+    pretrain_theta_optimiser = True      # the scripts' second pre-train optimiser on (theta - theta*)^2 is actually run
 
     def _common(self, theta_dist: ThetaFlow, priors, p, kernel_len, batch_dims, network_dims, target_dims, no_flows,
                 feat_window, learn_rate, pre_train, device, seed, early_stopping):
@@ -118,18 +119,20 @@ class _ModelVISSM:
                                         objective=OBJ_PATH_SQ, path_target=self.pretrain_path_target, out=self.out)
             # t1: (lf_sample - c)^2 reaches the theta-flow variables through the theta-bias of every flow layer
             self.theta_leaf.grad = None
-            (out["grad_theta"] * theta).sum().backward(retain_graph=True)
+            (out["grad_theta"] * theta).sum().backward(retain_graph=self.pretrain_theta_optimiser)
             self.grad[self.n_nma:].copy_(self.theta_leaf.grad)
-            # t2: (theta - theta*)^2, theta-flow variables only
-            self.theta_leaf.grad = None
-            ((theta - self.theta_star_t) ** 2).sum().backward()
-            self.grad2.zero_()
-            self.grad2[self.n_nma:].copy_(self.theta_leaf.grad)
+            if self.pretrain_theta_optimiser:
+                # t2: (theta - theta*)^2, theta-flow variables only
+                self.theta_leaf.grad = None
+                ((theta - self.theta_star_t) ** 2).sum().backward()
+                self.grad2.zero_()
+                self.grad2[self.n_nma:].copy_(self.theta_leaf.grad)
             m, v = self.slots["pre_path"]
             self.eng.adamax_step(self.blob, self.grad, m, v, 1e-3, 0.9, clip=0.0)
-            m, v = self.slots["pre_theta"]
-            tail = slice(self.n_nma, self.n_total)
-            self.eng.adamax_step(self.blob[tail], self.grad2[tail], m[tail], v[tail], 1e-3, 0.9, clip=0.0)
+            if self.pretrain_theta_optimiser:
+                m, v = self.slots["pre_theta"]
+                tail = slice(self.n_nma, self.n_total)
+                self.eng.adamax_step(self.blob[tail], self.grad2[tail], m[tail], v[tail], 1e-3, 0.9, clip=0.0)
             if self.theta_dist.tf_mask_grad:
                 self.theta_dist.constrain()
             return bool(torch.isfinite(out["terms"][:, self.finite_term]).all().item())
@@ -138,7 +141,7 @@ class _ModelVISSM:
             return True
         out = self.eng.elbo_fwd_bwd(self.blob[:self.n_nma], eps, theta.detach().contiguous(), self.idx_dev,
                                     objective=OBJ_ELBO, out=self.out)
-        prior = prior_log_prob(theta, self.prior_t)
+        prior = self._prior_lp(theta)
         host_loss = (out["grad_theta"] * theta).sum() - (prior - logq_theta).sum()
         self.theta_leaf.grad = None
         host_loss.backward()
@@ -158,6 +161,10 @@ class _ModelVISSM:
         if self.theta_dist.tf_mask_grad:
             self.theta_dist.constrain()
         return True
+
+    def _prior_lp(self, theta: torch.Tensor) -> torch.Tensor:
+        """log prior(theta) of the host-composed iteration: the diagonal Gaussian of AR.py:178-182."""
+        return prior_log_prob(theta, self.prior_t)
 
     def _main_body(self) -> None:
         m, v = self.slots["main"]
@@ -358,6 +365,110 @@ class LVR_VI_SSM(_ModelVISSM):
         return self.pre_train_count == 1000
 
 
+class LVB_VI_SSM(_ModelVISSM):
+    """lotka_volterra_partial_batch.py:190-675 (class VI_SSM there): the fixed-theta script's flow, feed and observation
+    model with a LEARNED theta - posterior and prior both end in a Softplus bijector (:358-365,741) -, the plain bivariate
+    transition density (:339-343) and p_val windows per iteration that tile p_val concatenated series (:493-494)."""
+
+    grad_clip = 1e9                                                      # lotka_volterra_partial_batch.py:461
+    pretrain_path_target = 75.0                                          # :416-417
+    theta_pos_index = ()                                                 # the script's theta histograms are commented out (:437-445)
+    has_obs_term = True
+    finite_term = 2                                                      # the script watches lf_log_prob (:527-531)
+    pretrain_theta_optimiser = False                                     # `t2` is built (:419-420) but never run (:525)
+
+    def __init__(self, obs, obs_bin, time_till, x0_mean, x0_std, theta_dist: ThetaFlow, priors, dt, T, p_val, kernel_len,
+                 batch_dims, network_dims, target_dims, no_flows, feat_window, learn_rate=1e-3, pre_train=True,
+                 device: Optional[torch.device] = None, seed: int = 1, early_stopping=1e99):
+        if not getattr(theta_dist, "softplus_out", False):
+            raise ValueError("the posterior of this script ends in tfb.Softplus (:741): build ThetaFlow(..., softplus_out=True)")
+        x0_std = np.asarray(x0_std, dtype=np.float64)
+        if not np.all(x0_std == x0_std[0]):
+            raise ValueError("x0_std must be the same for both components")
+        self._common(theta_dist, priors, p_val, kernel_len, batch_dims, network_dims, target_dims, no_flows, feat_window,
+                     learn_rate, pre_train, device, seed, early_stopping)
+        self.p_val = self.p
+        self.flow_dims = 2
+        self.dt, self.T = float(dt), float(T)
+        self.kernel_ext = self.kernel_len * self.no_flows + self.flow_dims * self.batch_dims + 2
+        self._series = (np.asarray(obs), np.asarray(obs_bin), np.asarray(time_till))
+        self.cfg = lvb_config(p=self.p_val, K=self.kernel_len, B=self.batch_dims, F=self.no_flows,
+                              H=len(self.network_dims) - 2, feat_window=self.feat_window,
+                              target_dims=self.target_dims, dt=self.dt, x0=np.asarray(x0_mean, dtype=np.float64))
+        self.cfg.obs_std = float(x0_std[0])          # this model's only use of the field: the scale of p(x0)
+
+    def _base_arrays(self):
+        obs, obs_bin, tt = self._series
+        return feed.lv_base_arrays(obs, obs_bin, tt, self.dt, self.T, self.target_dims, self.no_flows, self.kernel_len,
+                                   self.feat_window, p_val=self.p_val)
+
+    def _draw(self) -> np.ndarray:
+        return feed.sample_indices_lv(self.target_dims, self.batch_dims, self.p_val)       # :493-494, never with replacement
+
+    def _paths_from_lf(self, lf, idx):
+        return lf.reshape(self.p, -1, 2).transpose(1, 2)
+
+    def _pretrain_done(self, run, finite):
+        self.pre_train_count = self.pre_train_count + 1 if finite else 0      # :527-534
+        return self.pre_train_count == 1000
+
+    def _prior_lp(self, theta):
+        """TransformedDistribution(MultivariateNormalDiag(mean, scale), Softplus).log_prob(theta) (:358-365)."""
+        mean, scale = self.prior_t
+        u = theta + torch.log(-torch.expm1(-theta))
+        return (-0.5 * ((u - mean) / scale) ** 2 - 0.5 * math.log(2 * math.pi) - torch.log(scale)
+                - torch.log(-torch.expm1(-theta))).sum(dim=1)
+
+    def train(self, tensorboard_path, save_path, series_idx=None, num_epochs: int = 3000, log_every: int = 1):
+        """:471-600: a fixed number of epochs; pre-training until 1000 consecutive steps with a finite lf_log_prob."""
+        self.early_stopping = 1e99
+        series_idx_str = 'series_' + str(series_idx) + '_' if series_idx is not None else ''
+        for d in (tensorboard_path, os.path.dirname(save_path)):
+            if d and not os.path.exists(d):
+                os.makedirs(d)
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter('%s/%s' % (tensorboard_path, series_idx_str + datetime.now().strftime("%d:%m:%y-%H:%M:%S")))
+        except Exception:
+            writer = None
+        run = 0
+        for epoch in range(int(num_epochs)):
+            batch_select = self._draw()
+            if self.pre_train:
+                if run == 0:
+                    print("Initialising paths and parameters...")
+                finite = self._iteration(batch_select, pre_train=True)
+                if self._pretrain_done(run, finite):
+                    self.pre_train = False
+                    print("Finished pre-training...")
+                    run = 0
+            else:
+                self._iteration(batch_select, pre_train=False)
+                if writer is not None and run % log_every == 0:
+                    sc = self.read_scalars()
+                    for tag, key in (("loss/ELBO", "loss/ELBO"), ("loss/SDE_log_prob p(x)", "loss/SDE_log_prob"),
+                                     ("loss/theta_log_prob q(theta)", "loss/theta_log_prob"),
+                                     ("loss/obs_log_prob p(y|x)", "loss/obs_log_prob"),
+                                     ("loss/path_log_prob q(x)", "loss/path_log_prob"),
+                                     ("optimize/global_norm", "optimize/global_norm")):
+                        writer.add_scalar(tag, float(sc[key]), run)
+            if run % 1000 == 0:
+                self.save(save_path)
+            run += 1
+        if writer is not None:
+            writer.close()
+
+    def save_paths(self, PATH_obs):
+        """:605-675: windows at 0, batch_dims, ... < batch_dims * p_val, concatenated along time, written [p_val, 2T]."""
+        path_store = []
+        for index_temp in np.arange(0, self.batch_dims * self.p_val, self.batch_dims):
+            path_store.append(self.sample_paths(int(index_temp))[:, :, 1:].cpu().numpy())
+        paths = np.concatenate(path_store, axis=2)
+        with open(PATH_obs, 'w') as f:
+            np.savetxt(f, np.reshape(paths, (self.p_val, -1)))
+        return paths
+
+
 class SV_VI_SSM(_ModelVISSM):
     """SV_dense.py:139-402 (class VI_SSM there)."""
 
@@ -500,6 +611,10 @@ class LV_VI_SSM:
         self._main_iteration()
         self.lf_sample = self._lf_dev.reshape(self.p_val, -1, 2).transpose(1, 2)
         return True
+
+    def _prior_lp(self, theta: torch.Tensor) -> torch.Tensor:
+        """log prior(theta) of the host-composed iteration: the diagonal Gaussian of AR.py:178-182."""
+        return prior_log_prob(theta, self.prior_t)
 
     def _main_body(self) -> None:
         m, v = self.slots["main"]
