@@ -13,7 +13,7 @@ session records every feed_dict, with np.loadtxt patched to hand the script the 
 tests/golden/synth.py, and store what the script fed: the first two save_paths() feeds and the first two train()
 feeds.  Arrays too large to commit are stored as their first rows plus a sha256 of the whole array.
 
-Outputs: fhn_golden.npz, sv_golden.npz, lv_golden.npz
+Outputs: fhn_golden.npz, sv_golden.npz, lv_golden.npz, lvb_golden.npz
 """
 import hashlib
 import os
@@ -220,7 +220,30 @@ def main():
         out["train%d_batch_select" % k] = draws[k]
     np.savez_compressed(os.path.join(HERE, "lv_golden.npz"), **out)
     print("lv:", {k: getattr(v, "shape", None) for k, v in out.items()})
+    lv_batch()
+
+
+def lv_batch():
+    """lotka_volterra_partial_batch.py as committed: p_val = 3 windows per iteration over the first three series of the
+    concatenated file (:677-764); 3 save_paths feeds, then train feeds."""
+    obs, obs_bin, tt = synth.lv_inputs()
+    ns, feeds, draws, n0 = run_script("lotka_volterra_partial_batch.py", [obs, obs_bin, tt],
+                                      ["dat/our_files", "locally_variant/train", "model_saves"], 6, lambda ns, sess: None)
+    m = ns["var_model"]
+    out = {"hyper": np.array([m.p_val, m.kernel_len, m.batch_dims, m.no_flows, int(m.target_dims), 10]),
+           "dt": np.array(m.dt), "T": np.array(ns["T"]), "x0_mean": np.array(ns["x0_mean"]),
+           "obs_not_observed": np.array(ns["obs_not_observed"])}
+    assert len(feeds) == 6 and len(draws) == 3 and m.p_val == 3
+    for k in range(3):
+        pack(out, "paths%d" % k, feeds[k], m, ["bin_feed"])
+        pack(out, "train%d" % k, feeds[3 + k], m, ["bin_feed"])
+        out["train%d_batch_select" % k] = draws[k]
+    np.savez_compressed(os.path.join(HERE, "lvb_golden.npz"), **out)
+    print("lv batch:", {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
 if __name__ == "__main__":
-    main()
+    if "--only-lvb" in sys.argv:
+        lv_batch()
+    else:
+        main()

@@ -176,3 +176,44 @@ def test_lv_product_feed_matches_reference(lv_case):
     assert _sha(tf) == str(g["train0_time_feats_sha256"])
     assert np.array_equal(tf, g["time_feats_full"])
     assert np.array_equal(feed.sample_indices_lv(N, B, p), [0])
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def lvb_case():
+    """lotka_volterra_partial_batch.py as committed: p_val = 3 windows over the first three concatenated series."""
+    g = _golden("lvb_golden.npz")
+    p, K, B, F, N, fw = (int(v) for v in g["hyper"])
+    obs, obs_bin, tt = synth.lv_inputs()
+    obs = obs.copy()
+    obs[obs == -1] = float(g["obs_not_observed"])
+    sl = slice(0, p * B)                    # obs[:, :p_val * batch_dims] (:717-719)
+    return g, (p, K, B, F, N, fw), (obs[:, sl], obs_bin[:, sl], tt[:, sl]), float(g["dt"]), float(g["T"]), g["x0_mean"]
+
+
+def test_lv_batch_oracle_feed_matches_reference(lvb_case):
+    g, (p, K, B, F, N, fw), (obs, obs_bin, tt), dt, T, x0 = lvb_case
+    assert (p, K, B, F, N, fw) == (3, 20, 151, 3, 151, 10) and dt == 0.2 and T == 30
+    pads = O.pad_series_lv(obs, tt, x0, dt, T, N, p, F, K, fw)
+    L0 = F * K + 2 * B + 2
+    for tag in ("train0", "train1", "train2"):
+        sel = g[tag + "_batch_select"]
+        assert sorted(sel.tolist()) == [0, B, 2 * B]              # without replacement: always all p_val windows
+        tf, mask, shift, bin_feed = O.gather_feed_lv(pads, obs_bin, sel, L0, B)
+        _check_feed(g, tag, tf, mask, shift, {"bin_feed": bin_feed})
+        # the FIRST p_val states of the concatenated series are pinned (mask_vals, :237-240): only the window starting at 0
+        r0 = sel.tolist().index(0)
+        assert mask[r0, :, :p].max() == 0 and mask[r0, :, p:].min() == 1 and np.delete(mask, r0, 0).min() == 1
+
+
+def test_lv_batch_product_feed_matches_reference(lvb_case):
+    from viforssms_b200.config import lvb_config
+    g, (p, K, B, F, N, fw), (obs, obs_bin, tt), dt, T, x0 = lvb_case
+    cfg = lvb_config(p=p, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=N, dt=dt, x0=x0)
+    assert cfg.L0 == 364 and cfg.n_pinned == p
+    arrays = feed.lv_base_arrays(obs, obs_bin, tt, dt, T, N, F, K, fw, p_val=p)
+    for tag in ("train0", "train1", "train2"):
+        tf = table_gather(cfg, arrays, g[tag + "_batch_select"])
+        assert _sha(tf) == str(g[tag + "_time_feats_sha256"])
+    np.random.seed(5)
+    assert sorted(feed.sample_indices_lv(N, B, p).tolist()) == [0, B, 2 * B]

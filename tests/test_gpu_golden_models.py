@@ -76,6 +76,22 @@ def test_lv_device_gather_matches_reference_feed():
     _gather_check(cfg, arrays, g, ("paths0", "train0", "train1"), lambda n: (n, 2, B + 1))
 
 
+def test_lv_batch_device_gather_matches_reference_feed():
+    """lotka_volterra_partial_batch.py as committed (p_val = 3): time_feats, and the mask / shift that pin the first p_val
+    states of the concatenated series, bit for bit what the script fed to its session."""
+    from viforssms_b200.config import lvb_config
+    g = _golden("lvb_golden.npz")
+    p, K, B, F, N, fw = (int(v) for v in g["hyper"])
+    obs, obs_bin, tt = synth.lv_inputs()
+    obs = obs.copy()
+    obs[obs == -1] = float(g["obs_not_observed"])
+    dt, T = float(g["dt"]), float(g["T"])
+    cfg = lvb_config(p=p, K=K, B=B, F=F, H=3, feat_window=fw, target_dims=N, dt=dt, x0=g["x0_mean"])
+    sl = slice(0, p * B)
+    arrays = feed.lv_base_arrays(obs[:, sl], obs_bin[:, sl], tt[:, sl], dt, T, N, F, K, fw, p_val=p)
+    _gather_check(cfg, arrays, g, ("train0", "train1", "train2"), lambda n: (n, 2, B + 1))
+
+
 def test_rolling_variance_kernel_is_bit_exact_with_numpy_float32():
     """A14 (SV_dense.py:159-170): nma_rolling_var reproduces np.var on the float32 series bit for bit - for the window of
     the script (50), below numpy's 8-wide unroll, and above its 128-element pairwise block - and yields the golden
