@@ -2,7 +2,7 @@
 """Benchmark of the fused NMA ELBO + gradient + Adamax step: latent steps x MC samples per second.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
-                  [--config ar_1e8|ar_default|lv_fix_theta|fhn|sv] [--scaling weak|strong] [--rows P] [--T n]
+                  [--config ar_1e8|ar_default|lv_fix_theta|lv_batch|fhn|sv] [--scaling weak|strong] [--rows P] [--T n]
 
 Headline (default): BASELINE.json configs[4] - synthetic AR(1) series, T = 10^8, kernel_len = 50, time-sharded over the
 GPUs.  The other configs are the reference scripts' own shapes on synthetic series of the scripts'
@@ -34,7 +34,7 @@ def flops_per_row(cfg):
     feature MLP runs over the whole window and ends in a layer as wide as the flow's conv input (conv over 1 + L0-1
     channels)."""
     C = cfg.C
-    lv = cfg.model in (3, 4)
+    lv = cfg.model in (3, 4, 5)
     if lv:
         LW = cfg.L0 - 1
         feat = sum(LW * (cfg.Cf_in * C + 2 * C * C + C * cfg.Lin(i)) for i in range(cfg.F))
@@ -490,7 +490,32 @@ class LVFix(FacadeWorkload):
         return torch.tensor(np.log1p(np.exp([-1.0, -6.0, -1.0, -2.0])), dtype=torch.float32)
 
 
-WORKLOADS = {c.name: c for c in (AR1e8, ARDefault, LVFix, FHN, SV)}
+class LVBatch(FacadeWorkload):
+    name = "lv_batch"
+    title = ("Lotka-Volterra partial-observation SDE, learned softplus-theta (lotka_volterra_partial_batch.py:677-764, the file "
+             "BASELINE.json configs[1] names): three synthetic 151-step series, p_val=3, kernel_len=20, batch_dims=151, 3 flows")
+
+    def build(self, dev):
+        import lotka_volterra_partial_batch as mod
+        import lotka_volterra_partial_batch_fix_theta as fix
+        obs = fix.simulate(3).astype(np.float32)
+        self.series = (obs, np.ones_like(obs), np.zeros_like(obs))
+        priors = [(-1.0, np.sqrt(0.1)), (-6.0, np.sqrt(0.1)), (-1.0, np.sqrt(0.1)), (-2.0, np.sqrt(0.1))]
+        flow = mod.ThetaFlow(4, 4, base_loc=0., base_scale=1., activation="elu", softplus_out=True)
+        return mod.VI_SSM(obs, self.series[1], self.series[2], np.array([91., 99.], np.float32), np.array([1., 1.], np.float32),
+                          flow, priors, 0.2, 30, 3, 20, 151, [50] * 5, 151, 3, 10, learn_rate=1e-3, pre_train=False, device=dev)
+
+    def cpu_extra(self, idx, tf, mask, shift):
+        obs_bin = self.series[1]
+        B = self.cfg.B
+        bf = np.stack([obs_bin[:, i:i + B] for i in idx])
+        return {"mask": mask, "shift": shift, "bin_feed": torch.from_numpy(bf.astype(np.float32))}
+
+    def theta_center(self):
+        return torch.tensor(np.log1p(np.exp([-1.0, -6.0, -1.0, -2.0])), dtype=torch.float32)
+
+
+WORKLOADS = {c.name: c for c in (AR1e8, ARDefault, LVFix, LVBatch, FHN, SV)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -717,7 +742,7 @@ def main():
     if args.steps is None:
         args.steps = 200 if small else 10
     if args.cpu_steps is None:
-        args.cpu_steps = {"ar_1e8": 50, "ar_default": 100, "fhn": 100, "sv": 20, "lv_fix_theta": 100}[args.config]
+        args.cpu_steps = {"ar_1e8": 50, "ar_default": 100, "fhn": 100, "sv": 20, "lv_fix_theta": 100, "lv_batch": 40}[args.config]
     if args.no_graph and small:
         os.environ["NMA_FACADE_GRAPH"] = "0"
     if args.impl == "reference":
