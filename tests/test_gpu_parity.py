@@ -243,9 +243,11 @@ def test_tensor_core_weight_gradient_matches_fp64(K, Q):
     dict(p=5, K=20, B=13, F=3, H=3, feat_window=5),     # hidden stack, ragged block tails
     dict(p=4, K=7, B=5, F=2, H=0, feat_window=2),       # K not a multiple of the 10-tap unroll, no hidden layer
     dict(p=33, K=10, B=3, F=1, H=1, feat_window=1),     # rows straddling CTAs (4 position blocks per row)
+    dict(p=100, K=20, B=40, F=2, H=2, feat_window=4),   # SIMT: 2-3 channel splits of the conv, rows cut into 3 position segments
+    dict(p=2000, K=10, B=30, F=2, H=1, feat_window=3),  # SIMT: rows enough for the unsplit launches (one segment per row)
 ])
 def test_step_parity_small(shape, tc):
-    T = 400
+    T = max(400, 3 * shape["p"])
     cfg = ar_config(T=T, **shape)
     _check_step(cfg, T, seed=3, tc=tc)
 
@@ -392,12 +394,13 @@ def _fhn_case(cfg, target_dims, dt, seed):
     dict(p=6, K=8, B=6, F=3, H=3, feat_window=3),
     dict(p=9, K=20, B=11, F=3, H=3, feat_window=10),       # the script's kernel_len / network depth
     dict(p=4, K=4, B=3, F=2, H=1, feat_window=2),
+    dict(p=50, K=20, B=50, F=3, H=3, feat_window=10),      # the script's own shape: conv channel splits, row segments
 ])
 def test_fhn_step_parity(shape, objective, target):
     """fitz_nag_NVP.py: gather (window start 2*idx, look-ahead shifts of 5 slots, the longer time_till pad) bit-exact;
     flow with stride-2 head / identity-affine interleave / pair-swap Permute / BN affine, diag-Gaussian
     Euler-Maruyama ELBO and all gradients within 1e-4."""
-    target_dims, dt = 240, 0.1
+    target_dims, dt = (240 if shape["B"] < 50 else 500), 0.1
     cfg = fhn_config(target_dims=target_dims, dt=dt, **shape)
     arrays, idx, layout, params, eps, theta, tf64, bin_feed = _fhn_case(cfg, target_dims, dt, seed=7)
     eng = _engine(cfg)

@@ -177,6 +177,9 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     so.eps = reserve(p * h->L0); so.z0 = reserve(p * 8); so.theta = reserve(p * 8); so.u = reserve(p * 8); so.logq = reserve(p);
     so.gth = reserve(p * 8); so.terms = reserve(p * 4); so.relbo = reserve(p); so.flags = reserve(p);
     so.norm = reserve(1024 + 64); so.counter = reserve(4);
+    // channel split of the SIMT conv kernels: at most 2 x SMs + one item block's worth of CTAs are in a split launch
+    const int64_t split_ctas = 2 * h->sm_count + CONV_SPLIT_MAX;
+    const int64_t off_part = reserve(split_ctas * CONV_SPLIT_PART_FLOATS), off_ticket = reserve(split_ctas);
     h->arena_bytes = total;
     cudaError_t e = cudaMalloc(&h->arena, (size_t)total);
     if (e != cudaSuccess) {
@@ -216,6 +219,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     h->step.flags = (uint32_t*)(base + so.flags); h->step.norm = (float*)(base + so.norm);
     h->step.counter = (unsigned long long*)(base + so.counter);
     h->step.seed = 1;
+    h->split_part = (float*)(base + off_part); h->split_ticket = (unsigned*)(base + off_ticket);
     {
         const char* envb = getenv("NMA_TC_BF16");
         h->bf16_ok = bf16_path_ok(h);

@@ -14,8 +14,9 @@
 // ---------------------------------------------------------------------------
 // shared helpers on [50][pitch] shared-memory tiles
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void load_tile(float* tile, int pitch, const float* __restrict__ g, int gpitch, int nrows) {
-    const int n4 = gpitch / 4;
+__device__ __forceinline__ void load_tile(float* tile, int pitch, const float* __restrict__ g, int gpitch, int nrows,
+                                          int ncols = -1) {
+    const int n4 = (ncols < 0 ? gpitch : ncols) / 4;
     for (int t = threadIdx.x; t < nrows * n4; t += blockDim.x) {
         const int f = t / n4, j4 = t - f * n4;
         *reinterpret_cast<float4*>(tile + f * pitch + 4 * j4) =
@@ -103,6 +104,7 @@ struct EpiBwdArgs {
     float* g_hidw[NMA_MAXH]; float* g_hidb[NMA_MAXH]; float* g_gam[NMA_MAXH]; float* g_bet[NMA_MAXH];
     float* g_headw; float* g_headb; float* g_convb;
     int XP, XPn, L, N, NP, K, H, bn, D, S, p, permute_out, tile_pitch;
+    int seg, nseg;                 // a row is processed in nseg segments of seg positions (multiple of 4): one work unit each
     float cq;                      // d objective / d logq
 };
 
@@ -152,20 +154,24 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
             }
         }
     }
-    for (int r = blockIdx.x; r < a.p; r += gridDim.x) {
+    for (int u = blockIdx.x; u < a.p * a.nseg; u += gridDim.x) {
+        const int r = u / a.nseg, m0 = (u - r * a.nseg) * a.seg;     // this unit: positions [m0, m0 + n) of row r
+        const int n = min(N - m0, a.seg), cols = min(a.NP - m0, a.seg);
         __syncthreads();
         // E <- e_H ; zero G, dmu, dsr
-        load_tile(E, tp, a.h[a.H] + (size_t)r * NMA_C * a.NP, a.NP, NMA_C);
+        load_tile(E, tp, a.h[a.H] + (size_t)r * NMA_C * a.NP + m0, a.NP, NMA_C, cols);
         for (int t = tid; t < NMA_C * tp; t += blockDim.x) G[t] = 0.f;
         for (int t = tid; t < tp; t += blockDim.x) { dmu[t] = 0.f; dsr[t] = 0.f; }
         if (tid < NMA_C) {
             if (a.bn && a.H > 0) { bns[tid] = a.gam[a.H - 1][tid] * rs; bno[tid] = a.bet[a.H - 1][tid]; }
             else { bns[tid] = 1.f; bno[tid] = 0.f; }
         }
-        for (int j = tid; j < a.K && j < a.L; j += blockDim.x) a.dx[(size_t)r * a.XP + j] = 0.f;
+        if (m0 == 0)
+            for (int j = tid; j < a.K && j < a.L; j += blockDim.x) a.dx[(size_t)r * a.XP + j] = 0.f;
         __syncthreads();
         // affine layer + softplus head (AR.py:83-88)
-        for (int m = tid; m < N; m += blockDim.x) {
+        for (int ml = tid; ml < n; ml += blockDim.x) {
+            const int m = m0 + ml;
             const int mo = a.permute_out ? (m ^ 1) : m;
             const float dxo = a.dx_next[(size_t)r * a.XPn + mo];
             float dxin = dxo;
@@ -176,8 +182,8 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
                 const float xin = a.x_in[(size_t)r * a.XP + m + a.K];
                 float dsig = dxo * xin;
                 if (m >= N - a.S) dsig -= a.cq / sigma;     // logq -= log sigma over the last S slots
-                dmu[mh] = dxo;
-                dsr[mh] = dsig * sigmoid_f(sr);
+                dmu[mh - m0] = dxo;
+                dsr[mh - m0] = dsig * sigmoid_f(sr);
                 dxin = dxo * sigma;
             }
             a.dx[(size_t)r * a.XP + m + a.K] = dxin;
@@ -188,24 +194,24 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
             const int g = tid >> 1, which = tid & 1;
             const float* vec = which ? dsr : dmu;
             float acc = 0.f;
-            for (int m = 0; m < N; ++m) acc = fmaf(fmaf(E[g * tp + m], bns[g], bno[g]), vec[m], acc);
+            for (int m = 0; m < n; ++m) acc = fmaf(fmaf(E[g * tp + m], bns[g], bno[g]), vec[m], acc);
             acc_head += acc;
         } else if (tid < 2 * NMA_C + 2) {
             const float* vec = (tid & 1) ? dsr : dmu;
             float acc = 0.f;
-            for (int m = 0; m < N; ++m) acc += vec[m];
+            for (int m = 0; m < n; ++m) acc += vec[m];
             acc_headb += acc;
         }
         // G = d objective / d o_H
-        for (int t = tid; t < NMA_C * N; t += blockDim.x) {
-            const int g = t / N, m = t - g * N;
+        for (int t = tid; t < NMA_C * n; t += blockDim.x) {
+            const int g = t / n, m = t - g * n;
             G[g * tp + m] = fmaf(dmu[m], hw[2 * g], dsr[m] * hw[2 * g + 1]);
         }
         __syncthreads();
         for (int l = a.H - 1; l >= 0; --l) {
             // E = e_{l+1} (raw), G = grad w.r.t. o_{l+1}
             if (a.bn) {
-                row_sums(G, E, tp, N, v1, v2);
+                row_sums(G, E, tp, n, v1, v2);
                 __syncthreads();
                 if (tid < NMA_C) {
                     acc_bet[l] += v1[tid];
@@ -213,20 +219,20 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
                     bns[tid] = a.gam[l][tid] * rs;
                 }
                 __syncthreads();
-                for (int t = tid; t < NMA_C * N; t += blockDim.x) {
-                    const int g = t / N, m = t - g * N;
+                for (int t = tid; t < NMA_C * n; t += blockDim.x) {
+                    const int g = t / n, m = t - g * n;
                     G[g * tp + m] *= bns[g];
                 }
                 __syncthreads();
             }
-            for (int t = tid; t < NMA_C * N; t += blockDim.x) {
-                const int g = t / N, m = t - g * N;
+            for (int t = tid; t < NMA_C * n; t += blockDim.x) {
+                const int g = t / n, m = t - g * n;
                 G[g * tp + m] *= elu_grad_from_out(E[g * tp + m]);
             }
             __syncthreads();
-            row_sums(G, nullptr, tp, N, v1, nullptr);
+            row_sums(G, nullptr, tp, n, v1, nullptr);
             // E <- input of layer l: e_l, BN_{l-1}-transformed when l > 0
-            load_tile(E, tp, a.h[l] + (size_t)r * NMA_C * a.NP, a.NP, NMA_C);
+            load_tile(E, tp, a.h[l] + (size_t)r * NMA_C * a.NP + m0, a.NP, NMA_C, cols);
             for (int t = tid; t < NMA_C * PW_WPITCH; t += blockDim.x) {   // Wsm[g][f] = W_l[f][g]
                 const int g = t / PW_WPITCH, f = t - g * PW_WPITCH;
                 Wsm[t] = (f < NMA_C) ? a.hidw[l][f * NMA_C + g] : 0.f;
@@ -237,40 +243,40 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
             if (bn_in) {
                 if (tid < NMA_C) { bns[tid] = a.gam[l - 1][tid] * rs; bno[tid] = a.bet[l - 1][tid]; }
                 __syncthreads();
-                for (int t = tid; t < NMA_C * N; t += blockDim.x) {
-                    const int g = t / N, m = t - g * N;
+                for (int t = tid; t < NMA_C * n; t += blockDim.x) {
+                    const int g = t / n, m = t - g * n;
                     E[g * tp + m] = fmaf(E[g * tp + m], bns[g], bno[g]);
                 }
                 __syncthreads();
             }
             if (w_owner) wgrad_accum(E, G, tp, np4, f_own, gg_own, accW[l]);
             __syncthreads();
-            col_matvec_inplace(G, tp, N, Wsm);
+            col_matvec_inplace(G, tp, n, Wsm);
             if (bn_in) {
                 __syncthreads();
-                load_tile(E, tp, a.h[l] + (size_t)r * NMA_C * a.NP, a.NP, NMA_C);   // raw e_l again
+                load_tile(E, tp, a.h[l] + (size_t)r * NMA_C * a.NP + m0, a.NP, NMA_C, cols);   // raw e_l again
             }
             __syncthreads();
         }
         // E = e_0, G = grad w.r.t. e_0:  dA = G * elu'(e_0)
-        for (int t = tid; t < NMA_C * N; t += blockDim.x) {
-            const int g = t / N, m = t - g * N;
+        for (int t = tid; t < NMA_C * n; t += blockDim.x) {
+            const int g = t / n, m = t - g * n;
             G[g * tp + m] *= elu_grad_from_out(E[g * tp + m]);
         }
         __syncthreads();
-        row_sums(G, nullptr, tp, N, v1, nullptr);
+        row_sums(G, nullptr, tp, n, v1, nullptr);
         {
-            const int n4 = a.NP / 4;
+            const int n4 = cols / 4;
             for (int t = tid; t < NMA_C * n4; t += blockDim.x) {
                 const int f = t / n4, j4 = t - f * n4;
-                *reinterpret_cast<float4*>(a.dA + ((size_t)r * NMA_C + f) * a.NP + 4 * j4) =
+                *reinterpret_cast<float4*>(a.dA + ((size_t)r * NMA_C + f) * a.NP + m0 + 4 * j4) =
                     *reinterpret_cast<const float4*>(G + f * tp + 4 * j4);
             }
         }
         if (a.dat_hi) {
-            const long long qb = (long long)(a.K - 1) + (long long)r * a.Lin;
-            for (int t = tid; t < 14 * N; t += blockDim.x) {
-                const int fch = t / N, m = t - fch * N;
+            const long long qb = (long long)(a.K - 1) + (long long)r * a.Lin + m0;
+            for (int t = tid; t < 14 * n; t += blockDim.x) {
+                const int fch = t / n, m = t - fch * n;
                 float v[4], hi[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -285,7 +291,8 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
         }
         __syncthreads();
         if (tid < NMA_C) {
-            a.dtb[(size_t)r * NMA_C + tid] = v1[tid];
+            if (a.nseg == 1) a.dtb[(size_t)r * NMA_C + tid] = v1[tid];
+            else atomicAdd(a.dtb + (size_t)r * NMA_C + tid, v1[tid]);       // zeroed by the launcher
             acc_convb += v1[tid];
         }
     }
@@ -309,6 +316,17 @@ __global__ void __launch_bounds__(BWD_THREADS) k_epi_bwd(EpiBwdArgs a) {
 static int persistent_grid(const nma_handle_s* h, int p, int per_sm) {
     int g = h->sm_count * per_sm;
     return g < p ? g : p;
+}
+// segments of `seg` positions (a multiple of 4, >= 32) so that p x nseg work units fill ~2 CTAs per SM; one segment = the
+// whole padded row when there are rows enough
+static void row_segments(const nma_handle_s* h, int p, int N, int NP, int* seg, int* nseg) {
+    int want = (2 * h->sm_count + p - 1) / p;
+    const int most = (N + 31) / 32;
+    if (want > most) want = most;
+    if (want <= 1) { *seg = NP; *nseg = 1; return; }
+    int s = ((N + want - 1) / want + 3) & ~3;
+    *seg = s;
+    *nseg = (N + s - 1) / s;
 }
 
 int launch_epi_bwd(nma_handle_s* h, int i, const float* params, int p, int objective, float* gp, cudaStream_t st) {
@@ -335,15 +353,18 @@ int launch_epi_bwd(nma_handle_s* h, int i, const float* params, int p, int objec
     a.XP = (d.L + 3) & ~3; a.XPn = (h->fd[i + 1].L + 3) & ~3; a.L = d.L; a.N = d.N; a.NP = d.NP; a.K = h->cfg.K;
     a.H = h->cfg.H; a.bn = h->cfg.bn; a.D = h->cfg.D; a.S = h->S; a.p = p;
     a.permute_out = (h->cfg.D == 2 && i < h->cfg.F - 1) ? 1 : 0;
-    a.tile_pitch = d.NP | 4;
+    // fewer rows than CTAs the machine holds (the scripts' own shapes): split the rows into position segments
+    row_segments(h, p, d.N, d.NP, &a.seg, &a.nseg);
+    a.tile_pitch = a.seg | 4;
     a.cq = (objective == NMA_OBJ_ELBO) ? (float)h->cfg.scale : 0.f;
+    if (a.nseg > 1) NMA_CHECK_CUDA(cudaMemsetAsync(a.dtb, 0, (size_t)p * NMA_C * sizeof(float), st));
     const size_t smem = ((size_t)2 * NMA_C * a.tile_pitch + NMA_C * PW_WPITCH + 2 * a.tile_pitch + 4 * 64 + 128) * 4;
     static size_t configured = 0;
     if (configured < smem) {
         NMA_CHECK_CUDA(cudaFuncSetAttribute(k_epi_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_epi_bwd<<<persistent_grid(h, p, 2), BWD_THREADS, smem, st>>>(a);
+    k_epi_bwd<<<persistent_grid(h, p * a.nseg, 2), BWD_THREADS, smem, st>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -361,6 +382,8 @@ struct ConvDgradArgs {
     float* dx;           // [p][XP]
     int XP, Lin, LP, KP, rcmax, npb, row_pitch, x_off, p, need_dx;
     long long items_total;
+    float* part;         // channel split (gridDim.y > 1), conv_split_reduce
+    unsigned* ticket;
 };
 
 #define CONVD_WARPS 6
@@ -396,7 +419,12 @@ __global__ void __launch_bounds__(CONVD_WARPS * 32, 2) k_conv_dgrad(ConvDgradArg
     const int j0 = pb * CONV_TM;
 
     float2 acc[CONV_TM][5];
-    conv_main_loop(acc, smem, full_bar, rg, a.src, a.wdpk, row_first, my_r - row_first, j0 + a.x_off, warp, active, wide);
+    {
+        const int cper = (NMA_C + (int)gridDim.y - 1) / (int)gridDim.y, c0 = (int)blockIdx.y * cper;
+        conv_main_loop(acc, smem, full_bar, rg, a.src, a.wdpk, row_first, my_r - row_first, j0 + a.x_off, warp, active, wide,
+                       c0, min(NMA_C, c0 + cper));
+    }
+    if (!conv_split_reduce(acc, a.part, a.ticket)) return;
 
     // stage the result through shared memory for coalesced stores: tile[51][DG_PITCH], row 50 = x-channel
     float* tile = smem;
@@ -459,7 +487,10 @@ int launch_conv_dgrad(nma_handle_s* h, int i, int p, cudaStream_t st) {
         NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_conv_dgrad<<<(unsigned)((a.items_total + 31) / 32), CONVD_WARPS * 32, smem, st>>>(a);
+    const int item_ctas = (int)((a.items_total + 31) / 32);
+    const int nsplit = conv_split_count(item_ctas, NMA_C, h->sm_count);
+    a.part = h->split_part; a.ticket = h->split_ticket;
+    k_conv_dgrad<<<dim3((unsigned)item_ctas, nsplit), CONVD_WARPS * 32, smem, st>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -609,6 +640,7 @@ struct FeatBwdArgs {
     float* gw[4]; float* gb[4];
     int Lin, LP, Cf_in, p, tile_pitch;
     int top;                 // last dense(50) layer: 3; Lotka-Volterra: 2 (its 4th layer is the wide one, nma_lv.cu)
+    int seg, nseg;           // work unit = one segment of seg positions (multiple of 4) of one row (row_segments)
 };
 
 __global__ void __launch_bounds__(BWD_THREADS, 2) k_feat_bwd(FeatBwdArgs a) {
@@ -619,7 +651,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) k_feat_bwd(FeatBwdArgs a) {
     float* Wt = G + NMA_C * tp;               // [50][FB_WPITCH]
     float* v1 = Wt + NMA_C * FB_WPITCH;       // [64]
     float* wred = v1 + 64;                    // [50][50] cross-slice reduction of the weight-gradient tiles
-    const int np4 = tp / 4, n = a.Lin, n4 = a.LP / 4;
+    const int np4 = tp / 4;
     // weight-gradient ownership: 50 (5 x 10) tiles x 5 position slices
     const bool w_owner = tid < 250;
     const int slice = tid / 50, wt_tile = tid % 50;
@@ -647,25 +679,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) k_feat_bwd(FeatBwdArgs a) {
             for (int g = 0; g < 10; ++g) acc[i][g] = 0.f;
         float acc_b = 0.f;
 
-        for (int r = blockIdx.x; r < a.p; r += gridDim.x) {
+        for (int u = blockIdx.x; u < a.p * a.nseg; u += gridDim.x) {
+            const int r = u / a.nseg, m0 = (u - r * a.nseg) * a.seg;          // positions [m0, m0 + n) of row r
+            const int n = min(a.Lin - m0, a.seg), n4 = min(a.LP - m0, a.seg) / 4;
             __syncthreads();
-            // G = df * elu'(a_{l+1}),  X = a_l   (coalesced float4; columns >= Lin stay zero)
+            // G = df * elu'(a_{l+1}),  X = a_l   (coalesced float4; columns >= n are zero in G)
             {
-                const float* gsrc = a.df + (size_t)r * NMA_C * a.LP;
-                const float* esrc = a.act[l + 1] + (size_t)r * NMA_C * a.LP;
-                for (int t = tid; t < NMA_C * n4; t += blockDim.x) {
-                    const int f = t / n4, j4 = t - f * n4;
-                    // plain load: df is rewritten by this kernel between sweeps, the read-only path is not coherent
-                    const float4 gv = *reinterpret_cast<const float4*>(gsrc + (size_t)f * a.LP + 4 * j4);
-                    const float4 ev = __ldg(reinterpret_cast<const float4*>(esrc + (size_t)f * a.LP + 4 * j4));
-                    float4 o;
-                    o.x = (4 * j4 + 0 < n) ? gv.x * elu_grad_from_out(ev.x) : 0.f;
-                    o.y = (4 * j4 + 1 < n) ? gv.y * elu_grad_from_out(ev.y) : 0.f;
-                    o.z = (4 * j4 + 2 < n) ? gv.z * elu_grad_from_out(ev.z) : 0.f;
-                    o.w = (4 * j4 + 3 < n) ? gv.w * elu_grad_from_out(ev.w) : 0.f;
+                const float* gsrc = a.df + (size_t)r * NMA_C * a.LP + m0;
+                const float* esrc = a.act[l + 1] + (size_t)r * NMA_C * a.LP + m0;
+                for (int t = tid; t < NMA_C * np4; t += blockDim.x) {
+                    const int f = t / np4, j4 = t - f * np4;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j4 < n4) {
+                        // plain load: df is rewritten by this kernel between sweeps, the read-only path is not coherent
+                        const float4 gv = *reinterpret_cast<const float4*>(gsrc + (size_t)f * a.LP + 4 * j4);
+                        const float4 ev = __ldg(reinterpret_cast<const float4*>(esrc + (size_t)f * a.LP + 4 * j4));
+                        o.x = (4 * j4 + 0 < n) ? gv.x * elu_grad_from_out(ev.x) : 0.f;
+                        o.y = (4 * j4 + 1 < n) ? gv.y * elu_grad_from_out(ev.y) : 0.f;
+                        o.z = (4 * j4 + 2 < n) ? gv.z * elu_grad_from_out(ev.z) : 0.f;
+                        o.w = (4 * j4 + 3 < n) ? gv.w * elu_grad_from_out(ev.w) : 0.f;
+                    }
                     *reinterpret_cast<float4*>(G + f * tp + 4 * j4) = o;
                 }
-                const float* xsrc = a.act[l] + (size_t)r * nin * a.LP;
+                const float* xsrc = a.act[l] + (size_t)r * nin * a.LP + m0;
                 for (int t = tid; t < nin * n4; t += blockDim.x) {
                     const int f = t / n4, j4 = t - f * n4;
                     *reinterpret_cast<float4*>(X + f * tp + 4 * j4) =
@@ -713,7 +749,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) k_feat_bwd(FeatBwdArgs a) {
                     }
                 }
                 if (mg < n4) {
-                    float* dst = a.df + (size_t)r * NMA_C * a.LP + 4 * mg;
+                    float* dst = a.df + (size_t)r * NMA_C * a.LP + m0 + 4 * mg;
 #pragma unroll
                     for (int i = 0; i < 13; ++i) {
                         const int f = 4 * i + fg;
@@ -747,18 +783,20 @@ int launch_feat_bwd(nma_handle_s* h, int i, const float* params, int p, float* g
         a.gb[l] = gp + h->po[i].featb[l];
     }
     for (int l = 0; l < 5; ++l) a.act[l] = h->ws[i].a[l];
-    a.df = h->ws[i].df; a.Lin = d.Lin; a.LP = d.LP; a.Cf_in = h->Cf_in; a.p = p; a.tile_pitch = d.LP | 4;
+    a.df = h->ws[i].df; a.Lin = d.Lin; a.LP = d.LP; a.Cf_in = h->Cf_in; a.p = p;
     a.top = 3;
     if (h->is_lv) {          // three dense(50) layers over the whole window; df3 = d objective / d a3 (nma_lv.cu)
-        a.df = h->ws[i].df3; a.Lin = h->LW; a.LP = h->LWP; a.tile_pitch = h->LWP | 4; a.top = 2;
+        a.df = h->ws[i].df3; a.Lin = h->LW; a.LP = h->LWP; a.top = 2;
     }
+    row_segments(h, p, a.Lin, a.LP, &a.seg, &a.nseg);
+    a.tile_pitch = a.seg | 4;
     const size_t smem = ((size_t)2 * NMA_C * a.tile_pitch + NMA_C * FB_WPITCH + 64 + NMA_C * NMA_C) * 4;
     static size_t configured = 0;
     if (configured < smem) {
         NMA_CHECK_CUDA(cudaFuncSetAttribute(k_feat_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_feat_bwd<<<persistent_grid(h, p, 2), BWD_THREADS, smem, st>>>(a);
+    k_feat_bwd<<<persistent_grid(h, p * a.nseg, 2), BWD_THREADS, smem, st>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -119,6 +119,9 @@ struct nma_handle_s {
     // conv has 1 + LW input channels.  For the other models conv_cin = 51 and feat_out[i] = 50.
     int is_lv, conv_cin, LW, LWP;
     int feat_out[NMA_MAX_FLOWS];
+    // channel-split scratch of the SIMT conv kernels at small row counts (nma_conv_core.cuh: conv_split_reduce)
+    float* split_part;
+    unsigned* split_ticket;
     // ---- whole-iteration entry point (nma_step.cu: nma_train_step) ----
     StepWs step;
     // ---- gradient all-reduce inside the library (nma_comm.cu) ----

@@ -81,13 +81,17 @@ struct ConvRing {
 __device__ __forceinline__ void conv_main_loop(float2 (&acc)[CONV_TM][5], float* ring, uint64_t* full_bar,
                                                const ConvRing& rg, const ConvSrc& src, const float* wpk,
                                                int row0, int my_row, int my_x_off, int group, bool lane_active,
-                                               bool wide) {
+                                               bool wide, int c_begin = 0, int c_end = -1) {
+    // [c_begin, c_end): the input channels this CTA reduces over (a channel split of the launch, see conv_split_reduce)
+    if (c_end < 0) c_end = rg.cin;
+    const int nch = c_end - c_begin;
     const int tid = threadIdx.x;
     const int wslab = rg.ngroups * rg.KP * CONV_WPAD;  // floats
     const uint32_t bytes_per_stage = (uint32_t)(wslab + rg.rc * src.copy_floats) * 4u;
 
-    auto issue = [&](int c) {
-        int st = c % CONV_STAGES;
+    auto issue = [&](int cl) {
+        const int c = c_begin + cl;
+        int st = cl % CONV_STAGES;
         float* sbase = ring + (size_t)st * rg.stage_floats;
         mbar_expect_tx(&full_bar[st], bytes_per_stage);
         bulk_g2s(sbase, wpk + (size_t)c * wslab, (uint32_t)wslab * 4u, &full_bar[st]);
@@ -102,7 +106,7 @@ __device__ __forceinline__ void conv_main_loop(float2 (&acc)[CONV_TM][5], float*
     };
 
     if (tid == 0) {
-        for (int c = 0; c < CONV_STAGES && c < rg.cin; ++c) issue(c);
+        for (int c = 0; c < CONV_STAGES && c < nch; ++c) issue(c);
     }
 
 #pragma unroll
@@ -111,7 +115,7 @@ __device__ __forceinline__ void conv_main_loop(float2 (&acc)[CONV_TM][5], float*
         for (int q = 0; q < 5; ++q) acc[j][q] = make_float2(0.f, 0.f);
 
     const int nkb = rg.KP / CONV_TM;
-    for (int c = 0; c < rg.cin; ++c) {
+    for (int c = 0; c < nch; ++c) {
         const int st = c % CONV_STAGES;
         mbar_wait(&full_bar[st], (uint32_t)((c / CONV_STAGES) & 1));
         const float* sbase = ring + (size_t)st * rg.stage_floats;
@@ -160,6 +164,60 @@ __device__ __forceinline__ void conv_main_loop(float2 (&acc)[CONV_TM][5], float*
             }
         }
         __syncthreads();   // everyone is done reading this stage
-        if (tid == 0 && c + CONV_STAGES < rg.cin) issue(c + CONV_STAGES);
+        if (tid == 0 && c + CONV_STAGES < nch) issue(c + CONV_STAGES);
     }
+}
+
+// Channel split of a conv launch whose item count alone cannot fill the machine (the scripts' own shapes: p = 1..50 rows).
+// gridDim.y CTAs share one block of 32 items, each reducing over its own range of input channels.  Every CTA stores its
+// 100 accumulators per thread to `part` (coalesced float4), takes a ticket, and the CTA that draws the last one sums the
+// partials in split order - so the result does not depend on which CTA finishes last - and carries on into the epilogue.
+// Returns false for the CTAs that are done.  `ticket` is left at zero for the next launch.
+__device__ __forceinline__ bool conv_split_reduce(float2 (&acc)[CONV_TM][5], float* part, unsigned* ticket) {
+    const int nsplit = gridDim.y;
+    if (nsplit == 1) return true;
+    __shared__ unsigned s_ticket;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const size_t cta_f4 = (size_t)nthr * 25;
+    float4* mine = reinterpret_cast<float4*>(part) + ((size_t)blockIdx.x * nsplit + blockIdx.y) * cta_f4;
+#pragma unroll
+    for (int t = 0; t < 25; ++t) {
+        const float2 lo = acc[(2 * t) / 5][(2 * t) % 5], hi = acc[(2 * t + 1) / 5][(2 * t + 1) % 5];
+        __stcg(mine + (size_t)t * nthr + tid, make_float4(lo.x, lo.y, hi.x, hi.y));
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(ticket + blockIdx.x, 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(nsplit - 1)) return false;
+    __threadfence();
+    const float4* all = reinterpret_cast<const float4*>(part) + (size_t)blockIdx.x * nsplit * cta_f4;
+    float4 sum[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) sum[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < nsplit; ++s) {
+        const float4* src = all + (size_t)s * cta_f4 + tid;
+#pragma unroll
+        for (int t = 0; t < 25; ++t) {
+            const float4 v = __ldcg(src + (size_t)t * nthr);
+            sum[t].x += v.x; sum[t].y += v.y; sum[t].z += v.z; sum[t].w += v.w;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 25; ++t) {
+        acc[(2 * t) / 5][(2 * t) % 5] = make_float2(sum[t].x, sum[t].y);
+        acc[(2 * t + 1) / 5][(2 * t + 1) % 5] = make_float2(sum[t].z, sum[t].w);
+    }
+    if (tid == 0) ticket[blockIdx.x] = 0u;
+    return true;
+}
+
+// host side: number of channel splits for `item_ctas` CTAs of work over `cin` channels (>= one ring of channels per split)
+#define CONV_SPLIT_MAX 32
+#define CONV_SPLIT_PART_FLOATS (6 * 32 * 100)      // per CTA: up to 6 warps x 32 lanes x 100 accumulators
+static inline int conv_split_count(int item_ctas, int cin, int sm_count) {
+    int s = (2 * sm_count) / (item_ctas > 0 ? item_ctas : 1);
+    if (s > CONV_SPLIT_MAX) s = CONV_SPLIT_MAX;
+    if (s > cin / CONV_STAGES) s = cin / CONV_STAGES;
+    return s < 1 ? 1 : s;
 }

@@ -334,6 +334,8 @@ struct ConvFwdArgs {
     FlowEpiArgs e;
     int KP, rcmax, npb, row_pitch, p, cin;
     long long items_total;
+    float* part;             // channel split (gridDim.y > 1): partial accumulators and tickets, conv_split_reduce
+    unsigned* ticket;
 };
 
 __global__ void __launch_bounds__(CONVF_THREADS, 2) k_conv_fwd(ConvFwdArgs a) {
@@ -367,8 +369,13 @@ __global__ void __launch_bounds__(CONVF_THREADS, 2) k_conv_fwd(ConvFwdArgs a) {
     const int m0 = pb * CONV_TM;
 
     float2 acc[CONV_TM][5];
-    conv_main_loop(acc, smem, full_bar, rg, a.src, a.wpk, row_first, my_r - row_first, m0, warp, active, true);
+    {
+        const int cper = (a.cin + (int)gridDim.y - 1) / (int)gridDim.y, c0 = (int)blockIdx.y * cper;
+        conv_main_loop(acc, smem, full_bar, rg, a.src, a.wpk, row_first, my_r - row_first, m0, warp, active, true, c0,
+                       min(a.cin, c0 + cper));
+    }
     // (conv_main_loop ends with __syncthreads: the ring is free and is reused as the activation tile)
+    if (!conv_split_reduce(acc, a.part, a.ticket)) return;
 
     float* tile = smem;                               // [50][ITEM_PITCH], column = lane*10 + j
     __shared__ int col_r[ITEM_COLS];
@@ -461,7 +468,9 @@ int launch_conv_fwd(nma_handle_s* h, int i, const float* params, int p, bool sav
         configured = smem;
     }
     const long long grid = (a.items_total + 31) / 32;
-    k_conv_fwd<<<(unsigned)grid, CONVF_THREADS, smem, st>>>(a);
+    const int nsplit = conv_split_count((int)grid, a.cin, h->sm_count);
+    a.part = h->split_part; a.ticket = h->split_ticket;
+    k_conv_fwd<<<dim3((unsigned)grid, nsplit), CONVF_THREADS, smem, st>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -472,29 +481,33 @@ int launch_conv_fwd(nma_handle_s* h, int i, const float* params, int p, bool sav
 // (LW = L0 - 1 positions, no i*K offset, :343-344), runs 3 x dense(50, elu) and a 4th dense layer as wide as the
 // flow's conv input (feat_dims = L_i - 1 units), and the [window position w][unit m] result is transposed: it is
 // stored exactly like that, a4[r][w][m], which makes w the conv's input channel 1 + w and m its position.
-// p = 1 in the script (one series per iteration): one CTA per (row, flow), no tiling beyond that.
+// The script runs p = 1 (one series per iteration): the window positions are pointwise through all four layers, so a
+// (row, flow) is cut into gridDim.z segments of `seg` window positions, one CTA each.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(FEAT_THREADS) k_lv_feat_fwd(FeatArgs fa, SeriesView sv, const int64_t* __restrict__ idx,
                                                               const float* __restrict__ eps, int L0, int Cf_in, int LW,
-                                                              int LWP, int save) {
+                                                              int LWP, int save, int seg) {
     extern __shared__ __align__(128) float smem[];
     const int r = blockIdx.x, i = blockIdx.y;
+    const int w0 = (int)blockIdx.z * seg;                       // this CTA: window positions [w0, w0 + n)
+    const int n = min(LW - w0, seg), cols = min(LWP - w0, seg); // cols: padded to a multiple of 4
     const int Fd = fa.Lin[i], LP = fa.LP[i];
+    const int ld = seg;                                         // shared-memory pitch
     float* T0 = smem;
-    float* T1 = T0 + NMA_C * LWP;
-    float* Wsm = T1 + NMA_C * LWP;
+    float* T1 = T0 + NMA_C * ld;
+    float* Wsm = T1 + NMA_C * ld;
     float* bsm = Wsm + NMA_C * FEAT_WPITCH;
     const long long win0 = (long long)sv.D * idx[r];
-    if (i == 0) {
+    if (i == 0 && blockIdx.z == 0) {
         for (int t = threadIdx.x; t < fa.XP0; t += blockDim.x)
             fa.x0[(size_t)r * fa.XP0 + t] = (t < L0) ? eps[(size_t)r * L0 + t] : 0.f;
     }
-    float* ga0 = save ? fa.a[i][0] + (size_t)r * Cf_in * LWP : nullptr;
-    for (int t = threadIdx.x; t < Cf_in * LWP; t += blockDim.x) {
-        const int c = t / LWP, w = t - c * LWP;
-        const float v = (w < LW) ? series_val(sv, c, win0 + w) : 0.f;
-        T0[t] = v;
-        if (ga0) ga0[t] = v;
+    float* ga0 = save ? fa.a[i][0] + (size_t)r * Cf_in * LWP + w0 : nullptr;
+    for (int t = threadIdx.x; t < Cf_in * cols; t += blockDim.x) {
+        const int c = t / cols, w = t - c * cols;
+        const float v = (w < n) ? series_val(sv, c, win0 + w0 + w) : 0.f;
+        T0[c * ld + w] = v;
+        if (ga0) ga0[(size_t)c * LWP + w] = v;
     }
     float* cur = T0;
     float* nxt = T1;
@@ -503,21 +516,21 @@ __global__ void __launch_bounds__(FEAT_THREADS) k_lv_feat_fwd(FeatArgs fa, Serie
         const int nin = (l == 0) ? Cf_in : NMA_C;
         stage_dense_w(fa.w[i][l], fa.b[i][l], nin, Wsm, bsm);
         __syncthreads();
-        float* gout = save ? fa.a[i][l + 1] + (size_t)r * NMA_C * LWP : nullptr;
-        dense_tile_elu(cur, LWP, nin, Wsm, bsm, nxt, LWP, LWP / 4, gout, LWP, LW);
+        float* gout = save ? fa.a[i][l + 1] + (size_t)r * NMA_C * LWP + w0 : nullptr;
+        dense_tile_elu(cur, ld, nin, Wsm, bsm, nxt, ld, cols / 4, gout, LWP, n);
         float* t = cur; cur = nxt; nxt = t;
     }
     __syncthreads();
     // 4th layer: a4[w][m] = elu(b[m] + sum_f a3[f][w] W4[f][m]), lanes along the units m (kernel rows are read coalesced)
     const float* __restrict__ W4 = fa.w[i][3];
     const float* __restrict__ b4 = fa.b[i][3];
-    float* out = fa.a[i][4] + (size_t)r * LW * LP;
-    for (int t = threadIdx.x; t < LW * LP; t += blockDim.x) {
+    float* out = fa.a[i][4] + ((size_t)r * LW + w0) * LP;
+    for (int t = threadIdx.x; t < n * LP; t += blockDim.x) {
         const int w = t / LP, m = t - w * LP;
         float v = 0.f;
         if (m < Fd) {
             float acc = b4[m];
-            for (int f = 0; f < NMA_C; ++f) acc = fmaf(cur[f * LWP + w], __ldg(W4 + (size_t)f * Fd + m), acc);
+            for (int f = 0; f < NMA_C; ++f) acc = fmaf(cur[f * ld + w], __ldg(W4 + (size_t)f * Fd + m), acc);
             v = elu_f(acc);
         }
         out[t] = v;
@@ -539,7 +552,15 @@ int launch_lv_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx,
     }
     fa.x0 = h->ws[0].x;
     fa.XP0 = (h->fd[0].L + 3) & ~3;
-    const int smem = (2 * NMA_C * h->LWP + NMA_C * FEAT_WPITCH + 64) * 4;
+    // segments of the window so that p x F x nseg CTAs fill the machine (>= 16 positions each)
+    int seg = h->LWP, nseg = 1;
+    {
+        int want = (2 * h->sm_count) / (p * h->cfg.F);
+        const int most = (h->LW + 15) / 16;
+        if (want > most) want = most;
+        if (want > 1) { seg = ((h->LW + want - 1) / want + 3) & ~3; nseg = (h->LW + seg - 1) / seg; }
+    }
+    const int smem = (2 * NMA_C * seg + NMA_C * FEAT_WPITCH + 64) * 4;
     if (smem > 227 * 1024) { nma_set_error("Lotka-Volterra window of %d positions does not fit in shared memory", h->LW); return -1; }
     static int configured = 0;
     if (configured < smem) {
@@ -547,8 +568,8 @@ int launch_lv_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx,
         configured = smem;
     }
     SeriesView sv = nma_series_view(h);
-    k_lv_feat_fwd<<<dim3(p, h->cfg.F), FEAT_THREADS, smem, st>>>(fa, sv, idx, eps, h->L0, h->Cf_in, h->LW, h->LWP,
-                                                                  save ? 1 : 0);
+    k_lv_feat_fwd<<<dim3(p, h->cfg.F, nseg), FEAT_THREADS, smem, st>>>(fa, sv, idx, eps, h->L0, h->Cf_in, h->LW, h->LWP,
+                                                                        save ? 1 : 0, seg);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
