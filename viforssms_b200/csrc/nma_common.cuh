@@ -210,8 +210,15 @@ int launch_lv_feat4_bwd(nma_handle_s* h, int flow, const float* params, int p, f
 // instead of expm1f's ~30.  Absolute error <= ~2e-7 on outputs in (-1, 0]; expm1f's relative accuracy near 0 is
 // irrelevant downstream (the value is added to O(1) sums).  The fused feature kernel went from 314 M to 220 M warp
 // instructions per 2048 rows with this change alone (profiles/r01_feat_tc.md).
+// ex2.approx.ftz directly: __expf wraps the MUFU in a denormal-range guard (FSETP + two predicated FMULs) that cannot
+// matter here - an argument below -126 gives exp - 1 == -1 either way.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float elu_f(float z) {
-    const float e = __expf(fminf(z, 0.f)) - 1.f;
+    const float e = ex2_ftz(fminf(z, 0.f) * 1.4426950408889634f) - 1.f;
     return z > 0.f ? z : e;
 }
 // derivative of ELU expressed through its output e = elu(z): z>0 -> 1, else e+1

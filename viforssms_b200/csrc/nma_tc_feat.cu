@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_feat_fwd_tc(FeatTcArgs fa, Se
                 tmem_ld32(ta + TC_N, c2);
                 const float* b = bias_sm + l * 64 + half * 32;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] = valid ? elu_f(v[k] + c2[k] + b[k]) : 0.f;
+                for (int k = 0; k < 32; ++k) v[k] = elu_f(v[k] + c2[k] + b[k]);   // rows past the last position: finite, never stored
             }
             if (fa.save && valid) {
                 float* dst = fa.a[i][l + 1] + ((size_t)r * NMA_C + half * 32) * LP + j;
@@ -470,13 +470,25 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
     auto load_act = [&](float (&dst)[16], int l, bool ok, int r, int j) {
         const int nin = (l == 0) ? a.Cf_in : NMA_C;
         const float* src = a.act[l] + ((size_t)r * nin + 16 * cg) * LP + j;
+        // one branch on the lane's validity around 16 loads under warp-uniform predicates (a select per element compiles
+        // into a branch per element, which keeps the loads from being issued back to back)
+        if (ok) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) dst[k] = (ok && (16 * cg + k < nin)) ? __ldg(src + (size_t)k * LP) : 0.f;
+            for (int k = 0; k < 16; ++k) dst[k] = (16 * cg + k < nin) ? __ldg(src + (size_t)k * LP) : 0.f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[k] = 0.f;
+        }
     };
     auto load_raw = [&](float (&dst)[16], const float* base, bool ok, int r, int j) {
         const float* src = base + ((size_t)r * NMA_C + 16 * cg) * LP + j;
+        if (ok) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) dst[k] = (ok && (16 * cg + k < NMA_C)) ? src[(size_t)k * LP] : 0.f;
+            for (int k = 0; k < 16; ++k) dst[k] = (16 * cg + k < NMA_C) ? src[(size_t)k * LP] : 0.f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[k] = 0.f;
+        }
     };
     float g[16], al[16];
     {   // first tile: raw df and a_4
@@ -501,14 +513,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
         load_act(al, 3, valid, r, j);
 #pragma unroll
         for (int l = 3; l >= 0; --l) {
-            // the previous weight-gradient MMAs still read Aw / Bw: wait for them, then drain their accumulator
-            if (l < 3 || !first_tile) {
-                mbar_wait_backoff(&wbar, wph);
-                wph ^= 1u;
-                tc_fence_after();
-                tmem_sum16(tw, [&](int k, float x) { acc[(l + 1) & 3][k] += x; });
-            }
-            // ---- stage the operands of layer l (al holds a_l, prefetched one layer ahead) ----
+            // Order inside a layer: the data-gradient operand first, so that its MMAs - the ones the next layer waits for -
+            // are queued behind the previous layer's weight-gradient MMAs while the threads are still busy with that
+            // weight gradient's accumulator and with the next weight-gradient operands.
             if (l > 0) {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
@@ -518,7 +525,23 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
                         ft_split_store(Ad_hi + o, Ad_lo + o, g[4 * cc], g[4 * cc + 1], g[4 * cc + 2], g[4 * cc + 3]);
                     }
                 }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncthreads();
+                if (warp == 0) {
+                    mbar_wait_backoff(&wt_bar, tph);
+                    tph ^= 1u;
+                    ft_issue_layer(ad_hi_u, ad_lo_u, wt_u, TC_CCH / 2, tmem_d, &dbar);
+                }
             }
+            // the previous weight-gradient MMAs still read Aw / Bw: wait for them, then drain their accumulator
+            if (l < 3 || !first_tile) {
+                mbar_wait_backoff(&wbar, wph);
+                wph ^= 1u;
+                tc_fence_after();
+                tmem_sum16(tw, [&](int k, float x) { acc[(l + 1) & 3][k] += x; });
+            }
+            // ---- weight-gradient operands of layer l (al holds a_l, prefetched one layer ahead) ----
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int row = 16 * cg + k;
@@ -536,11 +559,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
             fence_proxy_async();
             __syncthreads();
             if (warp == 0) {
-                if (l > 0) {
-                    mbar_wait_backoff(&wt_bar, tph);
-                    tph ^= 1u;
-                    ft_issue_layer(ad_hi_u, ad_lo_u, wt_u, TC_CCH / 2, tmem_d, &dbar);
-                }
                 tc_fence_after();
                 if (elect_one()) {
                     constexpr uint32_t idesc_wide = umma_idesc_tf32(FT_M, 2 * TC_N, 0, 0);
@@ -754,25 +772,31 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
         {
             const float* p1 = a.e1 + ((size_t)r * NMA_C + 16 * cg) * NP + m;
             const float* p0 = a.e0 + ((size_t)r * NMA_C + 16 * cg) * NP + m;
+            // one branch on the lane's validity around the 32 loads (warp-uniform channel predicates inside): a select
+            // per element compiles into a branch per element and the loads are no longer issued back to back
+            float ehv[16];
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const bool ok = 16 * cg + k < NMA_C;
+                    ehv[k] = ok ? __ldg(p1 + (size_t)k * NP) : 0.f;
+                    e0v[k] = ok ? __ldg(p0 + (size_t)k * NP) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { ehv[k] = 0.f; e0v[k] = 0.f; }
+            }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const int ch = 16 * cg + k;
-                const bool ok = valid && ch < NMA_C;
-                const float eh = ok ? __ldg(p1 + (size_t)k * NP) : 0.f;
-                e0v[k] = ok ? __ldg(p0 + (size_t)k * NP) : 0.f;
-                hacc0[k] = fmaf(eh, dmu, hacc0[k]);
-                hacc1[k] = fmaf(eh, dsr, hacc1[k]);
-                g[k] = ok ? fmaf(dmu, hw[2 * ch], dsr * hw[2 * ch + 1]) * elu_grad_from_out(eh) : 0.f;
+                const int ch = 16 * cg + k;          // hw is zero past channel 49, dmu = dsr = 0 on invalid lanes
+                hacc0[k] = fmaf(ehv[k], dmu, hacc0[k]);
+                hacc1[k] = fmaf(ehv[k], dsr, hacc1[k]);
+                g[k] = fmaf(dmu, hw[2 * ch], dsr * hw[2 * ch + 1]) * elu_grad_from_out(ehv[k]);
             }
         }
         if (cg == 0) { hb0 += dmu; hb1 += dsr; }
-        if (!first_tile) {
-            mbar_wait_backoff(&wbar, wph);
-            wph ^= 1u;
-            tc_fence_after();
-            tmem_sum16(tw, [&](int k, float x) { acc[k] += x; });
-        }
-        // ---- operands: data gradient A = G [g/4][pos][4]; weight gradient A = [e_0; ones], B = G, K = positions ----
+        // ---- data gradient first: A = G [g/4][pos][4]; its MMAs queue behind the previous tile's weight-gradient MMAs
+        // while the threads drain that weight gradient and stage the next one ----
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const int ch = 4 * cg + cc;
@@ -781,6 +805,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
                 ft_split_store(Ad_hi + o, Ad_lo + o, g[4 * cc], g[4 * cc + 1], g[4 * cc + 2], g[4 * cc + 3]);
             }
         }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) ft_issue_layer(ad_hi_u, ad_lo_u, wt_u, TC_CCH / 2, tmem_d, &dbar);
+        if (!first_tile) {
+            mbar_wait_backoff(&wbar, wph);
+            wph ^= 1u;
+            tc_fence_after();
+            tmem_sum16(tw, [&](int k, float x) { acc[k] += x; });
+        }
+        // ---- weight gradient: A = [e_0; ones], B = G, K = positions ----
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int row = 16 * cg + k;
@@ -798,7 +833,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
         fence_proxy_async();
         __syncthreads();
         if (warp == 0) {
-            ft_issue_layer(ad_hi_u, ad_lo_u, wt_u, TC_CCH / 2, tmem_d, &dbar);
             tc_fence_after();
             if (elect_one()) {
                 constexpr uint32_t idesc_wide = umma_idesc_tf32(FT_M, 2 * TC_N, 0, 0);

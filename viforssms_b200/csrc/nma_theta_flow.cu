@@ -300,9 +300,11 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd_t(ThetaFlowArgs a) {
     float z[D], zn[D], h1[TF_H], h2[TF_H], h3[TF_H], out[2 * D];
 #pragma unroll
     for (int j = 0; j < D; ++j) z[j] = valid ? a.z0[(size_t)r * D + j] : 0.f;
-#pragma unroll
-    for (int k = 0; k < TF_NBMAX; ++k) {
-        if (k < nb) {
+    // the bijector loops stay rolled: unrolled 8 ways the kernel is ~47 k instructions of straight-line code, more than
+    // the instruction cache holds, and at the scripts' row counts (one or two warps) instruction fetch is all it waits for
+#pragma unroll 1
+    for (int k = 0; k < nb; ++k) {
+        {
 #pragma unroll
             for (int j = 0; j < D; ++j) zin[k][j] = z[j];
             mlp(sP + k * LP, z, h1, h2, h3, out);
@@ -330,10 +332,9 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd_t(ThetaFlowArgs a) {
     float gz[D], gzn[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) gz[j] = valid ? a.g_theta[(size_t)r * D + j] : 0.f;
-#pragma unroll
-    for (int kk = 0; kk < TF_NBMAX; ++kk) {
-        const int k = TF_NBMAX - 1 - kk;
-        if (k < nb) {
+#pragma unroll 1
+    for (int k = nb - 1; k >= 0; --k) {
+        {
             const float* P = sP + k * LP;
             float* G = a.g_params + (size_t)k * LP;
             if (k < nb - 1) {       // un-permute: z''_j = z'_{perm[j]}
