@@ -753,7 +753,7 @@ extern "C" int nma_tc_wgrad_raw(const float* d_in, const float* d_da, float* d_g
 #define WS_APOS (WS_KT + 8)                 // `in` positions per stage: tap offsets 0..3, padded to a multiple of 8
 #define WS_STAGES 6
 #define WS_LAG 3
-#define WS_FLUSH 8                          // stages per drain: 8 x 4 k-steps x 2 instructions = 64-MMA chains
+#define WS_FLUSH 32                         // stages per drain: 32 x 4 k-steps x 2 instructions = 256-MMA chains (raw error 5.5e-6 of the largest entry, 3.5e-6 at 8: profiles/r02_wgrad_ts.md)
 #define WS_IN_UNITS (8 * WS_APOS)           // 16-byte units of in_hi (or in_lo): 8 chunk slabs
 #define WS_DA_SLAB (WS_KT + 1)              // +1 unit: the transposing 2-byte reads of a warp hit 16 distinct banks
 #define WS_DA_UNITS (16 * WS_DA_SLAB)
@@ -866,8 +866,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
     // slabs of chunk 7 (channel slots 56..63) are never loaded: zero everything once
     for (int t = tid; t < WS_STAGES * WS_STAGE_UNITS; t += blockDim.x) smem_u[t] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
-        for (int i = 0; i < WS_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], WS_MMA_WARPS); mbar_init(&a_ready[i], 4); }
-        for (int i = 0; i < WS_TAPS; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 8); }
+        for (int i = 0; i < WS_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&a_ready[i], 4); }
+        for (int i = 0; i < WS_TAPS; ++i) { mbar_init(&acc_full[i], WS_MMA_WARPS); mbar_init(&acc_free[i], 8); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -876,6 +876,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    if (warp < 8) {
+        // every MMA accumulates (the two issuing warps are not ordered against each other, so none of them may be the one
+        // that overwrites): the tiles start at zero and the drain leaves them at zero
+        uint32_t z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = 0u;
+#pragma unroll
+        for (int t = 0; t < WS_TAPS; ++t)
+            tmem_st32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * TC_N + (warp >> 2) * 32), z);
+        tc_fence_before();
+    }
+    __syncthreads();
+    tc_fence_after();
     const uint32_t full_a = smem_addr_once(full), empty_a = smem_addr_once(empty), aready_a = smem_addr_once(a_ready);
     const uint32_t accfull_a = smem_addr_once(acc_full), accfree_a = smem_addr_once(acc_free);
     const uint32_t sbase = smem_addr_once(smem_u);
@@ -920,29 +933,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
             if (st >= WS_STAGES) { st -= WS_STAGES; ph ^= 1u; }
         }
     } else if (warp >= 9 && warp < 9 + WS_MMA_WARPS) {
-        // ===== MMA issuers: warp 9 + w owns taps w, w + WS_MMA_WARPS, ... =====
-        // A warp's own instruction stream must stay far below the ~41 cycles an instruction
-        // occupies the tensor pipe: taps and k-steps are unrolled with compile-time descriptor offsets (a rolled loop
-        // with runtime offsets cost ~7 uniform-datapath instructions per MMA and paced the kernel at ~2900 cycles per
-        // stage, profiles/r02_wgrad_ts.md), and the stage's position inside its row is tracked incrementally.
+        // ===== MMA issuers: warp 9 + w issues ALL taps of the stages si = w (mod WS_MMA_WARPS) =====
+        // ncu (profiles/r02_wgrad_ts.md): an issuing warp never waits for data (1.07 polls per barrier wait) and is busy
+        // ~85 % of the time - its own serial chain per stage (two barrier checks, elect, descriptor set-up, 16-32
+        // UTCHMMA, commits: ~1700 cycles) is what paced the kernel, not the tensor pipe (1024 cycles per stage).  Split
+        // by STAGE, each warp has two stage times for that chain.  The two warps are not ordered against each other, so
+        // no MMA overwrites: the tiles start at zero and the drain re-zeroes them.
+        // Taps and k-steps are unrolled with compile-time descriptor offsets (a rolled loop with runtime offsets cost ~7
+        // uniform-datapath instructions per MMA), and the stage's position inside its row is tracked incrementally.
         constexpr uint32_t idesc = umma_idesc_bf16(TC_M, TC_N, 0, 1);        // A from TMEM (K-major), B MN-major
         const uint32_t b_hi32 = desc_hi(WS_APOS * 16u);                        // stride offset: next channel chunk
-        int blk = (int)((long long)s_begin % a.spr);
-        const int nks_last = (int)((a.Nv - (long long)(a.spr - 1) * WS_KT + 15) / 16);
-        int st = 0, in_chunk = 0, ci = 0;
-        uint32_t ph = 0;                                                     // parity of full / a_ready for this ring pass
         const int mw = warp - 9;
-        for (int si = 0; si < nst; ++si) {
+        static_assert(WS_FLUSH % WS_MMA_WARPS == 0 && WS_STAGES % WS_MMA_WARPS == 0, "chunks and ring passes hold whole rounds of the issuing warps");
+        int blk = (int)(((long long)s_begin + mw) % a.spr);
+        const int nks_last = (int)((a.Nv - (long long)(a.spr - 1) * WS_KT + 15) / 16);
+        const int per_chunk = a.flush / WS_MMA_WARPS;                        // this warp's stages per drain chunk
+        const int nchunks = (nst + a.flush - 1) / a.flush;
+        int st = mw, in_chunk = 0, ci = 0;
+        uint32_t ph = 0;                                                     // parity of full / a_ready for this ring pass
+        for (int si = mw; si < nst; si += WS_MMA_WARPS) {
             const bool chunk_first = in_chunk == 0;
-            const bool chunk_last = (in_chunk == a.flush - 1) || (si == nst - 1);
+            const bool chunk_last = (in_chunk == per_chunk - 1) || (si + WS_MMA_WARPS >= nst);
             mbar_wait_spin(full_a + 8u * st, ph);
             mbar_wait_spin(aready_a + 8u * st, ph);
             tc_fence_after();
             const int nks = (blk == a.spr - 1) ? nks_last : WS_KT / 16;
-            if (chunk_first && ci > 0) {            // the previous chunk's sums have been drained from these tiles
+            if (chunk_first && ci > 0) {            // the previous chunk's sums have been drained (and zeroed) from these tiles
 #pragma unroll
                 for (int t = 0; t < WS_TAPS; ++t)
-                    if (t < nt && (t % WS_MMA_WARPS) == mw) mbar_wait_spin(accfree_a + 8u * t, (uint32_t)((ci - 1) & 1));
+                    if (t < nt) mbar_wait_spin(accfree_a + 8u * t, (uint32_t)((ci - 1) & 1));
                 tc_fence_after();
             }
             if (elect_one()) {
@@ -957,12 +976,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
                     if (ks < nks && !(a.diag & 4)) {
 #pragma unroll
                         for (int t = 0; t < WS_TAPS; ++t)
-                            if (t < nt && (t % WS_MMA_WARPS) == mw)
+                            if (t < nt)
                                 umma_bf16_ts(tmem + (uint32_t)(t * TC_N), ta + (uint32_t)(8 * ks),
-                                             desc_pack(bh0 + (uint32_t)(t + 16 * ks), b_hi32), idesc, (chunk_first && ks == 0) ? 0u : 1u);
+                                             desc_pack(bh0 + (uint32_t)(t + 16 * ks), b_hi32), idesc, 1u);
 #pragma unroll
                         for (int t = 0; t < WS_TAPS; ++t)
-                            if (t < nt && (t % WS_MMA_WARPS) == mw)
+                            if (t < nt)
                                 umma_bf16_ts(tmem + (uint32_t)(t * TC_N), ta + (uint32_t)(8 * ks),
                                              desc_pack(bl0 + (uint32_t)(t + 16 * ks), b_hi32), idesc, 1u);
                     }
@@ -970,14 +989,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
                 if (chunk_last) {
 #pragma unroll
                     for (int t = 0; t < WS_TAPS; ++t)
-                        if (t < nt && (t % WS_MMA_WARPS) == mw) tc_commit_a(accfull_a + 8u * t);
+                        if (t < nt) tc_commit_a(accfull_a + 8u * t);
                 }
                 tc_commit_a(empty_a + 8u * st);
             }
             __syncwarp();
-            if (++blk == a.spr) blk = 0;
-            if (++st == WS_STAGES) { st = 0; ph ^= 1u; }
+            blk += WS_MMA_WARPS;
+            while (blk >= a.spr) blk -= a.spr;
+            st += WS_MMA_WARPS;
+            if (st >= WS_STAGES) { st -= WS_STAGES; ph ^= 1u; }
             if (chunk_last) { in_chunk = 0; ++ci; } else ++in_chunk;
+        }
+        // a last chunk shorter than the number of issuing warps: the drain still expects this warp's arrival
+        if (ci < nchunks) {
+            if (ci > 0) {
+#pragma unroll
+                for (int t = 0; t < WS_TAPS; ++t)
+                    if (t < nt) mbar_wait_spin(accfree_a + 8u * t, (uint32_t)((ci - 1) & 1));
+            }
+            if (elect_one()) {
+#pragma unroll
+                for (int t = 0; t < WS_TAPS; ++t)
+                    if (t < nt) tc_commit_a(accfull_a + 8u * t);
+            }
+            __syncwarp();
         }
     } else {
         // ===== warps 0-7: dA -> TMEM (transposed), WS_LAG stages ahead of the accumulator drain =====
@@ -1029,6 +1064,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) acc[t][i] += v[i];
                             }
+                            {   // the next chunk accumulates onto zero
+                                uint32_t z[32];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) z[i] = 0u;
+                                tmem_st32(lane_addr + (uint32_t)(t * TC_N + half * 32), z);
+                            }
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_a(accfree_a + 8u * t);
@@ -1070,6 +1111,7 @@ static void wgrad_ts_geometry(ConvWgradTsArgs& a, long long rows, long long Lin,
     if (nq > a.nstages_total) nq = a.nstages_total;
     a.nq = nq;
     a.flush = WS_FLUSH;
+    { const char* e = getenv("NMA_WS_FLUSH"); if (e && atoi(e) >= 2) a.flush = atoi(e) & ~1; }   // timing experiment
     a.diag = nma_diag_bits();
 }
 
