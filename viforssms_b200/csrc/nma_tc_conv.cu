@@ -855,12 +855,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_conv_wgrad_ts(ConvWgradTsArgs
     __shared__ uint64_t full[WS_STAGES], empty[WS_STAGES], a_ready[WS_STAGES], acc_full[WS_TAPS], acc_free[WS_TAPS];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.y;
+    // tap group fastest in launch order: the groups of one range of stages run side by side and share its operands
+    // through L2 (with the range fastest every wave of CTAs swept the operands again: 2.4x the operand bytes from DRAM)
+    const int g = blockIdx.x, rng = blockIdx.y;
     const int base = a.K / a.ngroups, rem = a.K % a.ngroups;
     const int nt = base + (g < rem ? 1 : 0);                    // taps of this CTA
     const int k0 = g * base + (g < rem ? g : rem);              // first tap
-    const int s_begin = (int)((long long)a.nstages_total * blockIdx.x / a.nq);
-    const int s_end = (int)((long long)a.nstages_total * (blockIdx.x + 1) / a.nq);
+    const int s_begin = (int)((long long)a.nstages_total * rng / a.nq);
+    const int s_end = (int)((long long)a.nstages_total * (rng + 1) / a.nq);
     const int nst = s_end - s_begin;
 
     // slabs of chunk 7 (channel slots 56..63) are never loaded: zero everything once
@@ -1122,7 +1124,7 @@ static int launch_wgrad_ts(ConvWgradTsArgs& a, cudaStream_t st) {
         NMA_CHECK_CUDA(cudaFuncSetAttribute(k_conv_wgrad_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    k_conv_wgrad_ts<<<dim3(a.nq, a.ngroups), WS_THREADS, smem, st>>>(a);
+    k_conv_wgrad_ts<<<dim3(a.ngroups, a.nq), WS_THREADS, smem, st>>>(a);
     nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
