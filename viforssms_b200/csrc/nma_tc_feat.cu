@@ -96,6 +96,8 @@ struct FeatTcArgs {
     float* x0;                                // ws[0].x: aligned copy of eps
     int XP0, p, L0, K, Cf_in, feat_off, save, F, ks0;
     int bf;                                   // conv operand in the bf16 split [8][tin_Q][8 x bf16] (TcP<true>)
+    int diag;                                 // NMA_DIAG timing experiments (results invalid): 16 no activation saves, 32 no ELU,
+                                              // 64 no next-layer operand stores, 128 no MMAs
 };
 
 __device__ __forceinline__ void ft_split_store(float* hi_dst, float* lo_dst, float a, float b, float c, float d) {
@@ -224,7 +226,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_feat_fwd_tc(FeatTcArgs fa, Se
         bar_sync_named(bar_id, FT_SLOT_THREADS);
 
         for (int l = 0; l < 4; ++l) {
-            if (wslot == 0)
+            if (wslot == 0 && (fa.diag & 128)) {
+                if (elect_one()) tc_commit(&acc_bar[slot]);
+                __syncwarp();
+            } else if (wslot == 0)
                 ft_issue_layer(a_hi_u, a_lo_u, l == 0 ? w0_u : wl_u + (uint32_t)((l - 1) * FT_WLAYER_F * 4),
                                l == 0 ? fa.ks0 : TC_CCH / 2, tmem, &acc_bar[slot]);
             mbar_wait_backoff(&acc_bar[slot], phase);
@@ -239,15 +244,22 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_feat_fwd_tc(FeatTcArgs fa, Se
                 tmem_ld32(ta + TC_N, c2);
                 const float* b = bias_sm + l * 64 + half * 32;
 #pragma unroll
+                if (fa.diag & 32) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] = v[k] + c2[k] + b[k];
+                } else
+#pragma unroll
                 for (int k = 0; k < 32; ++k) v[k] = elu_f(v[k] + c2[k] + b[k]);   // rows past the last position: finite, never stored
             }
-            if (fa.save && valid) {
+            if (fa.save && valid && !(fa.diag & 16)) {
                 float* dst = fa.a[i][l + 1] + ((size_t)r * NMA_C + half * 32) * LP + j;
 #pragma unroll
                 for (int k = 0; k < 32; ++k)
                     if (half * 32 + k < NMA_C) dst[(size_t)k * LP] = v[k];
             }
-            if (l < 3) {
+            if (l < 3 && (fa.diag & 64)) {
+                bar_sync_named(bar_id, FT_SLOT_THREADS);
+            } else if (l < 3) {
                 // next layer's A operand: channels 32*half + 4cc .. +3 -> chunk 8*half + cc (channels >= 50 are zero)
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
@@ -350,6 +362,7 @@ int launch_feat_fwd_tc(nma_handle_s* h, const float* params, const int64_t* idx,
     fa.p = p; fa.L0 = h->L0; fa.K = h->cfg.K; fa.Cf_in = h->Cf_in; fa.feat_off = h->feat_off;
     fa.save = save ? 1 : 0; fa.F = F; fa.ks0 = (h->Cf_in + 7) / 8;
     fa.bf = h->use_bf16;
+    fa.diag = nma_diag_bits();
     const int smem = (3 * FT_WLAYER_F + 2 * fa.ks0 * FT_CHUNK_F + FT_SLOTS * 2 * FT_A_F + 256 + FT_SLOTS * FT_M) * 4;
     static int configured = 0;
     if (configured < smem) {
