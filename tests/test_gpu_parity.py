@@ -292,6 +292,33 @@ def test_rows_are_independent_and_gradient_is_a_sum():
     assert _rel(big["grad_theta"].reshape(rep, 64, 3)[3], small["grad_theta"]) < 1e-6
 
 
+def test_channel_split_forward_is_deterministic_and_row_count_invariant():
+    """FP32 SIMT conv at small row counts: the input channels of a launch are split over several CTAs whose partial sums the
+    last CTA adds in split order (nma_conv_core.cuh: conv_split_reduce) - so two runs give the same bits, and a row's
+    forward result does not depend on how many other rows (hence how many splits) the launch has."""
+    cfg_small = ar_config(p=4, K=20, B=13, F=3, H=3, feat_window=5, T=400)
+    cfg_big = ar_config(p=600, K=20, B=13, F=3, H=3, feat_window=5, T=400)     # rows enough for unsplit launches
+    arrays, idx, layout, params, eps, theta, _ = _ar_case(cfg_small, 400, seed=11)
+    dev = torch.device("cuda")
+    outs = []
+    for rep in range(2):
+        eng = _engine(cfg_small, tc=False)
+        eng.set_series(arrays)
+        out = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev))
+        torch.cuda.synchronize()
+        outs.append((out["terms"].clone(), out["lf"].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    eng = _engine(cfg_big, tc=False)
+    eng.set_series(arrays)
+    rep = 150
+    big = eng.elbo_fwd_bwd(params.to(dev), eps.to(dev).repeat(rep, 1), theta.to(dev).repeat(rep, 1),
+                           torch.from_numpy(idx).to(dev).repeat(rep))
+    torch.cuda.synchronize()
+    # the unsplit launch adds the channels in one running sum, the split one in partial sums: fp32 re-association only
+    assert _rel(big["terms"][:4], outs[0][0]) < 1e-5
+    assert _rel(big["lf"][:4], outs[0][1]) < 1e-5
+
+
 def test_forward_paths_matches_training_forward():
     cfg = ar_config(p=16)
     arrays, idx, layout, params, eps, theta, _ = _ar_case(cfg, 5000, seed=2)
