@@ -239,3 +239,33 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Sums of 16 per-lane values over the 32 lanes of a warp in 16 shuffles instead of 16 x 5: every step halves the number of
+// values a lane still carries (it keeps the half selected by one bit of its lane index and sends the other half to its
+// partner).  Returns, in EVERY lane, the full sum of value number  j = 8*bit4 + 4*bit3 + 2*bit2 + bit1  of the lane index
+// (the two lanes of a pair hold the same value); *j_out receives j.
+__device__ __forceinline__ float warp_sum16_transposed(const float (&v)[16], int lane, int* j_out) {
+    float w[8], x[4], y[2], z;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b3 ? w[i] : w[i + 4], keep = b3 ? w[i + 4] : w[i];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b2 ? x[i] : x[i + 2], keep = b2 ? x[i + 2] : x[i];
+        y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const float send = b1 ? y[0] : y[1], keep = b1 ? y[1] : y[0];
+        z = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+    *j_out = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+    return z;
+}

@@ -873,14 +873,19 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
             const int r0 = __shfl_sync(0xffffffffu, rk, 0), r1 = __shfl_sync(0xffffffffu, rk, 31);
             const bool two = __all_sync(0xffffffffu, rk == r0 || rk == r1);
             if (two) {
+                // 16 channel sums per row segment in 16 shuffles (warp_sum16_transposed) - one warp_sum per channel and
+                // segment was 160 shuffles and a quarter of this kernel's instruction stream
+                float part[16];
+                int j;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float s0 = warp_sum(rk == r0 ? g[k] : 0.f);
-                    const float s1 = warp_sum((rk == r1 && r1 != r0) ? g[k] : 0.f);
-                    if (lane == 0 && 16 * cg + k < NMA_C) {
-                        if (r0 >= 0) atomicAdd(a.dtb + (size_t)r0 * NMA_C + 16 * cg + k, s0);
-                        if (r1 >= 0 && r1 != r0) atomicAdd(a.dtb + (size_t)r1 * NMA_C + 16 * cg + k, s1);
-                    }
+                for (int k = 0; k < 16; ++k) part[k] = (rk == r0) ? g[k] : 0.f;
+                const float s0 = warp_sum16_transposed(part, lane, &j);
+                if (!(lane & 1) && r0 >= 0 && 16 * cg + j < NMA_C) atomicAdd(a.dtb + (size_t)r0 * NMA_C + 16 * cg + j, s0);
+                if (r1 != r0) {                                   // warp-uniform: the warp straddles two rows
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) part[k] = (rk == r1) ? g[k] : 0.f;
+                    const float s1 = warp_sum16_transposed(part, lane, &j);
+                    if (!(lane & 1) && r1 >= 0 && 16 * cg + j < NMA_C) atomicAdd(a.dtb + (size_t)r1 * NMA_C + 16 * cg + j, s1);
                 }
             } else if (valid) {
 #pragma unroll
