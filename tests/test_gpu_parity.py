@@ -319,6 +319,44 @@ def test_channel_split_forward_is_deterministic_and_row_count_invariant():
     assert _rel(big["lf"][:4], outs[0][1]) < 1e-5
 
 
+def test_second_stream_schedule_gives_the_same_step():
+    """At the scripts' row counts the step runs independent kernels side by side on the handle's second stream (weight
+    packing next to the feature forward, conv weight gradient next to data gradient + feature backward; nma_api.cu).
+    NMA_NO_AUX_STREAM=1 keeps everything on one stream: same forward bits, same gradients up to the order of the atomics -
+    eagerly and replayed from a CUDA graph."""
+    cfg = ar_config(p=50)
+    arrays, idx, layout, params, eps, theta, _ = _ar_case(cfg, 5000, seed=4)
+    dev = torch.device("cuda")
+    args = (params.to(dev), eps.to(dev), theta.to(dev), torch.from_numpy(idx).to(dev))
+    res = {}
+    for tc in (False, 7):
+        for no_aux in ("1", None):
+            if no_aux:
+                os.environ["NMA_NO_AUX_STREAM"] = no_aux
+            else:
+                os.environ.pop("NMA_NO_AUX_STREAM", None)
+            eng = _engine(cfg, tc)
+            eng.set_series(arrays)
+            out = eng.elbo_fwd_bwd(*args)
+            torch.cuda.synchronize()
+            res[(tc, no_aux)] = (out["terms"].clone(), out["grad_params"].clone(), out["grad_theta"].clone())
+        one, two = res[(tc, "1")], res[(tc, None)]
+        assert torch.equal(one[0], two[0])
+        assert _rel(two[1], one[1]) < 2e-6 and _rel(two[2], one[2]) < 2e-6
+    # the two-stream schedule inside a captured graph
+    eng = _engine(cfg, 7)
+    eng.set_series(arrays)
+    out = eng.elbo_fwd_bwd(*args)          # warm-up outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        out = eng.elbo_fwd_bwd(*args)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["terms"], res[(7, None)][0])
+    assert _rel(out["grad_params"], res[(7, None)][1]) < 2e-6
+
+
 def test_forward_paths_matches_training_forward():
     cfg = ar_config(p=16)
     arrays, idx, layout, params, eps, theta, _ = _ar_case(cfg, 5000, seed=2)

@@ -130,6 +130,10 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
+    h->aux = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
+    NMA_CHECK_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    NMA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    NMA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
 
     // ---- carve the workspace arena ----
     const int64_t p = cfg->p;
@@ -233,6 +237,9 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
 extern "C" int nma_destroy(nma_handle h) {
     if (!h) return 0;
     comm_release(h);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->aux) cudaStreamDestroy(h->aux);
     if (h->arena) cudaFree(h->arena);
     delete h;
     return 0;
@@ -328,14 +335,38 @@ extern "C" int nma_gather(nma_handle h, const int64_t* d_idx, int32_t p, float* 
     return launch_gather(h, d_idx, p, d_tf, d_mask, d_shift, (cudaStream_t)stream);
 }
 
+// Launches that do not fill the machine (the scripts' own row counts: under four 256-position tiles per SM) run their
+// independent kernels side by side on the handle's second stream; at thousands of rows every kernel fills the machine
+// by itself and the order of one stream is kept.
+static bool step_is_small(const nma_handle_s* h, int p) {
+    return (long long)p * h->fd[0].Lin < (long long)h->sm_count * 1024 && !getenv("NMA_NO_AUX_STREAM");
+}
+static int aux_fork(nma_handle_s* h, cudaStream_t st) {
+    NMA_CHECK_CUDA(cudaEventRecord(h->ev_fork, st));
+    NMA_CHECK_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    return 0;
+}
+static int aux_join(nma_handle_s* h, cudaStream_t st) {
+    NMA_CHECK_CUDA(cudaEventRecord(h->ev_join, h->aux));
+    NMA_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    return 0;
+}
+
 static int forward_all(nma_handle_s* h, const float* params, const float* eps, const float* theta, const int64_t* idx,
                        int p, bool save, cudaStream_t st) {
     int rc;
-    if ((rc = launch_pack_weights(h, params, save, st))) return rc;
+    const bool side = step_is_small(h, p);
+    if (side) {
+        // the conv tap kernels are packed next to theta-bias MLP + feature forward; the conv itself waits for both
+        if ((rc = aux_fork(h, st))) return rc;
+        if ((rc = launch_pack_weights(h, params, save, h->aux, 1))) return rc;
+        if ((rc = launch_pack_weights(h, params, save, st, 2))) return rc;
+    } else if ((rc = launch_pack_weights(h, params, save, st))) return rc;
     if ((rc = launch_theta_fwd(h, params, theta, p, st))) return rc;
     if ((rc = (h->is_lv ? launch_lv_feat_fwd(h, params, idx, eps, p, save, st)
                         : launch_feat_fwd_eps(h, params, idx, eps, p, save, st))))
         return rc;
+    if (side && (rc = aux_join(h, st))) return rc;
     for (int i = 0; i < h->cfg.F; ++i)
         if ((rc = launch_conv_fwd(h, i, params, p, save, st))) return rc;
     return 0;
@@ -360,23 +391,37 @@ int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d
     if ((rc = launch_elbo(h, d_theta, d_eps, d_idx, p, objective, path_target, d_terms, d_lf, d_grad_theta, d_flags,
                           true, st)))
         return rc;
+    const bool side = step_is_small(h, p);
     for (int i = h->cfg.F - 1; i >= 0; --i) {
         if ((rc = launch_epi_bwd(h, i, d_params, p, objective, d_grad_params, st))) return rc;
+        // the conv weight gradient needs dA only: at small row counts it runs on the second stream next to the data
+        // gradient and the feature backward (which need each other), and is joined before the flow's section is used
+        cudaStream_t ws = side ? h->aux : st;
+        if (side && (rc = aux_fork(h, st))) return rc;
         if (h->is_lv) {
+            if ((rc = launch_lv_conv_wgrad(h, i, p, d_grad_params, ws))) return rc;
             if ((rc = launch_lv_conv_dgrad(h, i, d_params, p, st))) return rc;
-            if ((rc = launch_lv_conv_wgrad(h, i, p, d_grad_params, st))) return rc;
             if ((rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
             if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
         } else {
+            if (side) {
+                if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, ws)
+                           : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, ws)
+                                       : launch_conv_wgrad(h, i, p, d_grad_params, ws))))
+                    return rc;
+            }
             if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, st) : launch_conv_dgrad(h, i, p, st)))) return rc;
-            if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, st)
-                       : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, st)
-                                   : launch_conv_wgrad(h, i, p, d_grad_params, st))))
-                return rc;
+            if (!side) {
+                if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, st)
+                           : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, st)
+                                       : launch_conv_wgrad(h, i, p, d_grad_params, st))))
+                    return rc;
+            }
             if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, st))) return rc;
         }
         // theta-bias MLP of this flow (AR.py:63-68): its gradient completes the flow's section of the blob
         if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, i, st))) return rc;
+        if (side && (rc = aux_join(h, st))) return rc;
         if (per_flow_collective && h->comm.comm) {
             int64_t off, count;
             flow_section(h, i, &off, &count);

@@ -122,6 +122,11 @@ struct nma_handle_s {
     // channel-split scratch of the SIMT conv kernels at small row counts (nma_conv_core.cuh: conv_split_reduce)
     float* split_part;
     unsigned* split_ticket;
+    // second stream for the kernels of a step that do not depend on each other (weight packing next to the feature
+    // forward; the conv weight gradient next to data gradient + feature backward): used when the launch does not fill the
+    // machine (the scripts' own row counts), joined back with events - also inside a captured graph
+    cudaStream_t aux;
+    cudaEvent_t ev_fork, ev_join;
     // ---- whole-iteration entry point (nma_step.cu: nma_train_step) ----
     StepWs step;
     // ---- gradient all-reduce inside the library (nma_comm.cu) ----
@@ -152,7 +157,8 @@ SeriesView nma_series_view(const nma_handle_s* h);
 
 // launchers (one per kernel family); all asynchronous on `st`
 int launch_gather(nma_handle_s* h, const int64_t* idx, int p, float* tf, float* mask, float* shift, cudaStream_t st);
-int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
+// which: 1 = conv tap / 1x1 kernels, 2 = feature kernels (tensor-core feature path), 3 = both
+int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st, int which = 3);
 int launch_theta_fwd(nma_handle_s* h, const float* params, const float* theta, int p, cudaStream_t st);
 int launch_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, int p, bool save, cudaStream_t st);
 int launch_conv_fwd(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
@@ -163,7 +169,7 @@ int launch_conv_dgrad_tcp(nma_handle_s* h, int flow, int p, cudaStream_t st);
 int launch_conv_wgrad_bf(nma_handle_s* h, int flow, int p, float* grad_params, cudaStream_t st);
 int conv_fwd_tcp_supported(const nma_handle_s* h);
 int launch_conv_fwd_tcp(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
-int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
+int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st, int which = 3);
 int launch_pack_feat_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
 int epi_bwd_tc_supported(const nma_handle_s* h);
 int launch_epi_bwd_tc(nma_handle_s* h, int flow, const float* params, int p, int objective, float* grad_params,

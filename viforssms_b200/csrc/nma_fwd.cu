@@ -71,8 +71,9 @@ __global__ void k_pack_dgrad(const float* __restrict__ W, int K, int KP, float* 
     }
 }
 
-int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
-    if (h->use_tc) return launch_pack_weights_tc(h, params, need_bwd, st);
+int launch_pack_weights(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st, int which) {
+    if (h->use_tc) return launch_pack_weights_tc(h, params, need_bwd, st, which);
+    if (!(which & 1)) return 0;
     for (int i = 0; i < h->cfg.F; ++i) {
         k_pack_fwd<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, h->KP, h->conv_cin, h->ws[i].wpk);
         nma_count_launch(1);

@@ -97,8 +97,8 @@ __global__ void k_tc_pack_w_bf_pair(const float* __restrict__ W, int K, int mode
     }
 }
 
-int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st) {
-    for (int i = 0; i < h->cfg.F; ++i) {
+int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st, int which) {
+    for (int i = 0; (which & 1) && i < h->cfg.F; ++i) {
         if (h->use_bf16 && h->tap_pairs) {
             k_tc_pack_w_bf_pair<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 0, (uint16_t*)h->ws[i].wtc_f, 0);
             if (need_bwd) k_tc_pack_w_bf_pair<<<148, 256, 0, st>>>(params + h->po[i].convw, h->cfg.K, 1, (uint16_t*)h->ws[i].wtc_d, 1);
@@ -119,7 +119,7 @@ int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, 
         }
     }
     NMA_CHECK_CUDA(cudaGetLastError());
-    if (h->use_tc_feat) return launch_pack_feat_tc(h, params, need_bwd, st);
+    if ((which & 2) && h->use_tc_feat) return launch_pack_feat_tc(h, params, need_bwd, st);
     return 0;
 }
 
