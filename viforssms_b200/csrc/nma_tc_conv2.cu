@@ -650,10 +650,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
                     v[i] = (ok && f < NMA_C) ? elu_f(v[i] + __ldg(tbr + (f < NMA_C ? f : 0))) : 0.f;
                 }
                 if (a.save && ok) {
-                    float* dst = a.h0 + ((size_t)r * NMA_C + half * 32) * a.NP + m;
+                    char* pb = reinterpret_cast<char*>(a.h0 + ((size_t)r * NMA_C + half * 32) * a.NP + m);
+                    const size_t step = (size_t)a.NP * sizeof(float);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (half * 32 + i < NMA_C) dst[(size_t)i * a.NP] = v[i];
+                    for (int i = 0; i < 32; ++i) {
+                        if (half * 32 + i < NMA_C) *reinterpret_cast<float*>(pb) = v[i];
+                        pb += step;
+                    }
                 }
                 if (BF) {
 #pragma unroll
@@ -731,10 +734,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_conv_fwd_tcp(ConvFwdP a) {
                     }
                 }
                 if (a.save && ok) {
-                    float* dst = a.h1 + ((size_t)r * NMA_C + half * 32) * a.NP + m;
+                    char* pb = reinterpret_cast<char*>(a.h1 + ((size_t)r * NMA_C + half * 32) * a.NP + m);
+                    const size_t step = (size_t)a.NP * sizeof(float);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (half * 32 + i < NMA_C) dst[(size_t)i * a.NP] = v[i];
+                    for (int i = 0; i < 32; ++i) {
+                        if (half * 32 + i < NMA_C) *reinterpret_cast<float*>(pb) = v[i];
+                        pb += step;
+                    }
                 }
             }
             if (ok) {

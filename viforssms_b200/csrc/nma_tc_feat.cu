@@ -486,8 +486,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
         // one branch on the lane's validity around 16 loads under warp-uniform predicates (a select per element compiles
         // into a branch per element, which keeps the loads from being issued back to back)
         if (ok) {
+            // running pointer: two integer instructions per load instead of a 64-bit multiply-add chain each
+            const char* pb = reinterpret_cast<const char*>(src);
+            const size_t step = (size_t)LP * sizeof(float);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) dst[k] = (16 * cg + k < nin) ? __ldg(src + (size_t)k * LP) : 0.f;
+            for (int k = 0; k < 16; ++k) {
+                dst[k] = (16 * cg + k < nin) ? __ldg(reinterpret_cast<const float*>(pb)) : 0.f;
+                pb += step;
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < 16; ++k) dst[k] = 0.f;
@@ -496,8 +502,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_feat_bwd_tc(FeatBwdTcArgs a) 
     auto load_raw = [&](float (&dst)[16], const float* base, bool ok, int r, int j) {
         const float* src = base + ((size_t)r * NMA_C + 16 * cg) * LP + j;
         if (ok) {
+            const char* pb = reinterpret_cast<const char*>(src);
+            const size_t step = (size_t)LP * sizeof(float);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) dst[k] = (16 * cg + k < NMA_C) ? src[(size_t)k * LP] : 0.f;
+            for (int k = 0; k < 16; ++k) {
+                dst[k] = (16 * cg + k < NMA_C) ? *reinterpret_cast<const float*>(pb) : 0.f;
+                pb += step;
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < 16; ++k) dst[k] = 0.f;
@@ -789,11 +800,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_epi_bwd_tc(EpiBwdTcArgs a) {
             // per element compiles into a branch per element and the loads are no longer issued back to back
             float ehv[16];
             if (valid) {
+                const char* pb1 = reinterpret_cast<const char*>(p1);
+                const char* pb0 = reinterpret_cast<const char*>(p0);
+                const size_t step = (size_t)NP * sizeof(float);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const bool ok = 16 * cg + k < NMA_C;
-                    ehv[k] = ok ? __ldg(p1 + (size_t)k * NP) : 0.f;
-                    e0v[k] = ok ? __ldg(p0 + (size_t)k * NP) : 0.f;
+                    ehv[k] = ok ? __ldg(reinterpret_cast<const float*>(pb1)) : 0.f;
+                    e0v[k] = ok ? __ldg(reinterpret_cast<const float*>(pb0)) : 0.f;
+                    pb1 += step; pb0 += step;
                 }
             } else {
 #pragma unroll
