@@ -183,6 +183,40 @@ def test_graph_replay_equals_eager_iterations(monkeypatch):
         assert abs(scal[0][k] - scal[1][k]) <= 1e-4 * max(1.0, abs(scal[0][k])), k
 
 
+def test_second_stream_train_step_equals_one_stream(monkeypatch):
+    """nma_train_step at the scripts' row counts runs flow 0's conv / feature backward on the handle's second stream next to
+    the theta-bias MLP backward, the prior terms and the theta posterior's backward, and joins right before the optimiser
+    (nma_api.cu, nma_step.cu).  NMA_NO_AUX_STREAM=1 keeps one stream: same draws, same variables up to the atomics' order -
+    eagerly and from the captured graph."""
+    import AR as ar_mod
+    from viforssms_b200.theta_flow import ThetaFlow
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "dat")
+    obs = np.loadtxt(os.path.join(d, "AR_obs_partial.txt"))
+    obs_bin = np.loadtxt(os.path.join(d, "AR_obs_binary.txt"))
+    tt = np.loadtxt(os.path.join(d, "AR_time_till.txt"))
+    blobs, scal = [], []
+    for no_aux, graph in (("1", "0"), (None, "0"), (None, "1")):
+        monkeypatch.setenv("NMA_FACADE_GRAPH", graph)
+        if no_aux:
+            monkeypatch.setenv("NMA_NO_AUX_STREAM", no_aux)
+        else:
+            monkeypatch.delenv("NMA_NO_AUX_STREAM", raising=False)
+        np.random.seed(1)
+        flow = ThetaFlow(3, 5, 1.5, 0.5, "elu")
+        m = ar_mod.VI_SSM(obs, 1.0, 10.0, flow, [(0.0, 10.0)] * 3, 5000, 20, 10, 10, [50, 50, 50], 2, 4, obs_bin, tt, seed=2)
+        m.build_flow()
+        for it in range(6):
+            m._iteration(m._draw(False), pre_train=it < 3)
+        torch.cuda.synchronize()
+        blobs.append(m.blob.clone()); scal.append(m.scalars)
+    for other in (1, 2):
+        diff = (blobs[0] - blobs[other]).abs()
+        assert (diff > 2e-5).float().mean().item() < 2e-3 and diff.max().item() <= 6 * 2e-3
+        for k in scal[0]:
+            assert abs(scal[0][k] - scal[other][k]) <= 1e-4 * max(1.0, abs(scal[0][k])), k
+
+
 @pytest.mark.parametrize("offset", [1, 2, 3, 5])
 def test_adamax_on_unaligned_tail_views(offset):
     """The second pre-train optimiser updates views into the tail of the blob (vi_ssm_models.py): any 4-byte offset."""

@@ -130,7 +130,7 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
-    h->aux = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
+    h->aux = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr; h->aux_pending = 0;
     NMA_CHECK_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     NMA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     NMA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -352,6 +352,12 @@ static int aux_join(nma_handle_s* h, cudaStream_t st) {
     return 0;
 }
 
+int step_aux_join(nma_handle_s* h, cudaStream_t st) {
+    if (!h->aux_pending) return 0;
+    h->aux_pending = 0;
+    return aux_join(h, st);
+}
+
 static int forward_all(nma_handle_s* h, const float* params, const float* eps, const float* theta, const int64_t* idx,
                        int p, bool save, cudaStream_t st) {
     int rc;
@@ -384,7 +390,7 @@ static void flow_section(const nma_handle_s* h, int i, int64_t* off, int64_t* co
 int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d_eps, const float* d_theta,
                           const int64_t* d_idx, int p, int objective, float path_target, float* d_terms, float* d_lf,
                           float* d_grad_params, float* d_grad_theta, uint32_t* d_flags, bool per_flow_collective,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool defer_last_join) {
     int rc;
     NMA_CHECK_CUDA(cudaMemsetAsync(d_grad_params, 0, (size_t)h->n_params * 4, st));
     if ((rc = forward_all(h, d_params, d_eps, d_theta, d_idx, p, true, st))) return rc;
@@ -394,6 +400,28 @@ int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d
     const bool side = step_is_small(h, p);
     for (int i = h->cfg.F - 1; i >= 0; --i) {
         if ((rc = launch_epi_bwd(h, i, d_params, p, objective, d_grad_params, st))) return rc;
+        if (i == 0 && side && defer_last_join && !(per_flow_collective && h->comm.comm)) {
+            // Last flow of the backward pass: nothing downstream of its conv / feature backward but the optimiser, while
+            // d/dtheta still has to go through the theta-bias MLP, the prior / entropy terms and the theta posterior (the
+            // caller's next kernels on st).  The whole conv / feature branch goes to the second stream and is joined by
+            // the caller right before the optimiser (step_aux_join).
+            if ((rc = aux_fork(h, st))) return rc;
+            if (h->is_lv) {
+                if ((rc = launch_lv_conv_wgrad(h, i, p, d_grad_params, h->aux))) return rc;
+                if ((rc = launch_lv_conv_dgrad(h, i, d_params, p, h->aux))) return rc;
+                if ((rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, h->aux))) return rc;
+            } else {
+                if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, h->aux)
+                           : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, h->aux)
+                                       : launch_conv_wgrad(h, i, p, d_grad_params, h->aux))))
+                    return rc;
+                if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, h->aux) : launch_conv_dgrad(h, i, p, h->aux)))) return rc;
+            }
+            if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, h->aux))) return rc;
+            if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, i, st))) return rc;
+            h->aux_pending = 1;
+            break;
+        }
         // the conv weight gradient needs dA only: at small row counts it runs on the second stream next to the data
         // gradient and the feature backward (which need each other), and is joined before the flow's section is used
         cudaStream_t ws = side ? h->aux : st;

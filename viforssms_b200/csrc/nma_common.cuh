@@ -127,6 +127,7 @@ struct nma_handle_s {
     // machine (the scripts' own row counts), joined back with events - also inside a captured graph
     cudaStream_t aux;
     cudaEvent_t ev_fork, ev_join;
+    int aux_pending;         // step_forward_backward left flow 0's conv / feature backward running on `aux` (step_aux_join)
     // ---- whole-iteration entry point (nma_step.cu: nma_train_step) ----
     StepWs step;
     // ---- gradient all-reduce inside the library (nma_comm.cu) ----
@@ -201,7 +202,9 @@ int launch_counter_bump(nma_handle_s* h, cudaStream_t st);
 int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d_eps, const float* d_theta,
                           const int64_t* d_idx, int p, int objective, float path_target, float* d_terms, float* d_lf,
                           float* d_grad_params, float* d_grad_theta, uint32_t* d_flags, bool per_flow_collective,
-                          cudaStream_t st);
+                          cudaStream_t st, bool defer_last_join = false);
+// waits (on st) for what step_forward_backward(defer_last_join = true) left running on the handle's second stream
+int step_aux_join(nma_handle_s* h, cudaStream_t st);
 // Lotka-Volterra instances (nma_lv.cu)
 int launch_lv_feat_fwd(nma_handle_s* h, const float* params, const int64_t* idx, const float* eps, int p, bool save,
                        cudaStream_t st);

@@ -300,7 +300,7 @@ extern "C" int nma_train_step(nma_handle h, float* d_blob, float* d_grad, float*
     }
     // 3. flow, ELBO terms, backward down to d/dtheta (per-flow all-reduce on the side stream when sharded)
     if ((rc = step_forward_backward(h, d_blob, w.eps, w.theta, d_idx, p, o->objective, o->path_target, w.terms, d_lf_out,
-                                    d_grad, w.g_theta, w.flags, true, st)))
+                                    d_grad, w.g_theta, w.flags, true, st, true)))
         return rc;
     // 4. prior / entropy of theta and the gradient entering the theta posterior
     {
@@ -317,6 +317,8 @@ extern "C" int nma_train_step(nma_handle h, float* d_blob, float* d_grad, float*
     if (nb > 0 && (rc = nma_theta_flow_bwd_ex(flow_params, w.tf_masks, w.tf_perms, w.z0, p, d, nb, w.tf_relu, w.g_theta,
                                               nullptr, o->prior_on ? 1.f : 0.f, o->tf_mask_grad, flow_grad, nullptr, stream)))
         return rc;
+    // (flow 0's conv / feature backward may still be running on the handle's second stream: small launches only)
+    if ((rc = step_aux_join(h, st))) return rc;
     // 6. the theta posterior's section of the gradient, then wait for every collective of this step
     if (h->comm.comm) {
         if (nb > 0 && (rc = comm_allreduce_after(h, flow_grad, n_flow, h->cfg.F, st))) return rc;
