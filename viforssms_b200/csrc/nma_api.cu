@@ -398,29 +398,33 @@ int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d
                           true, st)))
         return rc;
     const bool side = step_is_small(h, p);
+    const bool collectives = per_flow_collective && h->comm.comm;
     for (int i = h->cfg.F - 1; i >= 0; --i) {
         if ((rc = launch_epi_bwd(h, i, d_params, p, objective, d_grad_params, st))) return rc;
-        if (i == 0 && side && defer_last_join && !(per_flow_collective && h->comm.comm)) {
-            // Last flow of the backward pass: nothing downstream of its conv / feature backward but the optimiser, while
-            // d/dtheta still has to go through the theta-bias MLP, the prior / entropy terms and the theta posterior (the
-            // caller's next kernels on st).  The whole conv / feature branch goes to the second stream and is joined by
-            // the caller right before the optimiser (step_aux_join).
+        if (side && !collectives) {
+            // Small launches (the scripts' own row counts), no collective waiting for the flow's section: only the chain
+            // head backward -> data gradient -> head backward of the next flow is serial.  The conv weight gradient (needs
+            // dA) and the feature backward (needs the data gradient's df) leave it for the handle's second stream; the
+            // theta-bias MLP backward is short and stays, which keeps the d/dtheta accumulation in one stream.  For the
+            // last flow the data gradient leaves as well: st goes on to the theta chain of the caller.  Everything on the
+            // second stream is joined once - by nma_train_step right before the optimiser, else at the end of this call.
             if ((rc = aux_fork(h, st))) return rc;
             if (h->is_lv) {
                 if ((rc = launch_lv_conv_wgrad(h, i, p, d_grad_params, h->aux))) return rc;
-                if ((rc = launch_lv_conv_dgrad(h, i, d_params, p, h->aux))) return rc;
-                if ((rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, h->aux))) return rc;
-            } else {
-                if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, h->aux)
-                           : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, h->aux)
-                                       : launch_conv_wgrad(h, i, p, d_grad_params, h->aux))))
-                    return rc;
-                if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, h->aux) : launch_conv_dgrad(h, i, p, h->aux)))) return rc;
-            }
+            } else if ((rc = (h->use_bf16 ? launch_conv_wgrad_bf(h, i, p, d_grad_params, h->aux)
+                              : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, h->aux)
+                                          : launch_conv_wgrad(h, i, p, d_grad_params, h->aux))))
+                return rc;
+            cudaStream_t ds = (i == 0) ? h->aux : st;
+            if (h->is_lv) {
+                if ((rc = launch_lv_conv_dgrad(h, i, d_params, p, ds))) return rc;
+            } else if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, ds) : launch_conv_dgrad(h, i, p, ds)))) return rc;
+            if (i > 0 && (rc = aux_fork(h, st))) return rc;          // the feature backward waits for this flow's df
+            if (h->is_lv && (rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, h->aux))) return rc;
             if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, h->aux))) return rc;
             if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, i, st))) return rc;
             h->aux_pending = 1;
-            break;
+            continue;
         }
         // the conv weight gradient needs dA only: at small row counts it runs on the second stream next to the data
         // gradient and the feature backward (which need each other), and is joined before the flow's section is used
@@ -456,6 +460,7 @@ int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d
             if ((rc = comm_allreduce_after(h, d_grad_params + off, count, i, st))) return rc;
         }
     }
+    if (!defer_last_join && (rc = step_aux_join(h, st))) return rc;
     return 0;
 }
 
