@@ -171,6 +171,8 @@ int launch_conv_wgrad_bf(nma_handle_s* h, int flow, int p, float* grad_params, c
 int conv_fwd_tcp_supported(const nma_handle_s* h);
 int launch_conv_fwd_tcp(nma_handle_s* h, int flow, const float* params, int p, bool save, cudaStream_t st);
 int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st, int which = 3);
+int launch_pack_w1x1_fwd(nma_handle_s* h, int i, const float* params, cudaStream_t st);
+int launch_pack_w1x1_t(nma_handle_s* h, int i, const float* params, cudaStream_t st);
 int launch_pack_feat_tc(nma_handle_s* h, const float* params, bool need_bwd, cudaStream_t st);
 int epi_bwd_tc_supported(const nma_handle_s* h);
 int launch_epi_bwd_tc(nma_handle_s* h, int flow, const float* params, int p, int objective, float* grad_params,

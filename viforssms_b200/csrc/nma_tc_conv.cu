@@ -119,6 +119,14 @@ int launch_pack_weights_tc(nma_handle_s* h, const float* params, bool need_bwd, 
         }
     }
     NMA_CHECK_CUDA(cudaGetLastError());
+    if (which & 1) {
+        // the hidden 1x1 kernels of the tensor-core epilogues (forward: conv_fwd_tcp; backward: epi_bwd_tc)
+        int rc;
+        for (int i = 0; i < h->cfg.F; ++i) {
+            if (conv_fwd_tcp_supported(h) && (rc = launch_pack_w1x1_fwd(h, i, params, st))) return rc;
+            if (need_bwd && epi_bwd_tc_supported(h) && (rc = launch_pack_w1x1_t(h, i, params, st))) return rc;
+        }
+    }
     if ((which & 2) && h->use_tc_feat) return launch_pack_feat_tc(h, params, need_bwd, st);
     return 0;
 }

@@ -812,11 +812,20 @@ int conv_fwd_tcp_supported(const nma_handle_s* h) {
     return smem + 1024 <= 227 * 1024;      // (the bf16 operand tile is smaller: same bound)
 }
 
-int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool save, cudaStream_t st) {
-    const FlowDims& d = h->fd[i];
-    float* whid = h->ws[i].wtc_feat + (size_t)9 * TC_WSTAGE;     // slot 9 of the flow's pack buffer
+// hidden 1x1 kernel of flow i in the forward orientation -> slot 9 of the flow's pack buffer (part of the step's weight
+// packing, launch_pack_weights_tc: off the forward pass's serial chain)
+int launch_pack_w1x1_fwd(nma_handle_s* h, int i, const float* params, cudaStream_t st) {
+    float* whid = h->ws[i].wtc_feat + (size_t)9 * TC_WSTAGE;
     if (h->use_bf16) k_tc_pack_w1x1_bf<<<1, 256, 0, st>>>(params + h->po[i].hidw[0], (uint16_t*)whid);
     else k_tc_pack_w1x1<<<1, 256, 0, st>>>(params + h->po[i].hidw[0], whid);
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool save, cudaStream_t st) {
+    const FlowDims& d = h->fd[i];
+    float* whid = h->ws[i].wtc_feat + (size_t)9 * TC_WSTAGE;     // slot 9 of the flow's pack buffer (launch_pack_w1x1_fwd)
     ConvFwdP a;
     a.src.a_hi = h->ws[i].tin_hi; a.src.a_lo = h->ws[i].tin_lo; a.src.Qalloc = h->ws[i].tin_Q;
     a.src.wt = h->ws[i].wtc_f; a.src.K = h->cfg.K;
@@ -846,7 +855,7 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
             configured = smem;
         }
         k_conv_fwd_tcp<true, true><<<grid, P_THREADS, smem, st>>>(a);
-        nma_count_launch(2);
+        nma_count_launch(1);
         NMA_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
@@ -861,7 +870,7 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
             configured = smem;
         }
         k_conv_fwd_tcp<true, false><<<grid, P_THREADS, smem, st>>>(a);
-        nma_count_launch(2);
+        nma_count_launch(1);
         NMA_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
@@ -875,7 +884,7 @@ int launch_conv_fwd_tcp(nma_handle_s* h, int i, const float* params, int p, bool
         configured = smem;
     }
     k_conv_fwd_tcp<false, false><<<grid, P_THREADS, smem, st>>>(a);
-    nma_count_launch(2);
+    nma_count_launch(1);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

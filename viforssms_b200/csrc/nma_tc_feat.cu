@@ -1051,11 +1051,19 @@ int epi_bwd_tc_supported(const nma_handle_s* h) {
     return h->use_tc && h->use_tc_feat && h->cfg.H == 1 && !h->cfg.bn && h->cfg.D == 1;
 }
 
-int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int objective, float* gp, cudaStream_t st) {
-    const FlowDims& d = h->fd[i];
-    // slot 8 of the flow's pack buffer: the transposed hidden kernel (weights are constant during a step)
+// transposed hidden 1x1 kernel of flow i -> slot 8 of the flow's pack buffer (part of the step's weight packing)
+int launch_pack_w1x1_t(nma_handle_s* h, int i, const float* params, cudaStream_t st) {
     float* wt = h->ws[i].wtc_feat + (size_t)8 * FT_WLAYER_F;
     k_tc_pack_w1x1_t<<<1, 256, 0, st>>>(params + h->po[i].hidw[0], wt);
+    nma_count_launch(1);
+    NMA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int objective, float* gp, cudaStream_t st) {
+    const FlowDims& d = h->fd[i];
+    // slot 8 of the flow's pack buffer: the transposed hidden kernel (launch_pack_w1x1_t; weights are constant during a step)
+    float* wt = h->ws[i].wtc_feat + (size_t)8 * FT_WLAYER_F;
     EpiBwdTcArgs a;
     a.wpk = wt;
     a.headw = params + h->po[i].headw;
@@ -1089,7 +1097,7 @@ int launch_epi_bwd_tc(nma_handle_s* h, int i, const float* params, int p, int ob
     else
         k_dtb_from_dat<<<p, TC_CCH * 32, 0, st>>>(h->ws[i].dat_hi, h->ws[i].dat_lo, h->ws[i].dat_Q, h->cfg.K, d.Lin, d.N,
                                                  h->ws[i].dtb, gp + h->po[i].convb);
-    nma_count_launch(3);
+    nma_count_launch(2);
     NMA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
