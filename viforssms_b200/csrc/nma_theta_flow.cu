@@ -235,6 +235,32 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd(ThetaFlowArgs a) {
 // took 0.12 ms at ANY row count - a serial chain of dependent local-memory and global loads - which was 14 % of the
 // reference's own p = 50 iteration.
 // ---------------------------------------------------------------------------
+// Bias and kernel gradient of one masked dense layer of the theta posterior, summed over the rows of a warp: the NO bias
+// sums (go) and the NI x NO kernel sums (in[i] * go[o], kernel layout [i][o]) are taken 16 at a time through
+// warp_sum16_transposed and added to the gradient blob by the even lanes.  Masked kernel entries receive a gradient only
+// under TensorFlow's masked_dense semantics (mg), as before.
+template <int NI, int NO>
+__device__ __forceinline__ void tf_layer_wgrad(const float (&in)[NI], const float (&go)[NO], const float* mask, bool mg,
+                                               float* Gw, float* Gb, int lane) {
+    constexpr int N = (NI + 1) * NO;
+#pragma unroll
+    for (int g0 = 0; g0 < N; g0 += 16) {
+        float part[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int f = g0 + k;
+            part[k] = f < NO ? go[f < NO ? f : 0] : (f < N ? in[f < N ? (f - NO) / NO : 0] * go[(f - NO) % NO] : 0.f);
+        }
+        int j;
+        const float s = warp_sum16_transposed(part, lane, &j);
+        const int f = g0 + j;
+        if (!(lane & 1) && f < N) {
+            if (f < NO) atomicAdd(Gb + f, s);
+            else if (mg || mask[f - NO] != 0.f) atomicAdd(Gw + (f - NO), s);
+        }
+    }
+}
+
 template <int D>
 __global__ void __launch_bounds__(128) k_theta_flow_bwd_t(ThetaFlowArgs a) {
     constexpr int LP = (D * TF_H + TF_H) + 2 * (TF_H * TF_H + TF_H) + (TF_H * 2 * D + 2 * D);
@@ -365,67 +391,37 @@ __global__ void __launch_bounds__(128) k_theta_flow_bwd_t(ThetaFlowArgs a) {
             float g3[TF_H], g2[TF_H], g1[TF_H];
 #pragma unroll
             for (int i = 0; i < TF_H; ++i) g3[i] = g2[i] = g1[i] = 0.f;
+            // Per layer: the bias and kernel gradients are sums over the rows of a warp of (NI + 1) x NO products.  They go
+            // through warp_sum16_transposed 16 at a time (16 shuffles per 16 sums) - one warp_sum per entry was 750
+            // shuffles per bijector and most of this kernel's instruction stream.
             // layer 3 (no activation)
+            tf_layer_wgrad<TF_H, 2 * D>(h3, gout, sM + M3, mg, G + O3, G + OB3, lane);
 #pragma unroll
-            for (int o = 0; o < 2 * D; ++o) {
-                const float go = gout[o];
-                const float sb = warp_sum(go);
-                if (lane == 0) atomicAdd(G + OB3 + o, sb);
+            for (int o = 0; o < 2 * D; ++o)
 #pragma unroll
-                for (int i = 0; i < TF_H; ++i) {
-                    const float m = sM[M3 + i * 2 * D + o];
-                    if (mg || m != 0.f) {
-                        const float sw = warp_sum(h3[i] * go);
-                        if (lane == 0) atomicAdd(G + O3 + i * 2 * D + o, sw);
-                    }
-                    g3[i] = fmaf(go, P[O3 + i * 2 * D + o], g3[i]);
-                }
-            }
+                for (int i = 0; i < TF_H; ++i) g3[i] = fmaf(gout[o], P[O3 + i * 2 * D + o], g3[i]);
+            float go2[TF_H], go1[TF_H], go0[TF_H];
 #pragma unroll
-            for (int o = 0; o < TF_H; ++o) {
-                const float go = g3[o] * tf_dact(h3[o], relu);
-                const float sb = warp_sum(go);
-                if (lane == 0) atomicAdd(G + OB2 + o, sb);
+            for (int o = 0; o < TF_H; ++o) go2[o] = g3[o] * tf_dact(h3[o], relu);
+            tf_layer_wgrad<TF_H, TF_H>(h2, go2, sM + M2, mg, G + O2, G + OB2, lane);
 #pragma unroll
-                for (int i = 0; i < TF_H; ++i) {
-                    const float m = sM[M2 + i * TF_H + o];
-                    if (mg || m != 0.f) {
-                        const float sw = warp_sum(h2[i] * go);
-                        if (lane == 0) atomicAdd(G + O2 + i * TF_H + o, sw);
-                    }
-                    g2[i] = fmaf(go, P[O2 + i * TF_H + o], g2[i]);
-                }
-            }
+            for (int o = 0; o < TF_H; ++o)
 #pragma unroll
-            for (int o = 0; o < TF_H; ++o) {
-                const float go = g2[o] * tf_dact(h2[o], relu);
-                const float sb = warp_sum(go);
-                if (lane == 0) atomicAdd(G + OB1 + o, sb);
+                for (int i = 0; i < TF_H; ++i) g2[i] = fmaf(go2[o], P[O2 + i * TF_H + o], g2[i]);
 #pragma unroll
-                for (int i = 0; i < TF_H; ++i) {
-                    const float m = sM[M1 + i * TF_H + o];
-                    if (mg || m != 0.f) {
-                        const float sw = warp_sum(h1[i] * go);
-                        if (lane == 0) atomicAdd(G + O1 + i * TF_H + o, sw);
-                    }
-                    g1[i] = fmaf(go, P[O1 + i * TF_H + o], g1[i]);
-                }
-            }
+            for (int o = 0; o < TF_H; ++o) go1[o] = g2[o] * tf_dact(h2[o], relu);
+            tf_layer_wgrad<TF_H, TF_H>(h1, go1, sM + M1, mg, G + O1, G + OB1, lane);
 #pragma unroll
-            for (int o = 0; o < TF_H; ++o) {
-                const float go = g1[o] * tf_dact(h1[o], relu);
-                const float sb = warp_sum(go);
-                if (lane == 0) atomicAdd(G + OB0 + o, sb);
+            for (int o = 0; o < TF_H; ++o)
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    const float m = sM[i * TF_H + o];
-                    if (mg || m != 0.f) {
-                        const float sw = warp_sum(z[i] * go);
-                        if (lane == 0) atomicAdd(G + O0 + i * TF_H + o, sw);
-                    }
-                    gz[i] = fmaf(go, P[O0 + i * TF_H + o], gz[i]);
-                }
-            }
+                for (int i = 0; i < TF_H; ++i) g1[i] = fmaf(go1[o], P[O1 + i * TF_H + o], g1[i]);
+#pragma unroll
+            for (int o = 0; o < TF_H; ++o) go0[o] = g1[o] * tf_dact(h1[o], relu);
+            tf_layer_wgrad<D, TF_H>(z, go0, sM, mg, G + O0, G + OB0, lane);
+#pragma unroll
+            for (int o = 0; o < TF_H; ++o)
+#pragma unroll
+                for (int i = 0; i < D; ++i) gz[i] = fmaf(go0[o], P[O0 + i * TF_H + o], gz[i]);
         }
     }
     if (valid && a.g_z0)
