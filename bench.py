@@ -740,7 +740,7 @@ def main():
         args.warmup = 3
     small = args.config != "ar_1e8"
     if args.steps is None:
-        args.steps = 200 if small else 10
+        args.steps = 1000 if small else 10      # small shapes: >= ~0.6 s of timed region, so the 100 ms clock sampler sees it
     if args.cpu_steps is None:
         args.cpu_steps = {"ar_1e8": 50, "ar_default": 100, "fhn": 100, "sv": 20, "lv_fix_theta": 100, "lv_batch": 40}[args.config]
     if args.no_graph and small:
