@@ -130,10 +130,12 @@ extern "C" int nma_create(const nma_config* cfg, nma_handle* out) {
     }
     NMA_CHECK_CUDA(cudaGetDevice(&h->dev));
     NMA_CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->dev));
-    h->aux = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr; h->aux_pending = 0;
+    h->aux = nullptr; h->aux2 = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr; h->ev_join2 = nullptr; h->aux_pending = 0;
     NMA_CHECK_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    NMA_CHECK_CUDA(cudaStreamCreateWithFlags(&h->aux2, cudaStreamNonBlocking));
     NMA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     NMA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    NMA_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
 
     // ---- carve the workspace arena ----
     const int64_t p = cfg->p;
@@ -239,7 +241,9 @@ extern "C" int nma_destroy(nma_handle h) {
     comm_release(h);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->aux2) cudaStreamDestroy(h->aux2);
     if (h->arena) cudaFree(h->arena);
     delete h;
     return 0;
@@ -341,9 +345,9 @@ extern "C" int nma_gather(nma_handle h, const int64_t* d_idx, int32_t p, float* 
 static bool step_is_small(const nma_handle_s* h, int p) {
     return (long long)p * h->fd[0].Lin < (long long)h->sm_count * 1024 && !getenv("NMA_NO_AUX_STREAM");
 }
-static int aux_fork(nma_handle_s* h, cudaStream_t st) {
+static int aux_fork(nma_handle_s* h, cudaStream_t st, cudaStream_t to = nullptr) {
     NMA_CHECK_CUDA(cudaEventRecord(h->ev_fork, st));
-    NMA_CHECK_CUDA(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    NMA_CHECK_CUDA(cudaStreamWaitEvent(to ? to : h->aux, h->ev_fork, 0));
     return 0;
 }
 static int aux_join(nma_handle_s* h, cudaStream_t st) {
@@ -355,6 +359,8 @@ static int aux_join(nma_handle_s* h, cudaStream_t st) {
 int step_aux_join(nma_handle_s* h, cudaStream_t st) {
     if (!h->aux_pending) return 0;
     h->aux_pending = 0;
+    NMA_CHECK_CUDA(cudaEventRecord(h->ev_join2, h->aux2));
+    NMA_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join2, 0));
     return aux_join(h, st);
 }
 
@@ -415,13 +421,15 @@ int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d
                               : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, h->aux)
                                           : launch_conv_wgrad(h, i, p, d_grad_params, h->aux))))
                 return rc;
-            cudaStream_t ds = (i == 0) ? h->aux : st;
+            // (a third stream for the feature branch: weight gradient and feature backward do not depend on each other)
+            cudaStream_t ds = (i == 0) ? h->aux2 : st;
+            if (i == 0 && (rc = aux_fork(h, st, h->aux2))) return rc;
             if (h->is_lv) {
                 if ((rc = launch_lv_conv_dgrad(h, i, d_params, p, ds))) return rc;
             } else if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, ds) : launch_conv_dgrad(h, i, p, ds)))) return rc;
-            if (i > 0 && (rc = aux_fork(h, st))) return rc;          // the feature backward waits for this flow's df
-            if (h->is_lv && (rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, h->aux))) return rc;
-            if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, h->aux))) return rc;
+            if (i > 0 && (rc = aux_fork(h, st, h->aux2))) return rc;   // the feature backward waits for this flow's df
+            if (h->is_lv && (rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, h->aux2))) return rc;
+            if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, h->aux2))) return rc;
             if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, i, st))) return rc;
             h->aux_pending = 1;
             continue;

@@ -125,8 +125,8 @@ struct nma_handle_s {
     // second stream for the kernels of a step that do not depend on each other (weight packing next to the feature
     // forward; the conv weight gradient next to data gradient + feature backward): used when the launch does not fill the
     // machine (the scripts' own row counts), joined back with events - also inside a captured graph
-    cudaStream_t aux;
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t aux, aux2;  // aux: weight packing, conv weight gradients; aux2: feature backward (+ the last flow's data gradient)
+    cudaEvent_t ev_fork, ev_join, ev_join2;
     int aux_pending;         // step_forward_backward left flow 0's conv / feature backward running on `aux` (step_aux_join)
     // ---- whole-iteration entry point (nma_step.cu: nma_train_step) ----
     StepWs step;
