@@ -357,11 +357,14 @@ static int aux_join(nma_handle_s* h, cudaStream_t st) {
 }
 
 int step_aux_join(nma_handle_s* h, cudaStream_t st) {
-    if (!h->aux_pending) return 0;
-    h->aux_pending = 0;
-    NMA_CHECK_CUDA(cudaEventRecord(h->ev_join2, h->aux2));
-    NMA_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join2, 0));
-    return aux_join(h, st);
+    const int pending = h->aux_pending;      // bit 0: aux, bit 1: aux2 (a stream that was never forked must not be joined:
+    h->aux_pending = 0;                      // inside a capture that would pull an uncaptured event into the graph)
+    if (pending & 2) {
+        NMA_CHECK_CUDA(cudaEventRecord(h->ev_join2, h->aux2));
+        NMA_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join2, 0));
+    }
+    if (pending & 1) return aux_join(h, st);
+    return 0;
 }
 
 static int forward_all(nma_handle_s* h, const float* params, const float* eps, const float* theta, const int64_t* idx,
@@ -421,17 +424,20 @@ int step_forward_backward(nma_handle_s* h, const float* d_params, const float* d
                               : h->use_tc ? launch_conv_wgrad_tc(h, i, p, d_grad_params, h->aux)
                                           : launch_conv_wgrad(h, i, p, d_grad_params, h->aux))))
                 return rc;
-            // (a third stream for the feature branch: weight gradient and feature backward do not depend on each other)
-            cudaStream_t ds = (i == 0) ? h->aux2 : st;
-            if (i == 0 && (rc = aux_fork(h, st, h->aux2))) return rc;
+            // (FP32 SIMT models: a third stream for the feature branch - weight gradient and feature backward do not
+            // depend on each other; measured: LV batch 1.77 -> 1.56 ms.  The tensor-core kernels each claim whole SMs, 210 KB of
+            // shared memory per CTA, and three of them side by side were 3 % slower than two on the AR default shape)
+            cudaStream_t fs = h->use_tc ? h->aux : h->aux2;
+            cudaStream_t ds = (i == 0) ? fs : st;
+            if (i == 0 && fs != h->aux && (rc = aux_fork(h, st, fs))) return rc;
             if (h->is_lv) {
                 if ((rc = launch_lv_conv_dgrad(h, i, d_params, p, ds))) return rc;
             } else if ((rc = (h->use_tc ? launch_conv_dgrad_tc(h, i, p, ds) : launch_conv_dgrad(h, i, p, ds)))) return rc;
-            if (i > 0 && (rc = aux_fork(h, st, h->aux2))) return rc;   // the feature backward waits for this flow's df
-            if (h->is_lv && (rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, h->aux2))) return rc;
-            if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, h->aux2))) return rc;
+            if (i > 0 && (rc = aux_fork(h, st, fs))) return rc;       // the feature backward waits for this flow's df
+            if (h->is_lv && (rc = launch_lv_feat4_bwd(h, i, d_params, p, d_grad_params, fs))) return rc;
+            if ((rc = launch_feat_bwd(h, i, d_params, p, d_grad_params, fs))) return rc;
             if ((rc = launch_theta_bwd(h, d_params, d_theta, p, d_grad_params, d_grad_theta, i, st))) return rc;
-            h->aux_pending = 1;
+            h->aux_pending |= (fs == h->aux2) ? 3 : 1;
             continue;
         }
         // the conv weight gradient needs dA only: at small row counts it runs on the second stream next to the data
